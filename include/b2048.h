@@ -1,0 +1,184 @@
+/*
+ * b2048.h — C ABI of libb2048: the B200-native batched 2048 environment and
+ * rollout engine (hand-written sm_100a CUDA behind plain C entry points).
+ *
+ * Drop-in boundary.  The reference (pqpeqr/RL-2048-with-Reinforce-and-Actor-Critic)
+ * is pure Python: its seam is the class API in src/game2048.py, src/env.py,
+ * src/MLP.py and src/reinforce_agent.py.  Every entry point below names the
+ * reference function(s) (file:line) whose arithmetic it replaces; the Python
+ * host mirror in rl-2048-with-reinforce-and-actor-critic_b200/ binds these
+ * symbols with ctypes and re-exposes the reference's own class API.
+ *
+ * Contract (all entry points):
+ *   - plain C types only; no C++ / torch types cross the boundary;
+ *   - every buffer pointer is a DEVICE pointer owned by the caller unless a
+ *     parameter is documented as "host"; the library never frees caller memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); every call is asynchronous with respect to the host;
+ *   - return value: 0 = B2048_OK, otherwise a b2048_status; the message of the
+ *     last failure on the calling thread is returned by b2048_last_error();
+ *   - the device is whatever is current (cudaSetDevice) on the calling thread;
+ *     one process per GPU under multi-GPU.
+ *
+ * Packed board: one uint64 per board, sixteen 4-bit exponents; cell (r, c) of
+ * Game2048.board (game2048.py:16) lives in bits [4*(4r+c), 4*(4r+c)+4); 0 means
+ * empty, e means tile 2^e (e <= 15, i.e. tiles up to 32768).  A 15+15 merge is
+ * outside the domain and raises B2048_F_OVERFLOW for that board.
+ *
+ * Random streams: Philox4x32-10, key = (seed_lo, seed_hi),
+ * counter = (gid_lo, gid_hi, t, domain) with gid the GLOBAL board id
+ * (gid0 + index) and t the caller's global step index — so results do not
+ * depend on how boards are sharded over ranks.
+ *   domain B2048_DOM_STEP : w0 spawn cell, w1 spawn value, w2 env-side random
+ *                           action, w3 policy-sampling uniform
+ *   domain B2048_DOM_RESET: (w0, w1) first spawn, (w2, w3) second spawn
+ * spawn(wp, wv): n = #empty; n == 0 -> no-op; k = mulhi32(wp, n); the k-th
+ * empty cell in row-major order (np.argwhere order, game2048.py:109) receives
+ * exponent 2 if wv >= 0xE6666667 (u = wv/2^32 >= 0.9, game2048.py:117) else 1.
+ */
+#ifndef B2048_H_
+#define B2048_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B2048_OK = 0,
+    B2048_ERR_INVALID = 1,   /* bad argument (NULL pointer, bad mode, n < 0, size != 4 ...) */
+    B2048_ERR_CUDA = 2,      /* a CUDA runtime call failed */
+    B2048_ERR_UNSUPPORTED = 3/* configuration outside what the kernels implement */
+} b2048_status;
+
+/* flags byte written per board by reset_many / step_many */
+#define B2048_F_MASK      0x0Fu  /* bit a: action a is legal on the RETURNED board (0 up,1 right,2 down,3 left; game2048.py:9,95-99) */
+#define B2048_F_CHANGED   0x10u  /* the move changed the board (is_changed, game2048.py:50) */
+#define B2048_F_DONE      0x20u  /* terminated (game2048.py:172-187 after the spawn) */
+#define B2048_F_TRUNC     0x40u  /* truncated (env.py:279-286) */
+#define B2048_F_OVERFLOW  0x80u  /* a 32768+32768 merge happened: board left the 4-bit domain */
+
+#define B2048_DOM_STEP  0u
+#define B2048_DOM_RESET 1u
+
+enum { B2048_REWARD_SUM = 0, B2048_REWARD_LOG2 = 1 };            /* env.py:212-223 */
+enum { B2048_BONUS_OFF = 0, B2048_BONUS_RAW = 1, B2048_BONUS_LOG2 = 2 }; /* env.py:242-249 */
+enum { B2048_OBS_NONE = 0, B2048_OBS_RAW = 1, B2048_OBS_LOG2 = 2, B2048_OBS_ONEHOT = 3 }; /* env.py:131-150 */
+enum { B2048_ACT_BUFFER = 0,      /* actions read from the `action` buffer */
+       B2048_ACT_RANDOM_LEGAL = 1,/* uniform over the legal mask (tools/simple_action_gen.py:7-13) from Philox w2 */
+       B2048_ACT_RANDOM_ANY = 2   /* uniform over {0,1,2,3}, illegal moves included */ };
+
+/* Mirrors Game2048EnvConfig (env.py:19-40); doubles because the reference
+ * combines the reward in Python float64 (env.py:197-261). */
+typedef struct b2048_env_cfg {
+    int32_t reward_mode;            /* B2048_REWARD_*   */
+    int32_t bonus_mode;             /* B2048_BONUS_*    */
+    int32_t obs_mode;               /* B2048_OBS_*      */
+    int32_t use_action_mask;        /* env.py:38        */
+    int32_t max_steps;              /* env.py:40; <= 0 means None (never truncate) */
+    int32_t action_mode;            /* B2048_ACT_*      */
+    int32_t auto_reset;             /* 1: a board that terminated/truncated is reset in the same call */
+    int32_t reserved;
+    double base_reward_scale;       /* env.py:27 */
+    double empty_tile_reward;       /* env.py:29 */
+    double merge_reward;            /* env.py:30 */
+    double bonus_scale;             /* env.py:33 */
+    double step_reward;             /* env.py:35 */
+    double endgame_penalty;         /* env.py:36 */
+    double invalid_action_penalty;  /* env.py:39 */
+    float  obs_log2_scale;          /* env.py:24 (applied in float32 like numpy does) */
+    float  reserved_f;
+} b2048_env_cfg;
+
+typedef struct b2048_handle b2048_handle;
+
+/* Library-owned object holding the 65,536-entry row-transition tables
+ * (Game2048._row_move_left, game2048.py:120-137, tabulated on the device). */
+int b2048_create(b2048_handle** out);
+int b2048_destroy(b2048_handle* h);
+const char* b2048_last_error(void);
+int b2048_version(void);
+
+/* Copies the device tables back (host pointers; either may be NULL):
+ * lut_left[65536]  : row after a left move (4 nibbles);
+ * lut_merge[65536] : two nibbles = exponents of the (<= 2) merged tiles,
+ *                    0 = none, 1 = the out-of-domain 15+15 merge (exponent 16). */
+int b2048_get_row_lut(b2048_handle* h, uint16_t* lut_left_host, uint8_t* lut_merge_host);
+
+/* Game2048.reset + Game2048Env.reset (game2048.py:26-34, env.py:174-194) for n boards.
+ * score/step/max_exp may be NULL.  flags (may be NULL) receives the legal mask. */
+int b2048_reset_many(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t* step,
+                     uint8_t* max_exp, uint8_t* flags, int64_t n,
+                     uint64_t seed, uint64_t gid0, uint32_t t, void* stream);
+
+/* One fused environment step for n boards: Game2048.step/_move/_spawn/_is_done/
+ * get_action_mask (game2048.py:40-70, :95-99, :108-187) + Game2048Env.step/
+ * _compute_reward/_preprocess_board (env.py:131-150, :197-302).
+ *   board_in / board_out : may alias (in-place) or be consecutive slices of a rollout buffer
+ *   score, step, max_exp : per-board env state, updated in place; each may be NULL
+ *                          (step == NULL disables truncation; max_exp == NULL disables the bonus)
+ *   action               : uint8 per board, required for B2048_ACT_BUFFER (values taken & 3)
+ *   action_out           : optional; receives the action actually played (useful for random modes)
+ *   flags_in             : optional legal mask of board_in from the previous call (random-legal mode
+ *                          reads it instead of recomputing); NULL -> recomputed
+ *   merge_sum            : optional int32, sum of merged tiles (game2048.py:167-170)
+ *   reward / reward64    : optional float32 / float64 reward (the float32 is the rounded float64)
+ *   flags                : required uint8, B2048_F_*
+ *   obs                  : optional float32 [n,16] (raw/log2) or [n,16,17] (onehot) of the returned board
+ */
+int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out,
+                    uint32_t* score, uint32_t* step, uint8_t* max_exp,
+                    const uint8_t* action, uint8_t* action_out, const uint8_t* flags_in,
+                    const b2048_env_cfg* cfg /* host */,
+                    int32_t* merge_sum, float* reward, double* reward64, uint8_t* flags, float* obs,
+                    int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, void* stream);
+
+/* Move preview without spawn (Game2048._move, game2048.py:158-165): used by the
+ * differential tests and by get_action_mask-style callers. */
+int b2048_move_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out,
+                    const uint8_t* action, int32_t* merge_sum, uint8_t* merge_info /* [n,4] per line */,
+                    uint8_t* flags, int64_t n, void* stream);
+
+/* Observation encode only (Game2048Env._preprocess_board, env.py:131-150). */
+int b2048_encode_obs(const uint64_t* board, float* obs, int32_t obs_mode, float obs_log2_scale,
+                     int64_t n, void* stream);
+
+/* ---------------- policy / learner ---------------- */
+
+enum { B2048_ACTV_SIGMOID = 0, B2048_ACTV_RELU = 1 };   /* MLP.py:130-136 */
+#define B2048_MAX_LAYERS 8
+
+/* MLP parameters as the reference stores them (MLP.py:45-94): W_l is [in_l, out_l]
+ * row-major float32, b_l is [out_l].  Device pointers. */
+typedef struct b2048_mlp_desc {
+    int32_t n_layers;                     /* number of weight matrices (hidden + 1) */
+    int32_t activation;                   /* B2048_ACTV_* */
+    int32_t obs_mode;                     /* how the input vector is derived from the packed board */
+    float   obs_log2_scale;
+    int32_t dims[B2048_MAX_LAYERS + 1];   /* dims[0] = 16 or 272, dims[n_layers] = outputs */
+    const float* W[B2048_MAX_LAYERS];
+    const float* b[B2048_MAX_LAYERS];
+} b2048_mlp_desc;
+
+/* encode_observation -> forward_logits -> logits_to_probs -> sample / greedy
+ * (MLP.py:22-43, :139-196; reinforce_agent.py:126-192) fused, one call for n boards.
+ *   mask_flags : per-board flags byte (low 4 bits = legal mask); NULL = no mask
+ *   action     : out uint8; probs/logits: optional out float32 [n, n_out]
+ *   greedy     : 1 = first argmax of probs*mask (reinforce_agent.py:179-185)
+ *   precision  : 0 = fp32 CUDA cores (parity path); 1 = bf16 tcgen05 tensor cores (n >= 4096) */
+int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
+                      const b2048_mlp_desc* mlp /* host struct, device pointers inside */,
+                      uint8_t* action, float* probs, float* logits,
+                      int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
+                      int32_t greedy, int32_t precision, void* stream);
+
+/* y[t] = x[t] + c * y[t+1] over t < len[b] per board (compute_returns,
+ * reinforce_agent.py:255-273).  x, y are [T, B] (time-major, board contiguous). */
+int b2048_reverse_scan(const float* x, float* y, const int32_t* len, float c,
+                       int32_t T, int64_t B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2048_H_ */
