@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the b2048 hot path (see BASELINE.json / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload at every N (weak scaling): BASELINE.json configs[1] per GPU — random-action batched env
+stepping on 1,048,576 packed boards (uniform over the legal moves from the Philox action word,
+reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards of the rank.
+
+  value      env-steps/s, whole job, boards resident in HBM, CUDA-event time of the K launches (max over ranks)
+  e2e        the same metric through the host-facing API with HOST (pinned) buffers: per step the actions
+             are copied host->device and board/reward/flags device->host inside the timed region
+  roofline   HBM: 22 algorithmic bytes per env-step over the measured kernel time
+  cpu_baseline  the reference's algorithm on this box's host cores (Python port, all cores), rank 0, N=1 only
+  rollout    secondary: policy-rollout steps/s (MLP 16-256-256-4 forward + masked sampling + env step), 65,536 boards
+
+`--impl reference` times the CPU side alone (the reference is pure Python and cannot travel to the GPU
+box; oracle/pyport.py restates it at the same per-environment granularity).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "2048 env-steps/sec (random-legal batched env stepping, 1M packed boards per GPU)"
+UNIT = "env-steps/s"
+BOARDS_PER_GPU = 1 << 20
+ALGO_BYTES_PER_STEP = 22  # board r 8 + board w 8 + action/mask r 1 + reward w 4 + flags w 1
+RUNNER_ENV = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", base_reward_scale=0.5,
+                  bonus_mode="off", max_steps=1024)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_baseline(seconds: float = 10.0):
+    """The reference's algorithm on the host cores: per-env Python/NumPy port, one process per core."""
+    from oracle import pyport
+    cores = len(os.sched_getaffinity(0))
+    rate, nsteps = pyport.time_multiprocess(seconds, cores)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nsteps} random-legal env steps (runner-default env, reset-on-done) in ~{seconds:.0f} s, "
+                      f"{cores} processes of oracle/pyport.py (per-env Python+NumPy restatement of the reference)"}
+
+
+def cpu_native_baseline(n=1 << 18, steps=20):
+    """Extra context: the C oracle (same rules, compiled, multi-threaded) — a much stronger CPU baseline."""
+    import oracle
+    cores = len(os.sched_getaffinity(0))
+    cfg = oracle.make_cfg(action_mode="random_legal", auto_reset=True, **RUNNER_ENV)
+    secs = oracle.bench_steps(n, steps, cores, cfg)
+    return {"value": n * steps / secs, "unit": UNIT, "cores": cores, "kind": "port-native-C",
+            "sample": f"{n} boards x {steps} steps, oracle/b2048_oracle.c on {cores} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), args.warmup
+    from oracle import pyport
+    cores = len(os.sched_getaffinity(0))
+    # each "step" is a bounded sample: ~1 s of all-core stepping; total capped to a few minutes
+    per = min(1.0, 150.0 / (steps + warm))
+    for _ in range(warm):
+        pyport.time_multiprocess(per, cores)
+    t0 = time.perf_counter()
+    total = 0
+    rate_acc = 0.0
+    for _ in range(steps):
+        rate, n = pyport.time_multiprocess(per, cores)
+        total += n
+        rate_acc += rate
+    wall = time.perf_counter() - t0
+    value = rate_acc / steps
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "random-legal env stepping, runner-default Game2048Env, reset-on-done; "
+                                   "bounded sample per step on all host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{total} env steps in {steps} samples of {per:.2f} s x {cores} processes"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import b2048
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.boards
+    K, W = args.steps, max(3, args.warmup)
+
+    env = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=0xB200, gid0=rank * n,
+                               track_state=not args.lean)
+    env.reset_many()
+    # spread the boards over the episode distribution before timing (64 untimed steps)
+    for _ in range(64):
+        env.step_many(action_mode="random_legal", auto_reset=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        flush.zero_()
+        env.step_many(action_mode="random_legal", auto_reset=True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        for k in range(K):
+            flush.zero_()                      # evict boards from L2 between timed launches
+            starts[k].record()
+            env.step_many(action_mode="random_legal", auto_reset=True)
+            ends[k].record()
+        barrier()
+    kernel_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms = float(t.item())
+    value = world * n * K / (kernel_ms * 1e-3)
+    clocks = clk.summary()
+
+    # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region
+    Ke = min(K, 100)
+    h_act = torch.randint(0, 4, (n,), dtype=torch.uint8).pin_memory()
+    d_act = torch.empty(n, dtype=torch.uint8, device=dev)
+    h_board = torch.empty(n, dtype=torch.int64).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_flags = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        d_act.copy_(h_act, non_blocking=True)
+        rew, fl = env.step_many(d_act, auto_reset=True)
+        h_board.copy_(env.board, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_flags.copy_(fl, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        e2e_step()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / (float(te.item()) * 1e-3)
+    checksum = int(h_board.sum().item()) ^ int(h_flags.sum().item())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        per_launch_s = kernel_ms * 1e-3 / K
+        achieved = n * ALGO_BYTES_PER_STEP / per_launch_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": kernel_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"random-legal batched env stepping, {n} packed boards per GPU "
+                                   f"(BASELINE.json configs[1]), runner-default env, reset-on-done",
+                       "boards_per_gpu": n, "l2": "flushed between timed launches (256 MiB memset)",
+                       "state": "board only (22 B/step variant)" if args.lean else
+                                "board + score/step/max_tile counters kept per step (+18 B/step, not counted)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 1, "d2h_bytes_per_step": n * 13,
+                    "steps": Ke, "checksum": checksum},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "b2::step_kernel<true,1024>",
+                         "avg_launch_us": per_launch_s * 1e6},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            try:
+                line["cpu_baseline_native"] = cpu_native_baseline()
+            except Exception as e:  # the native leg is context only
+                line["cpu_baseline_native"] = {"error": str(e)}
+        if hasattr(b2048, "bench_rollout") and not args.no_rollout:
+            try:
+                line["rollout"] = b2048.bench_rollout(dev)
+            except Exception as e:
+                line["rollout"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--boards", type=int, default=BOARDS_PER_GPU)
+    ap.add_argument("--lean", action="store_true", help="board-only state (no score/step/max_tile arrays)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,384 @@
+// b2048_env.cu — environment kernels of libb2048 (sm_100a) and their C entry points.
+//
+//   K0 build_lut_kernel   Game2048._row_move_left tabulated over all 65,536 rows (game2048.py:120-137)
+//   K1 reset_kernel       Game2048.reset + Game2048Env.reset              (game2048.py:26-34, env.py:174-194)
+//   K2 step_kernel        fused Game2048.step + Game2048Env.step          (game2048.py:40-70, env.py:197-302)
+//      move_kernel        Game2048._move preview                          (game2048.py:158-165)
+//      obs_kernel         Game2048Env._preprocess_board                   (env.py:131-150)
+//
+// Data layout in HBM: structure-of-arrays, one element per board: board u64, score u32, step u32,
+// max_exp u8, action u8, reward f32, flags u8.  One thread owns one board; a warp touches 256 B of
+// boards, 32 B of actions / flags, 128 B of rewards per step, all fully coalesced.
+//
+// K2 is bound by instruction issue, not HBM: the 192 KB row tables are staged into
+// shared memory once per CTA by bulk async copies (TMA engine, cp.async.bulk + mbarrier) that
+// overlap the Philox block and the board loads; one persistent 1024-thread CTA per SM then
+// grid-strides over the boards.
+#include <cuda_runtime.h>
+
+#include "b2048_internal.h"
+#include "b2048_step.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------ K0
+__global__ void build_lut_kernel(uint16_t* __restrict__ lut_left, uint8_t* __restrict__ lut_merge) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= 65536u) return;
+    uint32_t out, merge;
+    row_move_left(row, out, merge);
+    lut_left[row] = (uint16_t)out;
+    lut_merge[row] = (uint8_t)merge;
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(256) reset_kernel(uint64_t* __restrict__ board, uint32_t* __restrict__ score,
+                                                     uint32_t* __restrict__ step, uint8_t* __restrict__ max_exp,
+                                                     uint8_t* __restrict__ flags, int64_t n, uint64_t seed,
+                                                     uint64_t gid0, uint32_t t) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Board b = reset_board(seed, gid0 + (uint64_t)i, t);
+        board[i] = to_u64(b);
+        if (score) score[i] = 0u;
+        if (step) step[i] = 0u;
+        if (max_exp) max_exp[i] = 2u;  // max_tile_seen = 4 (env.py:183)
+        if (flags) flags[i] = (uint8_t)legal_mask(b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+struct StepArgs {
+    const uint64_t* board_in;
+    uint64_t* board_out;
+    uint32_t* score;
+    uint32_t* step;
+    uint8_t* max_exp;
+    const uint8_t* action;
+    uint8_t* action_out;
+    const uint8_t* flags_in;
+    int32_t* merge_sum;
+    float* reward;
+    double* reward64;
+    uint8_t* flags;
+    float* obs;
+    const uint8_t* tables;  // device copy of the row tables
+    int64_t n;
+    uint64_t seed, gid0;
+    uint32_t t;
+    b2048_env_cfg cfg;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 128-bit coalesced observation stores for raw / log2: lane l of store round s writes row (l & 3) of
+// the board held by lane 8s + (l >> 2), so consecutive lanes write consecutive 16-byte chunks.
+__device__ __forceinline__ void store_obs16(float* __restrict__ obs, Board nb, int64_t warp_base, int64_t n, int lane,
+                                            int obs_mode, float scale) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int src = 8 * s + (lane >> 2);
+        uint32_t lo = __shfl_sync(0xFFFFFFFFu, nb.lo, src);
+        uint32_t hi = __shfl_sync(0xFFFFFFFFu, nb.hi, src);
+        int row = lane & 3;
+        uint32_t w = (row & 2) ? hi : lo;
+        uint32_t r16 = (w >> (16 * (row & 1))) & 0xFFFFu;
+        float v[4];
+        encode_row(r16, obs_mode, scale, v);
+        int64_t bi = warp_base + src;
+        if (bi < n) {
+            float4 q = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(obs + bi * 16 + row * 4) = q;
+        }
+    }
+}
+
+// onehot [16][17] float32 per board = 68 float4: the warp writes board after board, 128-bit per lane
+__device__ __forceinline__ void store_obs_onehot(float* __restrict__ obs, Board nb, int64_t warp_base, int64_t n,
+                                                 int lane) {
+    for (int j = 0; j < 32; ++j) {
+        int64_t bi = warp_base + j;
+        if (bi >= n) break;  // warp-uniform
+        uint32_t lo = __shfl_sync(0xFFFFFFFFu, nb.lo, j);
+        uint32_t hi = __shfl_sync(0xFFFFFFFFu, nb.hi, j);
+        uint64_t b = (uint64_t)lo | ((uint64_t)hi << 32);
+        float4* dst = reinterpret_cast<float4*>(obs + bi * 272);
+#pragma unroll
+        for (int q0 = 0; q0 < 96; q0 += 32) {
+            int q = q0 + lane;
+            if (q < 68) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int f = 4 * q + u;
+                    int cell = f / 17, ch = f - 17 * cell;
+                    int e = (int)((b >> (4 * cell)) & 0xFull);
+                    v[u] = (e == ch) ? 1.0f : 0.0f;
+                }
+                dst[q] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+template <bool kSmemLut, int kThreads>
+__global__ void __launch_bounds__(kThreads, kSmemLut ? 1 : 2) step_kernel(const __grid_constant__ StepArgs args) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const uint16_t* lut_left;
+    const uint8_t* lut_merge;
+
+    if (kSmemLut) {
+        // Stage both row tables (192 KB) into shared memory with the bulk-copy engine; completion is
+        // signalled on an mbarrier so the copy overlaps the first iteration's loads and Philox block.
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)),
+                         "r"((uint32_t)B2048_LUT_BYTES)
+                         : "memory");
+            constexpr uint32_t kChunk = 32768;
+#pragma unroll
+            for (uint32_t off = 0; off < (uint32_t)B2048_LUT_BYTES; off += kChunk) {
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                        smem_u32(smem + off)),
+                    "l"(args.tables + off), "r"(kChunk), "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+        }
+        lut_left = reinterpret_cast<const uint16_t*>(smem);
+        lut_merge = smem + B2048_LUT_LEFT_BYTES;
+    } else {
+        lut_left = reinterpret_cast<const uint16_t*>(args.tables);
+        lut_merge = args.tables + B2048_LUT_LEFT_BYTES;
+    }
+
+    const b2048_env_cfg& cfg = args.cfg;
+    StepOpts opt;
+    opt.track_step = args.step != nullptr;
+    opt.track_max = args.max_exp != nullptr;
+    opt.want_sum = cfg.reward_mode == B2048_REWARD_SUM || args.score != nullptr || args.merge_sum != nullptr;
+
+    bool lut_ready = !kSmemLut;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < args.n; base += stride) {
+        const int64_t i = base + tid;
+        const bool valid = i < args.n;
+        StepIO io;
+        io.board = Board{0u, 0u};
+        io.score = 0u;
+        io.step = 0u;
+        io.max_exp = 2u;
+        io.action = 0u;
+        io.mask_in = 0u;
+        io.have_mask_in = args.flags_in != nullptr;
+        if (valid) {
+            io.board = make_board(args.board_in[i]);
+            if (args.score) io.score = args.score[i];
+            if (args.step) io.step = args.step[i];
+            if (args.max_exp) io.max_exp = args.max_exp[i];
+            if (cfg.action_mode == B2048_ACT_BUFFER) io.action = args.action[i];
+            if (args.flags_in) io.mask_in = args.flags_in[i];
+        }
+        if (!lut_ready) {
+            // all threads wait on phase 0 of the table barrier (returns immediately once complete)
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+            lut_ready = true;
+        }
+        step_one(io, cfg, opt, args.seed, args.gid0 + (uint64_t)i, args.t, lut_left, lut_merge);
+        if (valid) {
+            args.board_out[i] = to_u64(io.board);
+            if (args.score) args.score[i] = io.score;
+            if (args.step) args.step[i] = io.step;
+            if (args.max_exp) args.max_exp[i] = (uint8_t)io.max_exp;
+            if (args.action_out) args.action_out[i] = (uint8_t)io.action_played;
+            if (args.merge_sum) args.merge_sum[i] = io.merge_sum;
+            if (args.reward) args.reward[i] = (float)io.reward;
+            if (args.reward64) args.reward64[i] = io.reward;
+            args.flags[i] = (uint8_t)io.flags;
+        }
+        if (args.obs != nullptr && cfg.obs_mode != B2048_OBS_NONE) {
+            const int64_t warp_base = base + (tid & ~31);
+            if (cfg.obs_mode == B2048_OBS_ONEHOT) store_obs_onehot(args.obs, io.board, warp_base, args.n, lane);
+            else store_obs16(args.obs, io.board, warp_base, args.n, lane, cfg.obs_mode, cfg.obs_log2_scale);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ previews
+__global__ void __launch_bounds__(256) move_kernel(const uint64_t* __restrict__ board_in, uint64_t* __restrict__ board_out,
+                                                    const uint8_t* __restrict__ action, int32_t* __restrict__ merge_sum,
+                                                    uint8_t* __restrict__ merge_info, uint8_t* __restrict__ flags,
+                                                    const uint8_t* __restrict__ tables, int64_t n) {
+    const uint16_t* lut_left = reinterpret_cast<const uint16_t*>(tables);
+    const uint8_t* lut_merge = tables + B2048_LUT_LEFT_BYTES;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Board b = make_board(board_in[i]);
+        MoveResult mv = move_board(b, action[i] & 3u, lut_left, lut_merge);
+        MergeStats ms = merge_stats(mv.merge, true, false);
+        uint32_t mask = legal_mask(mv.board);
+        bool changed = (mv.board.lo != b.lo) | (mv.board.hi != b.hi);
+        bool done = (mask == 0u) & ((mv.board.lo | mv.board.hi) != 0u);
+        board_out[i] = to_u64(mv.board);
+        if (merge_sum) merge_sum[i] = (int32_t)ms.sum;
+        if (merge_info) *reinterpret_cast<uint32_t*>(merge_info + 4 * i) = mv.merge;
+        if (flags)
+            flags[i] = (uint8_t)(mask | (changed ? B2048_F_CHANGED : 0u) | (done ? B2048_F_DONE : 0u) |
+                                 (ms.overflow ? B2048_F_OVERFLOW : 0u));
+    }
+}
+
+__global__ void __launch_bounds__(256) obs_kernel(const uint64_t* __restrict__ board, float* __restrict__ obs, int obs_mode,
+                                                   float scale, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+        int64_t i = base + threadIdx.x;
+        Board b = i < n ? make_board(board[i]) : Board{0u, 0u};
+        int64_t warp_base = base + (threadIdx.x & ~31);
+        if (obs_mode == B2048_OBS_ONEHOT) store_obs_onehot(obs, b, warp_base, n, lane);
+        else store_obs16(obs, b, warp_base, n, lane, obs_mode, scale);
+    }
+}
+
+static int grid_for(int64_t n, int threads, int num_sms, int per_sm) {
+    int64_t blocks = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)num_sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace b2
+
+// ================================================================================================ C ABI
+using namespace b2;
+
+extern "C" int b2048_create(b2048_handle** out) {
+    B2_REQUIRE(out != nullptr, "b2048_create: out is NULL");
+    b2048_handle* h = new b2048_handle();
+    B2_CUDA(cudaGetDevice(&h->device));
+    B2_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
+    B2_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    B2_CUDA(cudaMalloc(&h->d_tables, B2048_LUT_BYTES));
+    build_lut_kernel<<<256, 256>>>(reinterpret_cast<uint16_t*>(h->d_tables), h->d_tables + B2048_LUT_LEFT_BYTES);
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaDeviceSynchronize());
+    if (h->smem_optin >= B2048_LUT_BYTES) {
+        B2_CUDA(cudaFuncSetAttribute(step_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     B2048_LUT_BYTES));
+    }
+    *out = h;
+    return B2048_OK;
+}
+
+extern "C" int b2048_destroy(b2048_handle* h) {
+    if (!h) return B2048_OK;
+    cudaFree(h->d_tables);
+    delete h;
+    return B2048_OK;
+}
+
+extern "C" int b2048_get_row_lut(b2048_handle* h, uint16_t* lut_left_host, uint8_t* lut_merge_host) {
+    B2_REQUIRE(h != nullptr, "b2048_get_row_lut: handle is NULL");
+    if (lut_left_host) B2_CUDA(cudaMemcpy(lut_left_host, h->d_tables, B2048_LUT_LEFT_BYTES, cudaMemcpyDeviceToHost));
+    if (lut_merge_host)
+        B2_CUDA(cudaMemcpy(lut_merge_host, h->d_tables + B2048_LUT_LEFT_BYTES, B2048_LUT_MERGE_BYTES,
+                           cudaMemcpyDeviceToHost));
+    return B2048_OK;
+}
+
+extern "C" int b2048_reset_many(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t* step, uint8_t* max_exp,
+                                uint8_t* flags, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_reset_many: handle is NULL");
+    B2_REQUIRE(n >= 0, "b2048_reset_many: n < 0");
+    B2_REQUIRE(board != nullptr || n == 0, "b2048_reset_many: board is NULL");
+    if (n == 0) return B2048_OK;
+    reset_kernel<<<grid_for(n, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(board, score, step, max_exp, flags,
+                                                                                   n, seed, gid0, t);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out, uint32_t* score,
+                               uint32_t* step, uint8_t* max_exp, const uint8_t* action, uint8_t* action_out,
+                               const uint8_t* flags_in, const b2048_env_cfg* cfg, int32_t* merge_sum, float* reward,
+                               double* reward64, uint8_t* flags, float* obs, int64_t n, uint64_t seed, uint64_t gid0,
+                               uint32_t t, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_step_many: handle is NULL");
+    B2_REQUIRE(cfg != nullptr, "b2048_step_many: cfg is NULL");
+    B2_REQUIRE(n >= 0, "b2048_step_many: n < 0");
+    if (n == 0) return B2048_OK;
+    B2_REQUIRE(board_in && board_out && flags, "b2048_step_many: board_in/board_out/flags must not be NULL");
+    B2_REQUIRE(cfg->reward_mode == B2048_REWARD_SUM || cfg->reward_mode == B2048_REWARD_LOG2,
+               "b2048_step_many: unsupported reward mode");  // env.py:222-223
+    B2_REQUIRE(cfg->bonus_mode >= B2048_BONUS_OFF && cfg->bonus_mode <= B2048_BONUS_LOG2,
+               "b2048_step_many: unsupported bonus mode");  // env.py:248-249
+    B2_REQUIRE(cfg->obs_mode >= B2048_OBS_NONE && cfg->obs_mode <= B2048_OBS_ONEHOT,
+               "b2048_step_many: unsupported obs_mode");  // env.py:109-110
+    B2_REQUIRE(cfg->action_mode >= B2048_ACT_BUFFER && cfg->action_mode <= B2048_ACT_RANDOM_ANY,
+               "b2048_step_many: unsupported action_mode");
+    B2_REQUIRE(cfg->action_mode != B2048_ACT_BUFFER || action != nullptr,
+               "b2048_step_many: action buffer required for B2048_ACT_BUFFER");
+    StepArgs a;
+    a.board_in = board_in; a.board_out = board_out; a.score = score; a.step = step; a.max_exp = max_exp;
+    a.action = action; a.action_out = action_out; a.flags_in = flags_in; a.merge_sum = merge_sum;
+    a.reward = reward; a.reward64 = reward64; a.flags = flags; a.obs = obs; a.tables = h->d_tables;
+    a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg;
+    cudaStream_t s = (cudaStream_t)stream;
+    // Large batches: persistent CTAs with the tables in shared memory.  Small batches (the B=1
+    // drop-in env, unit tests): tables read through L1/L2, no 192 KB staging per launch.
+    const bool use_smem = h->smem_optin >= B2048_LUT_BYTES && n >= (int64_t)32768;
+    if (use_smem) {
+        int grid = grid_for(n, 1024, h->num_sms, 1);
+        step_kernel<true, 1024><<<grid, 1024, B2048_LUT_BYTES, s>>>(a);
+    } else {
+        int grid = grid_for(n, 256, h->num_sms, 8);
+        step_kernel<false, 256><<<grid, 256, 0, s>>>(a);
+    }
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+extern "C" int b2048_move_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out, const uint8_t* action,
+                               int32_t* merge_sum, uint8_t* merge_info, uint8_t* flags, int64_t n, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_move_many: handle is NULL");
+    B2_REQUIRE(n >= 0, "b2048_move_many: n < 0");
+    if (n == 0) return B2048_OK;
+    B2_REQUIRE(board_in && board_out && action, "b2048_move_many: board_in/board_out/action must not be NULL");
+    move_kernel<<<grid_for(n, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(board_in, board_out, action, merge_sum,
+                                                                                  merge_info, flags, h->d_tables, n);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+extern "C" int b2048_encode_obs(const uint64_t* board, float* obs, int32_t obs_mode, float obs_log2_scale, int64_t n,
+                                void* stream) {
+    B2_REQUIRE(n >= 0, "b2048_encode_obs: n < 0");
+    B2_REQUIRE(obs_mode >= B2048_OBS_RAW && obs_mode <= B2048_OBS_ONEHOT, "b2048_encode_obs: unsupported obs_mode");
+    if (n == 0) return B2048_OK;
+    B2_REQUIRE(board && obs, "b2048_encode_obs: board/obs must not be NULL");
+    int dev = 0, sms = 148;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    obs_kernel<<<grid_for(n, 256, sms, 8), 256, 0, (cudaStream_t)stream>>>(board, obs, obs_mode, obs_log2_scale, n);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}

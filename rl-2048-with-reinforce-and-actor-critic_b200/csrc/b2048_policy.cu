@@ -1,0 +1,181 @@
+// b2048_policy.cu — K3 policy_step and the plain MLP forward (fp32 CUDA-core path).
+//
+//   policy_step_kernel   encode_observation -> forward_logits -> logits_to_probs -> sample / greedy
+//                        (src/MLP.py:22-43, :139-196; src/reinforce_agent.py:126-192) fused: the packed
+//                        board is the only per-board input, the action byte (+ optional probs / logits)
+//                        the only output; activations never leave shared memory.
+//   mlp_forward_kernel   forward_logits only (critic values V(s), logits for tests / update)
+#include <cuda_runtime.h>
+
+#include "b2048_device.cuh"
+#include "b2048_internal.h"
+#include "b2048_mlp.cuh"
+
+namespace b2 {
+
+struct PolicyArgs {
+    MlpDev mlp;
+    const uint64_t* board;
+    const uint8_t* mask_flags;
+    uint8_t* action;
+    float* probs;
+    float* logits;
+    int64_t n;
+    uint64_t seed, gid0;
+    uint32_t t;
+    int greedy;
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 1) policy_step_kernel(const __grid_constant__ PolicyArgs args) {
+    extern __shared__ __align__(16) float arena[];
+    const MlpDev& m = args.mlp;
+    const int n_out = m.dims[m.n_layers];
+    const int64_t n_tiles = (args.n + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * kTileM;
+        tile_forward_hidden(arena, m, args.board, s0, args.n, nullptr);
+        float logit = tile_head(arena, m);
+        const int b = threadIdx.x >> 2, j = threadIdx.x & 3;
+        const int64_t s = s0 + b;
+        const bool valid = s < args.n;
+        uint32_t fl = 0xFu;
+        const bool use_mask = args.mask_flags != nullptr;
+        if (use_mask && valid) fl = args.mask_flags[s];
+        const bool legal = (fl >> j) & 1u;
+        if (j >= n_out) logit = -INFINITY;  // fewer than 4 outputs: the spare lanes never win
+        float p = quad_softmax(logit, legal, use_mask);
+        if (valid && j < n_out) {
+            if (args.probs) args.probs[s * n_out + j] = p;
+            if (args.logits) args.logits[s * n_out + j] = logit;
+        }
+        // gather the quad's probabilities
+        const int qbase = (threadIdx.x & 31) & ~3;
+        float p0 = __shfl_sync(0xFFFFFFFFu, p, qbase + 0), p1 = __shfl_sync(0xFFFFFFFFu, p, qbase + 1);
+        float p2 = __shfl_sync(0xFFFFFFFFu, p, qbase + 2), p3 = __shfl_sync(0xFFFFFFFFu, p, qbase + 3);
+        if (valid && j == 0 && args.action) {
+            uint32_t a;
+            if (args.greedy) {
+                // int(np.argmax(probs * mask)): first maximum wins (reinforce_agent.py:179-185)
+                float q0 = (fl & 1u) ? p0 : 0.0f, q1 = (fl & 2u) ? p1 : 0.0f, q2 = (fl & 4u) ? p2 : 0.0f,
+                      q3 = (fl & 8u) ? p3 : 0.0f;
+                if (!use_mask) { q0 = p0; q1 = p1; q2 = p2; q3 = p3; }
+                a = 0; float best = q0;
+                if (q1 > best) { best = q1; a = 1; }
+                if (q2 > best) { best = q2; a = 2; }
+                if (q3 > best) { best = q3; a = 3; }
+            } else {
+                // rng.choice(4, p=probs) == inverse CDF on one uniform (reinforce_agent.py:187); the uniform
+                // is word 3 of the board's Philox block for this step
+                Rand4 r = stream(args.seed, args.gid0 + (uint64_t)s, args.t, B2048_DOM_STEP);
+                float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
+                float u = ((float)(r.w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
+                a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
+                // never return a zero-probability (masked) action because of rounding at a CDF edge
+                float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
+                if (!(pa > 0.0f)) {
+                    if (p3 > 0.0f) a = 3;
+                    if (p2 > 0.0f) a = 2;
+                    if (p1 > 0.0f) a = 1;
+                    if (p0 > 0.0f) a = 0;
+                }
+            }
+            args.action[s] = (uint8_t)a;
+        }
+        __syncthreads();  // arena is reused by the next tile
+    }
+}
+
+struct ForwardArgs {
+    MlpDev mlp;
+    const uint64_t* board;
+    float* out;
+    int64_t n;
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const __grid_constant__ ForwardArgs args) {
+    extern __shared__ __align__(16) float arena[];
+    const MlpDev& m = args.mlp;
+    const int n_out = m.dims[m.n_layers];
+    const int64_t n_tiles = (args.n + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * kTileM;
+        tile_forward_hidden(arena, m, args.board, s0, args.n, nullptr);
+        float v = tile_head(arena, m);
+        const int b = threadIdx.x >> 2, j = threadIdx.x & 3;
+        if (s0 + b < args.n && j < n_out) args.out[(s0 + b) * n_out + j] = v;
+        __syncthreads();
+    }
+}
+
+int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
+    if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
+    if (d->n_layers < 1 || d->n_layers > B2048_MAX_LAYERS)
+        return fail(B2048_ERR_INVALID, std::string(who) + ": n_layers out of range");
+    if (d->activation != B2048_ACTV_SIGMOID && d->activation != B2048_ACTV_RELU)
+        return fail(B2048_ERR_INVALID, std::string(who) + ": unsupported activation");  // MLP.py:135-136
+    if (d->obs_mode < B2048_OBS_RAW || d->obs_mode > B2048_OBS_ONEHOT)
+        return fail(B2048_ERR_INVALID, std::string(who) + ": unsupported obs_mode");
+    const int in0 = d->obs_mode == B2048_OBS_ONEHOT ? 272 : 16;
+    if (d->dims[0] != in0) return fail(B2048_ERR_INVALID, std::string(who) + ": dims[0] must be 16 (raw/log2) or 272 (onehot)");
+    const int n_out = d->dims[d->n_layers];
+    if (n_out < 1 || n_out > 4) return fail(B2048_ERR_UNSUPPORTED, std::string(who) + ": 1..4 outputs supported");
+    for (int l = 1; l < d->n_layers; ++l)
+        if (d->dims[l] < 4 || d->dims[l] % 4 != 0 || d->dims[l] > 1024)
+            return fail(B2048_ERR_UNSUPPORTED, std::string(who) + ": hidden sizes must be multiples of 4 in [4,1024]");
+    for (int l = 0; l < d->n_layers; ++l)
+        if (!d->W[l] || !d->b[l]) return fail(B2048_ERR_INVALID, std::string(who) + ": NULL parameter pointer");
+    out->n_layers = d->n_layers; out->activation = d->activation; out->obs_mode = d->obs_mode;
+    out->obs_scale = d->obs_log2_scale;
+    for (int l = 0; l <= d->n_layers; ++l) out->dims[l] = d->dims[l];
+    for (int l = 0; l < d->n_layers; ++l) { out->W[l] = d->W[l]; out->b[l] = d->b[l]; }
+    *smem_bytes = mlp_arena_bytes(out->dims, out->n_layers);
+    if (*smem_bytes > (size_t)smem_optin)
+        return fail(B2048_ERR_UNSUPPORTED, std::string(who) + ": hidden layers too wide for the shared-memory activation arena");
+    return B2048_OK;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
+                                 const b2048_mlp_desc* mlp, uint8_t* action, float* probs, float* logits, int64_t n,
+                                 uint64_t seed, uint64_t gid0, uint32_t t, int32_t greedy, int32_t precision,
+                                 void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_policy_step: handle is NULL");
+    B2_REQUIRE(n >= 0, "b2048_policy_step: n < 0");
+    if (n == 0) return B2048_OK;
+    B2_REQUIRE(board != nullptr, "b2048_policy_step: board is NULL");
+    PolicyArgs a;
+    size_t smem = 0;
+    int st = validate_mlp(mlp, &a.mlp, &smem, h->smem_optin, "b2048_policy_step");
+    if (st != B2048_OK) return st;
+    if (precision != 0) return fail(B2048_ERR_UNSUPPORTED, "b2048_policy_step: precision 1 (bf16 tcgen05) not built in this library");
+    a.board = board; a.mask_flags = mask_flags; a.action = action; a.probs = probs; a.logits = logits;
+    a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.greedy = greedy;
+    B2_CUDA(cudaFuncSetAttribute(policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t tiles = (n + kTileM - 1) / kTileM;
+    int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    policy_step_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+extern "C" int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
+                                 int64_t n, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_mlp_forward: handle is NULL");
+    B2_REQUIRE(n >= 0, "b2048_mlp_forward: n < 0");
+    if (n == 0) return B2048_OK;
+    B2_REQUIRE(board != nullptr && out != nullptr, "b2048_mlp_forward: board/out is NULL");
+    ForwardArgs a;
+    size_t smem = 0;
+    int st = validate_mlp(mlp, &a.mlp, &smem, h->smem_optin, "b2048_mlp_forward");
+    if (st != B2048_OK) return st;
+    a.board = board; a.out = out; a.n = n;
+    B2_CUDA(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t tiles = (n + kTileM - 1) / kTileM;
+    int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    mlp_forward_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}

@@ -1,0 +1,271 @@
+"""GPU parity tests of the environment kernels, through the C ABI (ctypes), against the CPU oracle and the
+golden fixtures generated from the live reference.  Bit-exact everywhere (integer / byte work; the float64
+reward is combined in the reference's operation order)."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from helpers import ENV_CONFIGS, GOLDEN, full_env_kwargs, random_boards  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def b2048():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import b2048 as m
+    return m
+
+
+def to_dev(a):
+    if a.dtype == np.uint64:
+        a = a.view(np.int64)
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def make_env(b2048, name, n, seed, gid0, **over):
+    kw = full_env_kwargs(name)
+    kw.update(over)
+    return b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=gid0)
+
+
+def oracle_cfg(name, **over):
+    kw = full_env_kwargs(name)
+    kw.pop("size")
+    kw.update(over)
+    if kw["max_steps"] is None:
+        kw["max_steps"] = 0
+    return oracle.make_cfg(**kw)
+
+
+def test_device_row_tables_match_reference(b2048):
+    import ctypes as C
+    lib = b2048._lib.load()
+    h = b2048.get_handle(torch.device("cuda", 0))
+    left = np.zeros(65536, np.uint16)
+    merge = np.zeros(65536, np.uint8)
+    b2048._lib.check(lib.b2048_get_row_lut(h, left.ctypes.data_as(C.c_void_p), merge.ctypes.data_as(C.c_void_p)))
+    g = np.load(os.path.join(GOLDEN, "row_lut.npz"))
+    assert (left == g["left"]).all() and (merge == g["merge"]).all()
+
+
+def move_many(b2048, boards, actions):
+    import ctypes as C
+    lib = b2048._lib.load()
+    h = b2048.get_handle(torch.device("cuda", 0))
+    n = len(boards)
+    bi, ac = to_dev(boards), to_dev(actions)
+    bo = torch.zeros(n, dtype=torch.int64, device="cuda")
+    ms = torch.zeros(n, dtype=torch.int32, device="cuda")
+    mi = torch.zeros((n, 4), dtype=torch.uint8, device="cuda")
+    fl = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    b2048._lib.check(lib.b2048_move_many(h, p(bi), p(bo), p(ac), p(ms), p(mi), p(fl), n, None), "move_many")
+    torch.cuda.synchronize()
+    return u64(bo), ms.cpu().numpy(), mi.cpu().numpy(), fl.cpu().numpy()
+
+
+def test_moves_golden(b2048):
+    g = np.load(os.path.join(GOLDEN, "moves.npz"))
+    boards = g["boards"]
+    n = len(boards)
+    for a in range(4):
+        out, msum, minfo, fl = move_many(b2048, boards, np.full(n, a, np.uint8))
+        assert (out == g["result"][:, a]).all()
+        assert (msum == g["merge_sum"][:, a]).all()
+        assert (((fl & 0x10) != 0) == (g["changed"][:, a] != 0)).all()
+    # legal mask / done of the input boards: play the identity through step flags of a no-op is not possible,
+    # so use move results: mask of result boards is checked against the oracle below
+    out, _, _, fl = move_many(b2048, boards, np.zeros(n, np.uint8))
+    m, d = oracle.mask_done(out)
+    assert ((fl & 0x0F) == m).all() and (((fl & 0x20) != 0) == (d != 0)).all()
+
+
+def test_moves_random_1m(b2048):
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    boards = random_boards(rng, n)
+    actions = rng.integers(0, 4, n).astype(np.uint8)
+    out, msum, minfo, fl = move_many(b2048, boards, actions)
+    o, ms, mi, f = oracle.move_many(boards, actions)
+    assert (out == o).all() and (msum == ms).all() and (fl == f).all()
+    # per-line merge nibbles are reported in canonical-row order; compare as multisets per board
+    got = np.sort(np.concatenate([minfo & 0xF, minfo >> 4], 1), 1)
+    exp = np.sort(np.concatenate([mi & 0xF, mi >> 4], 1), 1)
+    assert (got == exp).all()
+
+
+def test_reset_many(b2048):
+    for n, seed, gid0 in ((1, 1, 0), (1000, 0xB200, 0), (70001, 2**63 + 5, 2**40)):
+        env = b2048.Batched2048Env(n, seed=seed, gid0=gid0)
+        env.reset_many()
+        st = oracle.reset_many(n, seed, gid0, 0)
+        assert (u64(env.board) == st["board"]).all()
+        assert (env.flags.cpu().numpy() == st["flags"]).all()
+        assert int(env.score.sum()) == 0 and int(env.step_count.sum()) == 0 and int(env.max_exp.min()) == 2
+
+
+@pytest.mark.parametrize("name", list(ENV_CONFIGS))
+def test_replayed_episodes_golden(b2048, name):
+    """The committed reference outputs (Game2048Env.step with replayed spawns), step by step."""
+    g = np.load(os.path.join(GOLDEN, "episodes.npz"))
+    seed, gid0 = int(g["seed"]), int(g["gid0"])
+    board = g[f"{name}/board"]
+    T, n = board.shape
+    mask_on = full_env_kwargs(name)["use_action_mask"]
+    env = make_env(b2048, name, n, seed, gid0)
+    env.reset_many()
+    assert (u64(env.board) == g[f"{name}/board0"]).all() and (env.flags.cpu().numpy() == g[f"{name}/flags0"]).all()
+    act = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    obs = torch.zeros((n, env.obs_width), dtype=torch.float32, device="cuda")
+    alive = np.ones(n, bool)
+    for t in range(1, T + 1):
+        rew, fl = env.step_many(action_mode="random_legal" if mask_on else "random_any", action_out=act,
+                                reward64_out=r64, obs_out=obs)
+        L = alive
+        assert (act.cpu().numpy()[L] == g[f"{name}/action"][t - 1][L]).all()
+        assert (u64(env.board)[L] == board[t - 1][L]).all()
+        assert (r64.cpu().numpy()[L] == g[f"{name}/reward"][t - 1][L]).all()
+        assert (rew.cpu().numpy()[L] == g[f"{name}/reward"][t - 1][L].astype(np.float32)).all()
+        assert (fl.cpu().numpy()[L] == g[f"{name}/flags"][t - 1][L]).all()
+        assert (env.score.cpu().numpy()[L] == g[f"{name}/score"][t - 1][L]).all()
+        assert (env.step_count.cpu().numpy()[L] == g[f"{name}/step"][t - 1][L]).all()
+        assert ((1 << env.max_exp.cpu().numpy().astype(np.int64))[L] == g[f"{name}/max_tile"][t - 1][L]).all()
+        if t <= g[f"{name}/obs"].shape[0]:
+            assert (obs.cpu().numpy()[L] == g[f"{name}/obs"][t - 1][L]).all()
+        alive = g[f"{name}/alive"][t - 1]
+
+
+def test_autoreset_golden(b2048):
+    g = np.load(os.path.join(GOLDEN, "autoreset.npz"))
+    seed, gid0 = int(g["seed"]), int(g["gid0"])
+    T, n = g["board"].shape
+    env = make_env(b2048, "runner_default", n, seed, gid0, max_steps=int(g["max_steps"]))
+    env.reset_many()
+    act = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(1, T + 1):
+        rew, fl = env.step_many(action_mode="random_legal", auto_reset=True, action_out=act, reward64_out=r64)
+        assert (u64(env.board) == g["board"][t - 1]).all()
+        assert (r64.cpu().numpy() == g["reward"][t - 1]).all()
+        assert (fl.cpu().numpy() == g["flags"][t - 1]).all()
+        assert (act.cpu().numpy() == g["action"][t - 1]).all()
+
+
+@pytest.mark.parametrize("name,n,auto_reset", [
+    ("runner_default", 40000, True),      # shared-memory-table kernel (n >= 32768), persistent CTAs
+    ("shaped_raw", 33333, True),          # ragged tail
+    ("onehot_log2bonus", 4097, False),    # global-table kernel
+    ("mask_off", 100, False),
+    ("dataclass_default", 1, False),      # B = 1, the drop-in env's case
+])
+def test_step_many_vs_oracle(b2048, name, n, auto_reset):
+    mask_on = full_env_kwargs(name)["use_action_mask"]
+    mode = "random_legal" if mask_on else "random_any"
+    seed, gid0, T = 987654321, 5 * 10**9, 130
+    env = make_env(b2048, name, n, seed, gid0)
+    env.reset_many()
+    cfg = oracle_cfg(name, action_mode=mode, auto_reset=auto_reset)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    act = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    r64 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    ms = torch.zeros(n, dtype=torch.int32, device="cuda")
+    obs = torch.zeros((n, env.obs_width), dtype=torch.float32, device="cuda")
+    for t in range(1, T + 1):
+        want_obs = t % 16 == 1
+        rew, fl = env.step_many(action_mode=mode, auto_reset=auto_reset, action_out=act, reward64_out=r64,
+                                merge_sum_out=ms, obs_out=obs if want_obs else None, use_prev_mask=bool(t % 2))
+        o = oracle.step_many(st, cfg, seed, gid0, t, want_obs=want_obs)
+        assert (act.cpu().numpy() == o["action"]).all(), t
+        assert (u64(env.board) == st["board"]).all(), t
+        assert (ms.cpu().numpy() == o["merge_sum"]).all()
+        assert (r64.cpu().numpy() == o["reward64"]).all() and (rew.cpu().numpy() == o["reward"]).all()
+        assert (fl.cpu().numpy() == o["flags"]).all()
+        assert (env.score.cpu().numpy() == st["score"]).all()
+        assert (env.step_count.cpu().numpy() == st["step"]).all()
+        assert (env.max_exp.cpu().numpy() == st["max_exp"]).all()
+        if want_obs:
+            cfg_obs = oracle_cfg(name, action_mode=mode, auto_reset=auto_reset)
+            assert (obs.cpu().numpy() == oracle.encode_obs(st["board"], full_env_kwargs(name)["obs_mode"],
+                                                           full_env_kwargs(name)["obs_log2_scale"])).all()
+
+
+def test_step_buffer_actions_and_untracked_state(b2048):
+    rng = np.random.default_rng(5)
+    n, seed, T = 50000, 3, 60
+    kw = full_env_kwargs("runner_default")
+    env = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, track_state=False)
+    env.reset_many()
+    cfg = oracle_cfg("runner_default", action_mode="buffer")
+    st = oracle.reset_many(n, seed, 0, 0)
+    for t in range(1, T + 1):
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        rew, fl = env.step_many(to_dev(a))
+        o = oracle.step_many(st, cfg, seed, 0, t, action=a, use_state=False)
+        assert (u64(env.board) == st["board"]).all()
+        assert (rew.cpu().numpy() == o["reward"]).all() and (fl.cpu().numpy() == o["flags"]).all()
+
+
+def test_sharding_invariance(b2048):
+    """Philox is keyed on the global board id: two 'ranks' holding halves reproduce the single-rank run."""
+    n, seed, T = 66000, 42, 40
+    full = make_env(b2048, "runner_default", n, seed, 0)
+    full.reset_many()
+    h0 = make_env(b2048, "runner_default", n // 2, seed, 0)
+    h1 = make_env(b2048, "runner_default", n - n // 2, seed, n // 2)
+    h0.reset_many(); h1.reset_many()
+    for t in range(T):
+        full.step_many(action_mode="random_legal", auto_reset=True)
+        h0.step_many(action_mode="random_legal", auto_reset=True)
+        h1.step_many(action_mode="random_legal", auto_reset=True)
+    assert torch.equal(full.board, torch.cat([h0.board, h1.board]))
+    assert torch.equal(full.flags, torch.cat([h0.flags, h1.flags]))
+    assert torch.equal(full.score, torch.cat([h0.score, h1.score]))
+
+
+def test_random_legal_statistics(b2048):
+    """tools/simple_action_gen.py:9-11: random-legal policy averages ~1.1k score (reference re-run: 1159, 123 steps)."""
+    n = 100000
+    env = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(max_steps=None), seed=2048)
+    env.reset_many()
+    alive = torch.ones(n, dtype=torch.bool, device="cuda")
+    final_score = torch.zeros(n, dtype=torch.int32, device="cuda")
+    length = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for t in range(1, 2000):
+        _, fl = env.step_many(action_mode="random_legal")
+        done = (fl & 0x20) != 0
+        newly = alive & done
+        final_score[newly] = env.score[newly]
+        length[newly] = t
+        alive &= ~done
+        if t % 50 == 0 and not bool(alive.any()):
+            break
+    assert not bool(alive.any())
+    mean_score = float(final_score.float().mean())
+    mean_len = float(length.float().mean())
+    assert 1050.0 < mean_score < 1200.0, mean_score
+    assert 110.0 < mean_len < 135.0, mean_len
+    assert int(final_score.min()) >= 20 and int(final_score.max()) < 20000
+
+
+def test_error_paths(b2048):
+    with pytest.raises(ValueError):
+        b2048.Batched2048Env(4, b2048.Game2048EnvConfig(size=5))
+    with pytest.raises(ValueError):
+        b2048.Batched2048Env(4, b2048.Game2048EnvConfig(obs_mode="bogus"))
+    env = b2048.Batched2048Env(4)
+    env.reset_many()
+    with pytest.raises(ValueError):
+        env.step_many(torch.zeros(3, dtype=torch.uint8, device="cuda"))
+    empty = b2048.Batched2048Env(0)
+    empty.reset_many()
+    empty.step_many(action_mode="random_legal")

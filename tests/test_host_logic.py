@@ -1,0 +1,111 @@
+"""CPU-side check of the PRODUCT's bit tricks and step body: the kernels' host+device headers
+(csrc/b2048_device.cuh, csrc/b2048_step.cuh) are compiled with g++ (tests/host_check) and compared
+bit-exactly with the independent cell-by-cell CPU oracle.  No GPU needed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import ENV_CONFIGS, GOLDEN, P, full_env_kwargs, host_check_lib, random_boards
+
+
+def test_row_tables_match_reference_fixture():
+    hc = host_check_lib()
+    left = np.zeros(65536, np.uint16)
+    merge = np.zeros(65536, np.uint8)
+    hc.hc_get_lut(P(left), P(merge))
+    g = np.load(os.path.join(GOLDEN, "row_lut.npz"))
+    assert (left == g["left"]).all() and (merge == g["merge"]).all()
+
+
+def test_moves_and_masks_random_boards():
+    hc = host_check_lib()
+    rng = np.random.default_rng(7)
+    n = 200000
+    boards = random_boards(rng, n)
+    for a in range(4):
+        act = np.full(n, a, np.uint8)
+        o, ms, _, fl = oracle.move_many(boards, act)
+        o2 = np.zeros(n, np.uint64); ms2 = np.zeros(n, np.int32); fl2 = np.zeros(n, np.uint8)
+        hc.hc_move_many(P(boards), P(o2), P(act), P(ms2), P(fl2), C.c_int64(n))
+        assert (o == o2).all() and (ms == ms2).all() and (fl == fl2).all()
+    m, _ = oracle.mask_done(boards)
+    m2 = np.zeros(n, np.uint8)
+    hc.hc_mask(P(boards), P(m2), C.c_int64(n))
+    assert (m == m2).all()
+
+
+def test_moves_golden_fixture():
+    hc = host_check_lib()
+    g = np.load(os.path.join(GOLDEN, "moves.npz"))
+    boards = g["boards"]
+    n = len(boards)
+    for a in range(4):
+        act = np.full(n, a, np.uint8)
+        o2 = np.zeros(n, np.uint64); ms2 = np.zeros(n, np.int32); fl2 = np.zeros(n, np.uint8)
+        hc.hc_move_many(P(boards), P(o2), P(act), P(ms2), P(fl2), C.c_int64(n))
+        assert (o2 == g["result"][:, a]).all() and (ms2 == g["merge_sum"][:, a]).all()
+    m2 = np.zeros(n, np.uint8)
+    hc.hc_mask(P(boards), P(m2), C.c_int64(n))
+    assert (m2 == g["mask"]).all()
+
+
+def test_reset_many():
+    hc = host_check_lib()
+    n = 50000
+    for seed, gid0, t in ((0xB200, 0, 0), (2**63 + 5, 2**40, 77)):
+        st = oracle.reset_many(n, seed, gid0, t)
+        b = np.zeros(n, np.uint64); f = np.zeros(n, np.uint8)
+        hc.hc_reset_many(P(b), P(f), C.c_int64(n), C.c_uint64(seed), C.c_uint64(gid0), C.c_uint32(t))
+        assert (b == st["board"]).all() and (f == st["flags"]).all()
+
+
+@pytest.mark.parametrize("name", list(ENV_CONFIGS))
+@pytest.mark.parametrize("auto_reset", [False, True])
+def test_step_body_vs_oracle(name, auto_reset):
+    hc = host_check_lib()
+    kw = full_env_kwargs(name)
+    kw.pop("size")
+    mask_on = kw["use_action_mask"]
+    if kw["max_steps"] is None:
+        kw["max_steps"] = 0
+    n, T, seed, gid0 = 4096, 220, 31337, 10**9
+    cfg = oracle.make_cfg(action_mode="random_legal" if mask_on else "random_any", auto_reset=auto_reset, **kw)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    board = st["board"].copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
+    flags_prev = st["flags"].copy()
+    for t in range(1, T + 1):
+        o = oracle.step_many(st, cfg, seed, gid0, t)
+        act = np.zeros(n, np.uint8); ms = np.zeros(n, np.int32); rw = np.zeros(n, np.float32)
+        rw64 = np.zeros(n, np.float64); fl = np.zeros(n, np.uint8)
+        # alternate between supplying the previous mask and letting the step recompute it
+        hc.hc_step_many(P(board), P(board), P(score), P(step), P(mx), None, P(act),
+                        P(flags_prev) if t % 2 else None, C.byref(cfg), P(ms), P(rw), P(rw64), P(fl),
+                        C.c_int64(n), C.c_uint64(seed), C.c_uint64(gid0), C.c_uint32(t))
+        assert (act == o["action"]).all()
+        assert (board == st["board"]).all()
+        assert (ms == o["merge_sum"]).all()
+        assert (rw64 == o["reward64"]).all() and (rw == o["reward"]).all()
+        assert (fl == o["flags"]).all()
+        assert (score == st["score"]).all() and (step == st["step"]).all() and (mx == st["max_exp"]).all()
+        flags_prev = fl.copy()
+
+
+def test_step_buffer_actions_including_illegal():
+    hc = host_check_lib()
+    rng = np.random.default_rng(3)
+    n, T, seed = 2048, 120, 5
+    kw = full_env_kwargs("shaped_raw"); kw.pop("size"); kw["max_steps"] = 50
+    cfg = oracle.make_cfg(action_mode="buffer", **kw)
+    st = oracle.reset_many(n, seed, 0, 0)
+    board = st["board"].copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
+    for t in range(1, T + 1):
+        a = rng.integers(0, 4, n).astype(np.uint8)
+        o = oracle.step_many(st, cfg, seed, 0, t, action=a)
+        ms = np.zeros(n, np.int32); rw64 = np.zeros(n, np.float64); fl = np.zeros(n, np.uint8)
+        hc.hc_step_many(P(board), P(board), P(score), P(step), P(mx), P(a), None, None, C.byref(cfg), P(ms), None,
+                        P(rw64), P(fl), C.c_int64(n), C.c_uint64(seed), C.c_uint64(0), C.c_uint32(t))
+        assert (board == st["board"]).all() and (rw64 == o["reward64"]).all() and (fl == o["flags"]).all()
+        assert (score == st["score"]).all() and (step == st["step"]).all() and (mx == st["max_exp"]).all()
