@@ -109,8 +109,8 @@ int b2048_get_row_lut(b2048_handle* h, uint16_t* lut_left_host, uint8_t* lut_mer
 /* Game2048.reset + Game2048Env.reset (game2048.py:26-34, env.py:174-194) for n boards.
  * score/step/max_exp may be NULL.  flags (may be NULL) receives the legal mask. */
 int b2048_reset_many(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t* step,
-                     uint8_t* max_exp, uint8_t* flags, int64_t n,
-                     uint64_t seed, uint64_t gid0, uint32_t t, void* stream);
+                     uint8_t* max_exp, uint8_t* flags, const uint8_t* spawn_replay /* [n,2] or NULL */,
+                     int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, void* stream);
 
 /* One fused environment step for n boards: Game2048.step/_move/_spawn/_is_done/
  * get_action_mask (game2048.py:40-70, :95-99, :108-187) + Game2048Env.step/
@@ -122,16 +122,25 @@ int b2048_reset_many(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t
  *   action_out           : optional; receives the action actually played (useful for random modes)
  *   flags_in             : optional legal mask of board_in from the previous call (random-legal mode
  *                          reads it instead of recomputing); NULL -> recomputed
+ *   spawn_replay         : optional uint8 per board; when bit 7 is set the spawn is NOT drawn from Philox
+ *                          but replayed: bits 0-3 = index k of the empty cell (row-major), bit 4 = tile is a 4.
+ *                          This is how the single-env drop-in reproduces the reference's NumPy-seeded games
+ *                          (rng.integers / rng.random of game2048.py:113,117 are drawn by the host wrapper).
  *   merge_sum            : optional int32, sum of merged tiles (game2048.py:167-170)
  *   reward / reward64    : optional float32 / float64 reward (the float32 is the rounded float64)
  *   flags                : required uint8, B2048_F_*
  *   obs                  : optional float32 [n,16] (raw/log2) or [n,16,17] (onehot) of the returned board
+ *   ep_len, ep_t         : optional run-to-termination rollout bookkeeping (ReinforceAgent.run_episode's
+ *                          `while not done`, reinforce_agent.py:221-236, for a whole batch): boards with
+ *                          ep_len[i] != 0 are finished and passed through untouched (reward 0); a board that
+ *                          terminates or truncates in this call gets ep_len[i] = ep_t.
  */
 int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out,
                     uint32_t* score, uint32_t* step, uint8_t* max_exp,
                     const uint8_t* action, uint8_t* action_out, const uint8_t* flags_in,
-                    const b2048_env_cfg* cfg /* host */,
+                    const uint8_t* spawn_replay, const b2048_env_cfg* cfg /* host */,
                     int32_t* merge_sum, float* reward, double* reward64, uint8_t* flags, float* obs,
+                    int32_t* ep_len, uint32_t ep_t,
                     int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, void* stream);
 
 /* Move preview without spawn (Game2048._move, game2048.py:158-165): used by the
@@ -173,10 +182,63 @@ int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mas
                       int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
                       int32_t greedy, int32_t precision, void* stream);
 
-/* y[t] = x[t] + c * y[t+1] over t < len[b] per board (compute_returns,
- * reinforce_agent.py:255-273).  x, y are [T, B] (time-major, board contiguous). */
+/* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1). */
+int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
+                      int64_t n, void* stream);
+
+/* forward_logits on explicit float32 inputs x[n, dims[0]] — the reference's own signature (MLP.py:159-196).
+ * act_out / pre_out: HOST arrays of device pointers (either array, or any entry, may be NULL):
+ * act_out[l+1] receives a_{l+1} [n, dims[l+1]] (act_out[n_layers] = logits), pre_out[l] receives z_l. */
+int b2048_dense_forward(b2048_handle* h, const float* x, const b2048_mlp_desc* mlp, float* const* act_out,
+                        float* const* pre_out, int64_t n, void* stream);
+
+/* y[t] = x[t] + c * y[t+1] over t < len[b] per board, 0 beyond (compute_returns,
+ * reinforce_agent.py:255-273).  x, y are [T, B] (time-major, board contiguous); len may be NULL (= T).
+ * b2048_reverse_scan: one thread per board with the recurrence in float64 exactly like the reference's
+ * Python loop when B >= 2048, a warp-shuffle affine suffix scan (float32) per board below that.
+ * b2048_reverse_scan_f64: always the float64 per-board recurrence (bit-exact to the reference). */
 int b2048_reverse_scan(const float* x, float* y, const int32_t* len, float c,
                        int32_t T, int64_t B, void* stream);
+int b2048_reverse_scan_f64(const float* x, float* y, const int32_t* len, double c,
+                           int32_t T, int64_t B, void* stream);
+
+/* _compute_advantages + _compute_weighted_stats (reinforce_agent.py:276-325, :864-881) over a [T, B]
+ * buffer of returns (or TD errors) v.  baseline_mode: 0 off, 1 each, 2 batch, 3 batch_norm.
+ * ep_weight[B] = episode rank weights (NULL = 1).  Outputs (either may be NULL):
+ *   adv[T,B]  the advantages;  coef[T,B] = adv * ep_weight[b] / (len[b] * n_traj), the per-sample weight
+ *   of grad log pi in update_batch (reinforce_agent.py:533-555); both 0 for t >= len[b].
+ * stats: device double[4] scratch, receives {sum w, sum w v, sum w (v-mean)^2, count}.
+ * ep_mean_scratch: device float[B], needed for mode 1. */
+int b2048_advantages(b2048_handle* h, const float* v, const int32_t* len, const float* ep_weight,
+                     int32_t baseline_mode, float n_traj, int32_t T, int64_t B, float* adv, float* coef,
+                     double* stats, float* ep_mean_scratch, void* stream);
+
+/* TD(0) errors of the critic block (reinforce_agent.py:439-447): td = r + gamma V(s') [t+1 < len] - V(s);
+ * gcoef = dLoss/dV * ep_weight/(len n_traj) with dLoss/dV = V - target (mse) or its Huber clip
+ * (_get_grad_logits_critic, reinforce_agent.py:884-910).  All buffers [T, B]. */
+int b2048_td_errors(b2048_handle* h, const float* reward, const float* value, const int32_t* len,
+                    const float* ep_weight, float gamma, int32_t huber, float huber_delta, float n_traj,
+                    int32_t T, int64_t B, float* td, float* gcoef, void* stream);
+
+/* Gradient accumulation of update_batch's actor / critic blocks (reinforce_agent.py:403-555, _backpropagation
+ * :639-678) over n samples (flattened [T,B] rollout; samples with coef == 0 contribute nothing).
+ * grads is a flat float32 vector laid out W_0, b_0, W_1, b_1, ... and is ACCUMULATED into (zero it first).
+ *   head_mode 0: += d/dtheta sum_s coef[s] log pi(action[s] | board[s])   (mask_flags: legal masks, may be NULL)
+ *   head_mode 1: += d/dtheta sum_s coef[s] V(board[s])
+ * workspace: device floats, at least b2048_backward_workspace_floats(mlp, chunk); samples are processed
+ * `chunk` at a time. */
+int64_t b2048_backward_workspace_floats(const b2048_mlp_desc* mlp, int64_t chunk);
+int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
+                       const uint8_t* action, const float* coef, const b2048_mlp_desc* mlp, float* grads,
+                       int64_t n, int32_t head_mode, float* workspace, int64_t workspace_floats,
+                       int64_t chunk, void* stream);
+
+/* clip_grads_global_norm (reinforce_agent.py:835-861) + SGD (:565-575) or Adam (:719-770) on a flat parameter
+ * vector.  optimizer 0 sgd / 1 adam; sign +1 ascent (actor), -1 descent (critic); adam_t = step count after
+ * increment.  grads is clipped in place; sumsq_out (device double[1]) receives the squared norm before clipping. */
+int b2048_apply_update(b2048_handle* h, float* theta, float* grads, float* adam_m, float* adam_v, int64_t n,
+                       int32_t optimizer, float lr, float sign, float max_grad_norm, float beta1, float beta2,
+                       int32_t adam_t, double* sumsq_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,12 +56,21 @@ SIGNATURES = {
     "b2048_destroy": [_vp],
     "b2048_version": [],
     "b2048_get_row_lut": [_vp, _vp, _vp],
-    "b2048_reset_many": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _u32, _vp],
-    "b2048_step_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp,
-                        _i64, _u64, _u64, _u32, _vp],
+    "b2048_reset_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _u32, _vp],
+    "b2048_step_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp,
+                        _vp, _u32, _i64, _u64, _u64, _u32, _vp],
     "b2048_move_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "b2048_encode_obs": [_vp, _vp, _i32, _f32, _i64, _vp],
-    # POLICY_SIGS
+    "b2048_policy_step": [_vp, _vp, _vp, C.POINTER(MlpDesc), _vp, _vp, _vp, _i64, _u64, _u64, _u32, _i32, _i32, _vp],
+    "b2048_mlp_forward": [_vp, _vp, C.POINTER(MlpDesc), _vp, _i64, _vp],
+    "b2048_dense_forward": [_vp, _vp, C.POINTER(MlpDesc), _vp, _vp, _i64, _vp],
+    "b2048_reverse_scan": [_vp, _vp, _vp, _f32, _i32, _i64, _vp],
+    "b2048_reverse_scan_f64": [_vp, _vp, _vp, C.c_double, _i32, _i64, _vp],
+    "b2048_advantages": [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
+    "b2048_td_errors": [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _f32, _f32, _i32, _i64, _vp, _vp, _vp],
+    "b2048_backward_workspace_floats": [C.POINTER(MlpDesc), _i64],
+    "b2048_mlp_backward": [_vp, _vp, _vp, _vp, _vp, C.POINTER(MlpDesc), _vp, _i64, _i32, _vp, _i64, _i64, _vp],
+    "b2048_apply_update": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp],
 }
 
 _lib = None
@@ -81,7 +90,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here == ABI mismatch, on purpose
         fn.argtypes = argtypes
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name == "b2048_backward_workspace_floats" else C.c_int
     _lib = lib
     return lib
 

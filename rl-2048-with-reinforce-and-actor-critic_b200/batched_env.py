@@ -111,14 +111,15 @@ class Batched2048Env:
         self.obs_width = 272 if self.config.obs_mode == "onehot" else 16
 
     # ------------------------------------------------------------------ reset
-    def reset_many(self, seed: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    def reset_many(self, seed: int | None = None, spawn_replay: torch.Tensor | None = None
+                   ) -> tuple[torch.Tensor, torch.Tensor]:
         """Game2048Env.reset for every board; returns (packed boards, flags)."""
         if seed is not None:
             self.seed = int(seed) & (2**64 - 1)
         self.t = 0
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b2048_reset_many(self._h, _ptr(self.board), _ptr(self.score), _ptr(self.step_count),
-                                                  _ptr(self.max_exp), _ptr(self.flags), self.num_envs, self.seed,
+                                                  _ptr(self.max_exp), _ptr(self.flags), _ptr(spawn_replay), self.num_envs, self.seed,
                                                   self.gid0, self.t, _stream()), "b2048_reset_many")
         return self.board, self.flags
 
@@ -128,7 +129,8 @@ class Batched2048Env:
                   action_out: torch.Tensor | None = None, merge_sum_out: torch.Tensor | None = None,
                   reward64_out: torch.Tensor | None = None, board_out: torch.Tensor | None = None,
                   reward_out: torch.Tensor | None = None, flags_out: torch.Tensor | None = None,
-                  use_prev_mask: bool = True):
+                  use_prev_mask: bool = True, spawn_replay: torch.Tensor | None = None,
+                  ep_len: torch.Tensor | None = None, ep_t: int = 0, flags_in: torch.Tensor | None = None):
         """One env step for every board.  ``actions`` uint8 [N] on the device, or None with
         ``action_mode`` 'random_legal' / 'random_any' (device-side Philox actions).
 
@@ -143,15 +145,17 @@ class Batched2048Env:
         cfg = make_env_cfg(self.config, mode, auto_reset, emit_obs=obs_out is not None)
         self.t += 1
         reward = reward_out if reward_out is not None else self.reward
-        flags_in = self.flags if (use_prev_mask and mode == "random_legal") else None
+        if flags_in is None:
+            flags_in = self.flags if (use_prev_mask and (mode == "random_legal" or ep_len is not None)) else None
         flags = flags_out if flags_out is not None else self.flags
         b_out = board_out if board_out is not None else self.board
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b2048_step_many(
                 self._h, _ptr(self.board), _ptr(b_out), _ptr(self.score), _ptr(self.step_count), _ptr(self.max_exp),
-                _ptr(actions) if mode == "buffer" else None, _ptr(action_out), _ptr(flags_in), C.byref(cfg),
+                _ptr(actions) if mode == "buffer" else None, _ptr(action_out), _ptr(flags_in), _ptr(spawn_replay),
+                C.byref(cfg),
                 _ptr(merge_sum_out), _ptr(reward), _ptr(reward64_out), _ptr(flags), _ptr(obs_out),
-                self.num_envs, self.seed, self.gid0, self.t, _stream()), "b2048_step_many")
+                _ptr(ep_len), int(ep_t), self.num_envs, self.seed, self.gid0, self.t, _stream()), "b2048_step_many")
         if board_out is not None:
             self.board = board_out
         if flags_out is not None:

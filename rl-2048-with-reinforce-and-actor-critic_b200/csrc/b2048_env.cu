@@ -34,11 +34,19 @@ __global__ void build_lut_kernel(uint16_t* __restrict__ lut_left, uint8_t* __res
 // ------------------------------------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(256) reset_kernel(uint64_t* __restrict__ board, uint32_t* __restrict__ score,
                                                      uint32_t* __restrict__ step, uint8_t* __restrict__ max_exp,
-                                                     uint8_t* __restrict__ flags, int64_t n, uint64_t seed,
+                                                     uint8_t* __restrict__ flags,
+                                                     const uint8_t* __restrict__ spawn_replay, int64_t n, uint64_t seed,
                                                      uint64_t gid0, uint32_t t) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Board b = reset_board(seed, gid0 + (uint64_t)i, t);
+        Board b;
+        if (spawn_replay) {  // the two spawns of Game2048.reset chosen by the host (game2048.py:32-33)
+            uint32_t r0 = spawn_replay[2 * i], r1 = spawn_replay[2 * i + 1];
+            b = place_kth_empty(Board{0u, 0u}, r0 & 0xFu, (r0 & 0x10u) ? 2u : 1u);
+            b = place_kth_empty(b, r1 & 0xFu, (r1 & 0x10u) ? 2u : 1u);
+        } else {
+            b = reset_board(seed, gid0 + (uint64_t)i, t);
+        }
         board[i] = to_u64(b);
         if (score) score[i] = 0u;
         if (step) step[i] = 0u;
@@ -57,6 +65,9 @@ struct StepArgs {
     const uint8_t* action;
     uint8_t* action_out;
     const uint8_t* flags_in;
+    const uint8_t* spawn_replay;
+    int32_t* ep_len;   // rollout mode: 0 = episode still running; otherwise frozen (finished at that many steps)
+    uint32_t ep_t;     // value stored in ep_len when an episode ends in this call
     int32_t* merge_sum;
     float* reward;
     double* reward64;
@@ -179,7 +190,9 @@ __global__ void __launch_bounds__(kThreads, kSmemLut ? 1 : 2) step_kernel(const 
         io.action = 0u;
         io.mask_in = 0u;
         io.have_mask_in = args.flags_in != nullptr;
+        io.replay = 0u;
         if (valid) {
+            if (args.spawn_replay) io.replay = args.spawn_replay[i];
             io.board = make_board(args.board_in[i]);
             if (args.score) io.score = args.score[i];
             if (args.step) io.step = args.step[i];
@@ -201,8 +214,24 @@ __global__ void __launch_bounds__(kThreads, kSmemLut ? 1 : 2) step_kernel(const 
             }
             lut_ready = true;
         }
+        bool frozen = false;
+        Board board_before = io.board;
+        if (args.ep_len && valid) frozen = args.ep_len[i] != 0;
         step_one(io, cfg, opt, args.seed, args.gid0 + (uint64_t)i, args.t, lut_left, lut_merge);
-        if (valid) {
+        if (valid && frozen) {
+            // finished episode of a run-to-termination rollout: pass the terminal state through untouched
+            uint32_t m = legal_mask(board_before);
+            uint32_t f = args.flags_in ? (uint32_t)args.flags_in[i]
+                                       : (m | ((m == 0u && (board_before.lo | board_before.hi) != 0u) ? B2048_F_DONE : 0u));
+            args.board_out[i] = to_u64(board_before);
+            if (args.action_out) args.action_out[i] = 0;
+            if (args.merge_sum) args.merge_sum[i] = 0;
+            if (args.reward) args.reward[i] = 0.0f;
+            if (args.reward64) args.reward64[i] = 0.0;
+            args.flags[i] = (uint8_t)(f & ~B2048_F_CHANGED);
+            io.board = board_before;
+        } else if (valid) {
+            if (args.ep_len && (io.flags & (B2048_F_DONE | B2048_F_TRUNC))) args.ep_len[i] = (int32_t)args.ep_t;
             args.board_out[i] = to_u64(io.board);
             if (args.score) args.score[i] = io.score;
             if (args.step) args.step[i] = io.step;
@@ -306,22 +335,24 @@ extern "C" int b2048_get_row_lut(b2048_handle* h, uint16_t* lut_left_host, uint8
 }
 
 extern "C" int b2048_reset_many(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t* step, uint8_t* max_exp,
-                                uint8_t* flags, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, void* stream) {
+                                uint8_t* flags, const uint8_t* spawn_replay, int64_t n, uint64_t seed, uint64_t gid0,
+                                uint32_t t, void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_reset_many: handle is NULL");
     B2_REQUIRE(n >= 0, "b2048_reset_many: n < 0");
     B2_REQUIRE(board != nullptr || n == 0, "b2048_reset_many: board is NULL");
     if (n == 0) return B2048_OK;
     reset_kernel<<<grid_for(n, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(board, score, step, max_exp, flags,
-                                                                                   n, seed, gid0, t);
+                                                                                   spawn_replay, n, seed, gid0, t);
     B2_CUDA(cudaGetLastError());
     return B2048_OK;
 }
 
 extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out, uint32_t* score,
                                uint32_t* step, uint8_t* max_exp, const uint8_t* action, uint8_t* action_out,
-                               const uint8_t* flags_in, const b2048_env_cfg* cfg, int32_t* merge_sum, float* reward,
-                               double* reward64, uint8_t* flags, float* obs, int64_t n, uint64_t seed, uint64_t gid0,
-                               uint32_t t, void* stream) {
+                               const uint8_t* flags_in, const uint8_t* spawn_replay, const b2048_env_cfg* cfg,
+                               int32_t* merge_sum, float* reward,
+                               double* reward64, uint8_t* flags, float* obs, int32_t* ep_len, uint32_t ep_t, int64_t n,
+                               uint64_t seed, uint64_t gid0, uint32_t t, void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_step_many: handle is NULL");
     B2_REQUIRE(cfg != nullptr, "b2048_step_many: cfg is NULL");
     B2_REQUIRE(n >= 0, "b2048_step_many: n < 0");
@@ -339,7 +370,8 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
                "b2048_step_many: action buffer required for B2048_ACT_BUFFER");
     StepArgs a;
     a.board_in = board_in; a.board_out = board_out; a.score = score; a.step = step; a.max_exp = max_exp;
-    a.action = action; a.action_out = action_out; a.flags_in = flags_in; a.merge_sum = merge_sum;
+    a.action = action; a.action_out = action_out; a.flags_in = flags_in; a.spawn_replay = spawn_replay; a.ep_len = ep_len; a.ep_t = ep_t;
+    a.merge_sum = merge_sum;
     a.reward = reward; a.reward64 = reward64; a.flags = flags; a.obs = obs; a.tables = h->d_tables;
     a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg;
     cudaStream_t s = (cudaStream_t)stream;

@@ -68,7 +68,8 @@ __device__ __forceinline__ void encode_input(float* x0 /*[kTileM][16+pad]*/, con
 template <int kEpi>
 __device__ __forceinline__ void tile_layer(const float* __restrict__ A, int K, int a_stride, const float* __restrict__ W,
                                            const float* __restrict__ bias, int N, float* __restrict__ Out, int o_stride,
-                                           int act_mode, bool apply_act, float* __restrict__ gout, int64_t s0, int64_t n) {
+                                           int act_mode, bool apply_act, float* __restrict__ gout, int64_t s0, int64_t n,
+                                           float* __restrict__ gpre = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* Aw = A + (warp * 8) * a_stride;
     for (int c0 = 0; c0 < N; c0 += 256) {
@@ -111,6 +112,7 @@ __device__ __forceinline__ void tile_layer(const float* __restrict__ A, int K, i
                     else v = z * activate_grad(Out[row * o_stride + c], act_mode);
                     Out[row * o_stride + c] = v;
                     if (gout != nullptr && s0 + row < n) gout[(s0 + row) * N + c] = v;
+                    if (gpre != nullptr && s0 + row < n) gpre[(s0 + row) * N + c] = z;
                 }
             }
         }

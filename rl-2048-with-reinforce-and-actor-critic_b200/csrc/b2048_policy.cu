@@ -107,6 +107,44 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const __gri
     }
 }
 
+// forward_logits on explicit float32 input vectors (the reference's own signature, src/MLP.py:159-196):
+// used by the drop-in MLP.forward_logits; returns logits and, optionally, every activation / pre-activation.
+struct DenseArgs {
+    MlpDev mlp;
+    const float* x;
+    float* act_out[B2048_MAX_LAYERS + 1];  // act_out[l+1] = a_{l+1} (act_out[L] = logits); may be NULL
+    float* pre_out[B2048_MAX_LAYERS];      // pre_out[l] = z_l; may be NULL
+    int64_t n;
+    int buf_stride;
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 1) dense_forward_kernel(const __grid_constant__ DenseArgs args) {
+    extern __shared__ __align__(16) float arena[];
+    const MlpDev& m = args.mlp;
+    const int L = m.n_layers;
+    const int bs = args.buf_stride;
+    float* buf0 = arena;
+    float* buf1 = arena + (size_t)kTileM * bs;
+    const int64_t n_tiles = (args.n + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t s0 = tile * kTileM;
+        const int in0 = m.dims[0];
+        for (int idx = threadIdx.x; idx < kTileM * in0; idx += kMlpThreads) {
+            int b = idx / in0, k = idx - b * in0;
+            buf0[b * bs + k] = (s0 + b < args.n) ? args.x[(s0 + b) * in0 + k] : 0.0f;
+        }
+        __syncthreads();
+        float* in = buf0;
+        float* out = buf1;
+        for (int l = 0; l < L; ++l) {
+            tile_layer<0>(in, m.dims[l], bs, m.W[l], m.b[l], m.dims[l + 1], out, bs, m.activation, l + 1 < L,
+                          args.act_out[l + 1], s0, args.n, args.pre_out[l]);
+            __syncthreads();
+            float* tmp = in; in = out; out = tmp;
+        }
+    }
+}
+
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
     if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
     if (d->n_layers < 1 || d->n_layers > B2048_MAX_LAYERS)
@@ -176,6 +214,42 @@ extern "C" int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b
     int64_t tiles = (n + kTileM - 1) / kTileM;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     mlp_forward_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+extern "C" int b2048_dense_forward(b2048_handle* h, const float* x, const b2048_mlp_desc* mlp, float* const* act_out,
+                                   float* const* pre_out, int64_t n, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_dense_forward: handle is NULL");
+    B2_REQUIRE(n >= 0, "b2048_dense_forward: n < 0");
+    if (n == 0) return B2048_OK;
+    B2_REQUIRE(x != nullptr && mlp != nullptr, "b2048_dense_forward: x/mlp is NULL");
+    B2_REQUIRE(mlp->n_layers >= 1 && mlp->n_layers <= B2048_MAX_LAYERS, "b2048_dense_forward: n_layers out of range");
+    B2_REQUIRE(mlp->activation == B2048_ACTV_SIGMOID || mlp->activation == B2048_ACTV_RELU,
+               "b2048_dense_forward: unsupported activation");
+    DenseArgs a;
+    int maxd = 0;
+    for (int l = 0; l <= mlp->n_layers; ++l) {
+        a.mlp.dims[l] = mlp->dims[l];
+        if (mlp->dims[l] > maxd) maxd = mlp->dims[l];
+        if (l < mlp->n_layers && (mlp->dims[l] < 4 || mlp->dims[l] % 4 != 0))
+            return fail(B2048_ERR_UNSUPPORTED, "b2048_dense_forward: layer input widths must be multiples of 4");
+    }
+    a.mlp.n_layers = mlp->n_layers; a.mlp.activation = mlp->activation; a.mlp.obs_mode = mlp->obs_mode;
+    a.mlp.obs_scale = mlp->obs_log2_scale;
+    for (int l = 0; l < mlp->n_layers; ++l) {
+        B2_REQUIRE(mlp->W[l] && mlp->b[l], "b2048_dense_forward: NULL parameter pointer");
+        a.mlp.W[l] = mlp->W[l]; a.mlp.b[l] = mlp->b[l];
+        a.pre_out[l] = pre_out ? pre_out[l] : nullptr;
+    }
+    for (int l = 0; l <= mlp->n_layers; ++l) a.act_out[l] = act_out ? act_out[l] : nullptr;
+    a.x = x; a.n = n; a.buf_stride = ((maxd + 3) / 4) * 4 + kPad;
+    size_t smem = (size_t)2 * kTileM * a.buf_stride * sizeof(float);
+    if (smem > (size_t)h->smem_optin) return fail(B2048_ERR_UNSUPPORTED, "b2048_dense_forward: layers too wide");
+    B2_CUDA(cudaFuncSetAttribute(dense_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t tiles = (n + kTileM - 1) / kTileM;
+    int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    dense_forward_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
     B2_CUDA(cudaGetLastError());
     return B2048_OK;
 }

@@ -28,6 +28,7 @@ struct StepIO {
     uint32_t action;      // used when cfg.action_mode == B2048_ACT_BUFFER
     uint32_t mask_in;     // legal mask of `board` if known (have_mask_in), else recomputed when needed
     bool have_mask_in;
+    uint32_t replay;      // bit 7 set: spawn replayed from the host: bits 0-3 = k-th empty cell, bit 4 = tile is a 4
     // outputs
     uint32_t action_played;
     int32_t merge_sum;
@@ -65,7 +66,10 @@ B2_HD void step_one(StepIO& io, const b2048_env_cfg& cfg, const StepOpts& opt, u
     io.score += ms.sum;  // game2048.py:53-54
 
     Board nb = mv.board;
-    if (changed) nb = spawn(nb, rnd.w0, rnd.w1);  // game2048.py:56-58
+    if (changed) {  // game2048.py:56-58
+        if (io.replay & 0x80u) nb = place_kth_empty(nb, io.replay & 0xFu, (io.replay & 0x10u) ? 2u : 1u);
+        else nb = spawn(nb, rnd.w0, rnd.w1);
+    }
     uint32_t mask = legal_mask(nb);
     bool done = (mask == 0u) & ((nb.lo | nb.hi) != 0u);  // == _is_done() for every board incl. the empty one
     bool invalid = !changed & !done;                      // env.py:273

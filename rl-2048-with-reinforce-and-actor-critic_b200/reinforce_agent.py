@@ -1,0 +1,460 @@
+"""Drop-in for the reference's ``src/reinforce_agent.py`` plus the batched rollout / update engine.
+
+``ReinforceAgent`` keeps the reference's constructor, attributes and methods (``select_action``,
+``run_episode``, ``compute_returns``, ``update_batch``, ``save_model`` / ``load_model``; reference
+src/reinforce_agent.py:50-252, :357-620).  Parameters live on the GPU as flat float32 vectors; every
+numeric step — policy forward + masked softmax + sampling, env step, returns scan, advantages, TD
+errors, back-propagation, global-norm clip, SGD / Adam — is a CUDA kernel reached through the C ABI.
+
+Added surface: ``rollout_many`` (run-to-termination or fixed-horizon rollouts of a whole
+``Batched2048Env``) and ``update_from_rollout``; ``update_batch`` packs reference-style trajectories
+into the same rollout buffers and calls the same kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from collections.abc import Callable
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib
+from .MLP import (DeviceMLP, MLPConfig, encode_observation, init_model_params, load_model_params,  # noqa: F401
+                  save_model_params, forward_logits, logits_to_probs)
+from .batched_env import Batched2048Env, _ptr, _stream, get_handle
+from .env import Game2048Env
+
+if not hasattr(logging, "VERBOSE"):  # the reference's custom level (src/utils/logging_ext.py)
+    logging.addLevelName(15, "VERBOSE")
+    logging.VERBOSE = 15
+if not hasattr(logging.Logger, "verbose"):
+    def _verbose(self, message, *args, **kwargs):
+        if self.isEnabledFor(15):
+            self._log(15, message, args, **kwargs)
+    logging.Logger.verbose = _verbose
+
+BASELINE = {"off": 0, "each": 1, "batch": 2, "batch_norm": 3}
+OPTIMIZER = {"sgd": 0, "adam": 1}
+
+
+@dataclass
+class ReinforceAgentConfig:
+    """Same 15 fields / defaults as the reference (src/reinforce_agent.py:24-46)."""
+    gamma: float = 1
+    learning_rate: float = 1e-3
+    baseline_mode: str = "off"                  # "off" / "each" / "batch" / "batch_norm"
+    model_seed: int = 0
+    reward_rank_weights: list[float] | None = None
+    optimizer: str = "sgd"
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    augmentation: bool = False
+    use_critic: bool = False
+    critic_learning_rate: float = 1e-3
+    max_grad_norm: float = 1.0
+    critic_loss_type: str = "mse"
+    huber_delta: float = 1.0
+
+
+@dataclass
+class Rollout:
+    """Time-major rollout buffers on the device.  boards/flags have T+1 slices (state before each step and
+    the final state); flags[t] low nibble is the legal mask of boards[t]."""
+    boards: torch.Tensor      # int64  [T+1, B]
+    flags: torch.Tensor       # uint8  [T+1, B]
+    actions: torch.Tensor     # uint8  [T, B]
+    rewards: torch.Tensor     # float32 [T, B]
+    length: torch.Tensor      # int32  [B]  episode length (steps); == T for fixed-horizon rollouts
+    T: int
+    ep_weight: torch.Tensor | None = None   # float32 [B] episode rank weights (None = 1)
+    n_traj: int | None = None               # divisor of the per-episode weight (defaults to B)
+
+    @property
+    def B(self) -> int:
+        return int(self.length.numel())
+
+    def total_reward(self) -> torch.Tensor:
+        t = torch.arange(self.T, device=self.rewards.device).unsqueeze(1)
+        return (self.rewards[: self.T].double() * (t < self.length.unsqueeze(0))).sum(0)
+
+
+class ReinforceAgent:
+    def __init__(self, env, mlp_config: MLPConfig, agent_config: ReinforceAgentConfig | None = None,
+                 initial_params_path: str | None = None):
+        self.env = env
+        self.mlp_config = mlp_config
+        self.agent_config = agent_config or ReinforceAgentConfig()
+        self.rng = np.random.default_rng(self.agent_config.model_seed)
+        self._logger = logging.getLogger(__name__ + ".ReinforceAgent")
+        if not self._logger.handlers:
+            self._logger.addHandler(logging.NullHandler())
+
+        ecfg = env.config
+        self.device = env.device if isinstance(env, Batched2048Env) else env._benv.device
+        self._obs_mode = ecfg.obs_mode
+        self._obs_scale = float(ecfg.obs_log2_scale) if ecfg.obs_mode == "log2" else 1.0
+        self._use_mask = bool(ecfg.use_action_mask)
+        input_dim = 272 if ecfg.obs_mode == "onehot" else 16
+        n_actions = 4
+        if not isinstance(env, Batched2048Env):
+            obs, _ = env.reset(seed=0)                                    # reinforce_agent.py:70-73
+            x, _ = encode_observation(obs)
+            input_dim = x.shape[0]
+            n_actions = env.action_space.n
+        self._lib = _lib.load()
+        self._h = get_handle(self.device)
+
+        if initial_params_path is None:
+            params = init_model_params(input_dim, self.mlp_config.hidden_sizes, n_actions, self.rng,
+                                       self.mlp_config.init_distribution, self.mlp_config.last_init_normal)
+        else:
+            params = load_model_params(initial_params_path)
+        self._actor = self._make_net(params)
+        self._adam_t = 0
+        self._critic: DeviceMLP | None = None
+        if self.agent_config.use_critic:                                  # separate critic network, :94-105
+            cparams = init_model_params(input_dim, self.mlp_config.hidden_sizes, 1, self.rng,
+                                        self.mlp_config.init_distribution, self.mlp_config.last_init_normal)
+            self._critic = self._make_net(cparams)
+            self._adam_t_c = 0
+        self._scratch: dict[str, torch.Tensor] = {}
+        self.last_update_info: dict[str, Any] = {}
+
+    # ------------------------------------------------------------------ parameters
+    def _make_net(self, params) -> DeviceMLP:
+        net = DeviceMLP(params, self.mlp_config.activation, self._obs_mode, self._obs_scale, self.device)
+        net.adam_m = torch.zeros_like(net.theta)
+        net.adam_v = torch.zeros_like(net.theta)
+        net.grad = torch.zeros_like(net.theta)
+        return net
+
+    @property
+    def params(self) -> dict[str, Any]:
+        """Reference layout {"W": [...], "b": [...]} (host copies of the device parameters)."""
+        return self._actor.to_params()
+
+    @params.setter
+    def params(self, value: dict[str, Any]) -> None:
+        dims = [np.asarray(value["W"][0]).shape[0]] + [np.asarray(W).shape[1] for W in value["W"]]
+        if dims == self._actor.dims:
+            self._actor.load_params(value)
+        else:
+            self._actor = self._make_net(value)
+
+    @property
+    def critic_params(self):
+        return None if self._critic is None else self._critic.to_params()
+
+    @critic_params.setter
+    def critic_params(self, value) -> None:
+        if value is None:
+            self._critic = None
+        elif self._critic is not None and [np.asarray(W).shape for W in value["W"]] == \
+                [(self._critic.dims[l], self._critic.dims[l + 1]) for l in range(self._critic.n_layers)]:
+            self._critic.load_params(value)
+        else:
+            self._critic = self._make_net(value)
+
+    def load_model(self, file_path: str | None = "params.npz") -> None:
+        self.params = load_model_params(file_path)
+        self.mlp_config.hidden_sizes = [int(d) for d in self._actor.dims[1:-1]]   # reinforce_agent.py:114
+        self._logger.info(f"Model parameters loaded from {file_path}")
+
+    def save_model(self, file_path: str | None = "params.npz") -> None:
+        save_model_params(self.params, file_path)                                 # actor only, like the reference
+
+    # ------------------------------------------------------------------ kernels
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        t = self._scratch.get(name)
+        n = int(np.prod(shape))
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._scratch[name] = t
+        return t[:n].view(*shape) if n else t[:0]
+
+    def policy_step(self, boards: torch.Tensor, flags: torch.Tensor | None, actions_out: torch.Tensor | None,
+                    seed: int, gid0: int, t: int, greedy: bool = False, probs_out: torch.Tensor | None = None,
+                    logits_out: torch.Tensor | None = None, precision: int = 0) -> None:
+        """encode_observation -> forward_logits -> logits_to_probs -> sample/greedy for a batch of packed boards."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2048_policy_step(
+                self._h, _ptr(boards), _ptr(flags) if self._use_mask else None, C.byref(self._actor.desc),
+                _ptr(actions_out), _ptr(probs_out), _ptr(logits_out), boards.numel(), seed & (2**64 - 1), gid0, t,
+                int(greedy), precision, _stream()), "b2048_policy_step")
+
+    def _values(self, boards: torch.Tensor, out: torch.Tensor) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2048_mlp_forward(self._h, _ptr(boards), C.byref(self._critic.desc), _ptr(out),
+                                                   boards.numel(), _stream()), "b2048_mlp_forward")
+
+    # ------------------------------------------------------------------ reference API: acting
+    def _obs_to_packed(self, obs) -> tuple[int, int]:
+        board = obs["board"] if isinstance(obs, dict) else obs
+        b = np.asarray(board)
+        if self._obs_mode == "onehot":
+            e = b.reshape(16, -1).argmax(1)
+        elif self._obs_mode == "log2":
+            e = np.rint(b.reshape(16) / np.float32(self._obs_scale)).astype(np.int64)
+        else:
+            e = np.array([0 if v == 0 else int(v).bit_length() - 1 for v in b.reshape(16).astype(np.int64)])
+        packed = 0
+        for i, x in enumerate(e):
+            packed |= int(x) << (4 * i)
+        mask = 0xF
+        if isinstance(obs, dict) and obs.get("action_mask") is not None:
+            mask = sum(int(v) << a for a, v in enumerate(obs["action_mask"]))
+        return packed, mask
+
+    def select_action(self, obs, rng: np.random.Generator, action_fn: Callable[[Any, np.ndarray | None], int] | None = None,
+                      use_greedy: bool = False):
+        """Same contract as reinforce_agent.py:126-192.  Probabilities come from the fused policy kernel; the
+        final draw uses the caller's NumPy generator (``rng.choice``) exactly like the reference, so a given
+        ``policy_seed`` reproduces the reference's episode.  Returns (action, probs, activations, pre_activations)."""
+        packed, mask = self._obs_to_packed(obs)
+        action_mask = obs["action_mask"] if isinstance(obs, dict) else None
+        b = torch.tensor([np.uint64(packed).astype(np.int64)], dtype=torch.int64, device=self.device)
+        f = torch.tensor([mask], dtype=torch.uint8, device=self.device)
+        probs_d = self._buf("sa_probs", (1, 4), torch.float32)
+        self.policy_step(b, f if action_mask is not None else None, None, 0, 0, 0, probs_out=probs_d)
+        probs = probs_d.cpu().numpy()[0].copy()
+        action = None
+        if action_fn is not None:
+            try:
+                candidate = int(action_fn(self.env.state, action_mask))
+            except Exception as e:
+                self._logger.exception(f"action_fn raised an exception: {e}. Falling back to policy.")
+            else:
+                if not (0 <= candidate < len(probs)):
+                    self._logger.warning(f"action_fn returned out-of-range action {candidate}, falling back to policy.")
+                elif action_mask is not None and not bool(action_mask[candidate]):
+                    self._logger.warning(f"action_fn returned masked-out action {candidate}, falling back to policy.")
+                else:
+                    action = candidate
+        if action is None:
+            if use_greedy:
+                p = probs * action_mask if action_mask is not None else probs
+                action = int(np.argmax(p))
+            else:
+                action = int(rng.choice(len(probs), p=probs))
+        return action, probs, [], []
+
+    def run_episode(self, env_seed: int, policy_seed: int, action_gen=None, use_greedy: bool = False) -> dict[str, Any]:
+        """One episode on the single-env drop-in (reinforce_agent.py:195-252); same trajectory dict."""
+        obs, info = self.env.reset(seed=env_seed)
+        state = self.env.render(mode="ansi")
+        policy_rng = np.random.default_rng(policy_seed)
+        obs_list, action_list, reward_list, states_list = [], [], [], []
+        done, total_reward = False, 0.0
+        while not done:
+            action, _, _, _ = self.select_action(obs, policy_rng, action_gen, use_greedy=use_greedy)
+            next_obs, reward, terminated, truncated, info = self.env.step(action)
+            reward = float(reward)
+            obs_list.append(obs); action_list.append(action); reward_list.append(reward); states_list.append(state)
+            total_reward += reward
+            obs = next_obs
+            done = terminated or truncated
+            state = self.env.render(mode="ansi")
+        return {"obs": obs_list, "actions": action_list, "rewards": reward_list, "total_reward": total_reward,
+                "states": states_list, "max_tile": self.env.max_tile_seen}
+
+    # ------------------------------------------------------------------ batched rollouts
+    def rollout_many(self, benv: Batched2048Env, max_steps: int | None = None, horizon: int | None = None,
+                     greedy: bool = False, precision: int = 0, reset: bool = True, check_every: int = 32) -> Rollout:
+        """Rolls the whole batch with the current policy.
+        horizon=None: every board plays to termination / truncation like run_episode (finished boards are
+        frozen by the step kernel); horizon=H: fixed H steps with reset-on-done (all lanes always live)."""
+        B = benv.num_envs
+        if reset:
+            benv.reset_many()
+        fixed = horizon is not None
+        cap = int(horizon) if fixed else int(max_steps or benv.config.max_steps or 4096)
+        boards = self._buf("ro_boards", (cap + 1, B), torch.int64)
+        flags = self._buf("ro_flags", (cap + 1, B), torch.uint8)
+        actions = self._buf("ro_actions", (cap, B), torch.uint8)
+        rewards = self._buf("ro_rewards", (cap, B), torch.float32)
+        length = torch.zeros(B, dtype=torch.int32, device=self.device)
+        boards[0].copy_(benv.board)
+        flags[0].copy_(benv.flags)
+        T = 0
+        for t in range(cap):
+            self.policy_step(boards[t], flags[t], actions[t], benv.seed, benv.gid0, benv.t + 1, greedy=greedy,
+                             precision=precision)
+            benv.board = boards[t]
+            benv.flags = flags[t]
+            benv.step_many(actions[t], auto_reset=fixed, board_out=boards[t + 1], reward_out=rewards[t],
+                           flags_out=flags[t + 1], ep_len=None if fixed else length, ep_t=t + 1, flags_in=flags[t])
+            T = t + 1
+            if not fixed and (T % check_every == 0 or T == cap):
+                if bool((length != 0).all()):
+                    break
+        if fixed:
+            length.fill_(T)
+        else:
+            length = torch.where(length == 0, torch.full_like(length, T), length)  # cut off by the cap
+        return Rollout(boards[: T + 1], flags[: T + 1], actions[:T], rewards[:T], length, T)
+
+    # ------------------------------------------------------------------ reference API: learning
+    def compute_returns(self, rewards: list[float]) -> np.ndarray:
+        """G_t = r_t + gamma G_{t+1} (reinforce_agent.py:255-273) with the float64 recurrence on the device."""
+        T = len(rewards)
+        if T == 0:
+            return np.zeros(0, dtype=np.float32)
+        x = torch.tensor(np.asarray(rewards, dtype=np.float32).reshape(T, 1), device=self.device)
+        y = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2048_reverse_scan_f64(_ptr(x), _ptr(y), None, float(self.agent_config.gamma), T, 1,
+                                                        _stream()), "b2048_reverse_scan_f64")
+        return y.cpu().numpy().reshape(T)
+
+    def _compute_episode_rank_weights(self, total_reward_list) -> np.ndarray:
+        """CVaR-style episode weights by reward rank (reinforce_agent.py:681-716).  Host-side: it is a sort of
+        n_traj scalars, not per-step arithmetic."""
+        conf = self.agent_config.reward_rank_weights
+        n = len(total_reward_list)
+        if n == 0:
+            return np.array([], dtype=np.float32)
+        if conf is None or len(conf) == 0:
+            return np.ones(n, dtype=np.float32)
+        conf = np.asarray(conf, dtype=np.float32)
+        order = np.argsort(total_reward_list)
+        w = np.zeros(n, dtype=np.float32)
+        bins = np.minimum(((np.arange(n) + 0.5) / n * len(conf)).astype(np.int64), len(conf) - 1)
+        w[order] = conf[bins]
+        m = np.mean(w)
+        return w / m if m > 1e-8 else w
+
+    def _trajectories_to_rollout(self, trajectories: list[dict[str, Any]]) -> Rollout:
+        B = len(trajectories)
+        lens = np.array([len(t["actions"]) for t in trajectories], dtype=np.int32)
+        T = int(lens.max()) if B else 0
+        boards = np.zeros((T + 1, B), dtype=np.uint64)
+        flags = np.zeros((T + 1, B), dtype=np.uint8)
+        actions = np.zeros((T, B), dtype=np.uint8)
+        rewards = np.zeros((T, B), dtype=np.float32)
+        for b, tr in enumerate(trajectories):
+            for t, o in enumerate(tr["obs"]):
+                boards[t, b], flags[t, b] = self._obs_to_packed(o)
+            actions[: lens[b], b] = np.asarray(tr["actions"], dtype=np.uint8)
+            rewards[: lens[b], b] = np.asarray(tr["rewards"], dtype=np.float32)
+        dev = self.device
+        return Rollout(torch.from_numpy(boards.view(np.int64)).to(dev), torch.from_numpy(flags).to(dev),
+                       torch.from_numpy(actions).to(dev), torch.from_numpy(rewards).to(dev),
+                       torch.from_numpy(lens).to(dev), T)
+
+    def _augment_rollout(self, ro: Rollout) -> Rollout:
+        """x8 dihedral augmentation of a rollout on packed boards (reinforce_agent.py:773-808, env.py:317-397)."""
+        from .symmetry import augment_rollout
+        return augment_rollout(ro)
+
+    def update_batch(self, trajectories: list[dict[str, Any]]) -> None:
+        """reinforce_agent.py:357-620 on reference-style trajectories (list of dicts from run_episode)."""
+        if len(trajectories) == 0:
+            return
+        ro = self._trajectories_to_rollout(trajectories)
+        w = self._compute_episode_rank_weights([t["total_reward"] for t in trajectories])
+        ro.ep_weight = torch.from_numpy(w).to(self.device)
+        self.update_from_rollout(ro)
+
+    def update_from_rollout(self, ro: Rollout, chunk: int = 1 << 18, allreduce=None) -> dict[str, Any]:
+        """One policy-gradient update from device-resident rollout buffers.  `allreduce(tensor)` (optional) sums
+        a tensor over ranks in place: the flat gradients and the advantage statistics are the only exchange."""
+        cfg = self.agent_config
+        if cfg.baseline_mode not in BASELINE:
+            raise ValueError(f"Unknown baseline mode: {cfg.baseline_mode}")          # reinforce_agent.py:325
+        if cfg.optimizer not in OPTIMIZER:
+            raise ValueError(f"Unknown optimizer: {cfg.optimizer}")                  # reinforce_agent.py:582
+        if cfg.use_critic and cfg.critic_loss_type not in ("mse", "huber"):
+            raise ValueError(f"Unknown critic loss type: {cfg.critic_loss_type}")    # reinforce_agent.py:908
+        if cfg.augmentation:
+            ro = self._augment_rollout(ro)
+        T, B = ro.T, ro.B
+        if B == 0 or T == 0:
+            return {}
+        if ro.ep_weight is None and cfg.reward_rank_weights:
+            w = self._compute_episode_rank_weights(ro.total_reward().cpu().numpy().tolist())
+            ro.ep_weight = torch.from_numpy(w).to(self.device)
+        n_traj = float(ro.n_traj if ro.n_traj is not None else B)
+        lib, h, dev = self._lib, self._h, self.device
+        n = T * B
+        boards = ro.boards[:T].reshape(-1)
+        mflags = ro.flags[:T].reshape(-1)
+        acts = ro.actions[:T].reshape(-1)
+        rewards = ro.rewards[:T].contiguous()
+        length = ro.length
+        stats = self._buf("stats", (4,), torch.float64)
+        ep_mean = self._buf("ep_mean", (B,), torch.float32)
+        adv = self._buf("adv", (T, B), torch.float32)
+        coef = self._buf("coef", (T, B), torch.float32)
+        info: dict[str, Any] = {}
+        mode = BASELINE[cfg.baseline_mode]
+
+        def advantages(values):
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2048_advantages(h, _ptr(values), _ptr(length), _ptr(ro.ep_weight), mode, n_traj, T, B,
+                                                _ptr(adv), _ptr(coef), _ptr(stats), _ptr(ep_mean), _stream()),
+                           "b2048_advantages")
+
+        def backward(net: DeviceMLP, cf: torch.Tensor, head_mode: int):
+            net.grad.zero_()
+            ws_floats = int(lib.b2048_backward_workspace_floats(C.byref(net.desc), min(chunk, n)))
+            ws = self._buf("bwd_ws", (ws_floats,), torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2048_mlp_backward(h, _ptr(boards), _ptr(mflags) if self._use_mask else None, _ptr(acts),
+                                                  _ptr(cf), C.byref(net.desc), _ptr(net.grad), n, head_mode, _ptr(ws),
+                                                  ws_floats, min(chunk, n), _stream()), "b2048_mlp_backward")
+            if allreduce is not None:
+                allreduce(net.grad)
+
+        def apply(net: DeviceMLP, lr: float, sign: float, t_adam: int) -> float:
+            sumsq = self._buf("sumsq_" + str(sign), (1,), torch.float64)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2048_apply_update(h, _ptr(net.theta), _ptr(net.grad), _ptr(net.adam_m), _ptr(net.adam_v),
+                                                  net.n_params, OPTIMIZER[cfg.optimizer], float(lr), float(sign),
+                                                  float(cfg.max_grad_norm), float(cfg.adam_beta1), float(cfg.adam_beta2),
+                                                  int(t_adam), _ptr(sumsq), _stream()), "b2048_apply_update")
+            return sumsq
+
+        if cfg.use_critic and self._critic is not None:
+            # critic block (reinforce_agent.py:403-498): V(s_t) for every stored state, TD(0) errors, critic grads
+            values = self._buf("values", (T, B), torch.float32)
+            self._values(boards, values)
+            td = self._buf("td", (T, B), torch.float32)
+            gcoef = self._buf("gcoef", (T, B), torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2048_td_errors(h, _ptr(rewards), _ptr(values), _ptr(length), _ptr(ro.ep_weight),
+                                               float(cfg.gamma), int(cfg.critic_loss_type == "huber"),
+                                               float(cfg.huber_delta), n_traj, T, B, _ptr(td), _ptr(gcoef), _stream()),
+                           "b2048_td_errors")
+            backward(self._critic, gcoef.reshape(-1), 1)
+            advantages(td)                                           # advantages := baseline-processed TD errors (:495-498)
+            info["td"] = td
+        else:
+            returns = self._buf("returns", (T, B), torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2048_reverse_scan_f64(_ptr(rewards), _ptr(returns), _ptr(length), float(cfg.gamma), T, B,
+                                                      _stream()), "b2048_reverse_scan_f64")
+            advantages(returns)
+            info["returns"] = returns
+        backward(self._actor, coef.reshape(-1), 0)
+
+        if cfg.optimizer == "adam":
+            self._adam_t += 1
+        ss_a = apply(self._actor, cfg.learning_rate, +1.0, self._adam_t)
+        ss_c = None
+        if cfg.use_critic and self._critic is not None:
+            if cfg.optimizer == "adam":
+                self._adam_t_c += 1
+            ss_c = apply(self._critic, cfg.critic_learning_rate, -1.0, getattr(self, "_adam_t_c", 0))
+        info["advantages"] = adv
+        info["actor_grad_norm"] = float(ss_a.cpu()[0]) ** 0.5
+        if ss_c is not None:
+            info["critic_grad_norm"] = float(ss_c.cpu()[0]) ** 0.5
+        self.last_update_info = info
+        if self._logger.isEnabledFor(logging.INFO):
+            self._logger.info(f"Global Grad Norms: Actor: {info['actor_grad_norm']:.4f}")
+            if ss_c is not None:
+                self._logger.info(f"Global Grad Norms: Critic: {info['critic_grad_norm']:.4f}")
+        return info

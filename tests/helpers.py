@@ -63,3 +63,52 @@ def host_check_lib():
 
 def P(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def load_update_fixture(tag):
+    """update_*.npz -> (meta, actor0, critic0, list of updates) ; each update has per-episode lists."""
+    import json
+    g = np.load(os.path.join(GOLDEN, f"update_{tag}.npz"))
+    meta = json.loads(str(g["meta"]))
+    L = int(g["n_layers"])
+
+    def params(prefix):
+        if f"{prefix}/W0" not in g:
+            return None
+        return {"W": [g[f"{prefix}/W{i}"] for i in range(L)], "b": [g[f"{prefix}/b{i}"] for i in range(L)]}
+
+    updates = []
+    for u in range(int(g["n_updates"])):
+        lens = g[f"u{u}/lens"]
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        eps = []
+        for i in range(len(lens)):
+            s = slice(offs[i], offs[i + 1])
+            eps.append(dict(boards=g[f"u{u}/boards"][s], masks=g[f"u{u}/masks"][s], actions=g[f"u{u}/actions"][s],
+                            rewards=g[f"u{u}/rewards"][s]))
+        updates.append(dict(episodes=eps, lens=lens, total_reward=g[f"u{u}/total_reward"], grad_norms=g[f"u{u}/grad_norms"],
+                            adv=g[f"u{u}/adv"], actor=params(f"u{u}/actor"), critic=params(f"u{u}/critic")))
+    return meta, params("actor0"), params("critic0"), updates
+
+
+def rank_weights(total_rewards, conf):
+    """reference _compute_episode_rank_weights (src/reinforce_agent.py:681-716), restated for the tests."""
+    n = len(total_rewards)
+    if not conf:
+        return np.ones(n, np.float32)
+    conf = np.asarray(conf, np.float32)
+    order = np.argsort(total_rewards)
+    w = np.zeros(n, np.float32)
+    for rank, idx in enumerate(order):
+        b = min(int((rank + 0.5) / n * len(conf)), len(conf) - 1)
+        w[idx] = conf[b]
+    m = w.mean()
+    return w / m if m > 1e-8 else w
+
+
+UPDATE_TAGS = ["reinforce_sgd", "reinforce_norm_sigmoid", "actor_critic_adam", "actor_critic_huber_sgd"]
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))

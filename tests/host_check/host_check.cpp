@@ -69,6 +69,7 @@ void hc_step_many(const uint64_t* board_in, uint64_t* board_out, uint32_t* score
         io.action = action ? action[i] : 0;
         io.have_mask_in = flags_in != nullptr;
         io.mask_in = flags_in ? flags_in[i] : 0;
+        io.replay = 0;
         b2::step_one(io, *cfg, opt, seed, gid0 + (uint64_t)i, t, g_left.data(), g_merge.data());
         board_out[i] = b2::to_u64(io.board);
         if (score) score[i] = io.score;
