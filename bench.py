@@ -49,28 +49,58 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons WHILE the timed region runs (NVML every ~2 ms; nvidia-smi fallback)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.sm, self.reasons, self.max_mhz, self.source = [], set(), None, "nvml"
         self._stop = threading.Event()
         self._th = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 6 and parts[0].isdigit():
+            self.sm.append(int(parts[0]))
+            self.max_mhz = int(parts[1]) if parts[1].isdigit() else self.max_mhz
+            for i, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if parts[2 + i].lower().startswith("active"):
+                    self.reasons.add(nm)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002 if self._nvml is not None else 0.05)
 
     def __enter__(self):
         self._th.start()
@@ -81,12 +111,9 @@ class ClockSampler:
         self._th.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def cpu_baseline(seconds: float = 10.0):
@@ -150,8 +177,7 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    info = b2048.dist.init_distributed("nccl")
     n = args.boards
     K, W = args.steps, max(3, args.warmup)
 
@@ -239,7 +265,7 @@ def run_b200(args):
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "b2::step_kernel<true,1024>",
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "b2::step_fast_kernel<RANDOM_LEGAL, %s>" % ("false" if args.lean else "true"),
                          "avg_launch_us": per_launch_s * 1e6},
         }
         if world == 1 and not args.no_cpu:
@@ -248,11 +274,21 @@ def run_b200(args):
                 line["cpu_baseline_native"] = cpu_native_baseline()
             except Exception as e:  # the native leg is context only
                 line["cpu_baseline_native"] = {"error": str(e)}
-        if hasattr(b2048, "bench_rollout") and not args.no_rollout:
-            try:
-                line["rollout"] = b2048.bench_rollout(dev)
-            except Exception as e:
-                line["rollout"] = {"error": repr(e)}
+    # secondary legs (every rank takes part: the update all-reduces gradients over NCCL)
+    extra = {}
+    if not args.no_rollout:
+        try:
+            r = b2048.bench_rollout(dev, gid0=rank * 65536)
+            v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            r["value_all_gpus"] = float(v.item())
+            extra["rollout"] = r
+            extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info)
+        except Exception as e:
+            extra["rollout_error"] = repr(e)
+    if rank == 0:
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -261,7 +297,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--boards", type=int, default=BOARDS_PER_GPU)
@@ -269,6 +305,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--train-boards", type=int, default=65536)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

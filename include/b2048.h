@@ -207,11 +207,17 @@ int b2048_reverse_scan_f64(const float* x, float* y, const int32_t* len, double 
  * ep_weight[B] = episode rank weights (NULL = 1).  Outputs (either may be NULL):
  *   adv[T,B]  the advantages;  coef[T,B] = adv * ep_weight[b] / (len[b] * n_traj), the per-sample weight
  *   of grad log pi in update_batch (reinforce_agent.py:533-555); both 0 for t >= len[b].
- * stats: device double[4] scratch, receives {sum w, sum w v, sum w (v-mean)^2, count}.
+ * stats: device double[4] = {sum w, sum w v, sum w v^2, count}; computed here unless stats_precomputed != 0
+ * (multi-GPU: b2048_weighted_stats on every rank, all-reduce the four doubles, then call this).
  * ep_mean_scratch: device float[B], needed for mode 1. */
 int b2048_advantages(b2048_handle* h, const float* v, const int32_t* len, const float* ep_weight,
                      int32_t baseline_mode, float n_traj, int32_t T, int64_t B, float* adv, float* coef,
-                     double* stats, float* ep_mean_scratch, void* stream);
+                     double* stats, int32_t stats_precomputed, float* ep_mean_scratch, void* stream);
+
+/* Adds {sum w, sum w v, sum w v^2, count} over t < len[b] into stats[0..3] (_compute_weighted_stats,
+ * reinforce_agent.py:864-881, as plain sums so they can be all-reduced across ranks). */
+int b2048_weighted_stats(b2048_handle* h, const float* v, const int32_t* len, const float* ep_weight,
+                         int32_t T, int64_t B, double* stats, void* stream);
 
 /* TD(0) errors of the critic block (reinforce_agent.py:439-447): td = r + gamma V(s') [t+1 < len] - V(s);
  * gcoef = dLoss/dV * ep_weight/(len n_traj) with dLoss/dV = V - target (mse) or its Huber clip

@@ -66,7 +66,8 @@ SIGNATURES = {
     "b2048_dense_forward": [_vp, _vp, C.POINTER(MlpDesc), _vp, _vp, _i64, _vp],
     "b2048_reverse_scan": [_vp, _vp, _vp, _f32, _i32, _i64, _vp],
     "b2048_reverse_scan_f64": [_vp, _vp, _vp, C.c_double, _i32, _i64, _vp],
-    "b2048_advantages": [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
+    "b2048_advantages": [_vp, _vp, _vp, _vp, _i32, _f32, _i32, _i64, _vp, _vp, _vp, _i32, _vp, _vp],
+    "b2048_weighted_stats": [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp],
     "b2048_td_errors": [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _f32, _f32, _i32, _i64, _vp, _vp, _vp],
     "b2048_backward_workspace_floats": [C.POINTER(MlpDesc), _i64],
     "b2048_mlp_backward": [_vp, _vp, _vp, _vp, _vp, C.POINTER(MlpDesc), _vp, _i64, _i32, _vp, _i64, _i64, _vp],

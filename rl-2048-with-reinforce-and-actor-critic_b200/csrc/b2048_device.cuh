@@ -33,7 +33,9 @@ B2_HD uint64_t to_u64(Board b) { return (uint64_t)b.lo | ((uint64_t)b.hi << 32);
 // ---------------------------------------------------------------- portable intrinsics
 B2_HD uint32_t prmt(uint32_t x, uint32_t y, uint32_t s) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(x, y, s);
+    uint32_t r;  // raw PRMT: selectors here never set the sign-replicate bit, so no "& 0x7777" is needed
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(s));
+    return r;
 #else
     uint64_t v = (uint64_t)x | ((uint64_t)y << 32);
     uint32_t r = 0;
@@ -71,6 +73,17 @@ B2_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #endif
 }
 
+// (on1 & mask) | (on0 & ~mask) in one LOP3
+B2_HD uint32_t bitsel(uint32_t mask, uint32_t on1, uint32_t on0) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(r) : "r"(on1), "r"(on0), "r"(mask));
+    return r;
+#else
+    return (on1 & mask) | (on0 & ~mask);
+#endif
+}
+
 // bit 3 of every nibble set iff that nibble is non-zero (exact, no cross-nibble carry)
 B2_HD uint32_t nz8(uint32_t x) { return (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
 
@@ -93,6 +106,33 @@ B2_HD Rand4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
         k1 += W1;
     }
     return Rand4{c0, c1, c2, c3};
+}
+
+// Round keys k_r = key + r * (W0, W1), computed once on the host and passed by value in the kernel
+// arguments so the per-board Philox block spends no instructions on the key schedule.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+B2_HD PhiloxKeys make_keys(uint64_t seed) {
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return k;
+}
+B2_HD Rand4 philox_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.k0[r];
+        c1 = (uint32_t)p1;
+        c2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.k1[r];
+        c3 = (uint32_t)p0;
+    }
+    return Rand4{c0, c1, c2, c3};
+}
+B2_HD Rand4 stream_keyed(const PhiloxKeys& k, uint64_t gid, uint32_t t, uint32_t domain) {
+    return philox_keyed((uint32_t)gid, (uint32_t)(gid >> 32), t, domain, k);
 }
 
 B2_HD Rand4 stream(uint64_t seed, uint64_t gid, uint32_t t, uint32_t domain) {
@@ -128,10 +168,10 @@ B2_HD Xform xform_for(uint32_t a) {
 }
 
 B2_HD uint32_t blk_transpose(uint32_t x, uint32_t s) {  // s in {0,12}
-    return (x & 0xF0F00F0Fu) | ((x << s) & 0x0F0F0000u) | ((x >> s) & 0x0000F0F0u);
+    return bitsel(0x0F0F0000u, x << s, bitsel(0x0000F0F0u, x >> s, x));  // the three masks partition the word
 }
 B2_HD uint32_t nib_swap(uint32_t x, uint32_t s) {  // s in {0,4}
-    return ((x << s) & 0xF0F0F0F0u) | ((x >> s) & 0x0F0F0F0Fu);
+    return bitsel(0xF0F0F0F0u, x << s, x >> s);
 }
 
 B2_HD Board canon_fwd(Board b, const Xform& x) {

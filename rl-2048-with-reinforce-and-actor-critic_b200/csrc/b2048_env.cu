@@ -16,8 +16,10 @@
 // grid-strides over the boards.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "b2048_internal.h"
-#include "b2048_step.cuh"
+#include "b2048_step_fast.cuh"
 
 namespace b2 {
 
@@ -29,6 +31,14 @@ __global__ void build_lut_kernel(uint16_t* __restrict__ lut_left, uint8_t* __res
     row_move_left(row, out, merge);
     lut_left[row] = (uint16_t)out;
     lut_merge[row] = (uint8_t)merge;
+}
+
+__global__ void build_small_tables_kernel(uint8_t* __restrict__ small) {
+    static_assert(B2048_SMALL_BYTES == B2048_TABLES_BYTES - B2048_LUT_BYTES, "small table size mismatch");
+    const uint32_t tid = threadIdx.x;
+    if (tid < 256u) small_table_entry_agg(tid, reinterpret_cast<AggEntry*>(small + B2048_SMALL_AGG_OFF)[tid]);
+    if (tid < 4u) small_table_entry_sel(tid, reinterpret_cast<SelEntry*>(small + B2048_SMALL_SEL_OFF)[tid]);
+    if (tid < 64u) small[B2048_SMALL_ACT_OFF + tid] = (uint8_t)small_table_entry_act(tid >> 2, tid & 3u);
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -78,6 +88,7 @@ struct StepArgs {
     uint64_t seed, gid0;
     uint32_t t;
     b2048_env_cfg cfg;
+    PhiloxKeys keys;   // Philox round keys of `seed` (host-computed)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -250,6 +261,99 @@ __global__ void __launch_bounds__(kThreads, kSmemLut ? 1 : 2) step_kernel(const 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K2 (fast path)
+// Same contract as step_kernel for the common configuration (see b2048_step_fast.cuh); all tables in
+// shared memory, brought in by one mbarrier-tracked bulk copy per CTA.
+template <int kAct, bool kTrack>
+__global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constant__ StepArgs args) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)),
+                     "r"((uint32_t)B2048_TABLES_BYTES)
+                     : "memory");
+        // small tables first (needed first), then the row tables in 32 KB pieces
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(smem + B2048_LUT_BYTES)),
+                     "l"(args.tables + B2048_LUT_BYTES), "r"((uint32_t)B2048_SMALL_BYTES), "r"(smem_u32(&mbar))
+                     : "memory");
+        constexpr uint32_t kChunk = 32768;
+#pragma unroll
+        for (uint32_t off = 0; off < (uint32_t)B2048_LUT_BYTES; off += kChunk) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + off)),
+                         "l"(args.tables + off), "r"(kChunk), "r"(smem_u32(&mbar))
+                         : "memory");
+        }
+    }
+    FastTables T;
+    T.left = reinterpret_cast<const uint16_t*>(smem);
+    T.merge = smem + B2048_LUT_LEFT_BYTES;
+    T.agg = reinterpret_cast<const AggEntry*>(smem + B2048_LUT_BYTES + B2048_SMALL_AGG_OFF);
+    T.sel = reinterpret_cast<const SelEntry*>(smem + B2048_LUT_BYTES + B2048_SMALL_SEL_OFF);
+    T.act = smem + B2048_LUT_BYTES + B2048_SMALL_ACT_OFF;
+
+    const b2048_env_cfg& cfg = args.cfg;
+    bool ready = false;
+    const int64_t stride = (int64_t)gridDim.x * 1024;
+    for (int64_t i = (int64_t)blockIdx.x * 1024 + tid; i < args.n; i += stride) {
+        FastIO io;
+        const uint2 bw = *reinterpret_cast<const uint2*>(args.board_in + i);
+        io.lo = bw.x; io.hi = bw.y;
+        io.score = 0u; io.step = 0u; io.max_exp = 2u; io.action = 0u; io.mask_in = 0u;
+        if (kTrack) { io.score = args.score[i]; io.step = args.step[i]; io.max_exp = args.max_exp[i]; }
+        if (kAct == B2048_ACT_BUFFER) io.action = args.action[i];
+        uint32_t fin = 0u;
+        if (args.flags_in) fin = args.flags_in[i];
+        if (kAct == B2048_ACT_RANDOM_LEGAL) io.mask_in = args.flags_in ? fin : legal_mask(Board{io.lo, io.hi});
+        bool frozen = false;
+        if (args.ep_len) frozen = args.ep_len[i] != 0;
+        if (!ready) {
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+            ready = true;
+        }
+        if (frozen) {   // finished episode of a run-to-termination rollout: pass through (see step_kernel)
+            uint32_t m = legal_mask(Board{io.lo, io.hi});
+            uint32_t f = args.flags_in ? fin : (m | ((m == 0u && (io.lo | io.hi) != 0u) ? B2048_F_DONE : 0u));
+            *reinterpret_cast<uint2*>(args.board_out + i) = bw;
+            if (args.action_out) args.action_out[i] = 0;
+            if (args.merge_sum) args.merge_sum[i] = 0;
+            args.reward[i] = 0.0f;
+            args.flags[i] = (uint8_t)(f & ~B2048_F_CHANGED);
+            continue;
+        }
+        step_fast<kAct, kTrack>(io, cfg, args.keys, args.seed, args.gid0 + (uint64_t)i, args.t, T);
+        if (args.ep_len && (io.flags & (B2048_F_DONE | B2048_F_TRUNC))) args.ep_len[i] = (int32_t)args.ep_t;
+        *reinterpret_cast<uint2*>(args.board_out + i) = make_uint2(io.lo, io.hi);
+        if (kTrack) { args.score[i] = io.score; args.step[i] = io.step; args.max_exp[i] = (uint8_t)io.max_exp; }
+        if (args.action_out) args.action_out[i] = (uint8_t)io.action;
+        if (args.merge_sum) args.merge_sum[i] = io.merge_sum;
+        args.reward[i] = io.reward;
+        args.flags[i] = (uint8_t)io.flags;
+    }
+}
+
+template <int kAct>
+static void launch_fast(bool track, int grid, size_t smem, cudaStream_t s, const StepArgs& a) {
+    if (track) step_fast_kernel<kAct, true><<<grid, 1024, smem, s>>>(a);
+    else step_fast_kernel<kAct, false><<<grid, 1024, smem, s>>>(a);
+}
+
 // ------------------------------------------------------------------------------------------------ previews
 __global__ void __launch_bounds__(256) move_kernel(const uint64_t* __restrict__ board_in, uint64_t* __restrict__ board_out,
                                                     const uint8_t* __restrict__ action, int32_t* __restrict__ merge_sum,
@@ -306,13 +410,21 @@ extern "C" int b2048_create(b2048_handle** out) {
     B2_CUDA(cudaGetDevice(&h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    B2_CUDA(cudaMalloc(&h->d_tables, B2048_LUT_BYTES));
+    B2_CUDA(cudaMalloc(&h->d_tables, B2048_TABLES_BYTES));
     build_lut_kernel<<<256, 256>>>(reinterpret_cast<uint16_t*>(h->d_tables), h->d_tables + B2048_LUT_LEFT_BYTES);
+    build_small_tables_kernel<<<1, 256>>>(h->d_tables + B2048_LUT_BYTES);
     B2_CUDA(cudaGetLastError());
     B2_CUDA(cudaDeviceSynchronize());
     if (h->smem_optin >= B2048_LUT_BYTES) {
         B2_CUDA(cudaFuncSetAttribute(step_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      B2048_LUT_BYTES));
+    }
+    if (h->smem_optin >= B2048_TABLES_BYTES) {
+#define B2_SET(A, TR) B2_CUDA(cudaFuncSetAttribute(step_fast_kernel<A, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES))
+        B2_SET(B2048_ACT_BUFFER, true); B2_SET(B2048_ACT_BUFFER, false);
+        B2_SET(B2048_ACT_RANDOM_LEGAL, true); B2_SET(B2048_ACT_RANDOM_LEGAL, false);
+        B2_SET(B2048_ACT_RANDOM_ANY, true); B2_SET(B2048_ACT_RANDOM_ANY, false);
+#undef B2_SET
     }
     *out = h;
     return B2048_OK;
@@ -373,12 +485,23 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
     a.action = action; a.action_out = action_out; a.flags_in = flags_in; a.spawn_replay = spawn_replay; a.ep_len = ep_len; a.ep_t = ep_t;
     a.merge_sum = merge_sum;
     a.reward = reward; a.reward64 = reward64; a.flags = flags; a.obs = obs; a.tables = h->d_tables;
-    a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg;
+    a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg; a.keys = make_keys(seed);
     cudaStream_t s = (cudaStream_t)stream;
     // Large batches: persistent CTAs with the tables in shared memory.  Small batches (the B=1
     // drop-in env, unit tests): tables read through L1/L2, no 192 KB staging per launch.
     const bool use_smem = h->smem_optin >= B2048_LUT_BYTES && n >= (int64_t)32768;
-    if (use_smem) {
+    const bool all_track = score && step && max_exp, none_track = !score && !step && !max_exp;
+    const bool fast = h->smem_optin >= B2048_TABLES_BYTES && n >= (int64_t)32768 && (all_track || none_track) &&
+                      cfg->use_action_mask && cfg->empty_tile_reward == 0.0 && cfg->merge_reward == 0.0 &&
+                      cfg->bonus_mode == B2048_BONUS_OFF && cfg->endgame_penalty == 0.0 && reward != nullptr &&
+                      reward64 == nullptr && spawn_replay == nullptr && (obs == nullptr || cfg->obs_mode == B2048_OBS_NONE) &&
+                      getenv("B2048_NO_FAST_STEP") == nullptr;
+    if (fast) {
+        int grid = grid_for(n, 1024, h->num_sms, 1);
+        if (cfg->action_mode == B2048_ACT_BUFFER) launch_fast<B2048_ACT_BUFFER>(all_track, grid, B2048_TABLES_BYTES, s, a);
+        else if (cfg->action_mode == B2048_ACT_RANDOM_LEGAL) launch_fast<B2048_ACT_RANDOM_LEGAL>(all_track, grid, B2048_TABLES_BYTES, s, a);
+        else launch_fast<B2048_ACT_RANDOM_ANY>(all_track, grid, B2048_TABLES_BYTES, s, a);
+    } else if (use_smem) {
         int grid = grid_for(n, 1024, h->num_sms, 1);
         step_kernel<true, 1024><<<grid, 1024, B2048_LUT_BYTES, s>>>(a);
     } else {

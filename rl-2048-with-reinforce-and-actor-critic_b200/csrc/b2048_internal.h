@@ -8,7 +8,7 @@
 #include "../../include/b2048.h"
 
 struct b2048_handle {
-    uint8_t* d_tables;   // [131072 B lut_left (u16 x 65536)] [65536 B lut_merge (u8 x 65536)]
+    uint8_t* d_tables;   // [131072 B lut_left (u16 x 65536)] [65536 B lut_merge (u8 x 65536)] [small tables]
     int device;
     int num_sms;
     int smem_optin;      // max opt-in dynamic shared memory per block
@@ -17,6 +17,8 @@ struct b2048_handle {
 #define B2048_LUT_LEFT_BYTES 131072
 #define B2048_LUT_MERGE_BYTES 65536
 #define B2048_LUT_BYTES (B2048_LUT_LEFT_BYTES + B2048_LUT_MERGE_BYTES)
+// the small tables of b2048_step_fast.cuh follow the row tables in the same allocation
+#define B2048_TABLES_BYTES (B2048_LUT_BYTES + 2048 + 128 + 64)
 
 namespace b2 {
 

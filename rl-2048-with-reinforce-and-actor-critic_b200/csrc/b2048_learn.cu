@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(256) reverse_scan_warp_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ K5
-// acc[0] += sum w, acc[1] += sum w*v, (pass 2) acc[2] += sum w*(v-mean)^2, acc[3] += count
+// Single pass: acc[0] += sum w, acc[1] += sum w*v, acc[2] += sum w*v*v, acc[3] += count (float64
+// accumulators; the weighted variance is acc[2]/acc[0] - mean^2).  Being plain sums, the four numbers
+// can be all-reduced across ranks before the advantages are formed.
 __global__ void __launch_bounds__(256) weighted_stats_kernel(const float* __restrict__ v, const int32_t* __restrict__ len,
-                                                              const float* __restrict__ w, int T, int64_t B, int pass,
+                                                              const float* __restrict__ w, int T, int64_t B,
                                                               double* __restrict__ acc) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    double mean = 0.0;
-    if (pass == 2) mean = acc[0] < 1e-8 ? 0.0 : acc[1] / acc[0];
     const int64_t total = (int64_t)T * B;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t b = i % B;
@@ -81,8 +81,7 @@ __global__ void __launch_bounds__(256) weighted_stats_kernel(const float* __rest
         if (t < L) {
             double wb = w ? (double)w[b] : 1.0;
             double val = (double)v[i];
-            if (pass == 1) { s0 += wb; s1 += wb * val; s3 += 1.0; }
-            else { double d = val - mean; s2 += wb * d * d; }
+            s0 += wb; s1 += wb * val; s2 += wb * val * val; s3 += 1.0;
         }
     }
     for (int d = 16; d > 0; d >>= 1) {
@@ -96,8 +95,7 @@ __global__ void __launch_bounds__(256) weighted_stats_kernel(const float* __rest
     if (threadIdx.x < 4) {
         double s = 0.0;
         for (int k = 0; k < 8; ++k) s += sh[threadIdx.x][k];
-        bool mine = pass == 1 ? (threadIdx.x != 2) : (threadIdx.x == 2);
-        if (mine && s != 0.0) atomicAdd(acc + threadIdx.x, s);
+        if (s != 0.0) atomicAdd(acc + threadIdx.x, s);
     }
 }
 
@@ -111,7 +109,11 @@ __global__ void __launch_bounds__(256) advantage_kernel(const float* __restrict_
     if (mode >= 2) {
         double sw = acc[0];
         if (sw < 1e-8) { mean = 0.0f; stdv = 1.0f; }       // reinforce_agent.py:874-875
-        else { mean = (float)(acc[1] / sw); stdv = (float)sqrt(acc[2] / sw); }
+        else {
+            double m = acc[1] / sw, var = acc[2] / sw - m * m;
+            mean = (float)m;
+            stdv = (float)sqrt(var > 0.0 ? var : 0.0);
+        }
         if (stdv < 1e-8f) stdv = 1e-8f;                      // reinforce_agent.py:319-320
     }
     const int64_t total = (int64_t)T * B;
@@ -424,8 +426,8 @@ extern "C" int b2048_reverse_scan_f64(const float* x, float* y, const int32_t* l
 
 extern "C" int b2048_advantages(b2048_handle* h, const float* v, const int32_t* len, const float* ep_weight,
                                 int32_t baseline_mode, float n_traj, int32_t T, int64_t B, float* adv, float* coef,
-                                double* stats /* device, >= 4 doubles, overwritten */, float* ep_mean_scratch /* [B] */,
-                                void* stream) {
+                                double* stats /* device, 4 doubles */, int32_t stats_precomputed,
+                                float* ep_mean_scratch /* [B] */, void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_advantages: handle is NULL");
     B2_REQUIRE(baseline_mode >= 0 && baseline_mode <= 3, "b2048_advantages: unknown baseline mode");  // reinforce_agent.py:325
     B2_REQUIRE(T >= 0 && B >= 0, "b2048_advantages: negative size");
@@ -433,16 +435,29 @@ extern "C" int b2048_advantages(b2048_handle* h, const float* v, const int32_t* 
     B2_REQUIRE(v && stats, "b2048_advantages: v/stats is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t total = (int64_t)T * B;
-    B2_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(double), s));
-    if (baseline_mode >= 2) {
-        weighted_stats_kernel<<<ew_grid(total, h->num_sms), 256, 0, s>>>(v, len, ep_weight, T, B, 1, stats);
-        weighted_stats_kernel<<<ew_grid(total, h->num_sms), 256, 0, s>>>(v, len, ep_weight, T, B, 2, stats);
+    if (baseline_mode >= 2 && !stats_precomputed) {
+        B2_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(double), s));
+        weighted_stats_kernel<<<ew_grid(total, h->num_sms), 256, 0, s>>>(v, len, ep_weight, T, B, stats);
     } else if (baseline_mode == 1) {
         B2_REQUIRE(ep_mean_scratch != nullptr, "b2048_advantages: ep_mean_scratch required for baseline 'each'");
         episode_mean_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(v, len, T, B, ep_mean_scratch);
     }
     advantage_kernel<<<ew_grid(total, h->num_sms), 256, 0, s>>>(v, len, ep_weight, ep_mean_scratch, stats, baseline_mode,
                                                                  n_traj, T, B, adv, coef);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+// The sums behind the "batch" / "batch_norm" baselines, ADDED into stats[0..3] (zero it first): callers that
+// shard episodes over ranks all-reduce the four doubles and then call b2048_advantages(stats_precomputed=1).
+extern "C" int b2048_weighted_stats(b2048_handle* h, const float* v, const int32_t* len, const float* ep_weight,
+                                    int32_t T, int64_t B, double* stats, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_weighted_stats: handle is NULL");
+    B2_REQUIRE(T >= 0 && B >= 0, "b2048_weighted_stats: negative size");
+    if (T == 0 || B == 0) return B2048_OK;
+    B2_REQUIRE(v && stats, "b2048_weighted_stats: v/stats is NULL");
+    weighted_stats_kernel<<<ew_grid((int64_t)T * B, h->num_sms), 256, 0, (cudaStream_t)stream>>>(v, len, ep_weight, T, B,
+                                                                                               stats);
     B2_CUDA(cudaGetLastError());
     return B2048_OK;
 }

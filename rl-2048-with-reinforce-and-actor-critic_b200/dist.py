@@ -1,0 +1,80 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in
+the CPU tests).  The path shards by construction — every board / episode is independent (reference
+src/reinforce_agent.py:195-252 touches no cross-environment state) — so ranks own contiguous ranges of the
+GLOBAL board id, the Philox streams are keyed on that id (results are independent of the world size) and
+nothing is exchanged during rollouts.  Per update the only exchange is one all-reduce(SUM) of the flat
+gradient per network (285 KB for the runner-default MLP) plus the four float64 baseline sums when the
+baseline is "batch" / "batch_norm"."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class DistInfo:
+    rank: int = 0
+    world_size: int = 1
+    local_rank: int = 0
+
+    @property
+    def is_distributed(self) -> bool:
+        return self.world_size > 1
+
+
+def init_distributed(backend: str | None = None) -> DistInfo:
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun); no-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return DistInfo(rank, world, local)
+
+
+def shard_range(total: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous [start, stop) range of global board ids owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(total), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """In-place SUM over ranks (identity for a single process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allreduce_max_(t: torch.Tensor) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t
+
+
+def make_sharded_env(total_boards: int, config, info: DistInfo, seed: int = 0, device=None, **kw):
+    """This rank's shard of a `total_boards`-board environment: gid0 = first global id of the shard."""
+    from .batched_env import Batched2048Env
+    start, stop = shard_range(total_boards, info.rank, info.world_size)
+    dev = device if device is not None else torch.device("cuda", info.local_rank)
+    return Batched2048Env(stop - start, config, device=dev, seed=seed, gid0=start, **kw)
+
+
+def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = None):
+    """update_from_rollout with gradients / baseline sums all-reduced over ranks; n_traj = global episode count
+    so that every rank applies exactly the update a single process holding all episodes would apply."""
+    if total_episodes is None:
+        n = torch.tensor([rollout.B], dtype=torch.int64, device=rollout.length.device)
+        allreduce_sum_(n)
+        total_episodes = int(n.item())
+    rollout.n_traj = total_episodes
+    return agent.update_from_rollout(rollout, allreduce=allreduce_sum_ if info.is_distributed else None)

@@ -392,9 +392,17 @@ class ReinforceAgent:
         mode = BASELINE[cfg.baseline_mode]
 
         def advantages(values):
+            pre = 0
             with torch.cuda.device(dev):
+                if allreduce is not None and mode >= 2:
+                    # episodes are sharded over ranks: the baseline statistics are global sums
+                    stats.zero_()
+                    _lib.check(lib.b2048_weighted_stats(h, _ptr(values), _ptr(length), _ptr(ro.ep_weight), T, B,
+                                                        _ptr(stats), _stream()), "b2048_weighted_stats")
+                    allreduce(stats)
+                    pre = 1
                 _lib.check(lib.b2048_advantages(h, _ptr(values), _ptr(length), _ptr(ro.ep_weight), mode, n_traj, T, B,
-                                                _ptr(adv), _ptr(coef), _ptr(stats), _ptr(ep_mean), _stream()),
+                                                _ptr(adv), _ptr(coef), _ptr(stats), pre, _ptr(ep_mean), _stream()),
                            "b2048_advantages")
 
         def backward(net: DeviceMLP, cf: torch.Tensor, head_mode: int):

@@ -40,3 +40,39 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
             "ms_per_step": ms / steps, "mlp": "16-256-256-4 ReLU", "precision": "fp32 CUDA cores" if precision == 0 else "bf16 tcgen05",
             "flops_per_step": FLOPS_PER_STEP, "achieved_tflops": rate * FLOPS_PER_STEP / 1e12,
             "gpu_launches": 2 * steps}
+
+
+def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2):
+    """BASELINE.json configs[2]: REINFORCE rollout (to termination, max_steps 1024) + one update (gamma 0.99,
+    baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks."""
+    from . import dist as bd
+    info = info or bd.DistInfo()
+    env = bd.make_sharded_env(boards * info.world_size, Game2048EnvConfig(**RUNNER_ENV), info, seed=0xB200, device=dev)
+    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                           ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
+    out = []
+    for it in range(iters):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        e[0].record()
+        ro = agent.rollout_many(env)
+        e[1].record()
+        upd = bd.sharded_update(agent, ro, info, total_episodes=boards * info.world_size)
+        e[2].record()
+        torch.cuda.synchronize()
+        live_steps = int(ro.length.sum().item())
+        t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), float(live_steps)], dtype=torch.float64, device=dev)
+        tm = t.clone()
+        bd.allreduce_max_(tm)
+        ts = t.clone()
+        bd.allreduce_sum_(ts)
+        out.append({"rollout_ms": float(tm[0]), "update_ms": float(tm[1]), "episode_steps": int(ts[2].item()),
+                    "T": ro.T, "mean_len": float(ro.length.float().mean().item()),
+                    "mean_return": float(ro.total_reward().mean().item()), "actor_grad_norm": upd["actor_grad_norm"]})
+    last = out[-1]
+    tot_ms = last["rollout_ms"] + last["update_ms"]
+    return {"metric": "REINFORCE iteration (rollout to termination + update)", "boards_per_gpu": boards,
+            "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],
+            "update_ms": last["update_ms"], "T": last["T"], "mean_len": last["mean_len"], "mean_return": last["mean_return"],
+            "actor_grad_norm": last["actor_grad_norm"], "iters": out,
+            "exchange": "1 all-reduce of the flat fp32 gradient (71,172 floats) + 4 float64 baseline sums per update"}

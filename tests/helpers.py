@@ -54,7 +54,7 @@ def host_check_lib():
         so = os.path.join(d, "libhostcheck.so")
         src = os.path.join(d, "host_check.cpp")
         hdr = os.path.join(ROOT, "rl-2048-with-reinforce-and-actor-critic_b200", "csrc")
-        deps = [src] + [os.path.join(hdr, f) for f in ("b2048_device.cuh", "b2048_step.cuh")]
+        deps = [src] + [os.path.join(hdr, f) for f in ("b2048_device.cuh", "b2048_step.cuh", "b2048_step_fast.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so, src])
         _hc = C.CDLL(so)

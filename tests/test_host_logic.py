@@ -109,3 +109,51 @@ def test_step_buffer_actions_including_illegal():
                         P(rw64), P(fl), C.c_int64(n), C.c_uint64(seed), C.c_uint64(0), C.c_uint32(t))
         assert (board == st["board"]).all() and (rw64 == o["reward64"]).all() and (fl == o["flags"]).all()
         assert (score == st["score"]).all() and (step == st["step"]).all() and (mx == st["max_exp"]).all()
+
+
+@pytest.mark.parametrize("reward_mode", ["log2", "sum"])
+@pytest.mark.parametrize("mode", ["random_legal", "random_any", "buffer"])
+@pytest.mark.parametrize("track", [True, False])
+def test_fast_step_body_vs_oracle(reward_mode, mode, track):
+    """The instruction-lean step body (csrc/b2048_step_fast.cuh) used by the large-batch kernel."""
+    hc = host_check_lib()
+    n, T, seed, gid0 = 6000, 260, 99, 2**33
+    cfg = oracle.make_cfg(reward_mode=reward_mode, base_reward_scale=0.5, step_reward=-0.125, max_steps=100,
+                          action_mode=mode, auto_reset=True)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    board = st["board"].copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
+    flags_prev = st["flags"].copy()
+    rng = np.random.default_rng(1)
+    for t in range(1, T + 1):
+        a = rng.integers(0, 4, n).astype(np.uint8) if mode == "buffer" else None
+        o = oracle.step_many(st, cfg, seed, gid0, t, action=a, use_state=track)
+        act = np.zeros(n, np.uint8); ms = np.zeros(n, np.int32); rw = np.zeros(n, np.float32); fl = np.zeros(n, np.uint8)
+        hc.hc_step_fast_many(P(board), P(board), P(score) if track else None, P(step) if track else None,
+                             P(mx) if track else None, P(a), P(act), P(flags_prev) if t % 3 else None, C.byref(cfg),
+                             P(ms), P(rw), P(fl), C.c_int64(n), C.c_uint64(seed), C.c_uint64(gid0), C.c_uint32(t))
+        assert (act == o["action"]).all(), t
+        assert (board == st["board"]).all(), t
+        assert (ms == o["merge_sum"]).all() and (rw == o["reward"]).all() and (fl == o["flags"]).all()
+        if track:
+            assert (score == st["score"]).all() and (step == st["step"]).all() and (mx == st["max_exp"]).all()
+        flags_prev = fl.copy()
+
+
+def test_fast_step_overflow_and_dense_boards():
+    hc = host_check_lib()
+    rng = np.random.default_rng(9)
+    n = 100000
+    boards = random_boards(rng, n)
+    cfg = oracle.make_cfg(reward_mode="sum", action_mode="random_any", auto_reset=False, max_steps=0)
+    st = dict(board=boards.copy(), score=np.zeros(n, np.uint32), step=np.zeros(n, np.uint32),
+              max_exp=np.full(n, 2, np.uint8), flags=np.zeros(n, np.uint8))
+    board = boards.copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
+    for t in range(1, 4):
+        o = oracle.step_many(st, cfg, 5, 0, t)
+        act = np.zeros(n, np.uint8); ms = np.zeros(n, np.int32); rw = np.zeros(n, np.float32); fl = np.zeros(n, np.uint8)
+        hc.hc_step_fast_many(P(board), P(board), P(score), P(step), P(mx), None, P(act), None, C.byref(cfg), P(ms), P(rw),
+                             P(fl), C.c_int64(n), C.c_uint64(5), C.c_uint64(0), C.c_uint32(t))
+        assert (board == st["board"]).all() and (fl == o["flags"]).all() and (ms == o["merge_sum"]).all()
+        assert (rw == o["reward"]).all() and (mx == st["max_exp"]).all() and (score == st["score"]).all()
+        if t == 1:
+            assert (fl & 0x80).any()      # the random boards contain 15+15 merges

@@ -149,7 +149,7 @@ def test_reverse_scan_and_advantages(b2048):
             adv = torch.zeros_like(xd); coef = torch.zeros_like(xd)
             stats = torch.zeros(4, dtype=torch.float64, device="cuda"); em = torch.zeros(B, device="cuda")
             b2048._lib.check(lib.b2048_advantages(h, p(y), p(ld), p(wd), mode_i, float(B), T, B, p(adv), p(coef), p(stats),
-                                                  p(em), None))
+                                                  0, p(em), None))
             refa = g[f"ret/{gamma}/{mode}/adv"]
             gota = np.concatenate([adv.cpu().numpy()[: lens[b], b] for b in range(B)])
             assert np.abs(gota - refa).max() <= TOL * max(1.0, np.abs(refa).max()), (gamma, mode)
