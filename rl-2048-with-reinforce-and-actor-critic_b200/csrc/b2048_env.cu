@@ -302,15 +302,30 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
     const b2048_env_cfg& cfg = args.cfg;
     bool ready = false;
     const int64_t stride = (int64_t)gridDim.x * 1024;
-    for (int64_t i = (int64_t)blockIdx.x * 1024 + tid; i < args.n; i += stride) {
+    int64_t i = (int64_t)blockIdx.x * 1024 + tid;
+    // software pipeline: the next iteration's board / action / mask are requested before the current
+    // board is processed, so the ~800-cycle HBM latency is off the critical path of every iteration
+    uint2 bw_next = make_uint2(0u, 0u);
+    uint32_t act_next = 0u, fin_next = 0u;
+    if (i < args.n) {
+        bw_next = *reinterpret_cast<const uint2*>(args.board_in + i);
+        if (kAct == B2048_ACT_BUFFER) act_next = args.action[i];
+        if (args.flags_in) fin_next = args.flags_in[i];
+    }
+    for (; i < args.n; i += stride) {
         FastIO io;
-        const uint2 bw = *reinterpret_cast<const uint2*>(args.board_in + i);
+        const uint2 bw = bw_next;
+        const uint32_t fin = fin_next;
         io.lo = bw.x; io.hi = bw.y;
-        io.score = 0u; io.step = 0u; io.max_exp = 2u; io.action = 0u; io.mask_in = 0u;
+        io.score = 0u; io.step = 0u; io.max_exp = 2u; io.mask_in = 0u;
+        io.action = act_next;
+        const int64_t inext = i + stride;
+        if (inext < args.n) {
+            bw_next = *reinterpret_cast<const uint2*>(args.board_in + inext);
+            if (kAct == B2048_ACT_BUFFER) act_next = args.action[inext];
+            if (args.flags_in) fin_next = args.flags_in[inext];
+        }
         if (kTrack) { io.score = args.score[i]; io.step = args.step[i]; io.max_exp = args.max_exp[i]; }
-        if (kAct == B2048_ACT_BUFFER) io.action = args.action[i];
-        uint32_t fin = 0u;
-        if (args.flags_in) fin = args.flags_in[i];
         if (kAct == B2048_ACT_RANDOM_LEGAL) io.mask_in = args.flags_in ? fin : legal_mask(Board{io.lo, io.hi});
         bool frozen = false;
         if (args.ep_len) frozen = args.ep_len[i] != 0;
