@@ -278,13 +278,14 @@ def run_b200(args):
     extra = {}
     if not args.no_rollout:
         try:
-            r = b2048.bench_rollout(dev, gid0=rank * 65536)
-            v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(v, op=dist.ReduceOp.SUM)
-            r["value_all_gpus"] = float(v.item())
-            extra["rollout"] = r
-            extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info)
+            for key, prec in (("rollout", 1), ("rollout_fp32", 0)):
+                r = b2048.bench_rollout(dev, gid0=rank * 65536, precision=prec)
+                v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(v, op=dist.ReduceOp.SUM)
+                r["value_all_gpus"] = float(v.item())
+                extra[key] = r
+            extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision=1)
         except Exception as e:
             extra["rollout_error"] = repr(e)
     if rank == 0:

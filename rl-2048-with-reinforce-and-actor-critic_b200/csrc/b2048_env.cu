@@ -422,6 +422,7 @@ using namespace b2;
 extern "C" int b2048_create(b2048_handle** out) {
     B2_REQUIRE(out != nullptr, "b2048_create: out is NULL");
     b2048_handle* h = new b2048_handle();
+    h->tc_image = nullptr;
     B2_CUDA(cudaGetDevice(&h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -448,6 +449,7 @@ extern "C" int b2048_create(b2048_handle** out) {
 extern "C" int b2048_destroy(b2048_handle* h) {
     if (!h) return B2048_OK;
     cudaFree(h->d_tables);
+    if (h->tc_image) cudaFree(h->tc_image);
     delete h;
     return B2048_OK;
 }

@@ -12,6 +12,7 @@ struct b2048_handle {
     int device;
     int num_sms;
     int smem_optin;      // max opt-in dynamic shared memory per block
+    uint8_t* tc_image;   // bf16 weight image of the tensor-core policy kernel (lazily allocated)
 };
 
 #define B2048_LUT_LEFT_BYTES 131072

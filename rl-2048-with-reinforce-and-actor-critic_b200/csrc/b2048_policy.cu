@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dense_forward_kernel(const __g
     }
 }
 
+int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
+                     uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
+                     int greedy, cudaStream_t stream);
+
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
     if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
     if (d->n_layers < 1 || d->n_layers > B2048_MAX_LAYERS)
@@ -188,7 +192,15 @@ extern "C" int b2048_policy_step(b2048_handle* h, const uint64_t* board, const u
     size_t smem = 0;
     int st = validate_mlp(mlp, &a.mlp, &smem, h->smem_optin, "b2048_policy_step");
     if (st != B2048_OK) return st;
-    if (precision != 0) return fail(B2048_ERR_UNSUPPORTED, "b2048_policy_step: precision 1 (bf16 tcgen05) not built in this library");
+    if (precision == 1) {
+        st = launch_policy_tc(h, mlp, board, mask_flags, action, probs, logits, n, seed, gid0, t, greedy, (cudaStream_t)stream);
+        if (st == B2048_ERR_UNSUPPORTED)
+            return fail(B2048_ERR_UNSUPPORTED,
+                        "b2048_policy_step: precision 1 (bf16 tcgen05) implements the 16-256-256-4 ReLU policy on raw/log2 "
+                        "observations only; use precision 0");
+        return st;
+    }
+    if (precision != 0) return fail(B2048_ERR_INVALID, "b2048_policy_step: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
     a.board = board; a.mask_flags = mask_flags; a.action = action; a.probs = probs; a.logits = logits;
     a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.greedy = greedy;
     B2_CUDA(cudaFuncSetAttribute(policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

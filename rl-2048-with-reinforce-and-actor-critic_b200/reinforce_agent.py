@@ -177,13 +177,21 @@ class ReinforceAgent:
 
     def policy_step(self, boards: torch.Tensor, flags: torch.Tensor | None, actions_out: torch.Tensor | None,
                     seed: int, gid0: int, t: int, greedy: bool = False, probs_out: torch.Tensor | None = None,
-                    logits_out: torch.Tensor | None = None, precision: int = 0) -> None:
-        """encode_observation -> forward_logits -> logits_to_probs -> sample/greedy for a batch of packed boards."""
+                    logits_out: torch.Tensor | None = None, precision: int | str = 0) -> None:
+        """encode_observation -> forward_logits -> logits_to_probs -> sample/greedy for a batch of packed boards.
+        precision: 0 = fp32 CUDA cores (parity path), 1 = bf16 tcgen05 tensor cores, "auto" = 1 when the batch has
+        at least 4096 boards and the network is the 16-256-256-4 ReLU shape the tensor-core kernel implements."""
+        if precision == "auto":
+            precision = 1 if (boards.numel() >= 4096 and self.tc_supported()) else 0
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b2048_policy_step(
                 self._h, _ptr(boards), _ptr(flags) if self._use_mask else None, C.byref(self._actor.desc),
                 _ptr(actions_out), _ptr(probs_out), _ptr(logits_out), boards.numel(), seed & (2**64 - 1), gid0, t,
                 int(greedy), precision, _stream()), "b2048_policy_step")
+
+    def tc_supported(self) -> bool:
+        a = self._actor
+        return (a.dims == [16, 256, 256, 4] and a.activation == "ReLU" and a.obs_mode in ("raw", "log2"))
 
     def _values(self, boards: torch.Tensor, out: torch.Tensor) -> None:
         with torch.cuda.device(self.device):
@@ -262,7 +270,7 @@ class ReinforceAgent:
 
     # ------------------------------------------------------------------ batched rollouts
     def rollout_many(self, benv: Batched2048Env, max_steps: int | None = None, horizon: int | None = None,
-                     greedy: bool = False, precision: int = 0, reset: bool = True, check_every: int = 32) -> Rollout:
+                     greedy: bool = False, precision: int | str = 0, reset: bool = True, check_every: int = 32) -> Rollout:
         """Rolls the whole batch with the current policy.
         horizon=None: every board plays to termination / truncation like run_episode (finished boards are
         frozen by the step kernel); horizon=H: fixed H steps with reset-on-done (all lanes always live)."""

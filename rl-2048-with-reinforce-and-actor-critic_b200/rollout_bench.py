@@ -14,7 +14,7 @@ RUNNER_ENV = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", ba
 FLOPS_PER_STEP = 2 * (16 * 256 + 256 * 256 + 256 * 4)
 
 
-def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, precision: int = 0, gid0: int = 0):
+def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, precision=0, gid0: int = 0):
     env = Batched2048Env(boards, Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=0xB200, gid0=gid0)
     agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
                            ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
@@ -37,12 +37,13 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
     ms = e0.elapsed_time(e1)
     rate = boards * steps / (ms * 1e-3)
     return {"metric": "policy-rollout steps/s", "value": rate, "unit": "rollout-steps/s", "boards": boards, "steps": steps,
-            "ms_per_step": ms / steps, "mlp": "16-256-256-4 ReLU", "precision": "fp32 CUDA cores" if precision == 0 else "bf16 tcgen05",
+            "ms_per_step": ms / steps, "mlp": "16-256-256-4 ReLU",
+            "precision": "fp32 CUDA cores" if precision == 0 else "bf16 tcgen05 (TMEM accumulators)",
             "flops_per_step": FLOPS_PER_STEP, "achieved_tflops": rate * FLOPS_PER_STEP / 1e12,
             "gpu_launches": 2 * steps}
 
 
-def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2):
+def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision=0):
     """BASELINE.json configs[2]: REINFORCE rollout (to termination, max_steps 1024) + one update (gamma 0.99,
     baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks."""
     from . import dist as bd
@@ -55,7 +56,7 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         torch.cuda.synchronize()
         e[0].record()
-        ro = agent.rollout_many(env)
+        ro = agent.rollout_many(env, precision=precision)
         e[1].record()
         upd = bd.sharded_update(agent, ro, info, total_episodes=boards * info.world_size)
         e[2].record()

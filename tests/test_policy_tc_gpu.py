@@ -1,0 +1,96 @@
+"""bf16 tcgen05 policy kernel (precision=1) against the fp32 reference arithmetic: 1e-2 relative (north_star's
+bf16 bar), sampled / greedy actions legal, distribution consistent with the fp32 probabilities."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from oracle import learner  # noqa: E402
+from helpers import random_boards, rel_err  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def b2048():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import b2048 as m
+    return m
+
+
+def dev64(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+@pytest.mark.parametrize("obs_mode,scale,n", [("log2", 0.0625, 4096), ("log2", 1.0, 70001), ("raw", 1.0, 12345)])
+def test_tc_policy_vs_fp32(b2048, obs_mode, scale, n):
+    rng = np.random.default_rng(3)
+    boards = random_boards(rng, n)
+    if obs_mode == "raw":        # keep raw tile values moderate so fp32 and bf16 are comparable
+        boards &= np.uint64(0x7777777777777777)
+    masks, _ = oracle.mask_done(boards)
+    params = b2048.init_model_params(16, [256, 256], 4, np.random.default_rng(0), "HeNormal")
+    params["b"] = [rng.normal(size=b.shape).astype(np.float32) * 0.1 for b in params["b"]]
+    env = b2048.Batched2048Env(1, b2048.Game2048EnvConfig(obs_mode=obs_mode, obs_log2_scale=scale))
+    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU"), b2048.ReinforceAgentConfig())
+    agent.params = params
+    assert agent.tc_supported()
+    bd, fl = dev64(boards), torch.from_numpy(masks).cuda()
+    logits = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    probs = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    act = torch.full((n,), 9, dtype=torch.uint8, device="cuda")
+    agent.policy_step(bd, fl, act, 5, 0, 1, greedy=True, probs_out=probs, logits_out=logits, precision=1)
+    torch.cuda.synchronize()
+    X = learner.encode(boards, obs_mode, scale)
+    ref_logits, _, _ = learner.forward(params, X, "ReLU")
+    err = rel_err(logits.cpu().numpy(), ref_logits)
+    assert err < 1e-2, err
+    ref_p = learner.probs_from_logits(ref_logits, masks)
+    p = probs.cpu().numpy()
+    assert np.abs(p.sum(1) - 1).max() < 1e-5
+    tight = obs_mode != "raw"      # raw tile values give logits of magnitude ~1e2: a 1e-2 relative logit error moves probs
+    if tight:
+        assert np.abs(p - ref_p).max() < 5e-2
+    a = act.cpu().numpy()
+    legal = masks != 0
+    assert (a < 4).all() and (((masks[legal] >> a[legal]) & 1) == 1).all()
+    # greedy agrees with the fp32 argmax wherever the fp32 margin is not tiny
+    m = np.stack([(masks >> k) & 1 for k in range(4)], 1)
+    q = ref_p * m
+    top2 = np.sort(q, 1)[:, -2:]
+    clear = legal & ((top2[:, 1] - top2[:, 0]) > 0.05)
+    assert (a[clear] == q[clear].argmax(1)).mean() > (0.999 if tight else 0.97)
+    # sampling: legal, and fp32 / bf16 paths draw from (nearly) the same distribution with the same uniforms
+    a1 = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    a0 = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    agent.policy_step(bd, fl, a1, 7, 0, 3, greedy=False, precision=1)
+    agent.policy_step(bd, fl, a0, 7, 0, 3, greedy=False, precision=0)
+    a1, a0 = a1.cpu().numpy(), a0.cpu().numpy()
+    assert (((masks[legal] >> a1[legal]) & 1) == 1).all()
+    assert (a1 == a0).mean() > (0.97 if tight else 0.9)
+
+
+def test_tc_policy_unsupported_shape_is_loud(b2048):
+    env = b2048.Batched2048Env(1, b2048.Game2048EnvConfig(obs_mode="log2"))
+    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[64, 64], activation="ReLU", init_distribution="HeNormal"),
+                                 b2048.ReinforceAgentConfig())
+    bd = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    act = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(b2048.B2048Error):
+        agent.policy_step(bd, None, act, 0, 0, 0, precision=1)
+    agent.policy_step(bd, None, act, 0, 0, 0, precision="auto")     # falls back to the fp32 kernel by design
+
+
+def test_tc_rollout_statistics(b2048):
+    """Rollouts driven by the tensor-core policy behave like the fp32 ones (same mean return within noise)."""
+    n = 8192
+    cfg = b2048.Game2048EnvConfig(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", base_reward_scale=0.5)
+    out = {}
+    for prec in (0, 1):
+        env = b2048.Batched2048Env(n, cfg, seed=11)
+        agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode="batch"))
+        ro = agent.rollout_many(env, precision=prec)
+        out[prec] = (float(ro.total_reward().mean()), float(ro.length.float().mean()))
+    assert abs(out[0][0] - out[1][0]) / out[0][0] < 0.05 and abs(out[0][1] - out[1][1]) / out[0][1] < 0.05
