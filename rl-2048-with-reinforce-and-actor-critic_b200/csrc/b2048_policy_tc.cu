@@ -2,7 +2,7 @@
 // fp32 accumulation.  Used for batches >= 4096 boards with the runner-default policy shape
 // (16 -> 256 -> 256 -> 4, ReLU); everything else runs on the fp32 CUDA-core path (b2048_policy.cu).
 //
-// One CTA (128 threads = 4 warps = the 128 TMEM lanes) owns a tile of 128 boards and loops over tiles:
+// One CTA (16 epilogue warps + 1 MMA/copy warp) owns a tile of 128 boards (= the 128 TMEM lanes) and loops over tiles:
 //
 //   A1 [128 x 16] bf16  <- packed boards (each thread encodes its own board: 16 nibbles -> 16 bf16)
 //   D1 = A1 . W1^T      one  tcgen05.mma  M128 N256 K16          -> TMEM columns   0..255
@@ -144,19 +144,43 @@ struct PolicyTcArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(TC_M, 1) policy_tc_kernel(const __grid_constant__ PolicyTcArgs args) {
+// Warp roles (17 warps = 544 threads, one CTA per SM):
+//   warps 0..15  epilogue warps.  Warp w owns TMEM lanes / board rows 32*(w%4) .. +31 (the hardware's lane-quarter
+//                rule) and the 64-column block g = w/4 of both accumulators, i.e. exactly one 128B-swizzle K slab of
+//                the layer-2 operand.  Group 0 (warps 0..3, one thread per board) also encodes the boards into A1 and
+//                finishes softmax / sampling.
+//   warp 16      issues every tcgen05.mma (one elected lane), the weight-image bulk copies and owns TMEM alloc/dealloc.
+// Pipelining inside a tile: layer-2 MMAs of K slab g are issued as soon as group g has written slab g, so the tensor
+// core runs under epilogue 1; across tiles: A1 of tile i+1 is encoded before epilogue 2 of tile i, so MMA1(i+1) runs
+// under epilogue 2(i).  All hand-offs are mbarriers (phase = tile parity); no __syncthreads in the loop.
+constexpr int TC_EPI_THREADS = 512;
+constexpr int TC_THREADS = TC_EPI_THREADS + 32;
+constexpr int SM_PART = SM_BAR + 128;                       // float [4 groups][128 rows][4] partial logits = 8192 B
+constexpr int SM_TOTAL2 = SM_PART + 8192;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_constant__ PolicyTcArgs args) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-    const uint32_t bar_img = s_u32(&bars[0]), bar_mma = s_u32(&bars[1]);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 32);
+    const uint32_t bar_img = s_u32(&bars[0]), bar_a1 = s_u32(&bars[1]), bar_d1 = s_u32(&bars[2]), bar_d2 = s_u32(&bars[3]),
+                   bar_d2free = s_u32(&bars[4]);
+    const uint32_t bar_slab0 = s_u32(&bars[5]);   // bars[5..8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 96);
 
     if (tid == 0) {
         mbar_init(bar_img, 1);
-        mbar_init(bar_mma, 1);
+        mbar_init(bar_a1, 128);
+        mbar_init(bar_d1, 1);
+        mbar_init(bar_d2, 1);
+        mbar_init(bar_d2free, TC_EPI_THREADS);
+        for (int g = 0; g < 4; ++g) mbar_init(bar_slab0 + 8u * g, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // one warp allocates all 512 TMEM columns (two fp32 accumulators of 256 columns)
+    if (warp == 16) {   // all 512 TMEM columns: D1 = columns 0..255, D2 = columns 256..511
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -165,165 +189,190 @@ __global__ void __launch_bounds__(TC_M, 1) policy_tc_kernel(const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-
-    if (tid == 0) {    // weight image -> shared memory (bulk async copies, completion on bar_img)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)IMG_BYTES)
-                     : "memory");
-        constexpr uint32_t kChunk = 16384;
-        for (uint32_t off = 0; off < (uint32_t)IMG_BYTES; off += kChunk) {
-            uint32_t sz = (uint32_t)IMG_BYTES - off < kChunk ? (uint32_t)IMG_BYTES - off : kChunk;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             s_u32(smem + off)),
-                         "l"(args.img + off), "r"(sz), "r"(bar_img)
-                         : "memory");
-        }
-    }
-
-    const float* sW3 = reinterpret_cast<const float*>(smem + IMG_W3);
-    const float* sB1 = reinterpret_cast<const float*>(smem + IMG_B1);
-    const float* sB2 = reinterpret_cast<const float*>(smem + IMG_B2);
-    const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
-    const uint32_t sA1 = s_u32(smem + SM_A1), sA2 = s_u32(smem + SM_A2);
-    const uint32_t sW1 = s_u32(smem + IMG_W1), sW2 = s_u32(smem + IMG_W2);
-    const uint32_t taddr_lane = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
-    uint32_t mma_phase = 0;
-    bool img_ready = false;
-
     const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t s = tile * TC_M + tid;
-        const bool valid = s < args.n;
-        // ---- A1: this thread's board as 16 bf16 (row = tid), no-swizzle K-major core matrices
-        uint64_t bd = valid ? args.board[s] : 0ull;
-        uint32_t packed[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint32_t e0 = (uint32_t)(bd >> (8 * j)) & 0xFu, e1 = (uint32_t)(bd >> (8 * j + 4)) & 0xFu;
-            float v0, v1;
-            if (args.obs_mode == B2048_OBS_RAW) { v0 = e0 ? (float)(1u << e0) : 0.0f; v1 = e1 ? (float)(1u << e1) : 0.0f; }
-            else { v0 = (float)e0 * args.obs_scale; v1 = (float)e1 * args.obs_scale; }
-            __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
-            packed[j] = *reinterpret_cast<uint32_t*>(&p);
-        }
-        {
-            uint8_t* a1 = smem + SM_A1 + (tid >> 3) * 256 + (tid & 7) * 16;
-            *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);         // k 0..7
-            *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);   // k 8..15
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (!img_ready) { mbar_wait(bar_img, 0); img_ready = true; }
 
-        // ---- layer 1: D1 = A1 . W1^T
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sW1), kIdesc, 0u);
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, mma_phase);
-        mma_phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        // ---- epilogue 1: A2[row = tid][k] = bf16(relu(D1 + b1)), 128B-swizzled K-major slabs
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_H; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr_lane + (uint32_t)c0, r);
-            uint8_t* rowp = smem + SM_A2 + (c0 >> 6) * 16384 + tid * 128;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {                    // four 16-byte chunks of 8 columns
-                uint32_t w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int c = c0 + q * 8 + u * 2;
-                    float v0 = fmaxf(__uint_as_float(r[q * 8 + u * 2]) + sB1[c], 0.0f);
-                    float v1 = fmaxf(__uint_as_float(r[q * 8 + u * 2 + 1]) + sB1[c + 1], 0.0f);
-                    __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
-                    w[u] = *reinterpret_cast<uint32_t*>(&p);
-                }
-                int chunk = ((c0 & 63) >> 3) + q;            // 16-byte chunk index inside the 128-byte row
-                *reinterpret_cast<uint4*>(rowp + ((chunk ^ (tid & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (warp == 16) {
+        // ============================ MMA / copy warp ============================
+        // Lane 0 does the work; the other lanes stay converged with it (__syncwarp per tile) so that the final
+        // aligned __syncthreads is reached by the whole warp together.
+        const uint32_t sA1 = s_u32(smem + SM_A1), sA2 = s_u32(smem + SM_A2);
+        const uint32_t sW1 = s_u32(smem + IMG_W1), sW2 = s_u32(smem + IMG_W2);
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)IMG_BYTES)
+                         : "memory");
+            constexpr uint32_t kChunk = 16384;
+            for (uint32_t off = 0; off < (uint32_t)IMG_BYTES; off += kChunk) {
+                uint32_t sz = (uint32_t)IMG_BYTES - off < kChunk ? (uint32_t)IMG_BYTES - off : kChunk;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 s_u32(smem + off)),
+                             "l"(args.img + off), "r"(sz), "r"(bar_img)
+                             : "memory");
             }
+            mbar_wait(bar_img, 0);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-
-        // ---- layer 2: D2 = A2 . W2^T, K = 256 as 16 instructions of K = 16 (4 slabs x 4)
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncwarp();
+        uint32_t ph = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (lane == 0) {
+                // layer 1 (D1 is free: every epilogue-1 read of the previous tile preceded its slab arrivals)
+                mbar_wait(bar_a1, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sW1), kIdesc, 0u);
+                umma_commit(bar_d1);
+                // layer 2, slab by slab as epilogue 1 produces them
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(bar_slab0 + 8u * g, ph);
+                    if (g == 0 && tile != (int64_t)blockIdx.x) mbar_wait(bar_d2free, ph ^ 1u);   // D2 drained by the previous tile's epilogue 2
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                uint32_t a_addr = sA2 + (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u;
-                uint32_t b_addr = sW2 + (uint32_t)(kk >> 2) * 32768u + (uint32_t)(kk & 3) * 32u;
-                umma_f16(tmem_base + 256u, desc_sw128(a_addr), desc_sw128(b_addr), kIdesc, kk > 0 ? 1u : 0u);
-            }
-            umma_commit(bar_mma);
-        }
-        mbar_wait(bar_mma, mma_phase);
-        mma_phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        // ---- epilogue 2: logits = relu(D2 + b2) . W3 + b3 on CUDA cores, then softmax / sampling
-        float lg0 = sB3[0], lg1 = sB3[1], lg2 = sB3[2], lg3 = sB3[3];
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_H; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr_lane + 256u + (uint32_t)c0, r);
-#pragma unroll
-            for (int u = 0; u < 32; ++u) {
-                float h = fmaxf(__uint_as_float(r[u]) + sB2[c0 + u], 0.0f);
-                float4 w = *reinterpret_cast<const float4*>(sW3 + (c0 + u) * 4);
-                lg0 = fmaf(h, w.x, lg0); lg1 = fmaf(h, w.y, lg1); lg2 = fmaf(h, w.z, lg2); lg3 = fmaf(h, w.w, lg3);
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM reads done before the next tile's MMAs
-
-        if (valid) {
-            uint32_t fl = 0xFu;
-            const bool use_mask = args.mask_flags != nullptr;
-            if (use_mask) fl = args.mask_flags[s];
-            float l0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, l1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
-            float l2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, l3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
-            float mx = fmaxf(fmaxf(l0, l1), fmaxf(l2, l3));
-            float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx), e3 = expf(l3 - mx);
-            float sum = e0 + e1 + e2 + e3;
-            float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
-            if (args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
-            if (args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
-            if (args.action) {
-                uint32_t a;
-                if (args.greedy) {
-                    float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
-                    float q2 = (!use_mask || (fl & 4u)) ? p2 : 0.0f, q3 = (!use_mask || (fl & 8u)) ? p3 : 0.0f;
-                    a = 0; float best = q0;
-                    if (q1 > best) { best = q1; a = 1; }
-                    if (q2 > best) { best = q2; a = 2; }
-                    if (q3 > best) { best = q3; a = 3; }
-                } else {
-                    Rand4 rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, args.t, B2048_DOM_STEP);
-                    float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
-                    float u = ((float)(rr.w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
-                    a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
-                    float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
-                    if (!(pa > 0.0f)) {
-                        if (p3 > 0.0f) a = 3;
-                        if (p2 > 0.0f) a = 2;
-                        if (p1 > 0.0f) a = 1;
-                        if (p0 > 0.0f) a = 0;
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t a_addr = sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u;
+                        uint32_t b_addr = sW2 + (uint32_t)g * 32768u + (uint32_t)q * 32u;
+                        umma_f16(tmem_base + 256u, desc_sw128(a_addr), desc_sw128(b_addr), kIdesc, (g | q) ? 1u : 0u);
                     }
                 }
-                args.action[s] = (uint8_t)a;
+                umma_commit(bar_d2);
             }
+            __syncwarp();
+            ph ^= 1u;
         }
-        __syncthreads();   // A1 / A2 / TMEM are reused by the next tile
+    } else {
+        // ============================ epilogue warps ============================
+        const int q = warp & 3, g = warp >> 2;
+        const int row = q * 32 + lane;                                          // board row inside the tile = TMEM lane
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
+        const float* sW3 = reinterpret_cast<const float*>(smem + IMG_W3);
+        const float* sB1 = reinterpret_cast<const float*>(smem + IMG_B1);
+        const float* sB2 = reinterpret_cast<const float*>(smem + IMG_B2);
+        const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
+        float* part = reinterpret_cast<float*>(smem + SM_PART);
+        uint32_t ph = 0;
+
+        auto encode_a1 = [&](int64_t tile) {   // group 0 only: this thread's board -> 16 bf16 in the A1 core matrices
+            const int64_t s = tile * TC_M + row;
+            uint64_t bd = (s < args.n) ? args.board[s] : 0ull;
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t e0 = (uint32_t)(bd >> (8 * j)) & 0xFu, e1 = (uint32_t)(bd >> (8 * j + 4)) & 0xFu;
+                float v0, v1;
+                if (args.obs_mode == B2048_OBS_RAW) { v0 = e0 ? (float)(1u << e0) : 0.0f; v1 = e1 ? (float)(1u << e1) : 0.0f; }
+                else { v0 = (float)e0 * args.obs_scale; v1 = (float)e1 * args.obs_scale; }
+                __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+                packed[j] = *reinterpret_cast<uint32_t*>(&p);
+            }
+            uint8_t* a1 = smem + SM_A1 + (row >> 3) * 256 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_a1);
+        };
+
+        if (g == 0 && (int64_t)blockIdx.x < n_tiles) encode_a1(blockIdx.x);
+        mbar_wait(bar_img, 0);                                                  // biases / W3 live in the image
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // ---- epilogue 1: slab g of A2 = bf16(relu(D1[:, 64g..64g+63] + b1))
+            mbar_wait(bar_d1, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint8_t* rowp = smem + SM_A2 + g * 16384 + row * 128;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld32(taddr + (uint32_t)(half * 32), r);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {                                // four 16-byte chunks of 8 columns
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        int c = g * 64 + half * 32 + c4 * 8 + u * 2;
+                        float v0 = fmaxf(__uint_as_float(r[c4 * 8 + u * 2]) + sB1[c], 0.0f);
+                        float v1 = fmaxf(__uint_as_float(r[c4 * 8 + u * 2 + 1]) + sB1[c + 1], 0.0f);
+                        __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+                        w[u] = *reinterpret_cast<uint32_t*>(&p);
+                    }
+                    int chunk = half * 4 + c4;
+                    *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // smem writes -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // D1 reads ordered before the next MMA1
+            mbar_arrive(bar_slab0 + 8u * g);
+            // ---- next tile's A1 while the tensor core works on layer 2 (A1 is free: MMA1 of this tile completed)
+            const int64_t next = tile + gridDim.x;
+            if (g == 0 && next < n_tiles) encode_a1(next);
+            // ---- epilogue 2: partial logits over this warp's 64 columns of relu(D2 + b2)
+            mbar_wait(bar_d2, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld32(taddr + 256u + (uint32_t)(half * 32), r);
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    int c = g * 64 + half * 32 + u;
+                    float hv = fmaxf(__uint_as_float(r[u]) + sB2[c], 0.0f);
+                    float4 w = *reinterpret_cast<const float4*>(sW3 + c * 4);
+                    l0 = fmaf(hv, w.x, l0); l1 = fmaf(hv, w.y, l1); l2 = fmaf(hv, w.z, l2); l3 = fmaf(hv, w.w, l3);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_d2free);                                             // D2 may be overwritten
+            *reinterpret_cast<float4*>(part + (g * TC_M + row) * 4) = make_float4(l0, l1, l2, l3);
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // the 16 epilogue warps only
+            if (g == 0) {
+                const int64_t s = tile * TC_M + row;
+                float4 p0v = *reinterpret_cast<const float4*>(part + (0 * TC_M + row) * 4);
+                float4 p1v = *reinterpret_cast<const float4*>(part + (1 * TC_M + row) * 4);
+                float4 p2v = *reinterpret_cast<const float4*>(part + (2 * TC_M + row) * 4);
+                float4 p3v = *reinterpret_cast<const float4*>(part + (3 * TC_M + row) * 4);
+                float lg0 = sB3[0] + ((p0v.x + p1v.x) + (p2v.x + p3v.x)), lg1 = sB3[1] + ((p0v.y + p1v.y) + (p2v.y + p3v.y));
+                float lg2 = sB3[2] + ((p0v.z + p1v.z) + (p2v.z + p3v.z)), lg3 = sB3[3] + ((p0v.w + p1v.w) + (p2v.w + p3v.w));
+                if (s < args.n) {
+                    uint32_t fl = 0xFu;
+                    const bool use_mask = args.mask_flags != nullptr;
+                    if (use_mask) fl = args.mask_flags[s];
+                    float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
+                    float m2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, m3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
+                    float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx), e3 = expf(m3 - mx);
+                    float sum = e0 + e1 + e2 + e3;
+                    float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
+                    if (args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
+                    if (args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
+                    if (args.action) {
+                        uint32_t a;
+                        if (args.greedy) {
+                            float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
+                            float q2 = (!use_mask || (fl & 4u)) ? p2 : 0.0f, q3 = (!use_mask || (fl & 8u)) ? p3 : 0.0f;
+                            a = 0; float best = q0;
+                            if (q1 > best) { best = q1; a = 1; }
+                            if (q2 > best) { best = q2; a = 2; }
+                            if (q3 > best) { best = q3; a = 3; }
+                        } else {
+                            Rand4 rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, args.t, B2048_DOM_STEP);
+                            float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
+                            float u = ((float)(rr.w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
+                            a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
+                            float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
+                            if (!(pa > 0.0f)) {
+                                if (p3 > 0.0f) a = 3;
+                                if (p2 > 0.0f) a = 2;
+                                if (p1 > 0.0f) a = 1;
+                                if (p0 > 0.0f) a = 0;
+                            }
+                        }
+                        args.action[s] = (uint8_t)a;
+                    }
+                }
+            }
+            ph ^= 1u;
+        }
     }
 
-    if (!img_ready) mbar_wait(bar_img, 0);   // never leave with bulk copies in flight
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
@@ -335,12 +384,12 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
                      int greedy, cudaStream_t stream) {
     if (mlp->n_layers != 3 || mlp->dims[0] != 16 || mlp->dims[1] != TC_H || mlp->dims[2] != TC_H || mlp->dims[3] != 4 ||
         mlp->activation != B2048_ACTV_RELU || (mlp->obs_mode != B2048_OBS_RAW && mlp->obs_mode != B2048_OBS_LOG2) ||
-        h->smem_optin < SM_TOTAL)
+        h->smem_optin < SM_TOTAL2)
         return B2048_ERR_UNSUPPORTED;
     if (!h->tc_image) {
         cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
         if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
-        e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
     }
     // the image is rebuilt on every call (71 K parameters, ~2 us): the library never caches stale weights
@@ -352,7 +401,7 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     a.obs_scale = mlp->obs_log2_scale;
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
-    policy_tc_kernel<<<grid, TC_M, SM_TOTAL, stream>>>(a);
+    policy_tc_kernel<<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
     return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
 }
 

@@ -392,6 +392,16 @@ class ReinforceAgent:
         acts = ro.actions[:T].reshape(-1)
         rewards = ro.rewards[:T].contiguous()
         length = ro.length
+        # Run-to-termination rollouts are ragged: slots with t >= len[b] carry no sample.  The per-sample work
+        # (forward / backward GEMMs) runs on the compacted list of live slots; the [T, B] grid is kept only for
+        # the per-episode time recurrences (returns scan, TD shift).  Pure index plumbing (torch).
+        live = None
+        n_live = int(length.sum().item())
+        if n_live < int(0.9 * n):
+            tgrid = torch.arange(T, device=dev, dtype=torch.int32).unsqueeze(1)
+            live = (tgrid < length.unsqueeze(0)).reshape(-1)
+            boards, mflags, acts = boards[live], mflags[live], acts[live]
+            n = n_live
         stats = self._buf("stats", (4,), torch.float64)
         ep_mean = self._buf("ep_mean", (B,), torch.float32)
         adv = self._buf("adv", (T, B), torch.float32)
@@ -414,6 +424,8 @@ class ReinforceAgent:
                            "b2048_advantages")
 
         def backward(net: DeviceMLP, cf: torch.Tensor, head_mode: int):
+            if live is not None:
+                cf = cf[live]
             net.grad.zero_()
             ws_floats = int(lib.b2048_backward_workspace_floats(C.byref(net.desc), min(chunk, n)))
             ws = self._buf("bwd_ws", (ws_floats,), torch.float32)
@@ -436,7 +448,13 @@ class ReinforceAgent:
         if cfg.use_critic and self._critic is not None:
             # critic block (reinforce_agent.py:403-498): V(s_t) for every stored state, TD(0) errors, critic grads
             values = self._buf("values", (T, B), torch.float32)
-            self._values(boards, values)
+            if live is None:
+                self._values(boards, values)
+            else:
+                vc = self._buf("values_c", (n,), torch.float32)
+                self._values(boards, vc)
+                values.zero_()
+                values.view(-1)[live] = vc
             td = self._buf("td", (T, B), torch.float32)
             gcoef = self._buf("gcoef", (T, B), torch.float32)
             with torch.cuda.device(dev):
