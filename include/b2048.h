@@ -182,6 +182,18 @@ int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mas
                       int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
                       int32_t greedy, int32_t precision, void* stream);
 
+/* ReinforceAgent.run_episode's loop (reinforce_agent.py:221-236) for a whole batch, issued from C: n_steps times
+ * { actions[t] = policy(boards[t], flags[t]); boards[t+1], flags[t+1], rewards[t] = step(boards[t], actions[t]) } for
+ * t = t_begin .. t_begin + n_steps - 1.  boards / flags are time-major [T+1, B], actions / rewards [T, B].
+ * ep_len != NULL: run-to-termination bookkeeping (see b2048_step_many); ep_len == NULL with cfg->auto_reset: fixed
+ * horizon with reset-on-done.  t0: the env's step index before step t = 0 (Philox counter = t0 + t + 1).
+ * use_mask: feed the legal masks to the policy (Game2048EnvConfig.use_action_mask). */
+int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* flags, uint8_t* actions, float* rewards,
+                       uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
+                       const b2048_env_cfg* cfg /* host */, const b2048_mlp_desc* mlp /* host */, int64_t B,
+                       int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
+                       int32_t greedy, int32_t precision, void* stream);
+
 /* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1). */
 int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
                       int64_t n, void* stream);

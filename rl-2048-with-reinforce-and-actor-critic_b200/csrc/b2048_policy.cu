@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dense_forward_kernel(const __g
 
 int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
                      uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
-                     int greedy, cudaStream_t stream);
+                     int greedy, cudaStream_t stream, bool rebuild_image);
 
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
     if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
@@ -180,10 +180,51 @@ int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int s
 
 using namespace b2;
 
+static int policy_step_impl(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const b2048_mlp_desc* mlp,
+                            uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0,
+                            uint32_t t, int32_t greedy, int32_t precision, void* stream, bool rebuild_image);
+
 extern "C" int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
                                  const b2048_mlp_desc* mlp, uint8_t* action, float* probs, float* logits, int64_t n,
                                  uint64_t seed, uint64_t gid0, uint32_t t, int32_t greedy, int32_t precision,
                                  void* stream) {
+    return policy_step_impl(h, board, mask_flags, mlp, action, probs, logits, n, seed, gid0, t, greedy, precision, stream,
+                            true);
+}
+
+// The rollout loop of ReinforceAgent.run_episode (reference src/reinforce_agent.py:221-236) for a whole batch, issued
+// from C so that a rollout step costs two kernel launches and no interpreter time: for k in [0, n_steps):
+//   t = t_begin + k;  actions[t] = policy(boards[t], flags[t]);  (boards[t+1], flags[t+1], rewards[t]) = step(...)
+extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* flags, uint8_t* actions, float* rewards,
+                                  uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
+                                  const b2048_env_cfg* cfg, const b2048_mlp_desc* mlp, int64_t B, int32_t t_begin,
+                                  int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
+                                  int32_t greedy, int32_t precision, void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_rollout_many: handle is NULL");
+    B2_REQUIRE(B >= 0 && n_steps >= 0 && t_begin >= 0, "b2048_rollout_many: negative size");
+    if (B == 0 || n_steps == 0) return B2048_OK;
+    B2_REQUIRE(boards && flags && actions && rewards && cfg && mlp, "b2048_rollout_many: NULL buffer");
+    b2048_env_cfg c = *cfg;
+    c.action_mode = B2048_ACT_BUFFER;
+    for (int32_t k = 0; k < n_steps; ++k) {
+        const int64_t t = (int64_t)t_begin + k;
+        const uint32_t t_env = t0 + (uint32_t)t + 1u;
+        uint64_t* b_in = boards + t * B;
+        uint8_t* f_in = flags + t * B;
+        int st = policy_step_impl(h, b_in, use_mask ? f_in : nullptr, mlp, actions + t * B, nullptr, nullptr, B, seed, gid0,
+                                  t_env, greedy, precision, stream, k == 0);
+        if (st != B2048_OK) return st;
+        st = b2048_step_many(h, b_in, b_in + B, score, step, max_exp, actions + t * B, nullptr, f_in, nullptr, &c, nullptr,
+                             rewards + t * B, nullptr, f_in + B, nullptr, ep_len, (uint32_t)(t + 1), B, seed, gid0, t_env,
+                             stream);
+        if (st != B2048_OK) return st;
+    }
+    return B2048_OK;
+}
+
+static int policy_step_impl(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const b2048_mlp_desc* mlp,
+                            uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0,
+                            uint32_t t, int32_t greedy, int32_t precision, void* stream, bool rebuild_image) {
     B2_REQUIRE(h != nullptr, "b2048_policy_step: handle is NULL");
     B2_REQUIRE(n >= 0, "b2048_policy_step: n < 0");
     if (n == 0) return B2048_OK;
@@ -193,7 +234,8 @@ extern "C" int b2048_policy_step(b2048_handle* h, const uint64_t* board, const u
     int st = validate_mlp(mlp, &a.mlp, &smem, h->smem_optin, "b2048_policy_step");
     if (st != B2048_OK) return st;
     if (precision == 1) {
-        st = launch_policy_tc(h, mlp, board, mask_flags, action, probs, logits, n, seed, gid0, t, greedy, (cudaStream_t)stream);
+        st = launch_policy_tc(h, mlp, board, mask_flags, action, probs, logits, n, seed, gid0, t, greedy, (cudaStream_t)stream,
+                              rebuild_image);
         if (st == B2048_ERR_UNSUPPORTED)
             return fail(B2048_ERR_UNSUPPORTED,
                         "b2048_policy_step: precision 1 (bf16 tcgen05) implements the 16-256-256-4 ReLU policy on raw/log2 "

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
 // error message) when the shape is outside what this kernel implements.
 int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
                      uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
-                     int greedy, cudaStream_t stream) {
+                     int greedy, cudaStream_t stream, bool rebuild_image) {
     if (mlp->n_layers != 3 || mlp->dims[0] != 16 || mlp->dims[1] != TC_H || mlp->dims[2] != TC_H || mlp->dims[3] != 4 ||
         mlp->activation != B2048_ACTV_RELU || (mlp->obs_mode != B2048_OBS_RAW && mlp->obs_mode != B2048_OBS_LOG2) ||
         h->smem_optin < SM_TOTAL2)
@@ -392,9 +392,11 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
         e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
     }
-    // the image is rebuilt on every call (71 K parameters, ~2 us): the library never caches stale weights
-    policy_tc_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[0], mlp->b[0], mlp->W[1], mlp->b[1], mlp->W[2], mlp->b[2],
-                                                      h->tc_image);
+    // The image is rebuilt on every stand-alone call (71 K parameters): the library never caches weights across
+    // calls.  b2048_rollout_many builds it once for the whole loop (parameters cannot change inside one call).
+    if (rebuild_image)
+        policy_tc_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[0], mlp->b[0], mlp->W[1], mlp->b[1], mlp->W[2], mlp->b[2],
+                                                          h->tc_image);
     PolicyTcArgs a;
     a.img = h->tc_image; a.board = board; a.mask_flags = mask_flags; a.action = action; a.probs = probs; a.logits = logits;
     a.n = n; a.keys = make_keys(seed); a.gid0 = gid0; a.t = t; a.greedy = greedy; a.obs_mode = mlp->obs_mode;

@@ -286,18 +286,26 @@ class ReinforceAgent:
         length = torch.zeros(B, dtype=torch.int32, device=self.device)
         boards[0].copy_(benv.board)
         flags[0].copy_(benv.flags)
+        if precision == "auto":
+            precision = 1 if (B >= 4096 and self.tc_supported()) else 0
+        from .batched_env import make_env_cfg
+        cfg = make_env_cfg(benv.config, "buffer", auto_reset=fixed, emit_obs=False)
+        t0 = benv.t
         T = 0
-        for t in range(cap):
-            self.policy_step(boards[t], flags[t], actions[t], benv.seed, benv.gid0, benv.t + 1, greedy=greedy,
-                             precision=precision)
-            benv.board = boards[t]
-            benv.flags = flags[t]
-            benv.step_many(actions[t], auto_reset=fixed, board_out=boards[t + 1], reward_out=rewards[t],
-                           flags_out=flags[t + 1], ep_len=None if fixed else length, ep_t=t + 1, flags_in=flags[t])
-            T = t + 1
-            if not fixed and (T % check_every == 0 or T == cap):
-                if bool((length != 0).all()):
-                    break
+        while T < cap:
+            chunk = min(check_every if not fixed else 256, cap - T)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.b2048_rollout_many(
+                    self._h, _ptr(boards), _ptr(flags), _ptr(actions), _ptr(rewards), _ptr(benv.score), _ptr(benv.step_count),
+                    _ptr(benv.max_exp), None if fixed else _ptr(length), C.byref(cfg), C.byref(self._actor.desc), B, T,
+                    chunk, benv.seed, benv.gid0, t0, int(self._use_mask), int(greedy), int(precision), _stream()),
+                    "b2048_rollout_many")
+            T += chunk
+            if not fixed and bool((length != 0).all()):
+                break
+        benv.t = t0 + T
+        benv.board = boards[T]
+        benv.flags = flags[T]
         if fixed:
             length.fill_(T)
         else:

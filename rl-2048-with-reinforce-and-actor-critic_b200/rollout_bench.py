@@ -19,19 +19,11 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
     agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
                            ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
     env.reset_many()
-    act = torch.zeros(boards, dtype=torch.uint8, device=dev)
-
-    def one():
-        agent.policy_step(env.board, env.flags, act, env.seed, env.gid0, env.t + 1, precision=precision)
-        env.step_many(act, auto_reset=True)
-
-    for _ in range(warmup):
-        one()
+    agent.rollout_many(env, horizon=steps, precision=precision, reset=False)   # warm-up; also sizes the rollout buffers
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(steps):
-        one()
+    agent.rollout_many(env, horizon=steps, precision=precision, reset=False)     # fixed horizon, reset-on-done
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)

@@ -30,7 +30,7 @@ def lib_path():
 def test_header_declares_the_expected_surface():
     syms = header_symbols()
     for s in ("b2048_create", "b2048_destroy", "b2048_reset_many", "b2048_step_many", "b2048_move_many",
-              "b2048_encode_obs", "b2048_policy_step", "b2048_mlp_forward", "b2048_dense_forward", "b2048_reverse_scan",
+              "b2048_encode_obs", "b2048_policy_step", "b2048_rollout_many", "b2048_mlp_forward", "b2048_dense_forward", "b2048_reverse_scan",
               "b2048_advantages", "b2048_weighted_stats", "b2048_td_errors", "b2048_mlp_backward", "b2048_apply_update", "b2048_last_error"):
         assert s in syms
 
