@@ -2,19 +2,24 @@
 // fp32 accumulation.  Used for batches >= 4096 boards with the runner-default policy shape
 // (16 -> 256 -> 256 -> 4, ReLU); everything else runs on the fp32 CUDA-core path (b2048_policy.cu).
 //
-// One CTA (16 epilogue warps + 1 MMA/copy warp) owns a tile of 128 boards (= the 128 TMEM lanes) and loops over tiles:
+// One CTA (16 epilogue warps + 1 MMA/copy warp) owns a tile of 128 boards (= the 128 TMEM lanes) and loops over tiles.
+// ALL THREE layers and BOTH hidden biases run on the tensor core; the epilogues only do ReLU + bf16 pack:
 //
-//   A1 [128 x 16] bf16  <- packed boards (each thread encodes its own board: 16 nibbles -> 16 bf16)
-//   D1 = A1 . W1^T      one  tcgen05.mma  M128 N256 K16          -> TMEM columns   0..255
-//   A2 = relu(D1 + b1)  tcgen05.ld 32x32b, bias + ReLU, bf16 pack, st.shared into the 128B-swizzled
-//                       K-major operand layout                      (activations never leave the SM)
-//   D2 = A2 . W2^T      sixteen tcgen05.mma M128 N256 K16         -> TMEM columns 256..511
-//   logits = relu(D2 + b2) . W3 + b3   in the epilogue on CUDA cores (N = 4 is below the UMMA minimum),
-//   masked softmax + inverse-CDF sample / greedy, one action byte per board.
+//   A1 [128 x 16] bf16  <- packed boards (one thread per board: 16 nibbles -> 16 bf16)
+//   D1 = A1 . W1^T + ONES1 . BIAS^T      2 tcgen05.mma (M128 N256 K16)          -> TMEM columns   0..255
+//   A2 = bf16(relu(D1))                  tcgen05.ld 32x32b -> packed max -> st.shared, 128B-swizzled K-major slabs
+//   D2 = A2 . W2^T + ONES2 . BIAS^T      16 + 1 tcgen05.mma (M128 N256 K16)     -> TMEM columns 256..511
+//   H2 = bf16(relu(D2))                  same epilogue, written over A2 (free once layer 2 has completed)
+//   D3 = H2 . W3^T                       16 tcgen05.mma (M128 N16 K16)          -> TMEM columns 256..271 (over D2)
+//   logits = D3[:, 0:4] + b3 -> masked softmax -> inverse-CDF sample / greedy -> one action byte per board
 //
-// Weights arrive as a pre-arranged shared-memory IMAGE (bf16, already in the UMMA canonical layouts) that a
-// small prep kernel builds from the reference-layout fp32 parameters; each CTA pulls the 142 KB image with
-// bulk async copies (cp.async.bulk + mbarrier) once and keeps it resident for all of its tiles.
+// The bias trick: BIAS is a [256 x 16] operand holding b1 in k = 0 and b2 in k = 1; ONES1 / ONES2 are A operands
+// whose every row is the unit vector e0 / e1.  They are 256-byte constants: their descriptors use a stride-byte-offset
+// of 0 so all sixteen 8-row groups read the same core matrix.
+//
+// Weights arrive as a pre-arranged shared-memory IMAGE (bf16, already in the UMMA canonical layouts) that a small prep
+// kernel builds from the reference-layout fp32 parameters; each CTA pulls the 153 KB image with bulk async copies
+// (cp.async.bulk + mbarrier) once and keeps it resident for all of its tiles.
 //
 // Reference arithmetic: encode_observation / forward_logits / logits_to_probs / select_action
 // (src/MLP.py:22-43, :139-196; src/reinforce_agent.py:126-192).  Parity bar for this path: 1e-2 relative.
@@ -29,20 +34,24 @@ namespace b2 {
 constexpr int TC_M = 128;          // boards per tile = TMEM lanes
 constexpr int TC_H = 256;          // hidden width (both layers)
 constexpr int TC_K1 = 16;          // input width
+constexpr int TC_N3 = 16;          // head width padded to the UMMA minimum for M = 128
 
 // ---- shared-memory image (byte offsets).  SW128 K-major slabs must be 1024-byte aligned.
 constexpr int IMG_W2 = 0;                          // 4 slabs [256 rows x 128 B] = 131072 B (SWIZZLE_128B, K-major)
 constexpr int IMG_W1 = 131072;                     // [32 row-groups][2 k-chunks][8 rows][16 B] = 8192 B (no swizzle)
-constexpr int IMG_W3 = IMG_W1 + 8192;              // float [256][4] = 4096 B
-constexpr int IMG_B1 = IMG_W3 + 4096;              // float [256]
-constexpr int IMG_B2 = IMG_B1 + 1024;              // float [256]
-constexpr int IMG_B3 = IMG_B2 + 1024;              // float [4] (+ pad to 16)
-constexpr int IMG_BYTES = IMG_B3 + 16;             // 145424
+constexpr int IMG_BIAS = IMG_W1 + 8192;            // same layout: k = 0 -> b1[n], k = 1 -> b2[n], rest 0
+constexpr int IMG_W3 = IMG_BIAS + 8192;            // 4 slabs [16 rows x 128 B] = 8192 B (SWIZZLE_128B), rows 4..15 zero
+constexpr int IMG_B3 = IMG_W3 + 8192;              // float [4]
+constexpr int IMG_ONES1 = IMG_B3 + 256;            // [2 k-chunks][8 rows][16 B] = 256 B: every row = e0
+constexpr int IMG_ONES2 = IMG_ONES1 + 256;         // every row = e1
+constexpr int IMG_BYTES = IMG_ONES2 + 256;         // 156416
 // ---- per-CTA working buffers after the image
 constexpr int SM_A2 = ((IMG_BYTES + 1023) / 1024) * 1024;   // 4 slabs [128 rows x 128 B] = 65536 B (SWIZZLE_128B)
 constexpr int SM_A1 = SM_A2 + 65536;                        // [16 row-groups][2][8][16 B] = 4096 B (no swizzle)
 constexpr int SM_BAR = SM_A1 + 4096;                        // mbarriers + tmem base
-constexpr int SM_TOTAL = SM_BAR + 64;
+constexpr int SM_TOTAL2 = SM_BAR + 256;
+static_assert(IMG_W3 % 1024 == 0 && SM_A2 % 1024 == 0 && IMG_BYTES % 16 == 0, "operand alignment");
+static_assert(SM_TOTAL2 <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // ------------------------------------------------------------------------------------------------ image prep
 // W (reference layout [in][out] fp32) -> bf16 UMMA B operands stored [n][k] K-major.
@@ -52,25 +61,34 @@ __global__ void __launch_bounds__(256) policy_tc_prepare_kernel(const float* __r
                                                                  uint8_t* __restrict__ img) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
+    auto put = [&](size_t off, float v) { *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(v); };
     // W2: element (n, k) -> slab k/64, row n, 16-byte chunk ((k%64)/8) ^ (n%8), element k%8
     for (int idx = tid; idx < TC_H * TC_H; idx += nth) {
         int k = idx / TC_H, n = idx - k * TC_H;          // W2[k][n] is contiguous in n: coalesced reads
         int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
-        size_t off = (size_t)IMG_W2 + (size_t)slab * 32768 + (size_t)n * 128 + (size_t)((kc ^ (n & 7)) * 16) + ke * 2;
-        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(W2[idx]);
+        put((size_t)IMG_W2 + (size_t)slab * 32768 + (size_t)n * 128 + (size_t)((kc ^ (n & 7)) * 16) + ke * 2, W2[idx]);
     }
-    // W1: element (n, k), k < 16 -> row-group n/8, k-chunk k/8, row n%8, element k%8 (no swizzle)
+    // W1 / BIAS: element (n, k), k < 16 -> row-group n/8, k-chunk k/8, row n%8, element k%8 (no swizzle)
     for (int idx = tid; idx < TC_K1 * TC_H; idx += nth) {
         int k = idx / TC_H, n = idx - k * TC_H;
-        size_t off = (size_t)IMG_W1 + (size_t)(n >> 3) * 256 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (k & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(W1[idx]);
+        size_t off = (size_t)(n >> 3) * 256 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (k & 7) * 2;
+        put(IMG_W1 + off, W1[idx]);
+        put(IMG_BIAS + off, k == 0 ? b1[n] : (k == 1 ? b2[n] : 0.0f));
     }
-    for (int idx = tid; idx < TC_H * 4; idx += nth) reinterpret_cast<float*>(img + IMG_W3)[idx] = W3[idx];
-    for (int idx = tid; idx < TC_H; idx += nth) {
-        reinterpret_cast<float*>(img + IMG_B1)[idx] = b1[idx];
-        reinterpret_cast<float*>(img + IMG_B2)[idx] = b2[idx];
+    // W3 (head): B operand rows j < 16 (4 real), K = 256 in four 128B-swizzled slabs of [16 rows x 128 B]
+    for (int idx = tid; idx < TC_N3 * TC_H; idx += nth) {
+        int j = idx / TC_H, k = idx - j * TC_H;
+        int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
+        put((size_t)IMG_W3 + (size_t)slab * 2048 + (size_t)j * 128 + (size_t)((kc ^ (j & 7)) * 16) + ke * 2,
+            j < 4 ? W3[k * 4 + j] : 0.0f);
     }
     if (tid < 4) reinterpret_cast<float*>(img + IMG_B3)[tid] = b3[tid];
+    // ONES1 / ONES2: [k-chunk][row][8 bf16]; chunk 0 of every row holds the unit vector
+    for (int idx = tid; idx < 2 * 8 * 8; idx += nth) {
+        int e = idx & 7, chunk = idx >> 6;
+        put(IMG_ONES1 + idx * 2, (chunk == 0 && e == 0) ? 1.0f : 0.0f);
+        put(IMG_ONES2 + idx * 2, (chunk == 0 && e == 1) ? 1.0f : 0.0f);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -100,8 +118,15 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint64_t desc_nosw_k16(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
+// constant A operand (ONES1 / ONES2): chunk 1 is LBO = 128 B after chunk 0, and SBO = 0 makes every 8-row group
+// read the same 128-byte core matrix
+__device__ __forceinline__ uint64_t desc_ones(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | (1ull << 46);
+}
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = 256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+constexpr uint32_t kIdescHead = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N3 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -127,6 +152,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct PolicyTcArgs {
     const uint8_t* img;
     const uint64_t* board;
@@ -146,20 +178,60 @@ struct PolicyTcArgs {
 // ------------------------------------------------------------------------------------------------ kernel
 // Warp roles (17 warps = 544 threads, one CTA per SM):
 //   warps 0..15  epilogue warps.  Warp w owns TMEM lanes / board rows 32*(w%4) .. +31 (the hardware's lane-quarter
-//                rule) and the 64-column block g = w/4 of both accumulators, i.e. exactly one 128B-swizzle K slab of
-//                the layer-2 operand.  Group 0 (warps 0..3, one thread per board) also encodes the boards into A1 and
-//                finishes softmax / sampling.
-//   warp 16      issues every tcgen05.mma (one elected lane), the weight-image bulk copies and owns TMEM alloc/dealloc.
-// Pipelining inside a tile: layer-2 MMAs of K slab g are issued as soon as group g has written slab g, so the tensor
-// core runs under epilogue 1; across tiles: A1 of tile i+1 is encoded before epilogue 2 of tile i, so MMA1(i+1) runs
-// under epilogue 2(i).  All hand-offs are mbarriers (phase = tile parity); no __syncthreads in the loop.
+//                rule) and, in every 64-column K slab of the next layer's operand, the 16 columns 16*(w/4) .. +15
+//                (slab-major epilogues: all warps finish slab 0 first).  Group 0 (warps 0..3, one thread per board) also encodes the boards into
+//                A1 and finishes softmax / sampling.
+//   warp 16      issues every tcgen05.mma (lane 0), the weight-image bulk copies and owns TMEM alloc/dealloc.
+// Pipelining: the MMAs of K slab g are issued as soon as group g has written slab g (tensor core runs under the
+// epilogues); A1 of tile i+1 is encoded right after epilogue 1 of tile i and MMA1(i+1) is issued as soon as layer 2
+// of tile i has been issued, so it runs under epilogue 2(i).  All hand-offs are mbarriers (phase = tile parity).
 constexpr int TC_EPI_THREADS = 512;
 constexpr int TC_THREADS = TC_EPI_THREADS + 32;
-constexpr int SM_PART = SM_BAR + 128;                       // float [4 groups][128 rows][4] partial logits = 8192 B
-constexpr int SM_TOTAL2 = SM_PART + 8192;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// bf16x2( relu(a), relu(b) ): convert, then one packed max against zero
+__device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
+    p = __hmax2(p, __floats2bfloat162_rn(0.0f, 0.0f));
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One epilogue pass, SLAB-MAJOR: for every 64-column K slab s of the next layer's operand, warp (q, g) converts the 16
+// accumulator columns 64 s + 16 g .. +15 of its 32 rows (ReLU -> bf16), stores them into the 128B-swizzled slab and
+// arrives on that slab's barrier.  All 16 warps finish slab 0 first, so the tensor core starts on the next layer
+// after a quarter of the epilogue instead of after all of it.
+__device__ __forceinline__ void relu_store_slabs(uint32_t tlane_col0, uint8_t* a2_row, int row, int g, int lane,
+                                                 uint32_t bar0) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        uint32_t r[16];
+        tmem_ld16(tlane_col0 + (uint32_t)(s * 64 + g * 16), r);
+        uint8_t* rowp = a2_row + s * 16384;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                                           // two 16-byte chunks of 8 columns
+            uint32_t w0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), w1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
+            uint32_t w2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), w3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
+            int chunk = g * 2 + c;
+            *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) * 16)) = make_uint4(w0, w1, w2, w3);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // smem writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");         // accumulator reads ordered before reuse
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8u * s);   // ONE arrival per warp: 32 same-address arrivals would serialise
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_constant__ PolicyTcArgs args) {
@@ -167,20 +239,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
     const uint32_t bar_img = s_u32(&bars[0]), bar_a1 = s_u32(&bars[1]), bar_d1 = s_u32(&bars[2]), bar_d2 = s_u32(&bars[3]),
-                   bar_d2free = s_u32(&bars[4]);
-    const uint32_t bar_slab0 = s_u32(&bars[5]);   // bars[5..8]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 96);
+                   bar_d3 = s_u32(&bars[4]), bar_free = s_u32(&bars[5]);
+    const uint32_t bar_slab0 = s_u32(&bars[6]);    // bars[6..9]   : A2 slab g written (layer-2 operand)
+    const uint32_t bar_hslab0 = s_u32(&bars[10]);  // bars[10..13] : H2 slab g written (head operand)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
 
     if (tid == 0) {
         mbar_init(bar_img, 1);
-        mbar_init(bar_a1, 128);
+        mbar_init(bar_a1, 4);                       // one arrival per warp everywhere (elected lane after __syncwarp)
         mbar_init(bar_d1, 1);
         mbar_init(bar_d2, 1);
-        mbar_init(bar_d2free, TC_EPI_THREADS);
-        for (int g = 0; g < 4; ++g) mbar_init(bar_slab0 + 8u * g, 128);
+        mbar_init(bar_d3, 1);
+        mbar_init(bar_free, TC_EPI_THREADS / 32);
+        for (int g = 0; g < 4; ++g) { mbar_init(bar_slab0 + 8u * g, TC_EPI_THREADS / 32); mbar_init(bar_hslab0 + 8u * g, TC_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {   // all 512 TMEM columns: D1 = columns 0..255, D2 = columns 256..511
+    if (warp == 16) {   // all 512 TMEM columns: D1 = columns 0..255, D2 = 256..511, D3 = 256..271 (over D2)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -190,13 +264,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
+    const int64_t first = blockIdx.x;
 
     if (warp == 16) {
         // ============================ MMA / copy warp ============================
         // Lane 0 does the work; the other lanes stay converged with it (__syncwarp per tile) so that the final
         // aligned __syncthreads is reached by the whole warp together.
         const uint32_t sA1 = s_u32(smem + SM_A1), sA2 = s_u32(smem + SM_A2);
-        const uint32_t sW1 = s_u32(smem + IMG_W1), sW2 = s_u32(smem + IMG_W2);
+        const uint32_t sW1 = s_u32(smem + IMG_W1), sW2 = s_u32(smem + IMG_W2), sW3 = s_u32(smem + IMG_W3);
+        const uint64_t dBias = desc_nosw_k16(s_u32(smem + IMG_BIAS));
+        const uint64_t dOnes1 = desc_ones(s_u32(smem + IMG_ONES1)), dOnes2 = desc_ones(s_u32(smem + IMG_ONES2));
         if (lane == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)IMG_BYTES)
                          : "memory");
@@ -211,18 +288,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
             mbar_wait(bar_img, 0);
         }
         __syncwarp();
+        auto issue_layer1 = [&](uint32_t ph) {   // D1 = A1 . W1^T + b1
+            mbar_wait(bar_a1, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sW1), kIdesc, 0u);
+            umma_f16(tmem_base, dOnes1, dBias, kIdesc, 1u);
+            umma_commit(bar_d1);
+        };
         uint32_t ph = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (lane == 0 && first < n_tiles) issue_layer1(0u);
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
             if (lane == 0) {
-                // layer 1 (D1 is free: every epilogue-1 read of the previous tile preceded its slab arrivals)
-                mbar_wait(bar_a1, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sW1), kIdesc, 0u);
-                umma_commit(bar_d1);
-                // layer 2, slab by slab as epilogue 1 produces them
+                // ---- layer 2, slab by slab as epilogue 1 produces them
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_slab0 + 8u * g, ph);
-                    if (g == 0 && tile != (int64_t)blockIdx.x) mbar_wait(bar_d2free, ph ^ 1u);   // D2 drained by the previous tile's epilogue 2
+                    if (g == 0 && tile != first) mbar_wait(bar_free, ph ^ 1u);   // D2/D3 drained by the previous tile
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -231,7 +311,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
                         umma_f16(tmem_base + 256u, desc_sw128(a_addr), desc_sw128(b_addr), kIdesc, (g | q) ? 1u : 0u);
                     }
                 }
+                umma_f16(tmem_base + 256u, dOnes2, dBias, kIdesc, 1u);           // + b2
                 umma_commit(bar_d2);
+                // ---- next tile's layer 1 runs under this tile's epilogue 2 (D1 was drained before the slab arrivals)
+                if (tile + gridDim.x < n_tiles) issue_layer1(ph ^ 1u);
+                // ---- head: D3 = H2 . W3^T, slab by slab as epilogue 2 produces them.  D3 overlays D2 columns 0..15,
+                //      which belong to slab 0 and have been drained by every warp before hslab[0] completes.
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(bar_hslab0 + 8u * g, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t a_addr = sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u;
+                        uint32_t b_addr = sW3 + (uint32_t)g * 2048u + (uint32_t)q * 32u;
+                        umma_f16(tmem_base + 256u, desc_sw128(a_addr), desc_sw128(b_addr), kIdescHead, (g | q) ? 1u : 0u);
+                    }
+                }
+                umma_commit(bar_d3);
             }
             __syncwarp();
             ph ^= 1u;
@@ -240,12 +336,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
         // ============================ epilogue warps ============================
         const int q = warp & 3, g = warp >> 2;
         const int row = q * 32 + lane;                                          // board row inside the tile = TMEM lane
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
-        const float* sW3 = reinterpret_cast<const float*>(smem + IMG_W3);
-        const float* sB1 = reinterpret_cast<const float*>(smem + IMG_B1);
-        const float* sB2 = reinterpret_cast<const float*>(smem + IMG_B2);
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
-        float* part = reinterpret_cast<float*>(smem + SM_PART);
+        uint8_t* a2_row = smem + SM_A2 + row * 128;                             // this row's line in slab 0
         uint32_t ph = 0;
 
         auto encode_a1 = [&](int64_t tile) {   // group 0 only: this thread's board -> 16 bf16 in the A1 core matrices
@@ -265,69 +358,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
             *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(bar_a1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a1);
         };
 
-        if (g == 0 && (int64_t)blockIdx.x < n_tiles) encode_a1(blockIdx.x);
-        mbar_wait(bar_img, 0);                                                  // biases / W3 live in the image
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            // ---- epilogue 1: slab g of A2 = bf16(relu(D1[:, 64g..64g+63] + b1))
+        if (g == 0 && first < n_tiles) encode_a1(first);
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab
             mbar_wait(bar_d1, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint8_t* rowp = smem + SM_A2 + g * 16384 + row * 128;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)(half * 32), r);
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {                                // four 16-byte chunks of 8 columns
-                    uint32_t w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        int c = g * 64 + half * 32 + c4 * 8 + u * 2;
-                        float v0 = fmaxf(__uint_as_float(r[c4 * 8 + u * 2]) + sB1[c], 0.0f);
-                        float v1 = fmaxf(__uint_as_float(r[c4 * 8 + u * 2 + 1]) + sB1[c + 1], 0.0f);
-                        __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
-                        w[u] = *reinterpret_cast<uint32_t*>(&p);
-                    }
-                    int chunk = half * 4 + c4;
-                    *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // smem writes -> visible to the tensor core
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // D1 reads ordered before the next MMA1
-            mbar_arrive(bar_slab0 + 8u * g);
-            // ---- next tile's A1 while the tensor core works on layer 2 (A1 is free: MMA1 of this tile completed)
+            relu_store_slabs(tlane, a2_row, row, g, lane, bar_slab0);
+            // ---- next tile's A1 (A1 is free: this tile's layer-1 MMAs completed before bar_d1)
             const int64_t next = tile + gridDim.x;
             if (g == 0 && next < n_tiles) encode_a1(next);
-            // ---- epilogue 2: partial logits over this warp's 64 columns of relu(D2 + b2)
+            // ---- epilogue 2: H2 = bf16(relu(D2)), slab by slab, written over A2 (layer 2 has completed)
             mbar_wait(bar_d2, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld32(taddr + 256u + (uint32_t)(half * 32), r);
-#pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    int c = g * 64 + half * 32 + u;
-                    float hv = fmaxf(__uint_as_float(r[u]) + sB2[c], 0.0f);
-                    float4 w = *reinterpret_cast<const float4*>(sW3 + c * 4);
-                    l0 = fmaf(hv, w.x, l0); l1 = fmaf(hv, w.y, l1); l2 = fmaf(hv, w.z, l2); l3 = fmaf(hv, w.w, l3);
-                }
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(bar_d2free);                                             // D2 may be overwritten
-            *reinterpret_cast<float4*>(part + (g * TC_M + row) * 4) = make_float4(l0, l1, l2, l3);
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // the 16 epilogue warps only
+            relu_store_slabs(tlane + 256u, a2_row, row, g, lane, bar_hslab0);
+            // ---- head result: every warp waits for D3 (the head MMAs also release A2 for the next tile's epilogue 1)
+            mbar_wait(bar_d3, ph);
             if (g == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t r4[4];
+                tmem_ld4(tlane + 256u, r4);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free);
                 const int64_t s = tile * TC_M + row;
-                float4 p0v = *reinterpret_cast<const float4*>(part + (0 * TC_M + row) * 4);
-                float4 p1v = *reinterpret_cast<const float4*>(part + (1 * TC_M + row) * 4);
-                float4 p2v = *reinterpret_cast<const float4*>(part + (2 * TC_M + row) * 4);
-                float4 p3v = *reinterpret_cast<const float4*>(part + (3 * TC_M + row) * 4);
-                float lg0 = sB3[0] + ((p0v.x + p1v.x) + (p2v.x + p3v.x)), lg1 = sB3[1] + ((p0v.y + p1v.y) + (p2v.y + p3v.y));
-                float lg2 = sB3[2] + ((p0v.z + p1v.z) + (p2v.z + p3v.z)), lg3 = sB3[3] + ((p0v.w + p1v.w) + (p2v.w + p3v.w));
+                const float lg0 = __uint_as_float(r4[0]) + sB3[0], lg1 = __uint_as_float(r4[1]) + sB3[1];
+                const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
                 if (s < args.n) {
                     uint32_t fl = 0xFu;
                     const bool use_mask = args.mask_flags != nullptr;
@@ -365,6 +424,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
                         args.action[s] = (uint8_t)a;
                     }
                 }
+            } else {
+                if (lane == 0) mbar_arrive(bar_free);      // this warp's D2 reads were fenced before its hslab arrivals
             }
             ph ^= 1u;
         }
