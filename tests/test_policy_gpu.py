@@ -368,3 +368,41 @@ def test_rollout_many_replays_in_oracle(b2048):
     assert ((((m >> actions) & 1) == 1) | (m == 0))[livem].all()
     info = agent.update_from_rollout(ro)
     assert np.isfinite(info["actor_grad_norm"]) and info["actor_grad_norm"] > 0
+
+
+def test_rollout_fixed_horizon_replays_in_oracle(b2048):
+    """Fixed-horizon rollout with reset-on-done through the C rollout loop (b2048_rollout_many)."""
+    n, seed, H = 33000, 5, 40
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 25
+    benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=3)
+    agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[32], activation="Sigmoid", init_distribution="XavierNormal"),
+                                 b2048.ReinforceAgentConfig())
+    ro = agent.rollout_many(benv, horizon=H)
+    assert ro.T == H and int(ro.length.min()) == H
+    boards = ro.boards.cpu().numpy().view(np.uint64); flags = ro.flags.cpu().numpy()
+    actions = ro.actions.cpu().numpy(); rewards = ro.rewards.cpu().numpy()
+    okw = dict(kw); okw.pop("size")
+    cfg = oracle.make_cfg(action_mode="buffer", auto_reset=True, **okw)
+    st = oracle.reset_many(n, seed, 3, 0)
+    for t in range(H):
+        o = oracle.step_many(st, cfg, seed, 3, t + 1, action=actions[t])
+        assert (st["board"] == boards[t + 1]).all() and (o["reward"] == rewards[t]).all() and (o["flags"] == flags[t + 1]).all()
+    assert (benv.score.cpu().numpy() == st["score"]).all() and benv.t == H
+    assert ((flags[1:] & 0x60) != 0).sum() >= n           # truncation at 25 steps resets every board at least once
+
+
+def test_trainer_smoke(b2048, tmp_path):
+    from b2048 import trainer
+    cfg = trainer.merge_config({"mlp": {"hidden_sizes": [32, 32]},
+                                "agent": {"optimizer": "adam", "learning_rate": 1e-3, "baseline_mode": "batch_norm"},
+                                "train": {"batch_size": 512, "num_batches": 34, "out_dir": str(tmp_path)},
+                                "eval": {"num_episodes": 256}})
+    rows = trainer.training(cfg)
+    assert len(rows) == 34 and all(np.isfinite(r["avg_reward"]) for r in rows)
+    files = os.listdir(tmp_path)
+    assert "config.json" in files and "training_stats.csv" in files and "final.npz" in files
+    lines = open(os.path.join(tmp_path, "training_stats.csv")).read().strip().splitlines()
+    assert lines[0] == "batch,avg_reward,max_reward,min_reward,max_tile_counts" and len(lines) == 35
+    cfg["eval"]["model_path"] = os.path.join(tmp_path, "final.npz")
+    res = trainer.evaluation(cfg)
+    assert res["avg_reward"] > 0 and sum(res["max_tile_counts"].values()) <= 256
