@@ -26,6 +26,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "b2048_device.cuh"
 #include "b2048_internal.h"
 
@@ -173,20 +176,24 @@ struct PolicyTcArgs {
     int greedy;
     int obs_mode;
     float obs_scale;
+    long long* debug_clock;   // optional: per-tile phase timestamps of CTA 0 (B2048_TC_DEBUG_CLOCK), else NULL
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-// Warp roles (17 warps = 544 threads, one CTA per SM):
+// Warp roles (21 warps = 672 threads, one CTA per SM):
 //   warps 0..15  epilogue warps.  Warp w owns TMEM lanes / board rows 32*(w%4) .. +31 (the hardware's lane-quarter
 //                rule) and, in every 64-column K slab of the next layer's operand, the 16 columns 16*(w/4) .. +15
-//                (slab-major epilogues: all warps finish slab 0 first).  Group 0 (warps 0..3, one thread per board) also encodes the boards into
-//                A1 and finishes softmax / sampling.
+//                (slab-major epilogues: all warps finish slab 0 first).
 //   warp 16      issues every tcgen05.mma (lane 0), the weight-image bulk copies and owns TMEM alloc/dealloc.
+//   warps 17..20 I/O warps, one thread per board: board load + A1 encode for the NEXT tile, and for the current tile
+//                the 4 logits out of D3 -> mask load -> softmax -> Philox sample -> action store.  Global-memory
+//                latency never sits on the MMA <-> epilogue critical path.
 // Pipelining: the MMAs of K slab g are issued as soon as group g has written slab g (tensor core runs under the
 // epilogues); A1 of tile i+1 is encoded right after epilogue 1 of tile i and MMA1(i+1) is issued as soon as layer 2
 // of tile i has been issued, so it runs under epilogue 2(i).  All hand-offs are mbarriers (phase = tile parity).
 constexpr int TC_EPI_THREADS = 512;
-constexpr int TC_THREADS = TC_EPI_THREADS + 32;
+constexpr int TC_IO_THREADS = 128;
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 + TC_IO_THREADS;   // 16 epilogue warps + MMA warp + 4 I/O warps
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
         mbar_init(bar_d1, 1);
         mbar_init(bar_d2, 1);
         mbar_init(bar_d3, 1);
-        mbar_init(bar_free, TC_EPI_THREADS / 32);
+        mbar_init(bar_free, TC_EPI_THREADS / 32 + TC_IO_THREADS / 32);
         for (int g = 0; g < 4; ++g) { mbar_init(bar_slab0 + 8u * g, TC_EPI_THREADS / 32); mbar_init(bar_hslab0 + 8u * g, TC_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -332,16 +339,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
             __syncwarp();
             ph ^= 1u;
         }
-    } else {
+    } else if (warp < 16) {
         // ============================ epilogue warps ============================
         const int q = warp & 3, g = warp >> 2;
         const int row = q * 32 + lane;                                          // board row inside the tile = TMEM lane
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
         uint8_t* a2_row = smem + SM_A2 + row * 128;                             // this row's line in slab 0
         uint32_t ph = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == 0 && (tile - first) / gridDim.x < 8;
+            long long* dc = dbg ? args.debug_clock + 8 * ((tile - first) / gridDim.x) : nullptr;
+            if (dbg) dc[0] = clock64();
+            // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab.  A2 is free once the previous tile's head MMAs
+            //      (which read H2 out of the same buffer) have completed.
+            mbar_wait(bar_d1, ph);
+            if (tile != first) mbar_wait(bar_d3, ph ^ 1u);
+            if (dbg) dc[1] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            relu_store_slabs(tlane, a2_row, row, g, lane, bar_slab0);
+            if (dbg) dc[2] = clock64();
+            // ---- epilogue 2: H2 = bf16(relu(D2)), slab by slab, written over A2 (layer 2 has completed)
+            mbar_wait(bar_d2, ph);
+            if (dbg) dc[3] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            relu_store_slabs(tlane + 256u, a2_row, row, g, lane, bar_hslab0);
+            if (lane == 0) mbar_arrive(bar_free);      // this warp's D2 reads were fenced before its hslab arrivals
+            if (dbg) dc[4] = clock64();
+            ph ^= 1u;
+        }
+    } else {
+        // ============================ I/O warps (17..20), one thread per board ============================
+        // They keep every global-memory latency (board loads, mask loads, action stores) and the softmax / Philox
+        // sampling off the MMA <-> epilogue critical path: encode A1 of tile i+1 while tile i is in flight, then pick
+        // up the 4 logits of tile i from D3.
+        const int q = warp & 3;                                                 // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
+        uint32_t ph = 0;
 
-        auto encode_a1 = [&](int64_t tile) {   // group 0 only: this thread's board -> 16 bf16 in the A1 core matrices
+        auto encode_a1 = [&](int64_t tile) {   // this thread's board -> 16 bf16 in the A1 core matrices
             const int64_t s = tile * TC_M + row;
             uint64_t bd = (s < args.n) ? args.board[s] : 0ull;
             uint32_t packed[8];
@@ -362,70 +399,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
             if (lane == 0) mbar_arrive(bar_a1);
         };
 
-        if (g == 0 && first < n_tiles) encode_a1(first);
+        if (first < n_tiles) encode_a1(first);
+        mbar_wait(bar_img, 0);                                                  // b3 lives in the image
         for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
-            // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab
+            const int64_t s = tile * TC_M + row;
+            const bool use_mask = args.mask_flags != nullptr;
+            uint32_t fl = 0xFu;
+            if (use_mask && s < args.n) fl = args.mask_flags[s];               // requested early, used after D3
+            // A1 is free once this tile's layer-1 MMAs have completed
             mbar_wait(bar_d1, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            relu_store_slabs(tlane, a2_row, row, g, lane, bar_slab0);
-            // ---- next tile's A1 (A1 is free: this tile's layer-1 MMAs completed before bar_d1)
             const int64_t next = tile + gridDim.x;
-            if (g == 0 && next < n_tiles) encode_a1(next);
-            // ---- epilogue 2: H2 = bf16(relu(D2)), slab by slab, written over A2 (layer 2 has completed)
-            mbar_wait(bar_d2, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            relu_store_slabs(tlane + 256u, a2_row, row, g, lane, bar_hslab0);
-            // ---- head result: every warp waits for D3 (the head MMAs also release A2 for the next tile's epilogue 1)
+            if (next < n_tiles) encode_a1(next);
             mbar_wait(bar_d3, ph);
-            if (g == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t r4[4];
-                tmem_ld4(tlane + 256u, r4);
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_free);
-                const int64_t s = tile * TC_M + row;
-                const float lg0 = __uint_as_float(r4[0]) + sB3[0], lg1 = __uint_as_float(r4[1]) + sB3[1];
-                const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
-                if (s < args.n) {
-                    uint32_t fl = 0xFu;
-                    const bool use_mask = args.mask_flags != nullptr;
-                    if (use_mask) fl = args.mask_flags[s];
-                    float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
-                    float m2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, m3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
-                    float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                    float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx), e3 = expf(m3 - mx);
-                    float sum = e0 + e1 + e2 + e3;
-                    float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
-                    if (args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
-                    if (args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
-                    if (args.action) {
-                        uint32_t a;
-                        if (args.greedy) {
-                            float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
-                            float q2 = (!use_mask || (fl & 4u)) ? p2 : 0.0f, q3 = (!use_mask || (fl & 8u)) ? p3 : 0.0f;
-                            a = 0; float best = q0;
-                            if (q1 > best) { best = q1; a = 1; }
-                            if (q2 > best) { best = q2; a = 2; }
-                            if (q3 > best) { best = q3; a = 3; }
-                        } else {
-                            Rand4 rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, args.t, B2048_DOM_STEP);
-                            float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
-                            float u = ((float)(rr.w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
-                            a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
-                            float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
-                            if (!(pa > 0.0f)) {
-                                if (p3 > 0.0f) a = 3;
-                                if (p2 > 0.0f) a = 2;
-                                if (p1 > 0.0f) a = 1;
-                                if (p0 > 0.0f) a = 0;
-                            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r4[4];
+            tmem_ld4(tlane + 256u, r4);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free);
+            const float lg0 = __uint_as_float(r4[0]) + sB3[0], lg1 = __uint_as_float(r4[1]) + sB3[1];
+            const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
+            if (s < args.n) {
+                float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
+                float m2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, m3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
+                float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx), e3 = expf(m3 - mx);
+                float sum = e0 + e1 + e2 + e3;
+                float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
+                if (args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
+                if (args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
+                if (args.action) {
+                    uint32_t a;
+                    if (args.greedy) {
+                        float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
+                        float q2 = (!use_mask || (fl & 4u)) ? p2 : 0.0f, q3 = (!use_mask || (fl & 8u)) ? p3 : 0.0f;
+                        a = 0; float best = q0;
+                        if (q1 > best) { best = q1; a = 1; }
+                        if (q2 > best) { best = q2; a = 2; }
+                        if (q3 > best) { best = q3; a = 3; }
+                    } else {
+                        Rand4 rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, args.t, B2048_DOM_STEP);
+                        float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
+                        float u = ((float)(rr.w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
+                        a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
+                        float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
+                        if (!(pa > 0.0f)) {
+                            if (p3 > 0.0f) a = 3;
+                            if (p2 > 0.0f) a = 2;
+                            if (p1 > 0.0f) a = 1;
+                            if (p0 > 0.0f) a = 0;
                         }
-                        args.action[s] = (uint8_t)a;
                     }
+                    args.action[s] = (uint8_t)a;
                 }
-            } else {
-                if (lane == 0) mbar_arrive(bar_free);      // this warp's D2 reads were fenced before its hslab arrivals
             }
             ph ^= 1u;
         }
@@ -462,9 +488,24 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     a.img = h->tc_image; a.board = board; a.mask_flags = mask_flags; a.action = action; a.probs = probs; a.logits = logits;
     a.n = n; a.keys = make_keys(seed); a.gid0 = gid0; a.t = t; a.greedy = greedy; a.obs_mode = mlp->obs_mode;
     a.obs_scale = mlp->obs_log2_scale;
+    a.debug_clock = nullptr;
+    if (getenv("B2048_TC_DEBUG_CLOCK")) {
+        static long long* dbg_buf = nullptr;
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+        a.debug_clock = dbg_buf;
+    }
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     policy_tc_kernel<<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
+    if (a.debug_clock) {
+        long long hbuf[64];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(hbuf, a.debug_clock, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 4; ++k)
+            fprintf(stderr, "[tc clock] tile %d: wait_d1+d3 %lld epi1 %lld wait_d2 %lld epi2 %lld | total %lld | to next %lld\n", k,
+                    hbuf[8 * k + 1] - hbuf[8 * k], hbuf[8 * k + 2] - hbuf[8 * k + 1], hbuf[8 * k + 3] - hbuf[8 * k + 2],
+                    hbuf[8 * k + 4] - hbuf[8 * k + 3], hbuf[8 * k + 4] - hbuf[8 * k], hbuf[8 * k + 8] - hbuf[8 * k]);
+    }
     return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
 }
 
