@@ -73,6 +73,20 @@ B2_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
 #endif
 }
 
+// x >> K for a compile-time K, issued on the FMA pipe (IMAD.HI by 2^(32-K)) instead of the integer ALU pipe:
+// the step kernel is bound by the ALU pipe (LOP3 / SHF / IADD3 at 16 lanes per clock per scheduler), the FMA pipe
+// is nearly idle, and ptxas keeps mul.hi with an immediate as IMAD.HI.U32.
+template <int K>
+B2_HD uint32_t shr_fma(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "n"(1u << (32 - K)));
+    return r;
+#else
+    return x >> K;
+#endif
+}
+
 // (on1 & mask) | (on0 & ~mask) in one LOP3
 B2_HD uint32_t bitsel(uint32_t mask, uint32_t on1, uint32_t on0) {
 #if defined(__CUDA_ARCH__)

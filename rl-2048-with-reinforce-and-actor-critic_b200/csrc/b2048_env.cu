@@ -16,6 +16,7 @@
 // grid-strides over the boards.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "b2048_internal.h"
@@ -89,6 +90,7 @@ struct StepArgs {
     uint32_t t;
     b2048_env_cfg cfg;
     PhiloxKeys keys;   // Philox round keys of `seed` (host-computed)
+    long long* debug_clock;   // optional phase timestamps of a few CTAs (B2048_STEP_DEBUG_CLOCK), else NULL
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -269,6 +271,10 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
     const int tid = threadIdx.x;
+    const bool dbg = args.debug_clock != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 147);
+    long long* dc = dbg ? args.debug_clock + (blockIdx.x == 0 ? 0 : 16) : nullptr;
+    int dci = 0;
+    if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dc[dci++] = (long long)gt; dc[dci++] = clock64(); }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -341,6 +347,7 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
                     : "memory");
             }
             ready = true;
+            if (dbg) dc[dci++] = clock64();
         }
         if (frozen) {   // finished episode of a run-to-termination rollout: pass through (see step_kernel)
             uint32_t m = legal_mask(Board{io.lo, io.hi});
@@ -360,7 +367,9 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
         if (args.merge_sum) args.merge_sum[i] = io.merge_sum;
         args.reward[i] = io.reward;
         args.flags[i] = (uint8_t)io.flags;
+        if (dbg && dci < 12) dc[dci++] = clock64();
     }
+    if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dc[14] = clock64(); dc[15] = (long long)gt; }
 }
 
 template <int kAct>
@@ -503,6 +512,12 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
     a.merge_sum = merge_sum;
     a.reward = reward; a.reward64 = reward64; a.flags = flags; a.obs = obs; a.tables = h->d_tables;
     a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg; a.keys = make_keys(seed);
+    a.debug_clock = nullptr;
+    static long long* dbg_buf = nullptr;
+    if (getenv("B2048_STEP_DEBUG_CLOCK")) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(long long));
+        a.debug_clock = dbg_buf;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     // Large batches: persistent CTAs with the tables in shared memory.  Small batches (the B=1
     // drop-in env, unit tests): tables read through L1/L2, no 192 KB staging per launch.
@@ -526,6 +541,17 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
         step_kernel<false, 256><<<grid, 256, 0, s>>>(a);
     }
     B2_CUDA(cudaGetLastError());
+    if (a.debug_clock && fast) {
+        long long hb[32];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hb, a.debug_clock, sizeof(hb), cudaMemcpyDeviceToHost);
+        for (int c = 0; c < 2; ++c) {
+            long long* d = hb + 16 * c;
+            fprintf(stderr, "[step clock] cta %d: start@%lld ns, staged +%lld cyc, iters:", c ? 147 : 0, d[0] - hb[0], d[2] - d[1]);
+            for (int k = 3; k < 12 && d[k]; ++k) fprintf(stderr, " %lld", d[k] - d[k - 1]);
+            fprintf(stderr, " | total %lld cyc, %lld ns\n", d[14] - d[1], d[15] - d[0]);
+        }
+    }
     return B2048_OK;
 }
 

@@ -89,7 +89,7 @@ B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& key
     const SelEntry s = T.sel[a];
     uint32_t clo = nib_swap(blk_transpose(io.lo, s.st), s.sm), chi = nib_swap(blk_transpose(io.hi, s.st), s.sm);
     uint32_t flo = prmt(clo, chi, s.f_lo), fhi = prmt(clo, chi, s.f_hi);
-    uint32_t i0 = flo & 0xFFFFu, i1 = flo >> 16, i2 = fhi & 0xFFFFu, i3 = fhi >> 16;
+    uint32_t i0 = flo & 0xFFFFu, i1 = shr_fma<16>(flo), i2 = fhi & 0xFFFFu, i3 = shr_fma<16>(fhi);
     uint32_t r0 = T.left[i0], r1 = T.left[i1], r2 = T.left[i2], r3 = T.left[i3];
     const AggEntry g0 = T.agg[T.merge[i0]], g1 = T.agg[T.merge[i1]], g2 = T.agg[T.merge[i2]], g3 = T.agg[T.merge[i3]];
     uint32_t agg = g0.agg + g1.agg + g2.agg + g3.agg;
@@ -107,10 +107,10 @@ B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& key
     }
 
     // ---- spawn: k-th empty cell in row-major order via nibble prefix sums (see file header)
-    const uint32_t nb_lo = nz8(vlo) >> 3, nb_hi = nz8(vhi) >> 3;   // bit 0 of each nibble: cell occupied
+    const uint32_t nb_lo = shr_fma<3>(nz8(vlo)), nb_hi = shr_fma<3>(nz8(vhi));   // bit 0 of each nibble: cell occupied
     const uint32_t zb_lo = nb_lo ^ 0x11111111u, zb_hi = nb_hi ^ 0x11111111u;
     const uint32_t P_lo = zb_lo * 0x11111111u, P_hi = zb_hi * 0x11111111u;   // nibble i = #empty among cells 0..i
-    const uint32_t c_lo = P_lo >> 28, c_hi = P_hi >> 28;
+    const uint32_t c_lo = shr_fma<28>(P_lo), c_hi = shr_fma<28>(P_hi);
     const uint32_t n_empty = c_lo + c_hi;
     uint32_t k = mulhi(rnd.w0, n_empty);
     const bool in_hi = k >= c_lo;
@@ -118,8 +118,8 @@ B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& key
     k = in_hi ? k - c_lo : k;
     const uint32_t addk = (0x7Fu - k) * 0x01010101u;
     const uint32_t Ge = ((P & 0x0F0F0F0Fu) + addk) & 0x80808080u;           // even cells with prefix > k
-    const uint32_t Go = (((P >> 4) & 0x0F0F0F0Fu) + addk) & 0x80808080u;    // odd cells
-    const uint32_t G = (Ge >> 7) | (Go >> 3);
+    const uint32_t Go = ((shr_fma<4>(P) & 0x0F0F0F0Fu) + addk) & 0x80808080u;    // odd cells
+    const uint32_t G = shr_fma<7>(Ge) | shr_fma<3>(Go);
     const uint32_t iso = G & (0u - G);                                       // 1 << (4 * cell)
     uint32_t val = rnd.w1 >= 0xE6666667u ? 2u : 1u;
     val = (changed && n_empty != 0u) ? val : 0u;                             // game2048.py:56-58, :110-111
@@ -132,13 +132,13 @@ B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& key
     // N: rows 0,1 at bit 4i, rows 2,3 at bit 4i+1
     const uint32_t N = (nb_lo | (spawned & ~hsel)) | ((nb_hi | (spawned & hsel)) << 1);
     const uint32_t MH = 0x03330333u, MV = 0x11113333u;
-    const uint32_t Nr = N >> 4;
-    const uint32_t EH = (nz8(nlo ^ (nlo >> 4)) >> 3) | (nz8(nhi ^ (nhi >> 4)) >> 2);
+    const uint32_t Nr = shr_fma<4>(N);
+    const uint32_t EH = shr_fma<3>(nz8(nlo ^ shr_fma<4>(nlo))) | shr_fma<2>(nz8(nhi ^ shr_fma<4>(nhi)));
     const uint32_t hmerge = ~EH & N & MH;
     const uint32_t left = (~N & Nr & MH) | hmerge;
     const uint32_t right = (N & ~Nr & MH) | hmerge;
-    const uint32_t Nd = ((N >> 16) & 0x00003333u) | ((N << 15) & 0x11110000u);
-    const uint32_t EV = (nz8(nlo ^ funnel_r(nlo, nhi, 16)) >> 3) | (nz8(nhi ^ (nhi >> 16)) >> 2);
+    const uint32_t Nd = (shr_fma<16>(N) & 0x00003333u) | ((N * 32768u) & 0x11110000u);
+    const uint32_t EV = shr_fma<3>(nz8(nlo ^ funnel_r(nlo, nhi, 16))) | shr_fma<2>(nz8(nhi ^ shr_fma<16>(nhi)));
     const uint32_t vmerge = ~EV & N & MV;
     const uint32_t up = (~N & Nd & MV) | vmerge;
     const uint32_t down = (N & ~Nd & MV) | vmerge;
@@ -153,7 +153,7 @@ B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& key
         __builtin_clz(orm | 1u);
 #endif
     if (kTrack && max_merged >= 3u && max_merged > io.max_exp) io.max_exp = max_merged;   // env.py:241-250 (bonus off)
-    const uint32_t base = cfg.reward_mode == B2048_REWARD_SUM ? msum : ((agg >> 20) & 0xFFu);
+    const uint32_t base = cfg.reward_mode == B2048_REWARD_SUM ? msum : (shr_fma<20>(agg) & 0xFFu);
     double r = dmul((double)base, cfg.base_reward_scale);
     r = dadd(r, cfg.step_reward);
     io.reward = (float)r;
