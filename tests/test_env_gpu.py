@@ -269,3 +269,29 @@ def test_error_paths(b2048):
     empty = b2048.Batched2048Env(0)
     empty.reset_many()
     empty.step_many(action_mode="random_legal")
+
+
+def test_step_many_full_size_1m(b2048):
+    """BASELINE.json configs[1] at full size: 1,048,576 boards, bit-exact vs the CPU oracle for a few steps, then
+    size-independent invariants over a longer run (score only grows inside an episode, masks consistent with done)."""
+    n, seed = 1 << 20, 0xB200
+    env = make_env(b2048, "runner_default", n, seed, 0)
+    env.reset_many()
+    cfg = oracle_cfg("runner_default", action_mode="random_legal", auto_reset=True)
+    st = oracle.reset_many(n, seed, 0, 0)
+    assert (u64(env.board) == st["board"]).all()
+    for t in range(1, 6):
+        rew, fl = env.step_many(action_mode="random_legal", auto_reset=True)
+        o = oracle.step_many(st, cfg, seed, 0, t)
+        assert (u64(env.board) == st["board"]).all() and (fl.cpu().numpy() == o["flags"]).all()
+        assert (rew.cpu().numpy() == o["reward"]).all() and (env.score.cpu().numpy() == st["score"]).all()
+    prev_score = env.score.clone()
+    for t in range(6, 200):
+        rew, fl = env.step_many(action_mode="random_legal", auto_reset=True)
+        ended = (fl & 0x60) != 0
+        assert bool(((env.score >= prev_score) | ended).all())           # score is monotone within an episode
+        assert bool((((fl & 0x0F) != 0) | ended | ((fl & 0x20) != 0)).all())   # a live board always has a legal move
+        assert not bool((fl & 0x80).any())                               # no 32768+32768 merge under a random policy
+        prev_score = env.score.clone()
+    m, d = oracle.mask_done(u64(env.board)[:100000])
+    assert ((env.flags.cpu().numpy()[:100000] & 0x0F) == m).all()
