@@ -244,12 +244,20 @@ int b2048_td_errors(b2048_handle* h, const float* reward, const float* value, co
  *   head_mode 0: += d/dtheta sum_s coef[s] log pi(action[s] | board[s])   (mask_flags: legal masks, may be NULL)
  *   head_mode 1: += d/dtheta sum_s coef[s] V(board[s])
  * workspace: device floats, at least b2048_backward_workspace_floats(mlp, chunk); samples are processed
- * `chunk` at a time. */
+ * `chunk` at a time.
+ *   precision : 0 = fp32 CUDA cores (parity path); 1 = bf16 tcgen05 tensor cores (16-256-256-(<=4) ReLU network,
+ *               raw / log2 observations, n >= 4096; anything else returns B2048_ERR_UNSUPPORTED); 2 = tensor cores
+ *               when they apply, else fp32.  The tensor-core path rounds activations and deltas to bf16 and
+ *               accumulates in fp32 (1e-2 relative parity bar). */
 int64_t b2048_backward_workspace_floats(const b2048_mlp_desc* mlp, int64_t chunk);
 int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
                        const uint8_t* action, const float* coef, const b2048_mlp_desc* mlp, float* grads,
                        int64_t n, int32_t head_mode, float* workspace, int64_t workspace_floats,
-                       int64_t chunk, void* stream);
+                       int64_t chunk, int32_t precision, void* stream);
+/* Test / debug access to the tensor-core path's workspace: byte offsets (from the workspace pointer rounded up to
+ * 1024 B) of the bf16 images H1, H2, DL2, DL1 ([64-sample tile][4 feature slabs][64 rows][128 B, 128-byte
+ * swizzle]) and A1^T, d3^T ([tile][16 rows][128 B]), then the total. */
+int b2048_backward_tc_layout(int64_t chunk, int64_t* out7);
 
 /* clip_grads_global_norm (reinforce_agent.py:835-861) + SGD (:565-575) or Adam (:719-770) on a flat parameter
  * vector.  optimizer 0 sgd / 1 adam; sign +1 ascent (actor), -1 descent (critic); adam_t = step count after

@@ -192,3 +192,39 @@ class Learner:
         if k["use_critic"]:
             self._step("critic", self.critic, gWc, gbc, k["critic_lr"], -1.0)
         return out
+
+
+# ---------------------------------------------------------------------------------------------- bf16 emulation
+# The tensor-core gradient path (csrc/b2048_learn_tc.cu) rounds operands to bfloat16 and accumulates in float32.
+# ReLU units whose pre-activation is within that rounding error of zero switch on / off relative to the float32
+# arithmetic, which shows up as a few-percent difference in a zero-mean gradient sum; to check the KERNELS (layouts,
+# indexing, masks) tightly, the tests compare them with this restatement of the same roundings.
+def bf16_round(x):
+    """round-to-nearest-even float32 -> bfloat16 -> float32"""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> np.uint32(16)) & np.uint32(1)) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def backprop_bf16(params, X, mask_bits, actions, coef, head_mode):
+    """Forward + backward of a 3-layer ReLU MLP with the tensor-core path's roundings.  Returns
+    (gW, gb, stages) where stages holds the bf16 intermediates A1, H1, H2, d3 (fp32), DL2, DL1."""
+    W = [bf16_round(w) for w in params["W"]]
+    b1, b2, b3 = bf16_round(params["b"][0]), bf16_round(params["b"][1]), params["b"][2].astype(np.float32)
+    A1 = bf16_round(X)
+    z1 = A1 @ W[0] + b1
+    H1 = bf16_round(np.maximum(z1, 0))
+    z2 = H1 @ W[1] + b2
+    H2 = bf16_round(np.maximum(z2, 0))
+    out = H2 @ W[2] + b3
+    if head_mode == 0:
+        p = probs_from_logits(out, mask_bits)
+        d3 = (coef[:, None] * (np.eye(4, dtype=np.float32)[actions] - p)).astype(np.float32)
+    else:
+        d3 = coef[:, None].astype(np.float32)
+    DL2 = bf16_round((d3 @ W[2].T) * (z2 > 0))
+    DL1 = bf16_round((DL2 @ W[1].T) * (z1 > 0))
+    d3b = bf16_round(d3)
+    gW = [A1.T @ DL1, H1.T @ DL2, H2.T @ d3b]
+    gb = [DL1.sum(0), DL2.sum(0), d3.sum(0)]
+    return gW, gb, dict(A1=A1, H1=H1, H2=H2, d3=d3, DL2=DL2, DL1=DL1)

@@ -20,6 +20,12 @@
 namespace b2 {
 
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who);
+// b2048_learn_tc.cu
+bool backward_tc_supported(const b2048_handle* h, const b2048_mlp_desc* mlp);
+int64_t backward_tc_workspace_bytes(int64_t chunk);
+int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
+                       const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
+                       uint8_t* workspace, int64_t chunk, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------ K4
 // One thread per board, sequential in t (the recurrence is evaluated in float64 with separately
@@ -491,13 +497,25 @@ extern "C" int64_t b2048_backward_workspace_floats(const b2048_mlp_desc* mlp, in
 extern "C" int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
                                   const uint8_t* action, const float* coef, const b2048_mlp_desc* mlp, float* grads,
                                   int64_t n, int32_t head_mode, float* workspace, int64_t workspace_floats,
-                                  int64_t chunk, void* stream) {
+                                  int64_t chunk, int32_t precision, void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_mlp_backward: handle is NULL");
     B2_REQUIRE(n >= 0, "b2048_mlp_backward: n < 0");
     if (n == 0) return B2048_OK;
     B2_REQUIRE(board && coef && grads && workspace, "b2048_mlp_backward: NULL buffer");
     B2_REQUIRE(head_mode == 1 || action != nullptr, "b2048_mlp_backward: action required for the policy head");
     B2_REQUIRE(chunk > 0, "b2048_mlp_backward: chunk must be positive");
+    B2_REQUIRE(precision >= 0 && precision <= 2, "b2048_mlp_backward: precision must be 0 (fp32), 1 (bf16 tcgen05) or 2 (auto)");
+    if (precision != 0) {
+        const bool ok = backward_tc_supported(h, mlp) && n >= 4096 &&
+                        workspace_floats * 4 >= backward_tc_workspace_bytes(chunk < n ? chunk : n);
+        if (ok)
+            return launch_backward_tc(h, board, mask_flags, action, coef, mlp, grads, n, head_mode,
+                                      reinterpret_cast<uint8_t*>(workspace), chunk < n ? chunk : n, (cudaStream_t)stream);
+        if (precision == 1)
+            return fail(B2048_ERR_UNSUPPORTED,
+                        "b2048_mlp_backward: the tcgen05 path needs a 16-256-256-(<=4) ReLU network, raw/log2 observations, "
+                        "n >= 4096 and a workspace of b2048_backward_workspace_floats()");
+    }
     BackwardArgs a;
     size_t smem = 0;
     int st = validate_mlp(mlp, &a.mlp, &smem, h->smem_optin, "b2048_mlp_backward");

@@ -374,9 +374,13 @@ class ReinforceAgent:
         ro.ep_weight = torch.from_numpy(w).to(self.device)
         self.update_from_rollout(ro)
 
-    def update_from_rollout(self, ro: Rollout, chunk: int = 1 << 18, allreduce=None) -> dict[str, Any]:
+    def update_from_rollout(self, ro: Rollout, chunk: int = 1 << 20, allreduce=None,
+                            precision: int | str = "auto") -> dict[str, Any]:
         """One policy-gradient update from device-resident rollout buffers.  `allreduce(tensor)` (optional) sums
-        a tensor over ranks in place: the flat gradients and the advantage statistics are the only exchange."""
+        a tensor over ranks in place: the flat gradients and the advantage statistics are the only exchange.
+        precision: 0 = fp32 CUDA cores (parity path), 1 = bf16 tcgen05 tensor cores (forward + backward + dW GEMMs),
+        "auto" = tensor cores whenever the network shape / batch allow it (b2048_mlp_backward, include/b2048.h)."""
+        prec = 2 if precision == "auto" else int(precision)
         cfg = self.agent_config
         if cfg.baseline_mode not in BASELINE:
             raise ValueError(f"Unknown baseline mode: {cfg.baseline_mode}")          # reinforce_agent.py:325
@@ -440,7 +444,7 @@ class ReinforceAgent:
             with torch.cuda.device(dev):
                 _lib.check(lib.b2048_mlp_backward(h, _ptr(boards), _ptr(mflags) if self._use_mask else None, _ptr(acts),
                                                   _ptr(cf), C.byref(net.desc), _ptr(net.grad), n, head_mode, _ptr(ws),
-                                                  ws_floats, min(chunk, n), _stream()), "b2048_mlp_backward")
+                                                  ws_floats, min(chunk, n), prec, _stream()), "b2048_mlp_backward")
             if allreduce is not None:
                 allreduce(net.grad)
 
