@@ -83,11 +83,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// Epilogues 1 / 2: relu + bf16 pack of this warp's 16 columns in each of the four K slabs; the result goes to the
-// shared-memory operand of the next MMA AND to the global activation image.  Returns the 64 "z > 0" bits of the
-// thread's columns (bit 16 s + 15 - i for column i of slab s).
-__device__ __forceinline__ uint64_t fb_relu_store(uint32_t tcol0, uint8_t* a2_row, uint8_t* g_tile_row, int row, int g,
-                                                  int lane, uint32_t bar0) {
+// Epilogues 1 / 2: relu + bf16 pack of this warp's 16 columns in each of the four K slabs into the shared-memory
+// operand of the next MMA.  The same bytes are the global activation image of the tile: the MMA warp streams each
+// finished slab out with bulk async copies (store_slab), so the epilogue threads issue no global stores (a per-thread
+// 16-byte store at a 128-byte stride costs 32 LSU wavefronts per instruction and was the kernel's bottleneck).
+// Returns the 64 "z > 0" bits of the thread's columns (bit 16 s + 15 - i for column i of slab s).
+__device__ __forceinline__ uint64_t fb_relu_store(uint32_t tcol0, uint8_t* a2_row, int row, int g, int lane, uint32_t bar0) {
     uint32_t mw[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -103,7 +104,6 @@ __device__ __forceinline__ uint64_t fb_relu_store(uint32_t tcol0, uint8_t* a2_ro
                                  relu_pack(r[c * 8 + 4], r[c * 8 + 5]), relu_pack(r[c * 8 + 6], r[c * 8 + 7]));
             const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
             *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = v;
-            *reinterpret_cast<uint4*>(g_tile_row + s * ACT_SLAB_BYTES + sw) = v;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -116,6 +116,22 @@ __device__ __forceinline__ uint64_t fb_relu_store(uint32_t tcol0, uint8_t* a2_ro
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// slab g of the [128 rows x 4 slabs] shared-memory tile -> the two 64-row tiles of a global activation image
+__device__ __forceinline__ void store_slab(uint8_t* img, int64_t tile, uint32_t sA2, int g) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint8_t* dst = img + (size_t)(tile * 2 + half) * ACT_TILE_BYTES + (size_t)g * ACT_SLAB_BYTES;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                     "r"(sA2 + (uint32_t)g * 16384u + (uint32_t)half * 8192u), "r"((uint32_t)ACT_SLAB_BYTES)
+                     : "memory");
+    }
+}
+// all bulk stores issued so far by this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_stores_read_done() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 constexpr int FB_THREADS = 512 + 32 + 128;
 
 __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_constant__ FbArgs args) {
@@ -127,6 +143,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
     const uint32_t bar_slab0 = s_u32(&bars[8]);     // [8..11]  H1 slab written
     const uint32_t bar_hslab0 = s_u32(&bars[12]);   // [12..15] H2 slab written
     const uint32_t bar_bslab0 = s_u32(&bars[16]);   // [16..19] DL2 slab written
+    const uint32_t bar_dslab0 = s_u32(&bars[20]);   // [20..23] DL1 slab written (D4 drained for that slab)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 192);
 
     if (tid == 0) {
@@ -137,11 +154,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
         mbar_init(bar_d3, 1);
         mbar_init(bar_dl3, 4);
         mbar_init(bar_d4, 1);
-        mbar_init(bar_free, 16);
+        mbar_init(bar_free, 1);                      // A2 buffer free: the DL1 image of the tile has been streamed out
         for (int g = 0; g < 4; ++g) {
             mbar_init(bar_slab0 + 8u * g, 16);
             mbar_init(bar_hslab0 + 8u * g, 16);
             mbar_init(bar_bslab0 + 8u * g, 16);
+            mbar_init(bar_dslab0 + 8u * g, 16);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -190,16 +208,18 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
         for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
             if (lane == 0) {
                 // ---- layer 2 (D2 = columns 256..511; the previous tile's D4 lives there until epilogue 4 is done)
+                //      (its D4 was drained before the DL1 slab arrivals this warp waited for at the end of that tile)
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_slab0 + 8u * g, ph);
-                    if (g == 0 && tile != first) mbar_wait(bar_free, ph ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         umma_f16(tmem_base + 256u, desc_sw128(sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u),
                                  desc_sw128(sW2 + (uint32_t)g * 32768u + (uint32_t)q * 32u), kIdesc, (g | q) ? 1u : 0u);
+                    store_slab(args.h1, tile, sA2, g);
                 }
                 umma_f16(tmem_base + 256u, dOnes2, dBias, kIdesc, 1u);
+                bulk_stores_read_done();                 // epilogue 2 overwrites H1 once bar_d2 completes
                 umma_commit(bar_d2);
                 // ---- head: D3 = columns 0..15 (D1 has been drained by every warp before the H1 slab arrivals)
                 for (int g = 0; g < 4; ++g) {
@@ -209,7 +229,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                     for (int q = 0; q < 4; ++q)
                         umma_f16(tmem_base, desc_sw128(sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u),
                                  desc_sw128(sW3 + (uint32_t)g * 2048u + (uint32_t)q * 32u), kIdescHead, (g | q) ? 1u : 0u);
+                    store_slab(args.h2, tile, sA2, g);
                 }
+                bulk_stores_read_done();                 // epilogue 3 overwrites H2 once bar_d3 completes
                 umma_commit(bar_d3);
                 // ---- the next tile's layer 1 may overwrite D1 / D3 as soon as the I/O warps have read D3
                 mbar_wait(bar_dl3, ph);
@@ -224,12 +246,23 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                         umma_f16(tmem_base + 256u, desc_sw128(sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u),
                                  desc_sw128_mn(sW2 + (uint32_t)(g * 64 + q * 16) * 128u, 32768u), kIdescBwd,
                                  (g | q) ? 1u : 0u);
+                    store_slab(args.dl2, tile, sA2, g);
                 }
+                bulk_stores_read_done();                 // epilogue 4 overwrites DL2 once bar_d4 completes
                 umma_commit(bar_d4);
+                // ---- DL1 leaves through the same buffer; the next tile's epilogue 1 may reuse it afterwards
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(bar_dslab0 + 8u * g, ph);
+                    store_slab(args.dl1, tile, sA2, g);
+                }
+                bulk_stores_read_done();
+                mbar_arrive(bar_free);
             }
             __syncwarp();
             ph ^= 1u;
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // image writes complete before exit
+        __syncwarp();
     } else if (warp < 16) {
         // ============================ epilogue warps ============================
         const int q = warp & 3, g = warp >> 2;
@@ -239,16 +272,15 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
         const float4* sD3 = reinterpret_cast<const float4*>(smem + FB_D3);
         uint32_t ph = 0;
         for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
-            const int64_t r = tile * TC_M + row;                                 // sample row inside the chunk
-            const size_t g_row = (size_t)(r >> 6) * ACT_TILE_BYTES + (size_t)(r & 63) * 128;
-            // ---- epilogue 1: H1 (A2 is free: the previous tile's D4 MMAs were waited for in its epilogue 4)
+            // ---- epilogue 1: H1 (A2 is free once the previous tile's DL1 image has been streamed out)
             mbar_wait(bar_d1, ph);
+            if (tile != first) mbar_wait(bar_free, ph ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t m1 = fb_relu_store(tlane, a2_row, args.h1 + g_row, row, g, lane, bar_slab0);
+            const uint64_t m1 = fb_relu_store(tlane, a2_row, row, g, lane, bar_slab0);
             // ---- epilogue 2: H2 over H1 (layer 2 has completed)
             mbar_wait(bar_d2, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t m2 = fb_relu_store(tlane + 256u, a2_row, args.h2 + g_row, row, g, lane, bar_hslab0);
+            const uint64_t m2 = fb_relu_store(tlane + 256u, a2_row, row, g, lane, bar_hslab0);
             // ---- epilogue 3: DL2 = (d3 . W3) [z2 > 0] over H2 (the head MMAs have completed)
             mbar_wait(bar_d3, ph);
             mbar_wait(bar_dl3, ph);
@@ -280,13 +312,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                     const uint4 v = make_uint4(out[0], out[1], out[2], out[3]);
                     const int sw = (chunk ^ (row & 7)) << 4;
                     *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = v;
-                    *reinterpret_cast<uint4*>(args.dl2 + g_row + s * ACT_SLAB_BYTES + sw) = v;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_bslab0 + 8u * s);
             }
-            // ---- epilogue 4: DL1 = D4 [z1 > 0] -> global only
+            // ---- epilogue 4: DL1 = D4 [z1 > 0] over DL2 (the backward MMAs have completed), streamed out by the MMA warp
             mbar_wait(bar_d4, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -305,13 +336,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                         out[k] = pack_bf16(lo, hi);
                     }
                     const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(args.dl1 + g_row + s * ACT_SLAB_BYTES + sw) =
-                        make_uint4(out[0], out[1], out[2], out[3]);
+                    *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = make_uint4(out[0], out[1], out[2], out[3]);
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dslab0 + 8u * s);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_free);
             ph ^= 1u;
         }
     } else {
