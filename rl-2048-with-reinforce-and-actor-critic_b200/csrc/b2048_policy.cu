@@ -148,6 +148,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dense_forward_kernel(const __g
 int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
                      uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
                      int greedy, cudaStream_t stream, bool rebuild_image);
+int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
+                      float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
+                      const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
+                      uint32_t t0, int use_mask, int greedy, cudaStream_t stream);
 
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
     if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
@@ -206,6 +210,12 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
     B2_REQUIRE(boards && flags && actions && rewards && cfg && mlp, "b2048_rollout_many: NULL buffer");
     b2048_env_cfg c = *cfg;
     c.action_mode = B2048_ACT_BUFFER;
+    if (precision == 1) {
+        // one persistent launch for the whole horizon (policy on tcgen05 + env step in the same kernel)
+        int st = launch_rollout_tc(h, mlp, boards, flags, actions, rewards, score, step, max_exp, ep_len, &c, B, t_begin, n_steps,
+                                   seed, gid0, t0, use_mask, greedy, (cudaStream_t)stream);
+        if (st != B2048_ERR_UNSUPPORTED) return st;
+    }
     for (int32_t k = 0; k < n_steps; ++k) {
         const int64_t t = (int64_t)t_begin + k;
         const uint32_t t_env = t0 + (uint32_t)t + 1u;

@@ -31,6 +31,7 @@
 
 #include "b2048_device.cuh"
 #include "b2048_internal.h"
+#include "b2048_step_fast.cuh"
 #include "b2048_tc.cuh"
 
 namespace b2 {
@@ -88,6 +89,20 @@ struct PolicyTcArgs {
     int obs_mode;
     float obs_scale;
     long long* debug_clock;   // optional: per-tile phase timestamps of CTA 0 (B2048_TC_DEBUG_CLOCK), else NULL
+    // ---- fused rollout (policy_tc_kernel<true>): time-major rollout record, env state, env configuration
+    uint64_t* ro_boards;      // [T + 1][n]
+    uint8_t* ro_flags;        // [T + 1][n]
+    uint8_t* ro_actions;      // [T][n]
+    float* ro_rewards;        // [T][n]
+    uint32_t* score;
+    uint32_t* step;
+    uint8_t* max_exp;
+    int32_t* ep_len;          // nullable: run-to-termination bookkeeping (0 = running, else frozen)
+    const uint8_t* tables;    // row tables + small tables (global memory; read through L1 / L2)
+    uint64_t seed;
+    int32_t t_begin, n_steps;
+    uint32_t t0;
+    b2048_env_cfg cfg;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -105,6 +120,12 @@ struct PolicyTcArgs {
 constexpr int TC_EPI_THREADS = 512;
 constexpr int TC_IO_THREADS = 128;
 constexpr int TC_THREADS = TC_EPI_THREADS + 32 + TC_IO_THREADS;   // 16 epilogue warps + MMA warp + 4 I/O warps
+constexpr int TC_ENV_GROUP = 128;                                 // fused rollout only: one env-step group = 4 warps
+constexpr int TC_ENV_THREADS = 2 * TC_ENV_GROUP;                  // two groups, alternating over the CTA's tiles
+constexpr int SM_ACT = SM_BAR + 256;                              // fused rollout only: 2 x 128 action bytes
+constexpr int SM_TBL = SM_ACT + 256;                              // fused rollout only: small step tables
+constexpr int SM_TOTAL_RO = SM_TBL + B2048_SMALL_BYTES;
+static_assert(SM_TOTAL_RO <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // One epilogue pass, SLAB-MAJOR: for every 64-column K slab s of the next layer's operand, warp (q, g) converts the 16
 // accumulator columns 64 s + 16 g .. +15 of its 32 rows (ReLU -> bf16), stores them into the 128B-swizzled slab and
@@ -131,7 +152,17 @@ __device__ __forceinline__ void relu_store_slabs(uint32_t tlane_col0, uint8_t* a
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_constant__ PolicyTcArgs args) {
+// kRollout = false: one policy step over all tiles (item = tile).
+// kRollout = true : the whole rollout loop of b2048_rollout_many in ONE launch.  A CTA owns the tiles
+//   first, first + grid, ... and walks the items (t, tile) for t = t_begin .. t_begin + n_steps - 1; boards are
+//   independent, so no grid-wide synchronisation is needed.  The I/O thread that samples a board's action also plays
+//   the env step for it (step_fast_rnd with the tables read through L1/L2, sharing the Philox block with the sampling
+//   word) and writes slice t + 1 of the record — which the same thread reads back when the tile comes round again.
+//   The MMA / epilogue warps see nothing but a longer item stream: weights, TMEM and barriers stay set up for the
+//   whole rollout, and a step costs no launch, no image reload and no separate env kernel.
+template <bool kRollout>
+__global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_THREADS, 1)
+    policy_tc_kernel(const __grid_constant__ PolicyTcArgs args) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -139,7 +170,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
                    bar_d3 = s_u32(&bars[4]), bar_free = s_u32(&bars[5]);
     const uint32_t bar_slab0 = s_u32(&bars[6]);    // bars[6..9]   : A2 slab g written (layer-2 operand)
     const uint32_t bar_hslab0 = s_u32(&bars[10]);  // bars[10..13] : H2 slab g written (head operand)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 128);
+    const uint32_t bar_act0 = s_u32(&bars[14]);    // [14..15] rollout: actions of env group g are in sAct[g]  (sampler -> env)
+    const uint32_t bar_step0 = s_u32(&bars[16]);   // [16..17] rollout: env group g has written its item out    (env -> sampler)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 192);
 
     if (tid == 0) {
         mbar_init(bar_img, 1);
@@ -148,6 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
         mbar_init(bar_d2, 1);
         mbar_init(bar_d3, 1);
         mbar_init(bar_free, TC_EPI_THREADS / 32 + TC_IO_THREADS / 32);
+        for (int g = 0; g < 2; ++g) { mbar_init(bar_act0 + 8u * g, TC_IO_THREADS / 32); mbar_init(bar_step0 + 8u * g, TC_ENV_GROUP / 32); }
         for (int g = 0; g < 4; ++g) { mbar_init(bar_slab0 + 8u * g, TC_EPI_THREADS / 32); mbar_init(bar_hslab0 + 8u * g, TC_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -162,6 +196,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
     const int64_t first = blockIdx.x;
+    // items of this CTA: its tiles, times the number of rollout steps
+    const int n_owned = first < n_tiles ? (int)((n_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
+    const int n_items = kRollout ? n_owned * args.n_steps : n_owned;
+    // With a single tile per CTA the next rollout item is the SAME boards one step later: its A1 can only be encoded
+    // after this item's env step, so layer 1 of the next item is issued after this item's head instead of before it.
+    const bool prefetch = !kRollout || n_owned > 1;
 
     if (warp == 16) {
         // ============================ MMA / copy warp ============================
@@ -193,13 +233,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
             umma_commit(bar_d1);
         };
         uint32_t ph = 0;
-        if (lane == 0 && first < n_tiles) issue_layer1(0u);
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+        if (lane == 0 && n_items > 0) issue_layer1(0u);
+        for (int item = 0; item < n_items; ++item) {
             if (lane == 0) {
+                if (!prefetch && item != 0) issue_layer1(ph);
                 // ---- layer 2, slab by slab as epilogue 1 produces them
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_slab0 + 8u * g, ph);
-                    if (g == 0 && tile != first) mbar_wait(bar_free, ph ^ 1u);   // D2/D3 drained by the previous tile
+                    if (g == 0 && item != 0) mbar_wait(bar_free, ph ^ 1u);   // D2/D3 drained by the previous tile
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -211,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
                 umma_f16(tmem_base + 256u, dOnes2, dBias, kIdesc, 1u);           // + b2
                 umma_commit(bar_d2);
                 // ---- next tile's layer 1 runs under this tile's epilogue 2 (D1 was drained before the slab arrivals)
-                if (tile + gridDim.x < n_tiles) issue_layer1(ph ^ 1u);
+                if (prefetch && item + 1 < n_items) issue_layer1(ph ^ 1u);
                 // ---- head: D3 = H2 . W3^T, slab by slab as epilogue 2 produces them.  D3 overlays D2 columns 0..15,
                 //      which belong to slab 0 and have been drained by every warp before hslab[0] completes.
                 for (int g = 0; g < 4; ++g) {
@@ -236,14 +277,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint8_t* a2_row = smem + SM_A2 + row * 128;                             // this row's line in slab 0
         uint32_t ph = 0;
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
-            const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == 0 && (tile - first) / gridDim.x < 8;
-            long long* dc = dbg ? args.debug_clock + 8 * ((tile - first) / gridDim.x) : nullptr;
+        for (int item = 0; item < n_items; ++item) {
+            const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == 0 && item < 8;
+            long long* dc = dbg ? args.debug_clock + 8 * item : nullptr;
             if (dbg) dc[0] = clock64();
             // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab.  A2 is free once the previous tile's head MMAs
             //      (which read H2 out of the same buffer) have completed.
             mbar_wait(bar_d1, ph);
-            if (tile != first) mbar_wait(bar_d3, ph ^ 1u);
+            if (item != 0) mbar_wait(bar_d3, ph ^ 1u);
             if (dbg) dc[1] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             relu_store_slabs(tlane, a2_row, row, g, lane, bar_slab0);
@@ -268,82 +309,237 @@ __global__ void __launch_bounds__(TC_THREADS, 1) policy_tc_kernel(const __grid_c
         const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
         uint32_t ph = 0;
 
-        auto encode_a1 = [&](int64_t tile) {   // this thread's board -> 16 bf16 in the A1 core matrices
-            const int64_t s = tile * TC_M + row;
-            uint64_t bd = (s < args.n) ? args.board[s] : 0ull;
-            uint32_t packed[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t e0 = (uint32_t)(bd >> (8 * j)) & 0xFu, e1 = (uint32_t)(bd >> (8 * j + 4)) & 0xFu;
-                float v0, v1;
-                if (args.obs_mode == B2048_OBS_RAW) { v0 = e0 ? (float)(1u << e0) : 0.0f; v1 = e1 ? (float)(1u << e1) : 0.0f; }
-                else { v0 = (float)e0 * args.obs_scale; v1 = (float)e1 * args.obs_scale; }
-                __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
-                packed[j] = *reinterpret_cast<uint32_t*>(&p);
-            }
-            uint8_t* a1 = smem + SM_A1 + (row >> 3) * 256 + (row & 7) * 16;
-            *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_a1);
-        };
+        // An item is (j, r): the CTA's j-th tile in rollout round r (plain policy step: r = 0 throughout).  The pair is
+        // advanced incrementally — these warps run long dependent chains alone on their schedulers, and an integer
+        // division by n_owned costs them more than the softmax.
+        auto tile_of = [&](int j) -> int64_t { return first + (int64_t)j * gridDim.x; };
+        auto slice_of = [&](int r) -> int64_t { return kRollout ? (int64_t)args.t_begin + r : 0; };
+        uint8_t* sAct = smem + SM_ACT;                                          // rollout: sampled actions of the item
 
-        if (first < n_tiles) encode_a1(first);
-        mbar_wait(bar_img, 0);                                                  // b3 lives in the image
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
-            const int64_t s = tile * TC_M + row;
-            const bool use_mask = args.mask_flags != nullptr;
-            uint32_t fl = 0xFu;
-            if (use_mask && s < args.n) fl = args.mask_flags[s];               // requested early, used after D3
-            // A1 is free once this tile's layer-1 MMAs have completed
-            mbar_wait(bar_d1, ph);
-            const int64_t next = tile + gridDim.x;
-            if (next < n_tiles) encode_a1(next);
-            mbar_wait(bar_d3, ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r4[4];
-            tmem_ld4(tlane + 256u, r4);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_free);
-            const float lg0 = __uint_as_float(r4[0]) + sB3[0], lg1 = __uint_as_float(r4[1]) + sB3[1];
-            const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
-            if (s < args.n) {
-                float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
-                float m2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, m3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
-                float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx), e3 = expf(m3 - mx);
-                float sum = e0 + e1 + e2 + e3;
-                float p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum, p3 = e3 / sum;
-                if (args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
-                if (args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
-                if (args.action) {
-                    uint32_t a;
-                    if (args.greedy) {
-                        float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
-                        float q2 = (!use_mask || (fl & 4u)) ? p2 : 0.0f, q3 = (!use_mask || (fl & 8u)) ? p3 : 0.0f;
-                        a = 0; float best = q0;
-                        if (q1 > best) { best = q1; a = 1; }
-                        if (q2 > best) { best = q2; a = 2; }
-                        if (q3 > best) { best = q3; a = 3; }
-                    } else {
-                        Rand4 rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, args.t, B2048_DOM_STEP);
-                        float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
-                        float u = ((float)(rr.w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
-                        a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
-                        float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
-                        if (!(pa > 0.0f)) {
-                            if (p3 > 0.0f) a = 3;
-                            if (p2 > 0.0f) a = 2;
-                            if (p1 > 0.0f) a = 1;
-                            if (p0 > 0.0f) a = 0;
-                        }
-                    }
-                    args.action[s] = (uint8_t)a;
+        if (warp < 21) {
+            // ---------------- sampler warps (17..20): A1 encode, D3 -> softmax -> action ----------------
+            const uint64_t* board_base = kRollout ? args.ro_boards : args.board;
+            const uint8_t* mask_base = kRollout ? args.ro_flags : args.mask_flags;
+            // Rollout: tile j of the CTA (item % n_owned) belongs to env group j & 1, so a board is always stepped by
+            // the same thread.  Group g's ord-th item is item_of(g, ord); bar_step[g] completes once per item of the
+            // group, in order, and the sampler waits for every phase exactly once, in order.  The boards / flags
+            // of an item are written by the same group one round (n_owned items, cnt[g] group items) earlier.
+            int steps_waited[2] = {0, 0};
+            auto wait_steps_through = [&](int g, int ord) {
+                while (steps_waited[g] <= ord) {
+                    mbar_wait(bar_step0 + 8u * g, (uint32_t)steps_waited[g] & 1u);
+                    ++steps_waited[g];
                 }
+            };
+            auto ord_of = [&](int j, int r) {   // ordinal of item (j, r) among the items of its group j & 1
+                return r * ((n_owned + 1 - (j & 1)) >> 1) + (j >> 1);
+            };
+            auto wait_inputs_of = [&](int j, int r) {   // written by the same group one round earlier
+                if (r > 0) wait_steps_through(j & 1, ord_of(j, r - 1));
+            };
+
+            auto encode_a1 = [&](int j, int r) {   // this thread's board -> 16 bf16 in the A1 core matrices
+                const int64_t s = tile_of(j) * TC_M + row;
+                uint64_t bd = (s < args.n) ? board_base[slice_of(r) * args.n + s] : 0ull;
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t e0 = (uint32_t)(bd >> (8 * j)) & 0xFu, e1 = (uint32_t)(bd >> (8 * j + 4)) & 0xFu;
+                    float v0, v1;
+                    if (args.obs_mode == B2048_OBS_RAW) { v0 = e0 ? (float)(1u << e0) : 0.0f; v1 = e1 ? (float)(1u << e1) : 0.0f; }
+                    else { v0 = (float)e0 * args.obs_scale; v1 = (float)e1 * args.obs_scale; }
+                    __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+                    packed[j] = *reinterpret_cast<uint32_t*>(&p);
+                }
+                uint8_t* a1 = smem + SM_A1 + (row >> 3) * 256 + (row & 7) * 16;
+                *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a1);
+            };
+
+            if (n_items > 0) encode_a1(0, 0);
+            mbar_wait(bar_img, 0);                                              // b3 lives in the image
+            int j = 0, r = 0;
+            for (int item = 0; item < n_items; ++item) {
+                int jn = j + 1, rn = r;                                          // the next item
+                if (jn == n_owned) { jn = 0; ++rn; }
+                const int64_t s = tile_of(j) * TC_M + row;
+                const int64_t slice = slice_of(r);
+                const bool valid = s < args.n;
+                const bool use_mask = args.mask_flags != nullptr;               // rollout: non-NULL iff the policy is masked
+                if (kRollout) wait_inputs_of(j, r);
+                uint32_t fl = 0xFu;
+                if (valid && use_mask) fl = mask_base[slice * args.n + s];      // requested early, used after D3
+                const uint32_t t_env = kRollout ? args.t0 + (uint32_t)slice + 1u : args.t;
+                uint32_t w3 = 0u;
+                if (valid && !args.greedy && (kRollout || args.action))
+                    w3 = stream_keyed(args.keys, args.gid0 + (uint64_t)s, t_env, B2048_DOM_STEP).w3;
+                // A1 is free once this item's layer-1 MMAs have completed
+                mbar_wait(bar_d1, ph);
+                if (prefetch && item + 1 < n_items) {
+                    if (kRollout) wait_inputs_of(jn, rn);
+                    encode_a1(jn, rn);
+                }
+                mbar_wait(bar_d3, ph);
+                const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == TC_EPI_THREADS + 32 && item < 8;
+                if (dbg) args.debug_clock[8 * item + 5] = clock64();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t r4[4];
+                tmem_ld4(tlane + 256u, r4);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free);
+                const float lg0 = __uint_as_float(r4[0]) + sB3[0], lg1 = __uint_as_float(r4[1]) + sB3[1];
+                const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
+                uint32_t a = 0;
+                if (valid) {
+                    float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
+                    float m2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, m3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
+                    // fast-math softmax (ex2.approx / rcp.approx, ~2^-21 relative): this thread is on the rollout's
+                    // critical path and the bf16 logits carry 2^-9 anyway
+                    float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    float e0 = __expf(m0 - mx), e1 = __expf(m1 - mx), e2 = __expf(m2 - mx), e3 = __expf(m3 - mx);
+                    float inv = __fdividef(1.0f, e0 + e1 + e2 + e3);
+                    float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv, p3 = e3 * inv;
+                    if (!kRollout && args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
+                    if (!kRollout && args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
+                    if (kRollout || args.action) {
+                        if (args.greedy) {
+                            float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
+                            float q2 = (!use_mask || (fl & 4u)) ? p2 : 0.0f, q3 = (!use_mask || (fl & 8u)) ? p3 : 0.0f;
+                            a = 0; float best = q0;
+                            if (q1 > best) { best = q1; a = 1; }
+                            if (q2 > best) { best = q2; a = 2; }
+                            if (q3 > best) { best = q3; a = 3; }
+                        } else {
+                            float c0 = p0, c1 = c0 + p1, c2 = c1 + p2, c3 = c2 + p3;
+                            float u = ((float)(w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
+                            a = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
+                            float pa = a == 0 ? p0 : a == 1 ? p1 : a == 2 ? p2 : p3;
+                            if (!(pa > 0.0f)) {
+                                if (p3 > 0.0f) a = 3;
+                                if (p2 > 0.0f) a = 2;
+                                if (p1 > 0.0f) a = 1;
+                                if (p0 > 0.0f) a = 0;
+                            }
+                        }
+                        if (kRollout) args.ro_actions[slice * args.n + s] = (uint8_t)a;
+                        else args.action[s] = (uint8_t)a;
+                    }
+                }
+                if (kRollout) {
+                    // hand the actions to the item's env group (one slot per group: its previous item must be finished)
+                    const int g = j & 1, ord = ord_of(j, r);
+                    wait_steps_through(g, ord - 1);
+                    sAct[g * TC_M + row] = (uint8_t)a;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_act0 + 8u * g);
+                    if (dbg) args.debug_clock[8 * item + 6] = clock64();
+                    if (!prefetch && item + 1 < n_items) {
+                        wait_inputs_of(jn, rn);
+                        encode_a1(jn, rn);
+                    }
+                }
+                j = jn; r = rn;
+                ph ^= 1u;
             }
-            ph ^= 1u;
+        } else if (kRollout) {
+            // ---------------- env warps (21..28): one thread per board plays the sampled action ----------------
+            // Two groups of four warps; group g owns the CTA's tiles j with j & 1 == g.  One warp per scheduler running
+            // the ~700-instruction step chain is latency-bound (about 6 K cycles per item, more than the 5 K the tensor
+            // pipeline needs), so the groups alternate and each has two item periods per step.
+            // Same contract as step_fast_kernel (b2048_env.cu); the row tables are read through L1 / L2 (shared memory
+            // is full of weights).  Everything a board's env thread reads back next time (board, flags, counters,
+            // episode length) it wrote itself; the sampler warps see the new slice through bar_step.
+            // The small tables (per-action selectors, merge statistics: 2.2 KB) are copied into shared memory so that
+            // the only L2 round trip on a step's dependency chain is the row lookup itself.
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(args.tables + B2048_LUT_BYTES);
+                uint4* dst = reinterpret_cast<uint4*>(smem + SM_TBL);
+                for (int i = tid - TC_THREADS; i < B2048_SMALL_BYTES / 16; i += TC_ENV_THREADS) dst[i] = src[i];
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_ENV_THREADS) : "memory");
+            }
+            const int grp = (warp - 21) >> 2;
+            const uint32_t bar_act = bar_act0 + 8u * grp, bar_step = bar_step0 + 8u * grp;
+            // this group's items: tiles grp, grp + 2, ... of every round
+            FastTables T;
+            T.left = reinterpret_cast<const uint16_t*>(args.tables);
+            T.merge = args.tables + B2048_LUT_LEFT_BYTES;
+            T.agg = reinterpret_cast<const AggEntry*>(smem + SM_TBL + B2048_SMALL_AGG_OFF);
+            T.sel = reinterpret_cast<const SelEntry*>(smem + SM_TBL + B2048_SMALL_SEL_OFF);
+            T.act = smem + SM_TBL + B2048_SMALL_ACT_OFF;
+
+            struct EnvIn { uint64_t bd; uint32_t score, step, max_exp, fin; int32_t ep; };
+            auto load_in = [&](int j, int r) {
+                EnvIn e = {0ull, 0u, 0u, 2u, 0u, 0};
+                const int64_t s = tile_of(j) * TC_M + row;
+                if (s < args.n) {
+                    const int64_t i = slice_of(r) * args.n + s;
+                    e.bd = args.ro_boards[i]; e.fin = args.ro_flags[i];
+                    e.score = args.score[s]; e.step = args.step[s]; e.max_exp = args.max_exp[s];
+                    if (args.ep_len) e.ep = args.ep_len[s];
+                }
+                return e;
+            };
+            const int own_tiles = (n_owned + 1 - grp) >> 1;   // tiles of this group per round
+            const int n_rounds = n_owned > 0 ? n_items / n_owned : 0;
+            int j = grp, r = own_tiles > 0 ? 0 : n_rounds;
+            EnvIn cur = r < n_rounds ? load_in(j, r) : EnvIn{0ull, 0u, 0u, 2u, 0u, 0};
+            while (r < n_rounds) {
+                int jn = j + 2, rn = r;                                          // the group's next item
+                if (jn >= n_owned) { jn = grp; ++rn; }
+                const int item = r * n_owned + j;
+                const int64_t s = tile_of(j) * TC_M + row;
+                const int64_t slice = slice_of(r);
+                const bool valid = s < args.n;
+                const uint32_t t_env = args.t0 + (uint32_t)slice + 1u;
+                FastIO io;
+                io.lo = (uint32_t)cur.bd; io.hi = (uint32_t)(cur.bd >> 32);
+                io.score = cur.score; io.step = cur.step; io.max_exp = cur.max_exp; io.mask_in = 0u;
+                const uint32_t fin = cur.fin;
+                const bool frozen = cur.ep != 0;
+                Rand4 rr = Rand4{0u, 0u, 0u, 0u};
+                if (valid && !frozen) rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, t_env, B2048_DOM_STEP);
+                // Next item's inputs: with several tiles per CTA this thread wrote them at least one item ago, so the
+                // loads go out now and land under this item's step; with one tile they are this step's outputs.
+                EnvIn nxt = cur;
+                if (own_tiles > 1 && rn < n_rounds) nxt = load_in(jn, rn);
+                mbar_wait(bar_act, ph);
+                const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && (tid - TC_THREADS) % TC_ENV_GROUP == 0 && item < 8;
+                if (dbg) args.debug_clock[8 * item + 7] = clock64();
+                if (valid) {
+                    const int64_t o = (slice + 1) * args.n + s;
+                    if (frozen) {
+                        args.ro_boards[o] = cur.bd;
+                        args.ro_rewards[slice * args.n + s] = 0.0f;
+                        io.flags = fin & ~B2048_F_CHANGED;
+                        args.ro_flags[o] = (uint8_t)io.flags;
+                    } else {
+                        io.action = sAct[grp * TC_M + row];
+                        step_fast_rnd<B2048_ACT_BUFFER, true>(io, args.cfg, rr, args.seed, args.gid0 + (uint64_t)s, t_env, T);
+                        if (args.ep_len && (io.flags & (B2048_F_DONE | B2048_F_TRUNC))) {
+                            args.ep_len[s] = (int32_t)(slice + 1);
+                            cur.ep = (int32_t)(slice + 1);
+                        }
+                        args.ro_boards[o] = (uint64_t)io.lo | ((uint64_t)io.hi << 32);
+                        args.score[s] = io.score; args.step[s] = io.step; args.max_exp[s] = (uint8_t)io.max_exp;
+                        args.ro_rewards[slice * args.n + s] = io.reward;
+                        args.ro_flags[o] = (uint8_t)io.flags;
+                    }
+                }
+                if (own_tiles == 1) {   // same boards next time: carry the state in registers
+                    nxt.bd = (uint64_t)io.lo | ((uint64_t)io.hi << 32);
+                    nxt.score = io.score; nxt.step = io.step; nxt.max_exp = io.max_exp; nxt.fin = io.flags; nxt.ep = cur.ep;
+                }
+                cur = nxt;
+                j = jn; r = rn;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_step);
+                ph ^= 1u;
+            }
         }
     }
 
@@ -361,6 +557,25 @@ void launch_tc_prepare(const b2048_mlp_desc* mlp, uint8_t* img, cudaStream_t str
                                                       mlp->dims[3], img);
 }
 
+static long long* debug_clock_buffer() {
+    static long long* dbg_buf = nullptr;
+    if (!getenv("B2048_TC_DEBUG_CLOCK")) return nullptr;
+    if (!dbg_buf) { cudaMalloc(&dbg_buf, 80 * sizeof(long long)); cudaMemset(dbg_buf, 0, 80 * sizeof(long long)); }
+    return dbg_buf;
+}
+static void print_debug_clock(long long* dbg, cudaStream_t stream) {
+    long long hbuf[80];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    for (int k = 0; k < 6; ++k)
+        fprintf(stderr,
+                "[tc clock] item %d: wait_d1+d3 %lld epi1 %lld wait_d2 %lld epi2 %lld | total %lld | to next %lld | io: d3 seen +%lld, "
+                "sample %lld | env: actions seen +%lld\n",
+                k, hbuf[8 * k + 1] - hbuf[8 * k], hbuf[8 * k + 2] - hbuf[8 * k + 1], hbuf[8 * k + 3] - hbuf[8 * k + 2],
+                hbuf[8 * k + 4] - hbuf[8 * k + 3], hbuf[8 * k + 4] - hbuf[8 * k], hbuf[8 * k + 8] - hbuf[8 * k],
+                hbuf[8 * k + 5] - hbuf[8 * k], hbuf[8 * k + 6] - hbuf[8 * k + 5], hbuf[8 * k + 7] - hbuf[8 * k]);
+}
+
 // Returns B2048_OK if the tensor-core path applies and was launched, B2048_ERR_UNSUPPORTED (without setting an
 // error message) when the shape is outside what this kernel implements.
 int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
@@ -373,8 +588,10 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     if (!h->tc_image) {
         cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
         if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
-        e = cudaFuncSetAttribute(policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
+        e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
+        e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
     }
     // The image is rebuilt on every stand-alone call (71 K parameters): the library never caches weights across
     // calls.  b2048_rollout_many builds it once for the whole loop (parameters cannot change inside one call).
@@ -386,24 +603,54 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     a.n = n; a.keys = make_keys(seed); a.gid0 = gid0; a.t = t; a.greedy = greedy; a.obs_mode = mlp->obs_mode;
     a.obs_scale = mlp->obs_log2_scale;
     a.debug_clock = nullptr;
-    if (getenv("B2048_TC_DEBUG_CLOCK")) {
-        static long long* dbg_buf = nullptr;
-        if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
-        a.debug_clock = dbg_buf;
-    }
+    a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
+    a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = seed; a.t_begin = 0; a.n_steps = 1;
+    a.t0 = 0;
+    a.debug_clock = debug_clock_buffer();
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
-    policy_tc_kernel<<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
-    if (a.debug_clock) {
-        long long hbuf[64];
-        cudaStreamSynchronize(stream);
-        cudaMemcpy(hbuf, a.debug_clock, sizeof(hbuf), cudaMemcpyDeviceToHost);
-        for (int k = 0; k < 4; ++k)
-            fprintf(stderr, "[tc clock] tile %d: wait_d1+d3 %lld epi1 %lld wait_d2 %lld epi2 %lld | total %lld | to next %lld\n", k,
-                    hbuf[8 * k + 1] - hbuf[8 * k], hbuf[8 * k + 2] - hbuf[8 * k + 1], hbuf[8 * k + 3] - hbuf[8 * k + 2],
-                    hbuf[8 * k + 4] - hbuf[8 * k + 3], hbuf[8 * k + 4] - hbuf[8 * k], hbuf[8 * k + 8] - hbuf[8 * k]);
-    }
+    policy_tc_kernel<false><<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
+    if (a.debug_clock) print_debug_clock(a.debug_clock, stream);
     return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
+}
+
+// The whole rollout loop of b2048_rollout_many in one launch (policy_tc_kernel<true>).  Returns
+// B2048_ERR_UNSUPPORTED (no error message) when the network / env configuration is outside what the fused kernel
+// implements; the caller then runs the two-kernels-per-step loop.
+int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
+                      float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
+                      const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
+                      uint32_t t0, int use_mask, int greedy, cudaStream_t stream) {
+    const bool net_ok = mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H &&
+                        mlp->dims[3] == 4 && mlp->activation == B2048_ACTV_RELU &&
+                        (mlp->obs_mode == B2048_OBS_RAW || mlp->obs_mode == B2048_OBS_LOG2) && h->smem_optin >= SM_TOTAL_RO;
+    const bool env_ok = score && step && max_exp && cfg->use_action_mask && cfg->empty_tile_reward == 0.0 &&
+                        cfg->merge_reward == 0.0 && cfg->bonus_mode == B2048_BONUS_OFF && cfg->endgame_penalty == 0.0 &&
+                        (cfg->reward_mode == B2048_REWARD_SUM || cfg->reward_mode == B2048_REWARD_LOG2);
+    const int64_t tiles = (B + TC_M - 1) / TC_M;
+    if (!net_ok || !env_ok || B < 4096 || tiles * (int64_t)n_steps > 0x7FFFFFFF || getenv("B2048_NO_FUSED_ROLLOUT") != nullptr)
+        return B2048_ERR_UNSUPPORTED;
+    if (!h->tc_image) {
+        cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
+        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
+        e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
+        e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
+    }
+    launch_tc_prepare(mlp, h->tc_image, stream);
+    PolicyTcArgs a;
+    a.img = h->tc_image; a.board = nullptr; a.mask_flags = use_mask ? flags : nullptr; a.action = nullptr; a.probs = nullptr;
+    a.logits = nullptr; a.n = B; a.keys = make_keys(seed); a.gid0 = gid0; a.t = 0; a.greedy = greedy;
+    a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
+    a.ro_boards = boards; a.ro_flags = flags; a.ro_actions = actions; a.ro_rewards = rewards; a.score = score; a.step = step;
+    a.max_exp = max_exp; a.ep_len = ep_len; a.tables = h->d_tables; a.seed = seed; a.t_begin = t_begin; a.n_steps = n_steps;
+    a.t0 = t0; a.cfg = *cfg; a.cfg.action_mode = B2048_ACT_BUFFER;
+    int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    a.debug_clock = debug_clock_buffer();
+    policy_tc_kernel<true><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);
+    if (a.debug_clock) print_debug_clock(a.debug_clock, stream);
+    return check_cuda(cudaGetLastError(), "policy_tc_kernel<rollout> launch");
 }
 
 }  // namespace b2

@@ -71,10 +71,11 @@ struct FastIO {
 };
 
 // kAct: B2048_ACT_*; kTrack: score / step / max_exp kept (and truncation evaluated)
+// step_fast_rnd takes the board's Philox block of (gid, t, B2048_DOM_STEP) from the caller (the fused rollout kernel
+// shares it with the policy's sampling word); step_fast computes it.
 template <int kAct, bool kTrack>
-B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& keys, uint64_t seed, uint64_t gid,
-                     uint32_t t, const FastTables& T) {
-    const Rand4 rnd = stream_keyed(keys, gid, t, B2048_DOM_STEP);
+B2_HD void step_fast_rnd(FastIO& io, const b2048_env_cfg& cfg, const Rand4& rnd, uint64_t seed, uint64_t gid, uint32_t t,
+                         const FastTables& T) {
 
     uint32_t a;
     if (kAct == B2048_ACT_BUFFER) a = io.action & 3u;
@@ -170,6 +171,12 @@ B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& key
     }
     io.lo = nlo; io.hi = nhi;
     io.flags = f | mask;
+}
+
+template <int kAct, bool kTrack>
+B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& keys, uint64_t seed, uint64_t gid,
+                     uint32_t t, const FastTables& T) {
+    step_fast_rnd<kAct, kTrack>(io, cfg, stream_keyed(keys, gid, t, B2048_DOM_STEP), seed, gid, t, T);
 }
 
 }  // namespace b2

@@ -94,3 +94,39 @@ def test_tc_rollout_statistics(b2048):
         ro = agent.rollout_many(env, precision=prec)
         out[prec] = (float(ro.total_reward().mean()), float(ro.length.float().mean()))
     assert abs(out[0][0] - out[1][0]) / out[0][0] < 0.05 and abs(out[0][1] - out[1][1]) / out[0][1] < 0.05
+
+
+@pytest.mark.parametrize("n,horizon,max_steps", [(4096, 24, 1024), (33000, None, 40), (33000, 50, 30), (150000, 12, 1024)])
+def test_fused_rollout_kernel_equals_two_kernel_loop(b2048, n, horizon, max_steps):
+    """policy_tc_kernel<rollout> (policy on tcgen05 + env step in ONE persistent launch for the whole horizon) must
+    reproduce the policy-kernel / step-kernel loop bit for bit: same boards, flags, actions, rewards, episode
+    lengths and counters.  Covers one tile per CTA (no prefetch), a mix of one and two, and many tiles per CTA;
+    run-to-termination (frozen episodes) and fixed horizon with reset-on-done."""
+    import os
+    from helpers import full_env_kwargs
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = max_steps
+    outs = []
+    for fused in (False, True):
+        if fused:
+            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+        else:
+            os.environ["B2048_NO_FUSED_ROLLOUT"] = "1"
+        try:
+            benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=77, gid0=5)
+            agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                         b2048.ReinforceAgentConfig())
+            agent.params = b2048.init_model_params(16, [256, 256], 4, np.random.default_rng(2), "HeNormal")
+            ro = agent.rollout_many(benv, horizon=horizon, precision=1)
+            torch.cuda.synchronize()
+            T = ro.T
+            outs.append(dict(T=T, boards=ro.boards[:T + 1].cpu().numpy(), flags=ro.flags[:T + 1].cpu().numpy(),
+                             actions=ro.actions[:T].cpu().numpy(), rewards=ro.rewards[:T].cpu().numpy(),
+                             length=ro.length.cpu().numpy(), score=benv.score.cpu().numpy(), step=benv.step_count.cpu().numpy(),
+                             max_exp=benv.max_exp.cpu().numpy()))
+        finally:
+            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+    a, b = outs
+    assert a["T"] == b["T"]
+    for k in ("length", "boards", "flags", "actions", "rewards", "score", "step", "max_exp"):
+        assert (a[k] == b[k]).all(), (k, int((a[k] != b[k]).sum()))
+    assert a["rewards"].sum() > 0
