@@ -194,9 +194,11 @@ int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* flags, uint8_
                        int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
                        int32_t greedy, int32_t precision, void* stream);
 
-/* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1). */
+/* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1).
+ *   precision : 0 = fp32 CUDA cores; 1 = bf16 tcgen05 (16-256-256-(<=4) ReLU, raw / log2 observations, n >= 4096,
+ *               else B2048_ERR_UNSUPPORTED); 2 = tensor cores when they apply, else fp32. */
 int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
-                      int64_t n, void* stream);
+                      int64_t n, int32_t precision, void* stream);
 
 /* forward_logits on explicit float32 inputs x[n, dims[0]] — the reference's own signature (MLP.py:159-196).
  * act_out / pre_out: HOST arrays of device pointers (either array, or any entry, may be NULL):

@@ -32,6 +32,7 @@
 namespace b2 {
 
 void launch_tc_prepare(const b2048_mlp_desc* mlp, uint8_t* img, cudaStream_t stream);
+int ensure_tc_image(b2048_handle* h);
 
 // ------------------------------------------------------------------------------------------------ layouts
 constexpr int ACT_TILE_BYTES = 32768;     // activation image of 64 samples: 4 slabs x [64 rows x 128 B]
@@ -635,10 +636,7 @@ int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* ma
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                        uint8_t* workspace, int64_t chunk, cudaStream_t stream) {
     static bool attr_set = false;
-    if (!h->tc_image) {
-        cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
-        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
-    }
+    { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TOTAL);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(fb_tc_kernel)");

@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dense_forward_kernel(const __g
 int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
                      uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
                      int greedy, cudaStream_t stream, bool rebuild_image);
+int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n,
+                      cudaStream_t stream);
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
                       float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                       const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
@@ -264,11 +266,20 @@ static int policy_step_impl(b2048_handle* h, const uint64_t* board, const uint8_
 }
 
 extern "C" int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
-                                 int64_t n, void* stream) {
+                                 int64_t n, int32_t precision, void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_mlp_forward: handle is NULL");
     B2_REQUIRE(n >= 0, "b2048_mlp_forward: n < 0");
     if (n == 0) return B2048_OK;
-    B2_REQUIRE(board != nullptr && out != nullptr, "b2048_mlp_forward: board/out is NULL");
+    B2_REQUIRE(board != nullptr && out != nullptr && mlp != nullptr, "b2048_mlp_forward: board/out/mlp is NULL");
+    B2_REQUIRE(precision >= 0 && precision <= 2, "b2048_mlp_forward: precision must be 0 (fp32), 1 (bf16 tcgen05) or 2 (auto)");
+    if (precision != 0) {
+        int st = launch_forward_tc(h, mlp, board, out, n, (cudaStream_t)stream);
+        if (st != B2048_ERR_UNSUPPORTED) return st;
+        if (precision == 1)
+            return fail(B2048_ERR_UNSUPPORTED,
+                        "b2048_mlp_forward: precision 1 (bf16 tcgen05) implements 16-256-256-(<=4) ReLU networks on raw/log2 "
+                        "observations with n >= 4096 only");
+    }
     ForwardArgs a;
     size_t smem = 0;
     int st = validate_mlp(mlp, &a.mlp, &smem, h->smem_optin, "b2048_mlp_forward");

@@ -81,6 +81,8 @@ struct PolicyTcArgs {
     uint8_t* action;
     float* probs;
     float* logits;
+    float* head_out;          // optional [n][n_out]: raw head outputs (b2048_mlp_forward on tensor cores)
+    int n_out;
     int64_t n;
     PhiloxKeys keys;
     uint64_t gid0;
@@ -405,6 +407,10 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                     float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv, p3 = e3 * inv;
                     if (!kRollout && args.probs) *reinterpret_cast<float4*>(args.probs + s * 4) = make_float4(p0, p1, p2, p3);
                     if (!kRollout && args.logits) *reinterpret_cast<float4*>(args.logits + s * 4) = make_float4(lg0, lg1, lg2, lg3);
+                    if (!kRollout && args.head_out) {
+                        const float lg[4] = {lg0, lg1, lg2, lg3};
+                        for (int k = 0; k < args.n_out; ++k) args.head_out[s * args.n_out + k] = lg[k];
+                    }
                     if (kRollout || args.action) {
                         if (args.greedy) {
                             float q0 = (!use_mask || (fl & 1u)) ? p0 : 0.0f, q1 = (!use_mask || (fl & 2u)) ? p1 : 0.0f;
@@ -557,6 +563,24 @@ void launch_tc_prepare(const b2048_mlp_desc* mlp, uint8_t* img, cudaStream_t str
                                                       mlp->dims[3], img);
 }
 
+// Allocates the handle's weight-image buffer (shared by the policy, rollout and training kernels; also used by
+// b2048_learn_tc.cu) and opts the kernels of this file into their dynamic shared memory sizes.
+int ensure_tc_image(b2048_handle* h) {
+    static bool attrs_set = false;
+    if (!h->tc_image) {
+        cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
+        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
+    }
+    if (!attrs_set) {
+        cudaError_t e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
+        e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
+        attrs_set = true;
+    }
+    return B2048_OK;
+}
+
 static long long* debug_clock_buffer() {
     static long long* dbg_buf = nullptr;
     if (!getenv("B2048_TC_DEBUG_CLOCK")) return nullptr;
@@ -585,14 +609,7 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
         mlp->activation != B2048_ACTV_RELU || (mlp->obs_mode != B2048_OBS_RAW && mlp->obs_mode != B2048_OBS_LOG2) ||
         h->smem_optin < SM_TOTAL2)
         return B2048_ERR_UNSUPPORTED;
-    if (!h->tc_image) {
-        cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
-        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
-        e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
-        e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
-    }
+    { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
     // The image is rebuilt on every stand-alone call (71 K parameters): the library never caches weights across
     // calls.  b2048_rollout_many builds it once for the whole loop (parameters cannot change inside one call).
     if (rebuild_image)
@@ -600,6 +617,7 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
                                                           h->tc_image);
     PolicyTcArgs a;
     a.img = h->tc_image; a.board = board; a.mask_flags = mask_flags; a.action = action; a.probs = probs; a.logits = logits;
+    a.head_out = nullptr; a.n_out = 4;
     a.n = n; a.keys = make_keys(seed); a.gid0 = gid0; a.t = t; a.greedy = greedy; a.obs_mode = mlp->obs_mode;
     a.obs_scale = mlp->obs_log2_scale;
     a.debug_clock = nullptr;
@@ -612,6 +630,29 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     policy_tc_kernel<false><<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
     if (a.debug_clock) print_debug_clock(a.debug_clock, stream);
     return check_cuda(cudaGetLastError(), "policy_tc_kernel launch");
+}
+
+// b2048_mlp_forward on the tensor cores: out[n][n_out] = head outputs of a 16-256-256-n_out (n_out <= 4) ReLU network
+// (the critic's V(s) for the TD targets, reinforce_agent.py:425-437).  B2048_ERR_UNSUPPORTED (silent) for other shapes.
+int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n,
+                      cudaStream_t stream) {
+    if (mlp->n_layers != 3 || mlp->dims[0] != 16 || mlp->dims[1] != TC_H || mlp->dims[2] != TC_H || mlp->dims[3] < 1 ||
+        mlp->dims[3] > 4 || mlp->activation != B2048_ACTV_RELU ||
+        (mlp->obs_mode != B2048_OBS_RAW && mlp->obs_mode != B2048_OBS_LOG2) || h->smem_optin < SM_TOTAL2 || n < 4096)
+        return B2048_ERR_UNSUPPORTED;
+    { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
+    launch_tc_prepare(mlp, h->tc_image, stream);
+    PolicyTcArgs a;
+    a.img = h->tc_image; a.board = board; a.mask_flags = nullptr; a.action = nullptr; a.probs = nullptr; a.logits = nullptr;
+    a.head_out = out; a.n_out = mlp->dims[3]; a.n = n; a.keys = make_keys(0); a.gid0 = 0; a.t = 0; a.greedy = 1;
+    a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
+    a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
+    a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = 0; a.t_begin = 0; a.n_steps = 1;
+    a.t0 = 0;
+    int64_t tiles = (n + TC_M - 1) / TC_M;
+    int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    policy_tc_kernel<false><<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "policy_tc_kernel (forward) launch");
 }
 
 // The whole rollout loop of b2048_rollout_many in one launch (policy_tc_kernel<true>).  Returns
@@ -630,18 +671,11 @@ int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boar
     const int64_t tiles = (B + TC_M - 1) / TC_M;
     if (!net_ok || !env_ok || B < 4096 || tiles * (int64_t)n_steps > 0x7FFFFFFF || getenv("B2048_NO_FUSED_ROLLOUT") != nullptr)
         return B2048_ERR_UNSUPPORTED;
-    if (!h->tc_image) {
-        cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
-        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
-        e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
-        e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
-    }
+    { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
     launch_tc_prepare(mlp, h->tc_image, stream);
     PolicyTcArgs a;
     a.img = h->tc_image; a.board = nullptr; a.mask_flags = use_mask ? flags : nullptr; a.action = nullptr; a.probs = nullptr;
-    a.logits = nullptr; a.n = B; a.keys = make_keys(seed); a.gid0 = gid0; a.t = 0; a.greedy = greedy;
+    a.logits = nullptr; a.head_out = nullptr; a.n_out = 4; a.n = B; a.keys = make_keys(seed); a.gid0 = gid0; a.t = 0; a.greedy = greedy;
     a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
     a.ro_boards = boards; a.ro_flags = flags; a.ro_actions = actions; a.ro_rewards = rewards; a.score = score; a.step = step;
     a.max_exp = max_exp; a.ep_len = ep_len; a.tables = h->d_tables; a.seed = seed; a.t_begin = t_begin; a.n_steps = n_steps;

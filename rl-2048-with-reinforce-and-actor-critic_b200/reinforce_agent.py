@@ -193,10 +193,10 @@ class ReinforceAgent:
         a = self._actor
         return (a.dims == [16, 256, 256, 4] and a.activation == "ReLU" and a.obs_mode in ("raw", "log2"))
 
-    def _values(self, boards: torch.Tensor, out: torch.Tensor) -> None:
+    def _values(self, boards: torch.Tensor, out: torch.Tensor, precision: int = 0) -> None:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b2048_mlp_forward(self._h, _ptr(boards), C.byref(self._critic.desc), _ptr(out),
-                                                   boards.numel(), _stream()), "b2048_mlp_forward")
+                                                   boards.numel(), int(precision), _stream()), "b2048_mlp_forward")
 
     # ------------------------------------------------------------------ reference API: acting
     def _obs_to_packed(self, obs) -> tuple[int, int]:
@@ -461,10 +461,10 @@ class ReinforceAgent:
             # critic block (reinforce_agent.py:403-498): V(s_t) for every stored state, TD(0) errors, critic grads
             values = self._buf("values", (T, B), torch.float32)
             if live is None:
-                self._values(boards, values)
+                self._values(boards, values, prec)
             else:
                 vc = self._buf("values_c", (n,), torch.float32)
-                self._values(boards, vc)
+                self._values(boards, vc, prec)
                 values.zero_()
                 values.view(-1)[live] = vc
             td = self._buf("td", (T, B), torch.float32)
