@@ -13,6 +13,8 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
   roofline   HBM: 22 algorithmic bytes per env-step over the measured kernel time
   cpu_baseline  the reference's algorithm on this box's host cores (Python port, all cores), rank 0, N=1 only
   rollout    secondary: policy-rollout steps/s (MLP 16-256-256-4 forward + masked sampling + env step), 65,536 boards
+  train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
+             one update; 65,536 / 262,144 boards per GPU)
 
 `--impl reference` times the CPU side alone (the reference is pure Python and cannot travel to the GPU
 box; oracle/pyport.py restates it at the same per-environment granularity).
@@ -286,6 +288,8 @@ def run_b200(args):
                 r["value_all_gpus"] = float(v.item())
                 extra[key] = r
             extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision=1)
+            extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision=1,
+                                                                      use_critic=True)
         except Exception as e:
             extra["rollout_error"] = repr(e)
     if rank == 0:
@@ -322,6 +326,7 @@ def main():
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--train-boards", type=int, default=65536)
+    ap.add_argument("--ac-boards", type=int, default=262144, help="actor-critic leg (BASELINE.json configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

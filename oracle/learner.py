@@ -222,9 +222,9 @@ def backprop_bf16(params, X, mask_bits, actions, coef, head_mode):
         d3 = (coef[:, None] * (np.eye(4, dtype=np.float32)[actions] - p)).astype(np.float32)
     else:
         d3 = coef[:, None].astype(np.float32)
-    DL2 = bf16_round((d3 @ W[2].T) * (z2 > 0))
-    DL1 = bf16_round((DL2 @ W[1].T) * (z1 > 0))
     d3b = bf16_round(d3)
+    DL2 = bf16_round((d3b @ W[2].T) * (z2 > 0))
+    DL1 = bf16_round((DL2 @ W[1].T) * (z1 > 0))
     gW = [A1.T @ DL1, H1.T @ DL2, H2.T @ d3b]
     gb = [DL1.sum(0), DL2.sum(0), d3.sum(0)]
     return gW, gb, dict(A1=A1, H1=H1, H2=H2, d3=d3, DL2=DL2, DL1=DL1)

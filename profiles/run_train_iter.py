@@ -6,5 +6,7 @@ import torch
 import b2048
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-r = b2048.bench_train_iter(torch.device("cuda", 0), boards=65536, iters=iters, precision=prec)
+boards = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+critic = bool(int(sys.argv[4])) if len(sys.argv) > 4 else False
+r = b2048.bench_train_iter(torch.device("cuda", 0), boards=boards, iters=iters, precision=prec, use_critic=critic)
 print(json.dumps(r))

@@ -9,7 +9,8 @@
 //      D1 = A1 W1^T + b1            -> H1 = relu(D1)        (epilogue 1: smem operand + global image + sign bits)
 //      D2 = H1 W2^T + b2            -> H2 = relu(D2)        (epilogue 2: same)
 //      D3 = H2 W3^T                 -> logits -> masked softmax -> d3 = coef (onehot(a) - pi)   (I/O warps)
-//      DL2 = (d3 W3) . [z2 > 0]     CUDA cores (K = n_out <= 4), written as the next A operand      (epilogue 3)
+//      D5 = d3 W3^T                 one MMA (K = 16): the head's W3 image read as an MN-major B operand
+//      DL2 = D5 . [z2 > 0]                                                                          (epilogue 3)
 //      D4 = DL2 W2                  the SAME shared-memory W2 image read as an MN-major B operand
 //      DL1 = D4 . [z1 > 0]                                                                          (epilogue 4)
 //    H1, H2, DL2, DL1 leave the SM as bf16 "activation images": per 64 samples, four 64-feature slabs of
@@ -25,6 +26,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "b2048_device.cuh"
 #include "b2048_internal.h"
 #include "b2048_tc.cuh"
@@ -39,8 +43,8 @@ constexpr int ACT_TILE_BYTES = 32768;     // activation image of 64 samples: 4 s
 constexpr int ACT_SLAB_BYTES = 8192;
 constexpr int SMALL_TILE_BYTES = 2048;    // small K-major image of 64 samples: [16 rows x 128 B]
 
-constexpr int FB_D3 = SM_BAR + 256;       // float4 [128]: head deltas of the tile in flight
-constexpr int FB_TOTAL = FB_D3 + 2048;
+constexpr int FB_D3A = SM_BAR + 256;      // head deltas of the tile in flight as a bf16 A operand [128 x 16], A1's layout
+constexpr int FB_TOTAL = FB_D3A + 4096;
 static_assert(FB_TOTAL <= 232448, "fb_tc_kernel exceeds the shared memory of an sm_100 CTA");
 
 struct TcWorkspace {       // byte offsets inside the caller's workspace for a chunk padded to `np` samples
@@ -66,6 +70,7 @@ struct FbArgs {
     int64_t n;
     int head_mode, n_out, obs_mode;
     float obs_scale;
+    long long* debug_clock;   // optional phase timestamps of CTA 0's first epilogue thread (B2048_TC_DEBUG_CLOCK)
 };
 
 // byte offset of (sample row r of the chunk, slab, 16-byte chunk) inside an activation image
@@ -145,7 +150,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
     const uint32_t bar_hslab0 = s_u32(&bars[12]);   // [12..15] H2 slab written
     const uint32_t bar_bslab0 = s_u32(&bars[16]);   // [16..19] DL2 slab written
     const uint32_t bar_dslab0 = s_u32(&bars[20]);   // [20..23] DL1 slab written (D4 drained for that slab)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 192);
+    const uint32_t bar_d5 = s_u32(&bars[24]);       // D5 = d3 W3^T complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 208);
 
     if (tid == 0) {
         mbar_init(bar_img, 1);
@@ -155,6 +161,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
         mbar_init(bar_d3, 1);
         mbar_init(bar_dl3, 4);
         mbar_init(bar_d4, 1);
+        mbar_init(bar_d5, 1);
         mbar_init(bar_free, 1);                      // A2 buffer free: the DL1 image of the tile has been streamed out
         for (int g = 0; g < 4; ++g) {
             mbar_init(bar_slab0 + 8u * g, 16);
@@ -234,9 +241,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                 }
                 bulk_stores_read_done();                 // epilogue 3 overwrites H2 once bar_d3 completes
                 umma_commit(bar_d3);
-                // ---- the next tile's layer 1 may overwrite D1 / D3 as soon as the I/O warps have read D3
+                // ---- backward through the head: D5 = d3 . W3^T into columns 0..255 (D1 / D3 are dead: the I/O warps have
+                //      read D3).  A = d3 as bf16 [128 x 16] (K-major, A1's layout); B = the head's W3 image [j][f]
+                //      read MN-major (N = f contiguous: 64-wide slabs 2048 B apart, 8 K rows = 1024 B).
                 mbar_wait(bar_dl3, ph);
-                if (tile + gridDim.x < n_tiles) issue_layer1(ph ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                umma_f16(tmem_base, desc_nosw_k16(s_u32(smem + FB_D3A)), desc_sw128_mn(sW3, 2048u), kIdescBwd, 0u);
+                umma_commit(bar_d5);
                 // ---- backward through layer 2: D4 = DL2 . W2 over K = out features; B = the W2 image [out][in]
                 //      read MN-major (N = in contiguous: 64-wide slabs 32768 B apart, 8 K rows = 1024 B)
                 for (int g = 0; g < 4; ++g) {
@@ -251,6 +262,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                 }
                 bulk_stores_read_done();                 // epilogue 4 overwrites DL2 once bar_d4 completes
                 umma_commit(bar_d4);
+                // ---- the next tile's layer 1 (D5 was drained by every warp before the DL2 slab arrivals)
+                if (tile + gridDim.x < n_tiles) issue_layer1(ph ^ 1u);
                 // ---- DL1 leaves through the same buffer; the next tile's epilogue 1 may reuse it afterwards
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_dslab0 + 8u * g, ph);
@@ -270,56 +283,56 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint8_t* a2_row = smem + SM_A2 + row * 128;
-        const float4* sD3 = reinterpret_cast<const float4*>(smem + FB_D3);
         uint32_t ph = 0;
         for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            const int64_t lt = (tile - first) / gridDim.x;
+            const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == 0 && lt < 6;
+            long long* dc = dbg ? args.debug_clock + 10 * lt : nullptr;
+            if (dbg) dc[0] = clock64();
             // ---- epilogue 1: H1 (A2 is free once the previous tile's DL1 image has been streamed out)
             mbar_wait(bar_d1, ph);
             if (tile != first) mbar_wait(bar_free, ph ^ 1u);
+            if (dbg) dc[1] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t m1 = fb_relu_store(tlane, a2_row, row, g, lane, bar_slab0);
+            if (dbg) dc[2] = clock64();
             // ---- epilogue 2: H2 over H1 (layer 2 has completed)
             mbar_wait(bar_d2, ph);
+            if (dbg) dc[3] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t m2 = fb_relu_store(tlane + 256u, a2_row, row, g, lane, bar_hslab0);
-            // ---- epilogue 3: DL2 = (d3 . W3) [z2 > 0] over H2 (the head MMAs have completed)
-            mbar_wait(bar_d3, ph);
-            mbar_wait(bar_dl3, ph);
-            const float4 d3 = sD3[row];
+            if (dbg) dc[4] = clock64();
+            // ---- epilogue 3: DL2 = D5 [z2 > 0] over H2 (D5 complete => the head MMAs that read H2 have completed)
+            mbar_wait(bar_d5, ph);
+            if (dbg) dc[5] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
+                uint32_t rr[16];
+                tmem_ld16(tlane + (uint32_t)(s * 64 + g * 16), rr);
                 const uint32_t mb = (uint32_t)(m2 >> (16 * s)) & 0xFFFFu;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int chunk = g * 2 + c;
-                    uint4 w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        w[j] = *reinterpret_cast<const uint4*>(smem + IMG_W3 + s * 2048 + j * 128 + ((chunk ^ j) << 4));
-                    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&w[0]);
-                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&w[1]);
-                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&w[2]);
-                    const uint32_t* w3 = reinterpret_cast<const uint32_t*>(&w[3]);
                     uint32_t out[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {                                // elements 2k, 2k+1 of the chunk
-                        float lo = d3.x * bf_lo(w0[k]) + d3.y * bf_lo(w1[k]) + d3.z * bf_lo(w2[k]) + d3.w * bf_lo(w3[k]);
-                        float hi = d3.x * bf_hi(w0[k]) + d3.y * bf_hi(w1[k]) + d3.z * bf_hi(w2[k]) + d3.w * bf_hi(w3[k]);
+                    for (int k = 0; k < 4; ++k) {
                         const int i0 = c * 8 + 2 * k;
-                        lo = (mb >> (15 - i0)) & 1u ? lo : 0.0f;
-                        hi = (mb >> (14 - i0)) & 1u ? hi : 0.0f;
+                        float lo = (mb >> (15 - i0)) & 1u ? __uint_as_float(rr[i0]) : 0.0f;
+                        float hi = (mb >> (14 - i0)) & 1u ? __uint_as_float(rr[i0 + 1]) : 0.0f;
                         out[k] = pack_bf16(lo, hi);
                     }
-                    const uint4 v = make_uint4(out[0], out[1], out[2], out[3]);
-                    const int sw = (chunk ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = v;
+                    const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = make_uint4(out[0], out[1], out[2], out[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_bslab0 + 8u * s);
             }
+            if (dbg) dc[6] = clock64();
             // ---- epilogue 4: DL1 = D4 [z1 > 0] over DL2 (the backward MMAs have completed), streamed out by the MMA warp
             mbar_wait(bar_d4, ph);
+            if (dbg) dc[7] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
@@ -344,6 +357,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_dslab0 + 8u * s);
             }
+            if (dbg) dc[8] = clock64();
             ph ^= 1u;
         }
     } else {
@@ -352,7 +366,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float* sB3 = reinterpret_cast<const float*>(smem + IMG_B3);
-        float4* sD3 = reinterpret_cast<float4*>(smem + FB_D3);
+        uint8_t* d3a = smem + FB_D3A + (row >> 3) * 256 + (row & 7) * 16;   // this row's two 16-byte K chunks
+        *reinterpret_cast<uint4*>(d3a + 128) = make_uint4(0u, 0u, 0u, 0u);    // k = 8..15 stay zero
         uint32_t ph = 0;
 
         auto encode_a1 = [&](int64_t tile) {
@@ -405,9 +420,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                 const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
                 float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
                 float m2 = (use_mask && !(fl & 4u)) ? -1e9f : lg2, m3 = (use_mask && !(fl & 8u)) ? -1e9f : lg3;
-                float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                float e0 = expf(m0 - mx), e1 = expf(m1 - mx), e2 = expf(m2 - mx), e3 = expf(m3 - mx);
-                float inv = 1.0f / (e0 + e1 + e2 + e3);
+                float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));   // fast-math softmax: this thread is on the tile's critical path
+                float e0 = __expf(m0 - mx), e1 = __expf(m1 - mx), e2 = __expf(m2 - mx), e3 = __expf(m3 - mx);
+                float inv = __fdividef(1.0f, e0 + e1 + e2 + e3);
                 d0 = cf * ((act == 0u ? 1.0f : 0.0f) - e0 * inv);                // reinforce_agent.py:340-344
                 d1 = cf * ((act == 1u ? 1.0f : 0.0f) - e1 * inv);
                 d2 = cf * ((act == 2u ? 1.0f : 0.0f) - e2 * inv);
@@ -415,16 +430,20 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
             } else {
                 d0 = cf;                                                          // value head: dLoss/dV * weight
             }
-            sD3[row] = make_float4(d0, d1, d2, d3);
-            // transposed bf16 copy for dW3 = H2^T d3 (rows >= n_out of the small image stay zero)
+            // d3 as the bf16 A operand of D5 = d3 W3^T (k = 0..3 real), then release the MMA warp
+            const uint32_t p01 = pack_bf16(d0, d1), p23 = pack_bf16(d2, d3);
+            *reinterpret_cast<uint4*>(d3a) = make_uint4(p01, p23, 0u, 0u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_dl3);
+            // off the critical path: transposed bf16 copy for dW3 = H2^T d3 (rows >= n_out of the small image stay
+            // zero) and the head bias gradient (sum over the warp's 32 samples)
+            const uint32_t pk[2] = {p01, p23};
             const float dv[4] = {d0, d1, d2, d3};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (j < args.n_out) {
-                    __nv_bfloat16 b = __float2bfloat16_rn(dv[j]);
-                    *reinterpret_cast<__nv_bfloat16*>(args.d3t + small_off(s, j)) = b;
-                }
-            // head bias gradient: sum over the warp's 32 samples
+                if (j < args.n_out)
+                    *reinterpret_cast<uint16_t*>(args.d3t + small_off(s, j)) = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float v = dv[j];
@@ -432,8 +451,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
                 if (lane == 0 && j < args.n_out && v != 0.0f) atomicAdd(args.gb3 + j, v);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_dl3);
             ph ^= 1u;
         }
     }
@@ -668,9 +685,26 @@ int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         cudaError_t e = cudaMemsetAsync(a.d3t, 0, (size_t)tiles * 2 * SMALL_TILE_BYTES, stream);
         if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(d3t)");
         int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+        a.debug_clock = nullptr;
+        if (getenv("B2048_TC_DEBUG_CLOCK")) {
+            static long long* dbg_buf = nullptr;
+            if (!dbg_buf) cudaMalloc(&dbg_buf, 80 * sizeof(long long));
+            a.debug_clock = dbg_buf;
+        }
         fb_tc_kernel<<<grid, FB_THREADS, FB_TOTAL, stream>>>(a);
         int st = check_cuda(cudaGetLastError(), "fb_tc_kernel launch");
         if (st != B2048_OK) return st;
+        if (a.debug_clock && c0 == 0) {
+            long long hb[80];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(hb, a.debug_clock, sizeof(hb), cudaMemcpyDeviceToHost);
+            for (int k = 0; k < 5; ++k) {
+                long long* d = hb + 10 * k;
+                fprintf(stderr, "[fb clock] tile %d: wait_d1 %lld epi1 %lld wait_d2 %lld epi2 %lld wait_d3 %lld epi3 %lld wait_d4 %lld epi4 %lld | to next %lld\n",
+                        k, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], d[6] - d[5], d[7] - d[6], d[8] - d[7],
+                        d[10] - d[0]);
+            }
+        }
         AtbArgs g;
         g.tiles64 = tiles * 2;
         // dW2 = H1^T DL2, db2 = column sums of DL2

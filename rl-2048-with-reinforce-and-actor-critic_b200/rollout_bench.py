@@ -32,17 +32,23 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
             "ms_per_step": ms / steps, "mlp": "16-256-256-4 ReLU",
             "precision": "fp32 CUDA cores" if precision == 0 else "bf16 tcgen05 (TMEM accumulators)",
             "flops_per_step": FLOPS_PER_STEP, "achieved_tflops": rate * FLOPS_PER_STEP / 1e12,
-            "gpu_launches": 2 * steps}
+            # fp32: policy kernel + step kernel per step; tcgen05: image prep + ONE persistent policy+env kernel per
+            # 256-step chunk (policy_tc_kernel<rollout>)
+            "gpu_launches": 2 * steps if precision == 0 else 2 * ((steps + 255) // 256)}
 
 
-def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision=0):
+def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision=0, use_critic: bool = False):
     """BASELINE.json configs[2]: REINFORCE rollout (to termination, max_steps 1024) + one update (gamma 0.99,
-    baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks."""
+    baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks.
+    use_critic=True is configs[3]: actor + separate critic (reference semantics, reinforce_agent.py:403-498), TD(0)
+    advantages, Adam, both networks 16-256-256-{4,1} ReLU."""
     from . import dist as bd
     info = info or bd.DistInfo()
     env = bd.make_sharded_env(boards * info.world_size, Game2048EnvConfig(**RUNNER_ENV), info, seed=0xB200, device=dev)
-    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
-                           ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
+    acfg = (ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, critic_learning_rate=5e-4, baseline_mode="batch_norm",
+                                 use_critic=True, optimizer="adam", model_seed=0) if use_critic else
+            ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
+    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"), acfg)
     out = []
     for it in range(iters):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -64,8 +70,10 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
                     "mean_return": float(ro.total_reward().mean().item()), "actor_grad_norm": upd["actor_grad_norm"]})
     last = out[-1]
     tot_ms = last["rollout_ms"] + last["update_ms"]
-    return {"metric": "REINFORCE iteration (rollout to termination + update)", "boards_per_gpu": boards,
+    return {"metric": ("actor-critic" if use_critic else "REINFORCE") + " iteration (rollout to termination + update)",
+            "boards_per_gpu": boards,
             "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],
             "update_ms": last["update_ms"], "T": last["T"], "mean_len": last["mean_len"], "mean_return": last["mean_return"],
             "actor_grad_norm": last["actor_grad_norm"], "iters": out,
-            "exchange": "1 all-reduce of the flat fp32 gradient (71,172 floats) + 4 float64 baseline sums per update"}
+            "exchange": ("1 all-reduce per network of the flat fp32 gradient (71,172 / 70,401 floats)" if use_critic else
+                         "1 all-reduce of the flat fp32 gradient (71,172 floats)") + " + 4 float64 baseline sums per update"}

@@ -236,3 +236,54 @@ def test_update_from_rollout_tc_matches_fp32(b2048):
     print("update tc vs fp32: grad norms", g0, g1, "step rel err", rel_err(d1, d0))
     assert abs(g0 - g1) / g0 < 2e-2, (g0, g1)
     assert rel_err(d1, d0) < 6e-2, rel_err(d1, d0)
+
+
+def test_tc_value_forward_vs_fp32(b2048):
+    """b2048_mlp_forward precision=1 (critic V(s) on tcgen05) vs the fp32 kernel: 1e-2 relative."""
+    from b2048 import _lib
+    lib = _lib.load()
+    n = 20000 + 11
+    rng = np.random.default_rng(9)
+    boards = random_boards(rng, n)
+    agent = make_agent(b2048, use_critic=True, seed=4)
+    p = agent.critic_params
+    p["b"] = [rng.normal(size=b.shape).astype(np.float32) * 0.1 for b in p["b"]]
+    agent.critic_params = p
+    bd = dev64(boards)
+    outs = []
+    for prec in (0, 1):
+        out = torch.zeros(n, dtype=torch.float32, device="cuda")
+        agent._values(bd, out, prec)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    ref, _, _ = learner.forward(agent.critic_params, learner.encode(boards, "log2", 0.0625), "ReLU")
+    assert rel_err(outs[0], ref[:, 0]) < 1e-3
+    assert rel_err(outs[1], ref[:, 0]) < 1e-2, rel_err(outs[1], ref[:, 0])
+
+
+def test_actor_critic_update_tc_matches_fp32(b2048):
+    """Actor-critic update (critic forward -> TD errors -> critic grads -> baseline-processed TD advantages -> actor
+    grads -> Adam on both networks) with every GEMM on tensor cores vs the fp32 kernels."""
+    from helpers import full_env_kwargs
+    n, seed = 8192, 33
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 40
+    outs = []
+    for prec in (0, 1):
+        benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=0)
+        agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode="batch_norm", learning_rate=1e-3,
+                                                                critic_learning_rate=5e-4, use_critic=True, optimizer="adam",
+                                                                model_seed=5))
+        a0 = agent._actor.theta.cpu().numpy().copy(); c0 = agent._critic.theta.cpu().numpy().copy()
+        ro = agent.rollout_many(benv, precision=0)
+        info = agent.update_from_rollout(ro, precision=prec)
+        outs.append((agent._actor.theta.cpu().numpy() - a0, agent._critic.theta.cpu().numpy() - c0,
+                     info["actor_grad_norm"], info["critic_grad_norm"], info["td"].cpu().numpy().copy()))
+    (da0, dc0, ga0, gc0, td0), (da1, dc1, ga1, gc1, td1) = outs
+    print("actor-critic tc vs fp32: grad norms", (ga0, ga1), (gc0, gc1), "td rel err", rel_err(td1, td0))
+    assert rel_err(td1, td0) < 1e-2
+    assert abs(ga0 - ga1) / ga0 < 3e-2 and abs(gc0 - gc1) / gc0 < 3e-2
+    # Adam normalises every coordinate to ~lr, so the parameter step is compared by direction
+    cos_a = float(np.dot(da0, da1) / (np.linalg.norm(da0) * np.linalg.norm(da1)))
+    cos_c = float(np.dot(dc0, dc1) / (np.linalg.norm(dc0) * np.linalg.norm(dc1)))
+    assert cos_a > 0.9 and cos_c > 0.9, (cos_a, cos_c)
