@@ -145,18 +145,14 @@ def run_reference(args):
     steps, warm = max(1, args.steps), args.warmup
     from oracle import pyport
     cores = len(os.sched_getaffinity(0))
-    # each "step" is a bounded sample: ~1 s of all-core stepping; total capped to a few minutes
-    per = min(1.0, 150.0 / (steps + warm))
-    for _ in range(warm):
-        pyport.time_multiprocess(per, cores)
+    # each "step" is a bounded sample of all-core stepping on one persistent worker pool; the whole run is capped
+    # at about a minute and a half of CPU work whatever K is
+    per = min(1.0, 90.0 / (steps + warm))
     t0 = time.perf_counter()
-    total = 0
-    rate_acc = 0.0
-    for _ in range(steps):
-        rate, n = pyport.time_multiprocess(per, cores)
-        total += n
-        rate_acc += rate
-    wall = time.perf_counter() - t0
+    samples = pyport.time_multiprocess_series(per, cores, steps + warm)[warm:]
+    wall = (time.perf_counter() - t0) * steps / (steps + warm)
+    total = sum(n for _, n in samples)
+    rate_acc = sum(r for r, _ in samples)
     value = rate_acc / steps
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
@@ -265,8 +261,14 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 1, "d2h_bytes_per_step": n * 13,
                     "steps": Ke, "checksum": checksum},
             "gpu_launches": K,
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on 1,048,576 boards
+            # from the `ncu --set full` capture summarised in profiles/r01_ncu_step_fast_kernel.csv (19.09 MB read: the
+            # boards, masks, counters and the row tables; the 14 MB of outputs are still in the 126 MB L2 when
+            # the profiled launch ends, so they do not show up as DRAM writes)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": 19089152 if (n == BOARDS_PER_GPU and not args.lean) else None,
+                         "traffic_source": "profiles/r01_ncu_step_fast_kernel.csv (bytes per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "b2::step_fast_kernel<RANDOM_LEGAL, %s>" % ("false" if args.lean else "true"),
                          "avg_launch_us": per_launch_s * 1e6},
         }
@@ -289,7 +291,7 @@ def run_b200(args):
                 extra[key] = r
             extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision=1)
             extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision=1,
-                                                                      use_critic=True)
+                                                                      use_critic=True, iters=3)
         except Exception as e:
             extra["rollout_error"] = repr(e)
     if rank == 0:

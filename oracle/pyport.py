@@ -219,3 +219,15 @@ def time_multiprocess(seconds: float, procs: int) -> tuple[float, int]:
         res = pool.map(_worker, [(seconds, 1000 + i) for i in range(procs)])
     rate = sum(n / dt for n, dt in res)
     return rate, sum(n for n, _ in res)
+
+
+def time_multiprocess_series(seconds: float, procs: int, count: int) -> list[tuple[float, int]]:
+    """`count` consecutive samples of time_multiprocess on ONE worker pool (no per-sample fork cost)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    out = []
+    with ctx.Pool(procs) as pool:
+        for k in range(count):
+            res = pool.map(_worker, [(seconds, 1000 + 131 * k + i) for i in range(procs)])
+            out.append((sum(n / dt for n, dt in res), sum(n for n, _ in res)))
+    return out

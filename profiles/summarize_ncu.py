@@ -11,6 +11,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.max.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg", "sm__cycles_elapsed.max",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
@@ -27,11 +28,11 @@ def main(rep, out):
     name_i = hdr.index("Kernel Name")
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["kernel", "metric", "unit"] + [f"launch{k}" for k in range(len(data))])
+        w.writerow(["metric", "unit"] + [f"launch{k}: {r[name_i][:48]}" for k, r in enumerate(data)])
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)
-                w.writerow([data[0][name_i][:60], k, units[i]] + [r[i] for r in data])
+                w.writerow([k, units[i]] + [r[i] for r in data])
 
 
 if __name__ == "__main__":
