@@ -150,6 +150,15 @@ int b2048_move_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_o
                     uint8_t* flags, int64_t n, void* stream);
 
 /* Observation encode only (Game2048Env._preprocess_board, env.py:131-150). */
+/* The 8 dihedral variants of (board, action, legal mask): Game2048Env.get_symmetries (env.py:317-397) and
+ * ReinforceAgent._augment_trajectories (reinforce_agent.py:773-808) on packed boards.  Inputs are [rows][n]
+ * (any of the three may be NULL together with its output); outputs are [rows][8 n], variant v of element (r, i) at
+ * r * 8n + v * n + i, variants in the reference's order (identity, three counter-clockwise quarter turns, then the
+ * same four for the left-right mirror).  The upper four flag bits are copied. */
+int b2048_symmetries(b2048_handle* h, const uint64_t* board, const uint8_t* flags, const uint8_t* action,
+                     uint64_t* board_out, uint8_t* flags_out, uint8_t* action_out, int64_t rows, int64_t n,
+                     void* stream);
+
 int b2048_encode_obs(const uint64_t* board, float* obs, int32_t obs_mode, float obs_log2_scale,
                      int64_t n, void* stream);
 

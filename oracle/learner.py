@@ -228,3 +228,37 @@ def backprop_bf16(params, X, mask_bits, actions, coef, head_mode):
     gW = [A1.T @ DL1, H1.T @ DL2, H2.T @ d3b]
     gb = [DL1.sum(0), DL2.sum(0), d3.sum(0)]
     return gW, gb, dict(A1=A1, H1=H1, H2=H2, d3=d3, DL2=DL2, DL1=DL1)
+
+
+# ---------------------------------------------------------------------------------------------- D4 symmetries
+def symmetries(boards, masks, actions):
+    """Game2048Env.get_symmetries (src/env.py:317-397) restated on packed boards, 4-bit masks and actions.
+    Returns (boards [8, n] uint64, masks [8, n] uint8, actions [8, n] uint8) in the reference's variant order:
+    identity + three np.rot90(k=1) turns (action (a-1)%4, mask np.roll(-1)), then the same four starting from
+    np.fliplr (actions 1 <-> 3, mask [0,3,2,1])."""
+    b = np.asarray(boards, dtype=np.uint64)
+    n = len(b)
+    cells = np.stack([((b >> np.uint64(4 * i)) & np.uint64(15)).astype(np.int64) for i in range(16)], axis=1).reshape(n, 4, 4)
+    mk = np.stack([(np.asarray(masks) >> k) & 1 for k in range(4)], axis=1).astype(np.int64)
+    ac = np.asarray(actions).astype(np.int64)
+    ob, om, oa = [], [], []
+
+    def pack(c):
+        flat = c.reshape(n, 16)
+        out = np.zeros(n, np.uint64)
+        for i in range(16):
+            out |= flat[:, i].astype(np.uint64) << np.uint64(4 * i)
+        return out
+
+    for flipped in (False, True):
+        cb = cells[:, :, ::-1].copy() if flipped else cells.copy()                  # np.fliplr per board
+        ca = np.where(ac == 1, 3, np.where(ac == 3, 1, ac)) if flipped else ac.copy()
+        cm = mk[:, [0, 3, 2, 1]].copy() if flipped else mk.copy()
+        for _ in range(4):
+            ob.append(pack(cb))
+            om.append(sum(cm[:, k] << k for k in range(4)).astype(np.uint8))
+            oa.append(ca.astype(np.uint8))
+            cb = np.rot90(cb, k=1, axes=(1, 2)).copy()
+            ca = (ca - 1) % 4
+            cm = np.roll(cm, shift=-1, axis=1)
+    return np.stack(ob), np.stack(om), np.stack(oa)

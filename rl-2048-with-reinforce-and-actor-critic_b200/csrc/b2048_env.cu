@@ -415,6 +415,56 @@ __global__ void __launch_bounds__(256) obs_kernel(const uint64_t* __restrict__ b
     }
 }
 
+// ------------------------------------------------------------------------------------------------ D4 symmetries
+// Game2048Env.get_symmetries (src/env.py:317-397) / _augment_trajectories (src/reinforce_agent.py:773-808) on packed
+// boards: variant v of (board, action, mask) is a nibble permutation of the board, a relabelling of the action and
+// a permutation of the four mask bits.  Variants in the reference's order: identity + three counter-clockwise
+// quarter turns (np.rot90 k=1, action (a-1)%4, mask roll -1), then the same four for the left-right mirror
+// (np.fliplr, actions 1 <-> 3, mask [0,3,2,1]).
+struct SymVariant {
+    uint64_t perm;    // nibble i = source cell of destination cell i
+    uint32_t amap;    // bits 2a..2a+1 = new label of action a
+    uint32_t mperm;   // bits 2i..2i+1 = source mask bit of destination mask bit i
+};
+__constant__ SymVariant kSym[8] = {
+    {0xFEDCBA9876543210ull, 0xE4u, 0xE4u}, {0xC840D951EA62FB73ull, 0x93u, 0x39u},
+    {0x0123456789ABCDEFull, 0x4Eu, 0x4Eu}, {0x37BF26AE159D048Cull, 0x39u, 0x93u},
+    {0xCDEF89AB45670123ull, 0x6Cu, 0x6Cu}, {0xFB73EA62D951C840ull, 0x1Bu, 0x1Bu},
+    {0x32107654BA98FEDCull, 0xC6u, 0xC6u}, {0x048C159D26AE37BFull, 0xB1u, 0xB1u},
+};
+
+// out arrays are [rows][8 * n]: variant v of element (r, i) goes to r * 8n + v * n + i, i.e. the batch axis becomes
+// eight concatenated copies (what update_batch sees after _augment_trajectories).
+__global__ void __launch_bounds__(256) symmetries_kernel(const uint64_t* __restrict__ board, const uint8_t* __restrict__ flags,
+                                                          const uint8_t* __restrict__ action, uint64_t* __restrict__ board_out,
+                                                          uint8_t* __restrict__ flags_out, uint8_t* __restrict__ action_out,
+                                                          int64_t rows, int64_t n) {
+    const int64_t total = rows * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / n, i = e - r * n;
+        const uint64_t b = board ? board[e] : 0ull;
+        const uint32_t f = flags ? flags[e] : 0u, a = action ? (action[e] & 3u) : 0u;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const SymVariant sv = kSym[v];
+            const int64_t o = r * 8 * n + (int64_t)v * n + i;
+            if (board_out) {
+                uint64_t nb = 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) nb |= ((b >> (4 * (uint32_t)((sv.perm >> (4 * c)) & 0xFull))) & 0xFull) << (4 * c);
+                board_out[o] = nb;
+            }
+            if (flags_out) {
+                uint32_t nf = f & 0xF0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nf |= ((f >> ((sv.mperm >> (2 * k)) & 3u)) & 1u) << k;
+                flags_out[o] = (uint8_t)nf;
+            }
+            if (action_out) action_out[o] = (uint8_t)((sv.amap >> (2 * a)) & 3u);
+        }
+    }
+}
+
 static int grid_for(int64_t n, int threads, int num_sms, int per_sm) {
     int64_t blocks = (n + threads - 1) / threads;
     int64_t cap = (int64_t)num_sms * per_sm;
@@ -552,6 +602,21 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
             fprintf(stderr, " | total %lld cyc, %lld ns\n", d[14] - d[1], d[15] - d[0]);
         }
     }
+    return B2048_OK;
+}
+
+extern "C" int b2048_symmetries(b2048_handle* h, const uint64_t* board, const uint8_t* flags, const uint8_t* action,
+                                uint64_t* board_out, uint8_t* flags_out, uint8_t* action_out, int64_t rows, int64_t n,
+                                void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_symmetries: handle is NULL");
+    B2_REQUIRE(rows >= 0 && n >= 0, "b2048_symmetries: negative size");
+    if (rows == 0 || n == 0) return B2048_OK;
+    B2_REQUIRE((board == nullptr) == (board_out == nullptr) && (flags == nullptr) == (flags_out == nullptr) &&
+                   (action == nullptr) == (action_out == nullptr),
+               "b2048_symmetries: every input needs its output buffer and vice versa");
+    symmetries_kernel<<<grid_for(rows * n, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        board, flags, action, board_out, flags_out, action_out, rows, n);
+    B2_CUDA(cudaGetLastError());
     return B2048_OK;
 }
 

@@ -1,7 +1,8 @@
 """D4 symmetry augmentation on packed boards (reference src/env.py:317-397 ``get_symmetries`` and
 src/reinforce_agent.py:773-808 ``_augment_trajectories``): the 8 (board, action, mask) variants are
 nibble permutations of the packed board, a relabelling of the action and a permutation of the 4 mask
-bits.  Pure data movement on the device (no arithmetic), expressed with torch indexing."""
+bits.  ``augment_rollout`` runs the CUDA kernel behind ``b2048_symmetries`` (include/b2048.h); the
+``transform_*`` helpers restate the same permutations with torch indexing (used by the tests)."""
 from __future__ import annotations
 
 import numpy as np
@@ -51,13 +52,25 @@ def transform_flags(flags: torch.Tensor, variant: int) -> torch.Tensor:
 
 def augment_rollout(ro):
     """Rollout with 8x the episodes (every dihedral variant), weights repeated, n_traj = 8 B."""
+    import ctypes as C
+    from . import _lib
+    from .batched_env import get_handle
     from .reinforce_agent import Rollout
-    T = ro.T
-    boards = torch.cat([transform_boards(ro.boards, v) for v in range(8)], dim=1)
-    flags = torch.cat([transform_flags(ro.flags, v) for v in range(8)], dim=1)
-    actions = torch.cat([transform_actions(ro.actions, v) for v in range(8)], dim=1)
+    T, B = ro.T, ro.B
+    dev = ro.boards.device
+    boards = torch.empty((T + 1, 8 * B), dtype=torch.int64, device=dev)
+    flags = torch.empty((T + 1, 8 * B), dtype=torch.uint8, device=dev)
+    actions = torch.empty((T, 8 * B), dtype=torch.uint8, device=dev)
+    lib, h = _lib.load(), get_handle(dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    src_b, src_f, src_a = ro.boards[: T + 1].contiguous(), ro.flags[: T + 1].contiguous(), ro.actions[:T].contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(lib.b2048_symmetries(h, p(src_b), p(src_f), None, p(boards), p(flags), None, T + 1, B, stream),
+                   "b2048_symmetries")
+        if T > 0:
+            _lib.check(lib.b2048_symmetries(h, None, None, p(src_a), None, None, p(actions), T, B, stream), "b2048_symmetries")
     rewards = ro.rewards.repeat(1, 8)
     length = ro.length.repeat(8)
     w = None if ro.ep_weight is None else ro.ep_weight.repeat(8)
-    return Rollout(boards.contiguous(), flags.contiguous(), actions.contiguous(), rewards.contiguous(), length, T, w,
-                   8 * ro.B)
+    return Rollout(boards, flags, actions, rewards.contiguous(), length, T, w, 8 * B)

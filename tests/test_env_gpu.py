@@ -295,3 +295,59 @@ def test_step_many_full_size_1m(b2048):
         prev_score = env.score.clone()
     m, d = oracle.mask_done(u64(env.board)[:100000])
     assert ((env.flags.cpu().numpy()[:100000] & 0x0F) == m).all()
+
+
+def test_symmetries_kernel_vs_reference_and_oracle(b2048):
+    """b2048_symmetries vs the reference's get_symmetries outputs (fixture) and vs the oracle on a larger batch;
+    augment_rollout uses it."""
+    import ctypes as C
+    from oracle import learner
+    from b2048 import _lib
+    lib = _lib.load()
+    h = b2048.batched_env.get_handle(torch.device("cuda", torch.cuda.current_device()))
+    g = np.load(os.path.join(GOLDEN, "symmetries.npz"))
+    rng = np.random.default_rng(4)
+    big_b = random_boards(rng, 3 * 5001).reshape(3, 5001)
+    big_m = rng.integers(0, 256, (3, 5001)).astype(np.uint8)
+    big_a = rng.integers(0, 4, (3, 5001)).astype(np.uint8)
+    for boards, masks, actions, want in ((g["boards"][None], g["masks"][None], g["actions"][None],
+                                          (g["out_boards"], g["out_masks"], g["out_actions"])), (big_b, big_m, big_a, None)):
+        rows, n = boards.shape
+        bd = torch.from_numpy(boards.view(np.int64)).cuda(); fl = torch.from_numpy(masks).cuda(); ac = torch.from_numpy(actions).cuda()
+        ob = torch.zeros((rows, 8 * n), dtype=torch.int64, device="cuda")
+        of = torch.zeros((rows, 8 * n), dtype=torch.uint8, device="cuda")
+        oa = torch.zeros((rows, 8 * n), dtype=torch.uint8, device="cuda")
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(lib.b2048_symmetries(h, p(bd), p(fl), p(ac), p(ob), p(of), p(oa), rows, n,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "b2048_symmetries")
+        torch.cuda.synchronize()
+        ob = ob.cpu().numpy().view(np.uint64).reshape(rows, 8, n); of = of.cpu().numpy().reshape(rows, 8, n)
+        oa = oa.cpu().numpy().reshape(rows, 8, n)
+        for r in range(rows):
+            eb, em, ea = learner.symmetries(boards[r], masks[r] & 0xF, actions[r])
+            assert (ob[r] == eb).all() and ((of[r] & 0xF) == em).all() and (oa[r] == ea).all()
+            assert ((of[r] & 0xF0) == (masks[r] & 0xF0)[None]).all()          # upper flag bits are copied
+        if want is not None:
+            assert (ob[0] == want[0]).all() and (of[0] == want[1]).all() and (oa[0] == want[2]).all()
+
+
+def test_augment_rollout_kernel_equals_torch_restatement(b2048):
+    """augment_rollout (b2048_symmetries kernel) vs the torch-indexing restatement of the same permutations."""
+    from b2048 import symmetry
+    from b2048.reinforce_agent import Rollout
+    rng = np.random.default_rng(8)
+    T, B = 5, 777
+    boards = torch.from_numpy(random_boards(rng, (T + 1) * B).reshape(T + 1, B).view(np.int64)).cuda()
+    flags = torch.from_numpy(rng.integers(0, 256, (T + 1, B)).astype(np.uint8)).cuda()
+    actions = torch.from_numpy(rng.integers(0, 4, (T, B)).astype(np.uint8)).cuda()
+    rewards = torch.from_numpy(rng.random((T, B)).astype(np.float32)).cuda()
+    length = torch.from_numpy(rng.integers(1, T + 1, B).astype(np.int32)).cuda()
+    ro = symmetry.augment_rollout(Rollout(boards, flags, actions, rewards, length, T))
+    torch.cuda.synchronize()
+    assert ro.B == 8 * B and ro.n_traj == 8 * B
+    for v in range(8):
+        sl = slice(v * B, (v + 1) * B)
+        assert torch.equal(ro.boards[:, sl], symmetry.transform_boards(boards, v))
+        assert torch.equal(ro.flags[:, sl], symmetry.transform_flags(flags, v))
+        assert torch.equal(ro.actions[:, sl], symmetry.transform_actions(actions, v))
+        assert torch.equal(ro.rewards[:, sl], rewards) and torch.equal(ro.length[sl], length)

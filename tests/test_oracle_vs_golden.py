@@ -168,3 +168,38 @@ def test_oracle_against_live_reference_random_episode():
         assert term == bool(o["flags"][0] & oracle.F_DONE) and trunc == bool(o["flags"][0] & oracle.F_TRUNC)
         if term or trunc:
             break
+
+
+def test_symmetries_oracle_vs_reference_fixture():
+    """oracle/learner.symmetries vs Game2048Env.get_symmetries outputs (tests/golden/symmetries.npz)."""
+    from oracle import learner
+    g = np.load(os.path.join(GOLDEN, "symmetries.npz"))
+    ob, om, oa = learner.symmetries(g["boards"], g["masks"], g["actions"])
+    assert (ob == g["out_boards"]).all() and (om == g["out_masks"]).all() and (oa == g["out_actions"]).all()
+
+
+def test_symmetry_kernel_tables_match_reference_fixture():
+    """The permutation constants compiled into symmetries_kernel (csrc/b2048_env.cu), applied on the CPU, reproduce
+    the reference's 8 variants — so the GPU kernel is pinned to the reference even without a GPU."""
+    import re
+    from helpers import ROOT
+    src = open(os.path.join(ROOT, "rl-2048-with-reinforce-and-actor-critic_b200", "csrc", "b2048_env.cu")).read()
+    body = src[src.index("__constant__ SymVariant kSym[8]"):]
+    body = body[:body.index("};")]
+    ent = re.findall(r"\{0x([0-9A-F]{16})ull, 0x([0-9A-F]{2})u, 0x([0-9A-F]{2})u\}", body)
+    assert len(ent) == 8
+    g = np.load(os.path.join(GOLDEN, "symmetries.npz"))
+    b, m, a = g["boards"], g["masks"].astype(np.uint32), g["actions"].astype(np.uint32)
+    for v, (perm, amap, mperm) in enumerate(ent):
+        perm, amap, mperm = int(perm, 16), int(amap, 16), int(mperm, 16)
+        nb = np.zeros_like(b)
+        for c in range(16):
+            src_cell = (perm >> (4 * c)) & 15
+            nb |= ((b >> np.uint64(4 * src_cell)) & np.uint64(15)) << np.uint64(4 * c)
+        nm = np.zeros_like(m)
+        for k in range(4):
+            nm |= ((m >> ((mperm >> (2 * k)) & 3)) & 1) << k
+        na = (amap >> (2 * a)) & 3
+        assert (nb == g["out_boards"][v]).all(), v
+        assert (nm == g["out_masks"][v]).all(), v
+        assert (na == g["out_actions"][v]).all(), v
