@@ -21,8 +21,8 @@ from b2048 import dist as bd  # noqa: E402
 ENV = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", base_reward_scale=0.5, max_steps=200)
 
 
-def make_agent(env, baseline):
-    return b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[64, 64], activation="ReLU", init_distribution="HeNormal"),
+def make_agent(env, baseline, hidden=(64, 64)):
+    return b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=list(hidden), activation="ReLU", init_distribution="HeNormal"),
                                 b2048.ReinforceAgentConfig(gamma=0.99, learning_rate=1e-2, baseline_mode=baseline, model_seed=3))
 
 
@@ -69,6 +69,38 @@ def main():
             gn = abs(upd["actor_grad_norm"] - u1["actor_grad_norm"]) / u1["actor_grad_norm"]
             print(f"baseline={baseline}: update rel err {rel:.2e}, grad-norm rel err {gn:.2e}")
             assert rel < 1e-3 and gn < 1e-3
+    # ---- 3. tensor-core paths (16-256-256-4): the fused rollout kernel is sharding-invariant bit for bit (Philox is
+    #         keyed on the global board id), and the all-reduced tcgen05 update equals the single-process one up to
+    #         the fp32 summation order of the gradient atomics
+    env = bd.make_sharded_env(total, cfg, info, seed=seed + 2)
+    agent = make_agent(env, "batch", hidden=(256, 256))
+    ro = agent.rollout_many(env, precision=1)
+    lo, hi = bd.shard_range(total, info.rank, info.world_size)
+    T_all = torch.tensor([ro.T], device=dev)
+    dist.all_reduce(T_all, op=dist.ReduceOp.MAX)
+    Tm = int(T_all.item())
+    acts = torch.zeros((Tm, total), dtype=torch.int32, device=dev)
+    lens = torch.zeros(total, dtype=torch.int32, device=dev)
+    acts[: ro.T, lo:hi] = ro.actions.int() * (torch.arange(ro.T, device=dev).unsqueeze(1) < ro.length.unsqueeze(0))
+    lens[lo:hi] = ro.length
+    bd.allreduce_sum_(acts)
+    bd.allreduce_sum_(lens)
+    upd = bd.sharded_update(agent, ro, info)
+    theta = agent._actor.theta.clone()
+    if info.rank == 0:
+        env1 = b2048.Batched2048Env(total, cfg, device=dev, seed=seed + 2)
+        a1 = make_agent(env1, "batch", hidden=(256, 256))
+        th0 = a1._actor.theta.clone()
+        r1 = a1.rollout_many(env1, precision=1)
+        assert torch.equal(r1.length, lens), "fused rollout: episode lengths differ between sharded and single-GPU runs"
+        live = torch.arange(r1.T, device=dev).unsqueeze(1) < r1.length.unsqueeze(0)
+        assert torch.equal((r1.actions.int() * live)[:Tm], acts[: r1.T]), "fused rollout: actions differ"
+        u1 = a1.update_from_rollout(r1, precision=1)
+        d_ref, d_got = a1._actor.theta - th0, theta - th0
+        rel = float((d_got - d_ref).norm() / d_ref.norm())
+        gn = abs(upd["actor_grad_norm"] - u1["actor_grad_norm"]) / u1["actor_grad_norm"]
+        print(f"tensor-core path: fused rollout sharding invariance OK; update rel err {rel:.2e}, grad-norm rel err {gn:.2e}")
+        assert rel < 1e-3 and gn < 1e-3
     dist.barrier()
     if info.rank == 0:
         print("multi-GPU check OK")
