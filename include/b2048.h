@@ -67,7 +67,10 @@ enum { B2048_BONUS_OFF = 0, B2048_BONUS_RAW = 1, B2048_BONUS_LOG2 = 2 }; /* env.
 enum { B2048_OBS_NONE = 0, B2048_OBS_RAW = 1, B2048_OBS_LOG2 = 2, B2048_OBS_ONEHOT = 3 }; /* env.py:131-150 */
 enum { B2048_ACT_BUFFER = 0,      /* actions read from the `action` buffer */
        B2048_ACT_RANDOM_LEGAL = 1,/* uniform over the legal mask (tools/simple_action_gen.py:7-13) from Philox w2 */
-       B2048_ACT_RANDOM_ANY = 2   /* uniform over {0,1,2,3}, illegal moves included */ };
+       B2048_ACT_RANDOM_ANY = 2,  /* uniform over {0,1,2,3}, illegal moves included */
+       B2048_ACT_PRIORITY = 3     /* first LEGAL action in the fixed order cfg.action_priority (nibble k = k-th
+                                     choice): tools/simple_action_gen.py:16-33, 0x3210 = up,right,down,left
+                                     (action_gen_1), 0x2310 = up,right,left,down (action_gen_2); 0 if none is legal */ };
 
 /* Mirrors Game2048EnvConfig (env.py:19-40); doubles because the reference
  * combines the reward in Python float64 (env.py:197-261). */
@@ -79,7 +82,7 @@ typedef struct b2048_env_cfg {
     int32_t max_steps;              /* env.py:40; <= 0 means None (never truncate) */
     int32_t action_mode;            /* B2048_ACT_*      */
     int32_t auto_reset;             /* 1: a board that terminated/truncated is reset in the same call */
-    int32_t reserved;
+    int32_t action_priority;        /* B2048_ACT_PRIORITY only (else 0) */
     double base_reward_scale;       /* env.py:27 */
     double empty_tile_reward;       /* env.py:29 */
     double merge_reward;            /* env.py:30 */

@@ -30,7 +30,7 @@ class EnvCfg(C.Structure):
     _fields_ = [
         ("reward_mode", C.c_int32), ("bonus_mode", C.c_int32), ("obs_mode", C.c_int32),
         ("use_action_mask", C.c_int32), ("max_steps", C.c_int32), ("action_mode", C.c_int32),
-        ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("auto_reset", C.c_int32), ("action_priority", C.c_int32),
         ("base_reward_scale", C.c_double), ("empty_tile_reward", C.c_double), ("merge_reward", C.c_double),
         ("bonus_scale", C.c_double), ("step_reward", C.c_double), ("endgame_penalty", C.c_double),
         ("invalid_action_penalty", C.c_double), ("obs_log2_scale", C.c_float), ("reserved_f", C.c_float),
@@ -40,7 +40,7 @@ class EnvCfg(C.Structure):
 REWARD = {"sum": 0, "log2": 1}
 BONUS = {"off": 0, "raw": 1, "log2": 2}
 OBS = {"none": 0, "raw": 1, "log2": 2, "onehot": 3}
-ACT = {"buffer": 0, "random_legal": 1, "random_any": 2}
+ACT = {"buffer": 0, "random_legal": 1, "random_any": 2, "priority": 3}
 
 F_MASK, F_CHANGED, F_DONE, F_TRUNC, F_OVERFLOW = 0x0F, 0x10, 0x20, 0x40, 0x80
 
@@ -48,9 +48,10 @@ F_MASK, F_CHANGED, F_DONE, F_TRUNC, F_OVERFLOW = 0x0F, 0x10, 0x20, 0x40, 0x80
 def make_cfg(reward_mode="sum", bonus_mode="off", obs_mode="none", use_action_mask=True, max_steps=1024,
              action_mode="buffer", auto_reset=False, base_reward_scale=1.0, empty_tile_reward=0.0,
              merge_reward=0.0, bonus_scale=1.0, step_reward=0.0, endgame_penalty=0.0,
-             invalid_action_penalty=-1.0, obs_log2_scale=1.0) -> EnvCfg:
+             invalid_action_penalty=-1.0, obs_log2_scale=1.0, action_priority=(0, 1, 2, 3)) -> EnvCfg:
+    prio = sum(int(a) << (4 * k) for k, a in enumerate(action_priority)) if action_mode == "priority" else 0
     return EnvCfg(REWARD[reward_mode], BONUS[bonus_mode], OBS[obs_mode], int(bool(use_action_mask)),
-                  int(max_steps) if max_steps else 0, ACT[action_mode], int(bool(auto_reset)), 0,
+                  int(max_steps) if max_steps else 0, ACT[action_mode], int(bool(auto_reset)), prio,
                   float(base_reward_scale), float(empty_tile_reward), float(merge_reward), float(bonus_scale),
                   float(step_reward), float(endgame_penalty), float(invalid_action_penalty),
                   float(obs_log2_scale), 0.0)

@@ -280,6 +280,13 @@ int orc_step_many(const uint64_t* board_in, uint64_t* board_out,
             a = action[i] & 3;
         } else if (cfg->action_mode == B2048_ACT_RANDOM_ANY) {
             a = (int)(w[2] >> 30);
+        } else if (cfg->action_mode == B2048_ACT_PRIORITY) { /* tools/simple_action_gen.py:16-33: first legal in a fixed order */
+            int m = action_mask(cell);
+            a = 0;
+            for (int k = 3; k >= 0; --k) {
+                int c = (cfg->action_priority >> (4 * k)) & 3;
+                if (m >> c & 1) a = c;
+            }
         } else { /* uniform over legal moves; falls back to 0 if none is legal */
             int m = action_mask(cell), nl = 0, legal[4];
             for (int k = 0; k < 4; ++k)

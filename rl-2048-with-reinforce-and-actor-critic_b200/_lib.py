@@ -15,7 +15,7 @@ B2048_MAX_LAYERS = 8
 REWARD = {"sum": 0, "log2": 1}
 BONUS = {"off": 0, "raw": 1, "log2": 2}
 OBS = {"none": 0, "raw": 1, "log2": 2, "onehot": 3}
-ACT = {"buffer": 0, "random_legal": 1, "random_any": 2}
+ACT = {"buffer": 0, "random_legal": 1, "random_any": 2, "priority": 3}
 ACTV = {"Sigmoid": 0, "ReLU": 1}
 
 F_MASK, F_CHANGED, F_DONE, F_TRUNC, F_OVERFLOW = 0x0F, 0x10, 0x20, 0x40, 0x80
@@ -27,7 +27,7 @@ class EnvCfg(C.Structure):
     _fields_ = [
         ("reward_mode", C.c_int32), ("bonus_mode", C.c_int32), ("obs_mode", C.c_int32),
         ("use_action_mask", C.c_int32), ("max_steps", C.c_int32), ("action_mode", C.c_int32),
-        ("auto_reset", C.c_int32), ("reserved", C.c_int32),
+        ("auto_reset", C.c_int32), ("action_priority", C.c_int32),
         ("base_reward_scale", C.c_double), ("empty_tile_reward", C.c_double), ("merge_reward", C.c_double),
         ("bonus_scale", C.c_double), ("step_reward", C.c_double), ("endgame_penalty", C.c_double),
         ("invalid_action_penalty", C.c_double), ("obs_log2_scale", C.c_float), ("reserved_f", C.c_float),

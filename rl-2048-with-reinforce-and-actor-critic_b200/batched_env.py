@@ -38,7 +38,7 @@ class Game2048EnvConfig:
 
 
 def make_env_cfg(config: Game2048EnvConfig, action_mode: str = "buffer", auto_reset: bool = False,
-                 emit_obs: bool = True) -> EnvCfg:
+                 emit_obs: bool = True, action_priority=(0, 1, 2, 3)) -> EnvCfg:
     if config.size != 4:
         raise ValueError(f"only size=4 boards are packable into 16 x 4-bit exponents (got size={config.size})")
     if config.obs_mode not in ("raw", "log2", "onehot"):
@@ -49,7 +49,9 @@ def make_env_cfg(config: Game2048EnvConfig, action_mode: str = "buffer", auto_re
         raise ValueError(f"Unsupported bonus mode: {config.bonus_mode}")      # src/env.py:249
     return EnvCfg(REWARD[config.reward_mode], BONUS[config.bonus_mode], OBS[config.obs_mode] if emit_obs else 0,
                   int(bool(config.use_action_mask)), int(config.max_steps) if config.max_steps else 0,
-                  ACT[action_mode], int(bool(auto_reset)), 0, float(config.base_reward_scale),
+                  ACT[action_mode], int(bool(auto_reset)),
+                  sum(int(a) << (4 * k) for k, a in enumerate(action_priority)) if action_mode == "priority" else 0,
+                  float(config.base_reward_scale),
                   float(config.empty_tile_reward), float(config.merge_reward), float(config.bonus_scale),
                   float(config.step_reward), float(config.endgame_penalty), float(config.invalid_action_penalty),
                   float(config.obs_log2_scale), 0.0)
@@ -130,9 +132,12 @@ class Batched2048Env:
                   reward64_out: torch.Tensor | None = None, board_out: torch.Tensor | None = None,
                   reward_out: torch.Tensor | None = None, flags_out: torch.Tensor | None = None,
                   use_prev_mask: bool = True, spawn_replay: torch.Tensor | None = None,
-                  ep_len: torch.Tensor | None = None, ep_t: int = 0, flags_in: torch.Tensor | None = None):
+                  ep_len: torch.Tensor | None = None, ep_t: int = 0, flags_in: torch.Tensor | None = None,
+                  action_priority=(0, 1, 2, 3)):
         """One env step for every board.  ``actions`` uint8 [N] on the device, or None with
-        ``action_mode`` 'random_legal' / 'random_any' (device-side Philox actions).
+        ``action_mode`` 'random_legal' / 'random_any' (device-side Philox actions) or 'priority' (the first legal
+        action in the order ``action_priority`` — the reference's scripted baselines, tools/simple_action_gen.py:16-33:
+        (0, 1, 2, 3) = up, right, down, left; (0, 1, 3, 2) = up, right, left, down).
 
         Returns (reward float32 [N], flags uint8 [N]); boards are updated in place (or written to
         ``board_out``, e.g. the next slice of a rollout buffer)."""
@@ -142,11 +147,11 @@ class Batched2048Env:
                 raise ValueError("actions required for action_mode='buffer'")
             if actions.dtype != torch.uint8 or actions.device != self.device or actions.numel() != self.num_envs:
                 raise ValueError("actions must be a uint8 tensor of shape [num_envs] on the env's device")
-        cfg = make_env_cfg(self.config, mode, auto_reset, emit_obs=obs_out is not None)
+        cfg = make_env_cfg(self.config, mode, auto_reset, emit_obs=obs_out is not None, action_priority=action_priority)
         self.t += 1
         reward = reward_out if reward_out is not None else self.reward
         if flags_in is None:
-            flags_in = self.flags if (use_prev_mask and (mode == "random_legal" or ep_len is not None)) else None
+            flags_in = self.flags if (use_prev_mask and (mode in ("random_legal", "priority") or ep_len is not None)) else None
         flags = flags_out if flags_out is not None else self.flags
         b_out = board_out if board_out is not None else self.board
         with torch.cuda.device(self.device):

@@ -351,6 +351,18 @@ B2_HD Board reset_board(uint64_t seed, uint64_t gid, uint32_t t) {
     return b;
 }
 
+// first legal action in the order prio (nibble k = k-th choice), 0 if the mask is empty
+// (tools/simple_action_gen.py:16-33)
+B2_HD uint32_t pick_priority(uint32_t mask, uint32_t prio) {
+    uint32_t a = 0u;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+        uint32_t c = (prio >> (4 * k)) & 3u;
+        a = ((mask >> c) & 1u) ? c : a;
+    }
+    return a;
+}
+
 // j-th (0-based) legal action of a 4-bit mask, 0 if the mask is empty
 B2_HD uint32_t pick_legal(uint32_t mask, uint32_t w) {
     uint32_t n = (uint32_t)popc(mask & 0xFu);

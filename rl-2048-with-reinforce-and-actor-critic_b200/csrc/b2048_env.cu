@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
             if (args.flags_in) fin_next = args.flags_in[inext];
         }
         if (kTrack) { io.score = args.score[i]; io.step = args.step[i]; io.max_exp = args.max_exp[i]; }
-        if (kAct == B2048_ACT_RANDOM_LEGAL) io.mask_in = args.flags_in ? fin : legal_mask(Board{io.lo, io.hi});
+        if (kAct == B2048_ACT_RANDOM_LEGAL || kAct == B2048_ACT_PRIORITY)
+            io.mask_in = args.flags_in ? fin : legal_mask(Board{io.lo, io.hi});
         bool frozen = false;
         if (args.ep_len) frozen = args.ep_len[i] != 0;
         if (!ready) {
@@ -499,6 +500,7 @@ extern "C" int b2048_create(b2048_handle** out) {
         B2_SET(B2048_ACT_BUFFER, true); B2_SET(B2048_ACT_BUFFER, false);
         B2_SET(B2048_ACT_RANDOM_LEGAL, true); B2_SET(B2048_ACT_RANDOM_LEGAL, false);
         B2_SET(B2048_ACT_RANDOM_ANY, true); B2_SET(B2048_ACT_RANDOM_ANY, false);
+        B2_SET(B2048_ACT_PRIORITY, true); B2_SET(B2048_ACT_PRIORITY, false);
 #undef B2_SET
     }
     *out = h;
@@ -552,7 +554,7 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
                "b2048_step_many: unsupported bonus mode");  // env.py:248-249
     B2_REQUIRE(cfg->obs_mode >= B2048_OBS_NONE && cfg->obs_mode <= B2048_OBS_ONEHOT,
                "b2048_step_many: unsupported obs_mode");  // env.py:109-110
-    B2_REQUIRE(cfg->action_mode >= B2048_ACT_BUFFER && cfg->action_mode <= B2048_ACT_RANDOM_ANY,
+    B2_REQUIRE(cfg->action_mode >= B2048_ACT_BUFFER && cfg->action_mode <= B2048_ACT_PRIORITY,
                "b2048_step_many: unsupported action_mode");
     B2_REQUIRE(cfg->action_mode != B2048_ACT_BUFFER || action != nullptr,
                "b2048_step_many: action buffer required for B2048_ACT_BUFFER");
@@ -582,6 +584,7 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
         int grid = grid_for(n, 1024, h->num_sms, 1);
         if (cfg->action_mode == B2048_ACT_BUFFER) launch_fast<B2048_ACT_BUFFER>(all_track, grid, B2048_TABLES_BYTES, s, a);
         else if (cfg->action_mode == B2048_ACT_RANDOM_LEGAL) launch_fast<B2048_ACT_RANDOM_LEGAL>(all_track, grid, B2048_TABLES_BYTES, s, a);
+        else if (cfg->action_mode == B2048_ACT_PRIORITY) launch_fast<B2048_ACT_PRIORITY>(all_track, grid, B2048_TABLES_BYTES, s, a);
         else launch_fast<B2048_ACT_RANDOM_ANY>(all_track, grid, B2048_TABLES_BYTES, s, a);
     } else if (use_smem) {
         int grid = grid_for(n, 1024, h->num_sms, 1);

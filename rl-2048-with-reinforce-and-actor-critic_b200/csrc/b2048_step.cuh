@@ -52,7 +52,7 @@ B2_HD void step_one(StepIO& io, const b2048_env_cfg& cfg, const StepOpts& opt, u
         a = rnd.w2 >> 30;
     } else {
         uint32_t m = io.have_mask_in ? (io.mask_in & 0xFu) : legal_mask(io.board);
-        a = pick_legal(m, rnd.w2);
+        a = cfg.action_mode == B2048_ACT_PRIORITY ? pick_priority(m, (uint32_t)cfg.action_priority) : pick_legal(m, rnd.w2);
     }
     io.action_played = a;
 

@@ -80,6 +80,7 @@ B2_HD void step_fast_rnd(FastIO& io, const b2048_env_cfg& cfg, const Rand4& rnd,
     uint32_t a;
     if (kAct == B2048_ACT_BUFFER) a = io.action & 3u;
     else if (kAct == B2048_ACT_RANDOM_ANY) a = rnd.w2 >> 30;
+    else if (kAct == B2048_ACT_PRIORITY) a = pick_priority(io.mask_in & 0xFu, (uint32_t)cfg.action_priority);
     else {
         uint32_t m4 = io.mask_in & 0xFu;
         a = T.act[m4 * 4u + mulhi(rnd.w2, (uint32_t)popc(m4))];

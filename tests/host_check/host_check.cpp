@@ -129,6 +129,7 @@ extern "C" void hc_step_fast_many(const uint64_t* board_in, uint64_t* board_out,
                       : run_fast<A, false>(board_in, board_out, score, step, max_exp, action, action_out, flags_in, cfg, merge_sum, reward, flags, n, seed, gid0, t))
     if (cfg->action_mode == B2048_ACT_BUFFER) RUN(B2048_ACT_BUFFER);
     else if (cfg->action_mode == B2048_ACT_RANDOM_ANY) RUN(B2048_ACT_RANDOM_ANY);
+    else if (cfg->action_mode == B2048_ACT_PRIORITY) RUN(B2048_ACT_PRIORITY);
     else RUN(B2048_ACT_RANDOM_LEGAL);
 #undef RUN
 }

@@ -112,14 +112,14 @@ def test_step_buffer_actions_including_illegal():
 
 
 @pytest.mark.parametrize("reward_mode", ["log2", "sum"])
-@pytest.mark.parametrize("mode", ["random_legal", "random_any", "buffer"])
+@pytest.mark.parametrize("mode", ["random_legal", "random_any", "buffer", "priority"])
 @pytest.mark.parametrize("track", [True, False])
 def test_fast_step_body_vs_oracle(reward_mode, mode, track):
     """The instruction-lean step body (csrc/b2048_step_fast.cuh) used by the large-batch kernel."""
     hc = host_check_lib()
     n, T, seed, gid0 = 6000, 260, 99, 2**33
     cfg = oracle.make_cfg(reward_mode=reward_mode, base_reward_scale=0.5, step_reward=-0.125, max_steps=100,
-                          action_mode=mode, auto_reset=True)
+                          action_mode=mode, auto_reset=True, action_priority=(0, 1, 3, 2))
     st = oracle.reset_many(n, seed, gid0, 0)
     board = st["board"].copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
     flags_prev = st["flags"].copy()
@@ -157,3 +157,25 @@ def test_fast_step_overflow_and_dense_boards():
         assert (rw == o["reward"]).all() and (mx == st["max_exp"]).all() and (score == st["score"]).all()
         if t == 1:
             assert (fl & 0x80).any()      # the random boards contain 15+15 merges
+
+
+@pytest.mark.parametrize("prio", [(0, 1, 2, 3), (0, 1, 3, 2), (3, 2, 1, 0)])
+def test_generic_step_body_priority_mode_vs_oracle(prio):
+    """B2048_ACT_PRIORITY (tools/simple_action_gen.py:16-33) in the generic step body."""
+    hc = host_check_lib()
+    n, T, seed, gid0 = 3000, 150, 17, 123
+    kw = full_env_kwargs("shaped_raw"); kw.pop("size"); kw["max_steps"] = 90
+    cfg = oracle.make_cfg(action_mode="priority", action_priority=prio, auto_reset=True, **kw)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    board = st["board"].copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
+    flags_prev = st["flags"].copy()
+    for t in range(1, T + 1):
+        o = oracle.step_many(st, cfg, seed, gid0, t)
+        act = np.zeros(n, np.uint8); ms = np.zeros(n, np.int32); rw = np.zeros(n, np.float32)
+        rw64 = np.zeros(n, np.float64); fl = np.zeros(n, np.uint8)
+        hc.hc_step_many(P(board), P(board), P(score), P(step), P(mx), None, P(act),
+                        P(flags_prev) if t % 2 else None, C.byref(cfg), P(ms), P(rw), P(rw64), P(fl),
+                        C.c_int64(n), C.c_uint64(seed), C.c_uint64(gid0), C.c_uint32(t))
+        assert (act == o["action"]).all() and (board == st["board"]).all() and (rw64 == o["reward64"]).all()
+        assert (fl == o["flags"]).all() and (score == st["score"]).all()
+        flags_prev = fl.copy()

@@ -203,3 +203,24 @@ def test_symmetry_kernel_tables_match_reference_fixture():
         assert (nb == g["out_boards"][v]).all(), v
         assert (nm == g["out_masks"][v]).all(), v
         assert (na == g["out_actions"][v]).all(), v
+
+
+@pytest.mark.parametrize("name,prio", [("urdl", (0, 1, 2, 3)), ("urld", (0, 1, 3, 2))])
+def test_priority_policies_oracle_vs_reference_fixture(name, prio):
+    """Episodes played by the reference's own action_gen_1 / action_gen_2 (tools/simple_action_gen.py:16-33) on the
+    reference env (tests/golden/priority.npz) vs the oracle in B2048_ACT_PRIORITY mode."""
+    g = np.load(os.path.join(GOLDEN, "priority.npz"))
+    seed, gid0 = int(g["seed"]), int(g["gid0"])
+    n = len(g[f"{name}/board0"])
+    cfg = oracle.make_cfg(reward_mode="sum", obs_mode="none", max_steps=0, action_mode="priority", action_priority=prio)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    assert (st["board"] == g[f"{name}/board0"]).all() and (st["flags"] == g[f"{name}/flags0"]).all()
+    alive = np.ones(n, bool)
+    for t in range(len(g[f"{name}/board"])):
+        o = oracle.step_many(st, cfg, seed, gid0, t + 1)
+        assert (o["action"][alive] == g[f"{name}/action"][t][alive]).all()
+        assert (st["board"][alive] == g[f"{name}/board"][t][alive]).all()
+        assert (o["reward64"][alive] == g[f"{name}/reward"][t][alive]).all()
+        assert (o["flags"][alive] == g[f"{name}/flags"][t][alive]).all()
+        assert (st["score"][alive] == g[f"{name}/score"][t][alive]).all()
+        alive = g[f"{name}/alive"][t]
