@@ -78,3 +78,43 @@ def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = 
         total_episodes = int(n.item())
     rollout.n_traj = total_episodes
     return agent.update_from_rollout(rollout, allreduce=allreduce_sum_ if info.is_distributed else None)
+
+
+def episode_rank_weights(total_reward: torch.Tensor, weights_conf, info: DistInfo | None = None) -> torch.Tensor:
+    """CVaR-style episode weights by GLOBAL reward rank (reference src/reinforce_agent.py:681-716) computed on the
+    device: sort the episode rewards, give the episode of rank r the configured weight of bin
+    int((r + 0.5) / n * num_bins), normalise to mean 1.  With `info.world_size > 1` the rewards of every rank are
+    all-gathered first (4 bytes per episode), so each rank gets the weights a single process holding all episodes
+    would compute, and returns those of its own episodes.
+
+    Ties: the reference sorts with NumPy's default (unstable) argsort, so which of two equal-reward episodes falls
+    on the far side of a bin boundary is an accident of introsort there; here the sort is stable by global episode
+    index.  The multiset of weights and every episode not sharing its reward with a boundary neighbour agree."""
+    n_local = int(total_reward.numel())
+    if weights_conf is None or len(weights_conf) == 0:
+        return torch.ones(n_local, dtype=torch.float32, device=total_reward.device)
+    conf = torch.as_tensor(list(weights_conf), dtype=torch.float32, device=total_reward.device)
+    r = total_reward.to(torch.float64).reshape(-1)
+    lo = 0
+    if info is not None and info.is_distributed:
+        sizes = torch.zeros(info.world_size, dtype=torch.int64, device=r.device)
+        sizes[info.rank] = n_local
+        allreduce_sum_(sizes)
+        sizes = [int(x) for x in sizes.tolist()]
+        full = torch.zeros(sum(sizes), dtype=torch.float64, device=r.device)
+        lo = sum(sizes[: info.rank])
+        full[lo: lo + n_local] = r
+        allreduce_sum_(full)          # disjoint slices: the sum is the concatenation (works on NCCL and gloo alike)
+        r = full
+    n = int(r.numel())
+    if n == 0:
+        return torch.zeros(0, dtype=torch.float32, device=total_reward.device)
+    order = torch.argsort(r, stable=True)
+    pct = (torch.arange(n, dtype=torch.float64, device=r.device) + 0.5) / n
+    bins = torch.clamp((pct * len(conf)).to(torch.int64), max=len(conf) - 1)
+    w = torch.zeros(n, dtype=torch.float32, device=r.device)
+    w[order] = conf[bins]
+    m = w.mean()
+    if float(m) > 1e-8:
+        w = w / m
+    return w[lo: lo + n_local].contiguous()

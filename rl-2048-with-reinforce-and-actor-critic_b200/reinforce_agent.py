@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 from collections.abc import Callable
 from dataclasses import dataclass
 from typing import Any
@@ -165,6 +166,35 @@ class ReinforceAgent:
 
     def save_model(self, file_path: str | None = "params.npz") -> None:
         save_model_params(self.params, file_path)                                 # actor only, like the reference
+
+    # The reference's save_model keeps the actor alone (reinforce_agent.py:119-123), so a run cannot be resumed: the
+    # critic, the Adam moments and the step counters are lost.  save_checkpoint / load_checkpoint keep all of it.
+    def save_checkpoint(self, file_path: str) -> None:
+        """Everything update_batch mutates: actor, critic, Adam moments and step counters (one .npz)."""
+        out = {"actor_theta": self._actor.theta.cpu().numpy(), "actor_dims": np.asarray(self._actor.dims, np.int64),
+               "actor_adam_m": self._actor.adam_m.cpu().numpy(), "actor_adam_v": self._actor.adam_v.cpu().numpy(),
+               "adam_t": np.int64(self._adam_t), "adam_t_c": np.int64(getattr(self, "_adam_t_c", 0)),
+               "has_critic": np.int64(self._critic is not None)}
+        if self._critic is not None:
+            out.update(critic_theta=self._critic.theta.cpu().numpy(), critic_dims=np.asarray(self._critic.dims, np.int64),
+                       critic_adam_m=self._critic.adam_m.cpu().numpy(), critic_adam_v=self._critic.adam_v.cpu().numpy())
+        np.savez(file_path, **out)
+
+    def load_checkpoint(self, file_path: str) -> None:
+        ck = np.load(file_path if str(file_path).endswith(".npz") else str(file_path) + ".npz")
+
+        def restore(net, prefix):
+            if [int(d) for d in ck[prefix + "_dims"]] != [int(d) for d in net.dims]:
+                raise ValueError(f"checkpoint {prefix} shape {ck[prefix + '_dims'].tolist()} != network {net.dims}")
+            net.theta.copy_(torch.from_numpy(ck[prefix + "_theta"]).to(self.device))
+            net.adam_m.copy_(torch.from_numpy(ck[prefix + "_adam_m"]).to(self.device))
+            net.adam_v.copy_(torch.from_numpy(ck[prefix + "_adam_v"]).to(self.device))
+
+        restore(self._actor, "actor")
+        if int(ck["has_critic"]) and self._critic is not None:
+            restore(self._critic, "critic")
+        self._adam_t = int(ck["adam_t"])
+        self._adam_t_c = int(ck["adam_t_c"])
 
     # ------------------------------------------------------------------ kernels
     def _buf(self, name: str, shape, dtype) -> torch.Tensor:
@@ -394,8 +424,11 @@ class ReinforceAgent:
         if B == 0 or T == 0:
             return {}
         if ro.ep_weight is None and cfg.reward_rank_weights:
-            w = self._compute_episode_rank_weights(ro.total_reward().cpu().numpy().tolist())
-            ro.ep_weight = torch.from_numpy(w).to(self.device)
+            # global reward ranks on the device (all-gathered over ranks when the episodes are sharded)
+            from . import dist as bd
+            dinfo = bd.DistInfo(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+                                int(os.environ.get("LOCAL_RANK", "0"))) if allreduce is not None else None
+            ro.ep_weight = bd.episode_rank_weights(ro.total_reward(), cfg.reward_rank_weights, dinfo)
         n_traj = float(ro.n_traj if ro.n_traj is not None else B)
         lib, h, dev = self._lib, self._h, self.device
         n = T * B

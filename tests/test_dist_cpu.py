@@ -65,6 +65,11 @@ def _worker(rank, world, port, out):
         for t in range(1, T + 1):
             oracle.step_many(full, cfg, seed, 0, t)
         assert (boards.numpy().view(np.uint64) == full["board"]).all()
+    # 4b. episode rank weights: all-gathered global ranks == the single-process weights of the same episodes
+    rew = torch.from_numpy(np.random.default_rng(5).normal(size=total) * 50)
+    w_mine = bd.episode_rank_weights(rew[lo:hi].clone(), [0.0, 0.5, 1.0, 2.5], info)
+    w_full = bd.episode_rank_weights(rew, [0.0, 0.5, 1.0, 2.5])
+    assert torch.allclose(w_mine, w_full[lo:hi])
     # 5. max-over-ranks timing reduction used by bench.py
     tm = torch.tensor([float(rank + 1)], dtype=torch.float64)
     bd.allreduce_max_(tm)

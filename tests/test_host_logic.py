@@ -179,3 +179,25 @@ def test_generic_step_body_priority_mode_vs_oracle(prio):
         assert (act == o["action"]).all() and (board == st["board"]).all() and (rw64 == o["reward64"]).all()
         assert (fl == o["flags"]).all() and (score == st["score"]).all()
         flags_prev = fl.copy()
+
+
+def test_episode_rank_weights_vs_reference_fixture():
+    """dist.episode_rank_weights (torch sort; runs on the GPU in production) vs the reference's
+    _compute_episode_rank_weights outputs (tests/golden/rank_weights.npz).  Tie-free inputs: identical per episode.
+    Tied inputs: identical multiset, identical for every episode whose reward is unique."""
+    import sys
+    import torch
+    from helpers import GOLDEN, ROOT
+    sys.path.insert(0, ROOT)
+    from b2048 import dist as bd
+    g = np.load(os.path.join(GOLDEN, "rank_weights.npz"))
+    for k in range(int(g["n_cases"])):
+        r, conf, want = g[f"case{k}/reward"], g[f"case{k}/conf"].tolist(), g[f"case{k}/weights"]
+        got = bd.episode_rank_weights(torch.from_numpy(r), conf).numpy()
+        if not int(g[f"case{k}/ties"]):
+            assert np.allclose(got, want, rtol=1e-6, atol=0), k
+        else:
+            assert np.allclose(np.sort(got), np.sort(want), rtol=1e-6), k
+            vals, counts = np.unique(r, return_counts=True)
+            uniq = np.isin(r, vals[counts == 1])
+            assert np.allclose(got[uniq], want[uniq], rtol=1e-6), k

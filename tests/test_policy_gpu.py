@@ -406,3 +406,31 @@ def test_trainer_smoke(b2048, tmp_path):
     cfg["eval"]["model_path"] = os.path.join(tmp_path, "final.npz")
     res = trainer.evaluation(cfg)
     assert res["avg_reward"] > 0 and sum(res["max_tile_counts"].values()) <= 256
+
+
+def test_checkpoint_round_trip_and_rank_weights(b2048, tmp_path):
+    """save_checkpoint / load_checkpoint restore everything an update mutates (actor, critic, Adam moments, step
+    counters): an agent resumed from the checkpoint takes exactly the step the original takes.  The update runs with
+    reward_rank_weights (global reward ranks on the device, reinforce_agent.py:681-716)."""
+    from helpers import full_env_kwargs
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 30
+
+    def make():
+        env = b2048.Batched2048Env(2048, b2048.Game2048EnvConfig(**kw), seed=9)
+        agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[64, 32], activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(use_critic=True, optimizer="adam", baseline_mode="batch_norm",
+                                                                reward_rank_weights=[0.0, 0.5, 1.0, 2.5], model_seed=4))
+        return env, agent
+
+    env, a = make()
+    a.update_from_rollout(a.rollout_many(env))
+    path = str(tmp_path / "ck.npz")
+    a.save_checkpoint(path)
+    env2, b = make()
+    b.load_checkpoint(path)
+    assert torch.equal(a._actor.theta, b._actor.theta) and torch.equal(a._critic.adam_v, b._critic.adam_v)
+    env.seed = env2.seed = 123                       # the same second rollout + update from both
+    a.update_from_rollout(a.rollout_many(env))
+    b.update_from_rollout(b.rollout_many(env2))
+    assert torch.equal(a._actor.theta, b._actor.theta) and torch.equal(a._critic.theta, b._critic.theta)
+    assert a._adam_t == b._adam_t == 2
