@@ -88,7 +88,12 @@ def training(cfg: dict[str, Any], info: bd.DistInfo | None = None, device=None, 
         writer = csv.DictWriter(fcsv, fieldnames=["batch", "avg_reward", "max_reward", "min_reward", "max_tile_counts"])
         writer.writeheader()
     best = -float("inf")
-    for step in range(int(tr["num_batches"])):
+    # resume: ``train.resume`` = path of a checkpoint written by an earlier run (actor, critic, Adam moments, step
+    # counters — everything the reference's actor-only save_model loses); ``train.start_batch`` continues the seeds
+    start = int(tr.get("start_batch", 0))
+    if tr.get("resume"):
+        agent.load_checkpoint(tr["resume"])
+    for step in range(start, int(tr["num_batches"])):
         t0 = time.perf_counter()
         env.seed = (int(cfg["seed"]) + 0x9E3779B97F4A7C15 * (step + 1)) & (2**64 - 1)      # fresh episodes every batch
         ro = agent.rollout_many(env, precision=tr.get("precision", "auto"))
@@ -113,6 +118,7 @@ def training(cfg: dict[str, Any], info: bd.DistInfo | None = None, device=None, 
         fcsv.close()
     if info.rank == 0 and out_dir:
         agent.save_model(os.path.join(out_dir, "final.npz"))
+        agent.save_checkpoint(os.path.join(out_dir, "final_checkpoint.npz"))
     return rows
 
 
