@@ -135,19 +135,24 @@ static_assert(SM_TOTAL_RO <= 232448, "exceeds the 227 KB shared memory of an sm_
 // after a quarter of the epilogue instead of after all of it.
 __device__ __forceinline__ void relu_store_slabs(uint32_t tlane_col0, uint8_t* a2_row, int row, int g, int lane,
                                                  uint32_t bar0) {
+    // software-pipelined: the TMEM load of slab s + 1 is in flight while slab s is converted and stored
+    uint32_t r[2][16];
+    tmem_ld16_issue(tlane_col0 + (uint32_t)(g * 16), r[0]);
+    tmem_ld_wait(r[0]);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        uint32_t r[16];
-        tmem_ld16(tlane_col0 + (uint32_t)(s * 64 + g * 16), r);
+        if (s + 1 < 4) tmem_ld16_issue(tlane_col0 + (uint32_t)((s + 1) * 64 + g * 16), r[(s + 1) & 1]);
+        const uint32_t(&v)[16] = r[s & 1];
         uint8_t* rowp = a2_row + s * 16384;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {                                           // two 16-byte chunks of 8 columns
-            uint32_t w0 = relu_pack(r[c * 8 + 0], r[c * 8 + 1]), w1 = relu_pack(r[c * 8 + 2], r[c * 8 + 3]);
-            uint32_t w2 = relu_pack(r[c * 8 + 4], r[c * 8 + 5]), w3 = relu_pack(r[c * 8 + 6], r[c * 8 + 7]);
+            uint32_t w0 = relu_pack(v[c * 8 + 0], v[c * 8 + 1]), w1 = relu_pack(v[c * 8 + 2], v[c * 8 + 3]);
+            uint32_t w2 = relu_pack(v[c * 8 + 4], v[c * 8 + 5]), w3 = relu_pack(v[c * 8 + 6], v[c * 8 + 7]);
             int chunk = g * 2 + c;
             *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) * 16)) = make_uint4(w0, w1, w2, w3);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // smem writes -> visible to the tensor core
+        if (s + 1 < 4) tmem_ld_wait(r[(s + 1) & 1]);                            // next slab's accumulators have landed
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");         // accumulator reads ordered before reuse
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8u * s);   // ONE arrival per warp: 32 same-address arrivals would serialise

@@ -102,11 +102,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// bf16x2( relu(a), relu(b) ): convert, then one packed max against zero
+// bf16x2( relu(a), relu(b) ) in ONE instruction (F2FP with the .relu modifier; a in the low half): the epilogues are
+// issue-bound (16 warps on 4 schedulers), so every instruction per column pair counts
 __device__ __forceinline__ uint32_t relu_pack(uint32_t a_bits, uint32_t b_bits) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
-    p = __hmax2(p, __floats2bfloat162_rn(0.0f, 0.0f));
-    return *reinterpret_cast<uint32_t*>(&p);
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(b_bits)), "f"(__uint_as_float(a_bits)));
+    return d;
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -119,6 +120,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// asynchronous halves of tmem_ld16: issue now, wait later (tcgen05.wait::ld covers every outstanding load of the thread)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// The destination registers of an issued load are valid only after the wait: the empty asm makes every later use of
+// them depend on a statement the compiler keeps behind the wait (asm volatile statements are not reordered).
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
 
 // MN-major SWIZZLE_128B operand (the contiguous dimension is M or N, not K): a [K rows][64 MN elements = 128 B] atom
 // of 8 K-rows (1024 B); the next 8 K-rows are SBO = 1024 B away, the next 64 MN elements LBO bytes away.
