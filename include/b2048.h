@@ -199,12 +199,17 @@ int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mas
  * t = t_begin .. t_begin + n_steps - 1.  boards / flags are time-major [T+1, B], actions / rewards [T, B].
  * ep_len != NULL: run-to-termination bookkeeping (see b2048_step_many); ep_len == NULL with cfg->auto_reset: fixed
  * horizon with reset-on-done.  t0: the env's step index before step t = 0 (Philox counter = t0 + t + 1).
- * use_mask: feed the legal masks to the policy (Game2048EnvConfig.use_action_mask). */
+ * use_mask: feed the legal masks to the policy (Game2048EnvConfig.use_action_mask).
+ * precision 1 with the 16-256-256-4 ReLU policy and a plain reward configuration runs the whole chunk as ONE
+ * persistent kernel (tcgen05 policy + env step); anything else is a policy-kernel / step-kernel loop.
+ * slot_map (device int32[n_slots], may be NULL): play only the listed boards — run-to-termination callers pass the
+ * boards still alive at the start of the chunk, so finished episodes cost nothing; slices t > ep_len[b] of a board
+ * that is not listed are left untouched.  Fused kernel only. */
 int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* flags, uint8_t* actions, float* rewards,
                        uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                        const b2048_env_cfg* cfg /* host */, const b2048_mlp_desc* mlp /* host */, int64_t B,
                        int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
-                       int32_t greedy, int32_t precision, void* stream);
+                       int32_t greedy, int32_t precision, const int32_t* slot_map, int64_t n_slots, void* stream);
 
 /* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1).
  *   precision : 0 = fp32 CUDA cores; 1 = bf16 tcgen05 (16-256-256-(<=4) ReLU, raw / log2 observations, n >= 4096,

@@ -153,7 +153,7 @@ int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
                       float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                       const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
-                      uint32_t t0, int use_mask, int greedy, cudaStream_t stream);
+                      uint32_t t0, int use_mask, int greedy, const int32_t* slot_map, int64_t n_slots, cudaStream_t stream);
 
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
     if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
@@ -205,7 +205,8 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
                                   uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                                   const b2048_env_cfg* cfg, const b2048_mlp_desc* mlp, int64_t B, int32_t t_begin,
                                   int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
-                                  int32_t greedy, int32_t precision, void* stream) {
+                                  int32_t greedy, int32_t precision, const int32_t* slot_map, int64_t n_slots,
+                                  void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_rollout_many: handle is NULL");
     B2_REQUIRE(B >= 0 && n_steps >= 0 && t_begin >= 0, "b2048_rollout_many: negative size");
     if (B == 0 || n_steps == 0) return B2048_OK;
@@ -215,9 +216,11 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
     if (precision == 1) {
         // one persistent launch for the whole horizon (policy on tcgen05 + env step in the same kernel)
         int st = launch_rollout_tc(h, mlp, boards, flags, actions, rewards, score, step, max_exp, ep_len, &c, B, t_begin, n_steps,
-                                   seed, gid0, t0, use_mask, greedy, (cudaStream_t)stream);
+                                   seed, gid0, t0, use_mask, greedy, slot_map, n_slots, (cudaStream_t)stream);
         if (st != B2048_ERR_UNSUPPORTED) return st;
     }
+    B2_REQUIRE(slot_map == nullptr, "b2048_rollout_many: slot_map needs the fused tensor-core rollout kernel (precision 1, "
+                                    "16-256-256-4 ReLU policy, plain reward configuration, B >= 4096)");
     for (int32_t k = 0; k < n_steps; ++k) {
         const int64_t t = (int64_t)t_begin + k;
         const uint32_t t_env = t0 + (uint32_t)t + 1u;

@@ -101,6 +101,9 @@ struct PolicyTcArgs {
     uint8_t* max_exp;
     int32_t* ep_len;          // nullable: run-to-termination bookkeeping (0 = running, else frozen)
     const uint8_t* tables;    // row tables + small tables (global memory; read through L1 / L2)
+    const int32_t* slot_map;  // nullable: slot s of the launch is board slot_map[s] (run-to-termination rollouts launch
+                              // the live boards only); n = number of slots, ro_stride = boards per record slice
+    int64_t ro_stride;
     uint64_t seed;
     int32_t t_begin, n_steps;
     uint32_t t0;
@@ -347,7 +350,11 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
 
             auto encode_a1 = [&](int j, int r) {   // this thread's board -> 16 bf16 in the A1 core matrices
                 const int64_t s = tile_of(j) * TC_M + row;
-                uint64_t bd = (s < args.n) ? board_base[slice_of(r) * args.n + s] : 0ull;
+                uint64_t bd = 0ull;
+                if (s < args.n) {
+                    const int64_t b = (kRollout && args.slot_map) ? args.slot_map[s] : s;
+                    bd = board_base[slice_of(r) * (kRollout ? args.ro_stride : args.n) + b];
+                }
                 uint32_t packed[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -375,14 +382,16 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 const int64_t s = tile_of(j) * TC_M + row;
                 const int64_t slice = slice_of(r);
                 const bool valid = s < args.n;
+                const int64_t b = (kRollout && valid && args.slot_map) ? args.slot_map[s] : s;   // board behind the slot
+                const int64_t stride = kRollout ? args.ro_stride : args.n;
                 const bool use_mask = args.mask_flags != nullptr;               // rollout: non-NULL iff the policy is masked
                 if (kRollout) wait_inputs_of(j, r);
                 uint32_t fl = 0xFu;
-                if (valid && use_mask) fl = mask_base[slice * args.n + s];      // requested early, used after D3
+                if (valid && use_mask) fl = mask_base[slice * stride + b];      // requested early, used after D3
                 const uint32_t t_env = kRollout ? args.t0 + (uint32_t)slice + 1u : args.t;
                 uint32_t w3 = 0u;
                 if (valid && !args.greedy && (kRollout || args.action))
-                    w3 = stream_keyed(args.keys, args.gid0 + (uint64_t)s, t_env, B2048_DOM_STEP).w3;
+                    w3 = stream_keyed(args.keys, args.gid0 + (uint64_t)b, t_env, B2048_DOM_STEP).w3;
                 // A1 is free once this item's layer-1 MMAs have completed
                 mbar_wait(bar_d1, ph);
                 if (prefetch && item + 1 < n_items) {
@@ -436,7 +445,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                                 if (p0 > 0.0f) a = 0;
                             }
                         }
-                        if (kRollout) args.ro_actions[slice * args.n + s] = (uint8_t)a;
+                        if (kRollout) args.ro_actions[slice * stride + b] = (uint8_t)a;
                         else args.action[s] = (uint8_t)a;
                     }
                 }
@@ -487,10 +496,11 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 EnvIn e = {0ull, 0u, 0u, 2u, 0u, 0};
                 const int64_t s = tile_of(j) * TC_M + row;
                 if (s < args.n) {
-                    const int64_t i = slice_of(r) * args.n + s;
+                    const int64_t b = args.slot_map ? args.slot_map[s] : s;
+                    const int64_t i = slice_of(r) * args.ro_stride + b;
                     e.bd = args.ro_boards[i]; e.fin = args.ro_flags[i];
-                    e.score = args.score[s]; e.step = args.step[s]; e.max_exp = args.max_exp[s];
-                    if (args.ep_len) e.ep = args.ep_len[s];
+                    e.score = args.score[b]; e.step = args.step[b]; e.max_exp = args.max_exp[b];
+                    if (args.ep_len) e.ep = args.ep_len[b];
                 }
                 return e;
             };
@@ -505,6 +515,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 const int64_t s = tile_of(j) * TC_M + row;
                 const int64_t slice = slice_of(r);
                 const bool valid = s < args.n;
+                const int64_t b = (valid && args.slot_map) ? args.slot_map[s] : s;
                 const uint32_t t_env = args.t0 + (uint32_t)slice + 1u;
                 FastIO io;
                 io.lo = (uint32_t)cur.bd; io.hi = (uint32_t)(cur.bd >> 32);
@@ -512,7 +523,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 const uint32_t fin = cur.fin;
                 const bool frozen = cur.ep != 0;
                 Rand4 rr = Rand4{0u, 0u, 0u, 0u};
-                if (valid && !frozen) rr = stream_keyed(args.keys, args.gid0 + (uint64_t)s, t_env, B2048_DOM_STEP);
+                if (valid && !frozen) rr = stream_keyed(args.keys, args.gid0 + (uint64_t)b, t_env, B2048_DOM_STEP);
                 // Next item's inputs: with several tiles per CTA this thread wrote them at least one item ago, so the
                 // loads go out now and land under this item's step; with one tile they are this step's outputs.
                 EnvIn nxt = cur;
@@ -521,22 +532,22 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && (tid - TC_THREADS) % TC_ENV_GROUP == 0 && item < 8;
                 if (dbg) args.debug_clock[8 * item + 7] = clock64();
                 if (valid) {
-                    const int64_t o = (slice + 1) * args.n + s;
+                    const int64_t o = (slice + 1) * args.ro_stride + b;
                     if (frozen) {
                         args.ro_boards[o] = cur.bd;
-                        args.ro_rewards[slice * args.n + s] = 0.0f;
+                        args.ro_rewards[slice * args.ro_stride + b] = 0.0f;
                         io.flags = fin & ~B2048_F_CHANGED;
                         args.ro_flags[o] = (uint8_t)io.flags;
                     } else {
                         io.action = sAct[grp * TC_M + row];
-                        step_fast_rnd<B2048_ACT_BUFFER, true>(io, args.cfg, rr, args.seed, args.gid0 + (uint64_t)s, t_env, T);
+                        step_fast_rnd<B2048_ACT_BUFFER, true>(io, args.cfg, rr, args.seed, args.gid0 + (uint64_t)b, t_env, T);
                         if (args.ep_len && (io.flags & (B2048_F_DONE | B2048_F_TRUNC))) {
-                            args.ep_len[s] = (int32_t)(slice + 1);
+                            args.ep_len[b] = (int32_t)(slice + 1);
                             cur.ep = (int32_t)(slice + 1);
                         }
                         args.ro_boards[o] = (uint64_t)io.lo | ((uint64_t)io.hi << 32);
-                        args.score[s] = io.score; args.step[s] = io.step; args.max_exp[s] = (uint8_t)io.max_exp;
-                        args.ro_rewards[slice * args.n + s] = io.reward;
+                        args.score[b] = io.score; args.step[b] = io.step; args.max_exp[b] = (uint8_t)io.max_exp;
+                        args.ro_rewards[slice * args.ro_stride + b] = io.reward;
                         args.ro_flags[o] = (uint8_t)io.flags;
                     }
                 }
@@ -628,7 +639,7 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     a.debug_clock = nullptr;
     a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
     a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = seed; a.t_begin = 0; a.n_steps = 1;
-    a.t0 = 0;
+    a.t0 = 0; a.slot_map = nullptr; a.ro_stride = n;
     a.debug_clock = debug_clock_buffer();
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
@@ -653,7 +664,7 @@ int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
     a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
     a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
     a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = 0; a.t_begin = 0; a.n_steps = 1;
-    a.t0 = 0;
+    a.t0 = 0; a.slot_map = nullptr; a.ro_stride = n;
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     policy_tc_kernel<false><<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
@@ -666,25 +677,28 @@ int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
                       float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                       const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
-                      uint32_t t0, int use_mask, int greedy, cudaStream_t stream) {
+                      uint32_t t0, int use_mask, int greedy, const int32_t* slot_map, int64_t n_slots, cudaStream_t stream) {
     const bool net_ok = mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H &&
                         mlp->dims[3] == 4 && mlp->activation == B2048_ACTV_RELU &&
                         (mlp->obs_mode == B2048_OBS_RAW || mlp->obs_mode == B2048_OBS_LOG2) && h->smem_optin >= SM_TOTAL_RO;
     const bool env_ok = score && step && max_exp && cfg->use_action_mask && cfg->empty_tile_reward == 0.0 &&
                         cfg->merge_reward == 0.0 && cfg->bonus_mode == B2048_BONUS_OFF && cfg->endgame_penalty == 0.0 &&
                         (cfg->reward_mode == B2048_REWARD_SUM || cfg->reward_mode == B2048_REWARD_LOG2);
-    const int64_t tiles = (B + TC_M - 1) / TC_M;
+    // slot_map: only the listed boards are played (n_slots of them); without it all B boards
+    const int64_t n = slot_map ? n_slots : B;
+    const int64_t tiles = (n + TC_M - 1) / TC_M;
     if (!net_ok || !env_ok || B < 4096 || tiles * (int64_t)n_steps > 0x7FFFFFFF || getenv("B2048_NO_FUSED_ROLLOUT") != nullptr)
         return B2048_ERR_UNSUPPORTED;
+    if (n == 0) return B2048_OK;
     { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
     launch_tc_prepare(mlp, h->tc_image, stream);
     PolicyTcArgs a;
     a.img = h->tc_image; a.board = nullptr; a.mask_flags = use_mask ? flags : nullptr; a.action = nullptr; a.probs = nullptr;
-    a.logits = nullptr; a.head_out = nullptr; a.n_out = 4; a.n = B; a.keys = make_keys(seed); a.gid0 = gid0; a.t = 0; a.greedy = greedy;
+    a.logits = nullptr; a.head_out = nullptr; a.n_out = 4; a.n = n; a.keys = make_keys(seed); a.gid0 = gid0; a.t = 0; a.greedy = greedy;
     a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
     a.ro_boards = boards; a.ro_flags = flags; a.ro_actions = actions; a.ro_rewards = rewards; a.score = score; a.step = step;
     a.max_exp = max_exp; a.ep_len = ep_len; a.tables = h->d_tables; a.seed = seed; a.t_begin = t_begin; a.n_steps = n_steps;
-    a.t0 = t0; a.cfg = *cfg; a.cfg.action_mode = B2048_ACT_BUFFER;
+    a.t0 = t0; a.cfg = *cfg; a.cfg.action_mode = B2048_ACT_BUFFER; a.slot_map = slot_map; a.ro_stride = B;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     a.debug_clock = debug_clock_buffer();
     policy_tc_kernel<true><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);

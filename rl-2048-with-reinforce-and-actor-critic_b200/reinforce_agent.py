@@ -322,24 +322,46 @@ class ReinforceAgent:
         cfg = make_env_cfg(benv.config, "buffer", auto_reset=fixed, emit_obs=False)
         t0 = benv.t
         T = 0
+        # Run-to-termination on the fused tensor-core kernel: every chunk plays only the boards that are still alive
+        # (slot_map), so finished episodes cost nothing.  Slices beyond an episode's end are then never written: the
+        # rewards buffer is zeroed first (total_reward sums whole columns) and the final state is gathered below.
+        compact = (not fixed) and int(precision) == 1 and B >= 4096 and self.tc_supported() and \
+            os.environ.get("B2048_NO_FUSED_ROLLOUT") is None and os.environ.get("B2048_NO_COMPACT_ROLLOUT") is None
+        slot_map, n_slots = None, 0
+        if compact:
+            rewards.zero_()
         while T < cap:
             chunk = min(check_every if not fixed else 256, cap - T)
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.b2048_rollout_many(
                     self._h, _ptr(boards), _ptr(flags), _ptr(actions), _ptr(rewards), _ptr(benv.score), _ptr(benv.step_count),
                     _ptr(benv.max_exp), None if fixed else _ptr(length), C.byref(cfg), C.byref(self._actor.desc), B, T,
-                    chunk, benv.seed, benv.gid0, t0, int(self._use_mask), int(greedy), int(precision), _stream()),
-                    "b2048_rollout_many")
+                    chunk, benv.seed, benv.gid0, t0, int(self._use_mask), int(greedy), int(precision),
+                    _ptr(slot_map), n_slots, _stream()), "b2048_rollout_many")
             T += chunk
-            if not fixed and bool((length != 0).all()):
-                break
+            if not fixed:
+                if compact:
+                    slot_map = torch.nonzero(length == 0).reshape(-1).to(torch.int32)   # boards still playing
+                    n_slots = int(slot_map.numel())
+                    if n_slots == 0:
+                        break
+                elif bool((length != 0).all()):
+                    break
         benv.t = t0 + T
-        benv.board = boards[T]
-        benv.flags = flags[T]
         if fixed:
             length.fill_(T)
         else:
             length = torch.where(length == 0, torch.full_like(length, T), length)  # cut off by the cap
+        if compact:
+            # the last written slice of board b is length[b]
+            idx = length.long().unsqueeze(0)
+            benv.board = boards[: T + 1].gather(0, idx).reshape(-1)
+            fl = flags[: T + 1].gather(0, idx).reshape(-1)
+            # like the frozen pass-through of the step kernel: an episode that ended before T no longer reports "changed"
+            benv.flags = torch.where(length < T, fl & 0xEF, fl)
+            return Rollout(boards[: T + 1], flags[: T + 1], actions[:T], rewards[:T], length, T)
+        benv.board = boards[T]
+        benv.flags = flags[T]
         return Rollout(boards[: T + 1], flags[: T + 1], actions[:T], rewards[:T], length, T)
 
     # ------------------------------------------------------------------ reference API: learning
