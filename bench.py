@@ -12,6 +12,7 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
              are copied host->device and board/reward/flags device->host inside the timed region
   roofline   HBM: 22 algorithmic bytes per env-step over the measured kernel time
   cpu_baseline  the reference's algorithm on this box's host cores (Python port, all cores), rank 0, N=1 only
+  env_trained_boards  secondary: the same env-step measurement on boards harvested from a trained policy (north_star)
   rollout    secondary: policy-rollout steps/s (MLP 16-256-256-4 forward + masked sampling + env step), 65,536 boards
   train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
              one update; 65,536 / 262,144 boards per GPU)
@@ -289,6 +290,12 @@ def run_b200(args):
                     dist.all_reduce(v, op=dist.ReduceOp.SUM)
                 r["value_all_gpus"] = float(v.item())
                 extra[key] = r
+            r = b2048.bench_env_trained_boards(dev, boards=n, gid0=rank * n)
+            v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            r["value_all_gpus"] = float(v.item())
+            extra["env_trained_boards"] = r
             extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision=1)
             extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision=1,
                                                                       use_critic=True, iters=3)

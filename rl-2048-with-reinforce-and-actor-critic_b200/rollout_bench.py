@@ -77,3 +77,56 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
             "actor_grad_norm": last["actor_grad_norm"], "iters": out,
             "exchange": ("1 all-reduce per network of the flat fp32 gradient (71,172 / 70,401 floats)" if use_critic else
                          "1 all-reduce of the flat fp32 gradient (71,172 floats)") + " + 4 float64 baseline sums per update"}
+
+
+def bench_env_trained_boards(dev, boards: int = 1 << 20, train_batches: int = 100, harvest_steps: int = 256, steps: int = 200,
+                             gid0: int = 0, seed: int = 0xB200):
+    """north_star: env throughput "on synthetic random-policy and trained-policy boards" (input 2b).
+    A 16-256-256-4 policy is trained for `train_batches` REINFORCE batches of 8,192 episodes (Adam, a few seconds), then
+    `boards` boards are played `harvest_steps` greedy steps with it (fuller boards, higher tiles than random play) and
+    the fused env step is timed on THAT state distribution: the harvested boards are restored before every timed launch
+    and the L2 is flushed, exactly like the headline measurement."""
+    acfg = ReinforceAgentConfig(gamma=0.99, learning_rate=1e-3, baseline_mode="batch_norm", optimizer="adam", model_seed=0)
+    tenv = Batched2048Env(8192, Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=seed + 1, gid0=gid0)
+    agent = ReinforceAgent(tenv, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"), acfg)
+    first = last = 0.0
+    for b in range(train_batches):
+        tenv.seed = (seed + 0x9E3779B97F4A7C15 * (b + 1)) & (2**64 - 1)
+        ro = agent.rollout_many(tenv, precision="auto")
+        avg = float(ro.total_reward().mean())
+        first = avg if b == 0 else first
+        last = avg
+        agent.update_from_rollout(ro)
+    env = Batched2048Env(boards, Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=seed, gid0=gid0)
+    env.reset_many()
+    for _ in range(harvest_steps):                       # the random-policy reference distribution of the headline number
+        env.step_many(action_mode="random_legal", auto_reset=True)
+    rnd_board = env.board.clone()
+    env.reset_many()
+    agent.rollout_many(env, horizon=harvest_steps, greedy=True, precision="auto", reset=False)
+    saved = [t.clone() for t in (env.board, env.flags, env.score, env.step_count, env.max_exp)]
+
+    def stats(bd):
+        shifts = torch.arange(16, device=dev, dtype=torch.int64) * 4
+        cells = (bd.unsqueeze(-1) >> shifts) & 15
+        return {"mean_max_exponent": float(cells.max(dim=1).values.float().mean()),
+                "mean_occupied_cells": float((cells > 0).sum(dim=1).float().mean())}
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = 0.0
+    for k in range(steps + 3):
+        for dst, src in zip((env.board, env.flags, env.score, env.step_count, env.max_exp), saved):
+            dst.copy_(src)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.step_many(action_mode="random_legal", auto_reset=True)
+        e1.record()
+        e1.synchronize()
+        if k >= 3:
+            ms += e0.elapsed_time(e1)
+    return {"metric": "env-steps/s on trained-policy boards", "value": boards * steps / (ms * 1e-3), "unit": "env-steps/s",
+            "boards": boards, "steps": steps, "ms_per_step": ms / steps,
+            "policy": f"16-256-256-4 ReLU, {train_batches} REINFORCE batches of 8192 episodes (avg return {first:.0f} -> {last:.0f}), "
+                      f"{harvest_steps} greedy steps",
+            "trained_boards": stats(saved[0]), "random_policy_boards": stats(rnd_board), "gpu_launches": steps}
