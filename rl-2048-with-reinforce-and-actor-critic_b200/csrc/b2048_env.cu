@@ -266,7 +266,11 @@ __global__ void __launch_bounds__(kThreads, kSmemLut ? 1 : 2) step_kernel(const 
 // ------------------------------------------------------------------------------------------------ K2 (fast path)
 // Same contract as step_kernel for the common configuration (see b2048_step_fast.cuh); all tables in
 // shared memory, brought in by one mbarrier-tracked bulk copy per CTA.
-template <int kAct, bool kTrack>
+// kPlain: no rollout bookkeeping and no optional outputs (ep_len, action_out, merge_sum, debug clocks all NULL), the
+// previous legal masks supplied, fewer than 2^31 boards — the configuration of every large env-only batch.  The loop
+// then carries no frozen-episode logic, no predicated-off stores, one wait for the tables before the loop and 32-bit
+// indices (one IMAD.WIDE per address instead of a LEA pair): the kernel is bound by issue slots, not by memory.
+template <int kAct, bool kTrack, bool kPlain>
 __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constant__ StepArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
@@ -306,6 +310,46 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
     T.act = smem + B2048_LUT_BYTES + B2048_SMALL_ACT_OFF;
 
     const b2048_env_cfg& cfg = args.cfg;
+    if constexpr (kPlain) {
+        const uint32_t n = (uint32_t)args.n, stride = gridDim.x * 1024u;
+        uint32_t i = blockIdx.x * 1024u + (uint32_t)tid;
+        // software pipeline: the next iteration's inputs are requested before the current board is processed
+        uint2 bw_next = make_uint2(0u, 0u);
+        uint32_t act_next = 0u, fin_next = 0u, score_next = 0u, step_next = 0u, max_next = 2u;
+        auto request = [&](uint32_t k) {
+            bw_next = *reinterpret_cast<const uint2*>(args.board_in + k);
+            if (kAct == B2048_ACT_BUFFER) act_next = args.action[k];
+            else if (kAct != B2048_ACT_RANDOM_ANY) fin_next = args.flags_in[k];
+            if (kTrack) { score_next = args.score[k]; step_next = args.step[k]; max_next = args.max_exp[k]; }
+        };
+        if (i < n) request(i);
+        {   // the tables have to be in shared memory before the first lookup
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+        }
+        for (; i < n; i += stride) {
+            FastIO io;
+            io.lo = bw_next.x; io.hi = bw_next.y;
+            io.score = score_next; io.step = step_next; io.max_exp = max_next;
+            io.action = act_next; io.mask_in = fin_next;
+            const uint32_t inext = i + stride;
+            if (inext < n) request(inext);
+            step_fast<kAct, kTrack>(io, cfg, args.keys, args.seed, args.gid0 + (uint64_t)i, args.t, T);
+            *reinterpret_cast<uint2*>(args.board_out + i) = make_uint2(io.lo, io.hi);
+            if (kTrack) { args.score[i] = io.score; args.step[i] = io.step; args.max_exp[i] = (uint8_t)io.max_exp; }
+            args.reward[i] = io.reward;
+            args.flags[i] = (uint8_t)io.flags;
+        }
+        return;
+    }
     bool ready = false;
     const int64_t stride = (int64_t)gridDim.x * 1024;
     int64_t i = (int64_t)blockIdx.x * 1024 + tid;
@@ -375,8 +419,16 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
 
 template <int kAct>
 static void launch_fast(bool track, int grid, size_t smem, cudaStream_t s, const StepArgs& a) {
-    if (track) step_fast_kernel<kAct, true><<<grid, 1024, smem, s>>>(a);
-    else step_fast_kernel<kAct, false><<<grid, 1024, smem, s>>>(a);
+    const bool plain = a.ep_len == nullptr && a.action_out == nullptr && a.merge_sum == nullptr && a.debug_clock == nullptr &&
+                       (kAct == B2048_ACT_BUFFER || kAct == B2048_ACT_RANDOM_ANY || a.flags_in != nullptr) &&
+                       a.n < ((int64_t)1 << 31) - (int64_t)grid * 1024;
+    if (plain) {
+        if (track) step_fast_kernel<kAct, true, true><<<grid, 1024, smem, s>>>(a);
+        else step_fast_kernel<kAct, false, true><<<grid, 1024, smem, s>>>(a);
+    } else {
+        if (track) step_fast_kernel<kAct, true, false><<<grid, 1024, smem, s>>>(a);
+        else step_fast_kernel<kAct, false, false><<<grid, 1024, smem, s>>>(a);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ previews
@@ -496,7 +548,9 @@ extern "C" int b2048_create(b2048_handle** out) {
                                      B2048_LUT_BYTES));
     }
     if (h->smem_optin >= B2048_TABLES_BYTES) {
-#define B2_SET(A, TR) B2_CUDA(cudaFuncSetAttribute(step_fast_kernel<A, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES))
+#define B2_SET(A, TR)                                                                                                       \
+    B2_CUDA(cudaFuncSetAttribute(step_fast_kernel<A, TR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES)); \
+    B2_CUDA(cudaFuncSetAttribute(step_fast_kernel<A, TR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES))
         B2_SET(B2048_ACT_BUFFER, true); B2_SET(B2048_ACT_BUFFER, false);
         B2_SET(B2048_ACT_RANDOM_LEGAL, true); B2_SET(B2048_ACT_RANDOM_LEGAL, false);
         B2_SET(B2048_ACT_RANDOM_ANY, true); B2_SET(B2048_ACT_RANDOM_ANY, false);
