@@ -12,6 +12,7 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
              are copied host->device and board/reward/flags device->host inside the timed region
   roofline   HBM: 22 algorithmic bytes per env-step over the measured kernel time
   cpu_baseline  the reference's algorithm on this box's host cores (Python port, all cores), rank 0, N=1 only
+  env_multi_step  secondary: env-steps/s with 64 steps per launch (state kept in registers across the steps)
   env_trained_boards  secondary: the same env-step measurement on boards harvested from a trained policy (north_star)
   rollout    secondary: policy-rollout steps/s (MLP 16-256-256-4 forward + masked sampling + env step), 65,536 boards
   train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
@@ -279,8 +280,31 @@ def run_b200(args):
                 line["cpu_baseline_native"] = cpu_native_baseline()
             except Exception as e:  # the native leg is context only
                 line["cpu_baseline_native"] = {"error": str(e)}
+    # ---- secondary: the same stepping with 64 steps per launch (b2048_step_many_n: state in registers across steps)
+    multi = None
+    if not args.lean:
+        Kn, Tn = 20, 64
+        for _ in range(3):
+            env.step_many_n(Tn, action_mode="random_legal", auto_reset=True)
+        s2 = [torch.cuda.Event(enable_timing=True) for _ in range(Kn)]
+        e2 = [torch.cuda.Event(enable_timing=True) for _ in range(Kn)]
+        barrier()
+        for k in range(Kn):
+            flush.zero_()
+            s2[k].record()
+            env.step_many_n(Tn, action_mode="random_legal", auto_reset=True)
+            e2[k].record()
+        barrier()
+        tn = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(s2, e2))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        multi = {"metric": "env-steps/s, 64 steps per launch (b2048_step_many_n)", "value": world * n * Kn * Tn / (float(tn.item()) * 1e-3),
+                 "unit": UNIT, "steps_per_launch": Tn, "launches": Kn, "ms_per_launch": float(tn.item()) / Kn,
+                 "note": "boards, counters and legal masks stay in registers across the 64 steps; only the final state is written"}
     # secondary legs (every rank takes part: the update all-reduces gradients over NCCL)
     extra = {}
+    if multi is not None:
+        extra["env_multi_step"] = multi
     if not args.no_rollout:
         try:
             for key, prec in (("rollout", 1), ("rollout_fp32", 0)):

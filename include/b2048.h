@@ -148,6 +148,21 @@ int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_o
 
 /* Move preview without spawn (Game2048._move, game2048.py:158-165): used by the
  * differential tests and by get_action_mask-style callers. */
+/* n_steps consecutive b2048_step_many calls (step indices t, t + 1, ..., t + n_steps - 1) of a DEVICE-SIDE action mode
+ * (random legal / random any / priority) in ONE launch, in place: every thread keeps its board, counters and legal
+ * mask in registers across the steps, so the steps cost no HBM traffic, no launches and no table staging — random or
+ * scripted play-outs of whole games (tools/simple_action_gen.py) are one call.  Bit-identical to the single-step calls.
+ *   flags       : in/out; with flags_valid != 0 its low 4 bits are the legal masks of `board` (as left by a previous
+ *                 call), else they are recomputed; on return the flags of the last step
+ *   reward_last : optional, reward of the last step;  reward_sum : optional, += float32 sum of the step rewards
+ *   episodes    : optional int32, += number of steps that ended an episode (meaningful with cfg->auto_reset)
+ * Plain reward configuration only (base reward x scale + step reward, action mask on; score / step / max_exp all
+ * given or all NULL); B2048_ERR_UNSUPPORTED otherwise. */
+int b2048_step_many_n(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t* step, uint8_t* max_exp,
+                      uint8_t* flags, int32_t flags_valid, const b2048_env_cfg* cfg, float* reward_last,
+                      float* reward_sum, int32_t* episodes, int64_t n, int32_t n_steps, uint64_t seed,
+                      uint64_t gid0, uint32_t t, void* stream);
+
 int b2048_move_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out,
                     const uint8_t* action, int32_t* merge_sum, uint8_t* merge_info /* [n,4] per line */,
                     uint8_t* flags, int64_t n, void* stream);

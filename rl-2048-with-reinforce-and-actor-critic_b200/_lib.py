@@ -59,6 +59,7 @@ SIGNATURES = {
     "b2048_reset_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _u32, _vp],
     "b2048_step_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp,
                         _vp, _u32, _i64, _u64, _u64, _u32, _vp],
+    "b2048_step_many_n": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(EnvCfg), _vp, _vp, _vp, _i64, _i32, _u64, _u64, _u32, _vp],
     "b2048_move_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "b2048_encode_obs": [_vp, _vp, _i32, _f32, _i64, _vp],
     "b2048_symmetries": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],

@@ -167,6 +167,25 @@ class Batched2048Env:
             self.flags = flags_out
         return reward, flags
 
+    def step_many_n(self, n_steps: int, *, action_mode: str = "random_legal", auto_reset: bool = False,
+                    action_priority=(0, 1, 2, 3), reward_sum_out: torch.Tensor | None = None,
+                    episodes_out: torch.Tensor | None = None):
+        """`n_steps` consecutive env steps of a device-side action mode ('random_legal', 'random_any', 'priority') in
+        ONE kernel launch: boards, counters and legal masks stay in registers across the steps (b2048_step_many_n).
+        Identical to calling step_many n_steps times.  Returns (reward of the last step, flags of the last step);
+        ``reward_sum_out`` (float32 [N]) and ``episodes_out`` (int32 [N]) are accumulated into when given."""
+        if action_mode not in ("random_legal", "random_any", "priority"):
+            raise ValueError("step_many_n needs a device-side action mode")
+        cfg = make_env_cfg(self.config, action_mode, auto_reset, emit_obs=False, action_priority=action_priority)
+        track = self.score is not None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2048_step_many_n(
+                self._h, _ptr(self.board), _ptr(self.score), _ptr(self.step_count), _ptr(self.max_exp), _ptr(self.flags), 1,
+                C.byref(cfg), _ptr(self.reward), _ptr(reward_sum_out), _ptr(episodes_out), self.num_envs, int(n_steps),
+                self.seed, self.gid0, self.t + 1, _stream()), "b2048_step_many_n")
+        self.t += int(n_steps)
+        return self.reward, self.flags
+
     # ------------------------------------------------------------------ views
     def encode_obs(self, board: torch.Tensor | None = None) -> torch.Tensor:
         """Game2048Env._preprocess_board (src/env.py:131-150) for every board -> float32 [N,16] / [N,16*17]."""

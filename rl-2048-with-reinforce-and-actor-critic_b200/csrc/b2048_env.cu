@@ -431,6 +431,103 @@ static void launch_fast(bool track, int grid, size_t smem, cudaStream_t s, const
     }
 }
 
+// ------------------------------------------------------------------------------------------------ multi-step
+// n_steps consecutive steps of a device-side action mode in ONE launch: each thread keeps its board, counters and legal
+// mask in registers across the steps and writes only the final state — no per-step HBM traffic, no per-step launch
+// or table staging.  Same result as n_steps single-step launches with t, t + 1, ... (tested bit for bit).
+struct StepNArgs {
+    uint64_t* board;
+    uint32_t* score;
+    uint32_t* step;
+    uint8_t* max_exp;
+    uint8_t* flags;          // in (low 4 bits = legal mask of board, when flags_valid) / out (flags of the last step)
+    float* reward_last;      // optional: reward of the last step
+    float* reward_sum;       // optional: += float32 sum of the per-step rewards (step order)
+    int32_t* episodes;       // optional: += number of steps that terminated or truncated an episode
+    const uint8_t* tables;
+    int64_t n;
+    int32_t n_steps, flags_valid;
+    uint64_t seed, gid0;
+    uint32_t t;
+    b2048_env_cfg cfg;
+    PhiloxKeys keys;
+};
+
+template <int kAct, bool kTrack>
+__global__ void __launch_bounds__(1024, 1) step_fast_n_kernel(const __grid_constant__ StepNArgs args) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)),
+                     "r"((uint32_t)B2048_TABLES_BYTES)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(smem + B2048_LUT_BYTES)),
+                     "l"(args.tables + B2048_LUT_BYTES), "r"((uint32_t)B2048_SMALL_BYTES), "r"(smem_u32(&mbar))
+                     : "memory");
+        constexpr uint32_t kChunk = 32768;
+#pragma unroll
+        for (uint32_t off = 0; off < (uint32_t)B2048_LUT_BYTES; off += kChunk)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + off)),
+                         "l"(args.tables + off), "r"(kChunk), "r"(smem_u32(&mbar))
+                         : "memory");
+    }
+    FastTables T;
+    T.left = reinterpret_cast<const uint16_t*>(smem);
+    T.merge = smem + B2048_LUT_LEFT_BYTES;
+    T.agg = reinterpret_cast<const AggEntry*>(smem + B2048_LUT_BYTES + B2048_SMALL_AGG_OFF);
+    T.sel = reinterpret_cast<const SelEntry*>(smem + B2048_LUT_BYTES + B2048_SMALL_SEL_OFF);
+    T.act = smem + B2048_LUT_BYTES + B2048_SMALL_ACT_OFF;
+    const b2048_env_cfg& cfg = args.cfg;
+    bool ready = false;
+    const int64_t stride = (int64_t)gridDim.x * 1024;
+    for (int64_t i = (int64_t)blockIdx.x * 1024 + tid; i < args.n; i += stride) {
+        FastIO io;
+        const uint2 bw = *reinterpret_cast<const uint2*>(args.board + i);
+        io.lo = bw.x; io.hi = bw.y;
+        io.score = 0u; io.step = 0u; io.max_exp = 2u; io.action = 0u;
+        if (kTrack) { io.score = args.score[i]; io.step = args.step[i]; io.max_exp = args.max_exp[i]; }
+        io.mask_in = args.flags_valid ? (uint32_t)args.flags[i] : legal_mask(Board{io.lo, io.hi});
+        io.flags = io.mask_in;
+        io.reward = 0.0f;
+        if (!ready) {
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok)
+                    : "r"(smem_u32(&mbar))
+                    : "memory");
+            }
+            ready = true;
+        }
+        float rsum = 0.0f;
+        int32_t eps = 0;
+        const uint64_t gid = args.gid0 + (uint64_t)i;
+        for (int32_t k = 0; k < args.n_steps; ++k) {
+            io.mask_in = io.flags & 0xFu;          // the flags of a step carry the legal mask of the board it returns
+            step_fast<kAct, kTrack>(io, cfg, args.keys, args.seed, gid, args.t + (uint32_t)k, T);
+            rsum += io.reward;
+            eps += (io.flags & (B2048_F_DONE | B2048_F_TRUNC)) ? 1 : 0;
+        }
+        *reinterpret_cast<uint2*>(args.board + i) = make_uint2(io.lo, io.hi);
+        if (kTrack) { args.score[i] = io.score; args.step[i] = io.step; args.max_exp[i] = (uint8_t)io.max_exp; }
+        args.flags[i] = (uint8_t)io.flags;
+        if (args.reward_last) args.reward_last[i] = io.reward;
+        if (args.reward_sum) args.reward_sum[i] += rsum;
+        if (args.episodes) args.episodes[i] += eps;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ previews
 __global__ void __launch_bounds__(256) move_kernel(const uint64_t* __restrict__ board_in, uint64_t* __restrict__ board_out,
                                                     const uint8_t* __restrict__ action, int32_t* __restrict__ merge_sum,
@@ -555,6 +652,11 @@ extern "C" int b2048_create(b2048_handle** out) {
         B2_SET(B2048_ACT_RANDOM_LEGAL, true); B2_SET(B2048_ACT_RANDOM_LEGAL, false);
         B2_SET(B2048_ACT_RANDOM_ANY, true); B2_SET(B2048_ACT_RANDOM_ANY, false);
         B2_SET(B2048_ACT_PRIORITY, true); B2_SET(B2048_ACT_PRIORITY, false);
+#define B2_SET_N(A, TR) B2_CUDA(cudaFuncSetAttribute(step_fast_n_kernel<A, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES))
+        B2_SET_N(B2048_ACT_RANDOM_LEGAL, true); B2_SET_N(B2048_ACT_RANDOM_LEGAL, false);
+        B2_SET_N(B2048_ACT_RANDOM_ANY, true); B2_SET_N(B2048_ACT_RANDOM_ANY, false);
+        B2_SET_N(B2048_ACT_PRIORITY, true); B2_SET_N(B2048_ACT_PRIORITY, false);
+#undef B2_SET_N
 #undef B2_SET
     }
     *out = h;
@@ -673,6 +775,46 @@ extern "C" int b2048_symmetries(b2048_handle* h, const uint64_t* board, const ui
                "b2048_symmetries: every input needs its output buffer and vice versa");
     symmetries_kernel<<<grid_for(rows * n, 256, h->num_sms, 8), 256, 0, (cudaStream_t)stream>>>(
         board, flags, action, board_out, flags_out, action_out, rows, n);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
+extern "C" int b2048_step_many_n(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_t* step, uint8_t* max_exp,
+                                 uint8_t* flags, int32_t flags_valid, const b2048_env_cfg* cfg, float* reward_last,
+                                 float* reward_sum, int32_t* episodes, int64_t n, int32_t n_steps, uint64_t seed,
+                                 uint64_t gid0, uint32_t t, void* stream) {
+    B2_REQUIRE(h != nullptr && cfg != nullptr, "b2048_step_many_n: handle / cfg is NULL");
+    B2_REQUIRE(n >= 0 && n_steps >= 0, "b2048_step_many_n: negative size");
+    if (n == 0 || n_steps == 0) return B2048_OK;
+    B2_REQUIRE(board && flags, "b2048_step_many_n: board / flags must not be NULL");
+    B2_REQUIRE(cfg->action_mode == B2048_ACT_RANDOM_LEGAL || cfg->action_mode == B2048_ACT_RANDOM_ANY ||
+                   cfg->action_mode == B2048_ACT_PRIORITY,
+               "b2048_step_many_n: needs a device-side action mode (random_legal, random_any or priority)");
+    const bool all_track = score && step && max_exp, none_track = !score && !step && !max_exp;
+    const bool ok = h->smem_optin >= B2048_TABLES_BYTES && (all_track || none_track) && cfg->use_action_mask &&
+                    cfg->empty_tile_reward == 0.0 && cfg->merge_reward == 0.0 && cfg->bonus_mode == B2048_BONUS_OFF &&
+                    cfg->endgame_penalty == 0.0 &&
+                    (cfg->reward_mode == B2048_REWARD_SUM || cfg->reward_mode == B2048_REWARD_LOG2);
+    if (!ok)
+        return fail(B2048_ERR_UNSUPPORTED,
+                    "b2048_step_many_n: implemented for the plain reward configuration (base reward x scale + step "
+                    "reward, action mask on) with score / step / max_exp all present or all absent; call "
+                    "b2048_step_many n_steps times otherwise");
+    StepNArgs a;
+    a.board = board; a.score = score; a.step = step; a.max_exp = max_exp; a.flags = flags; a.reward_last = reward_last;
+    a.reward_sum = reward_sum; a.episodes = episodes; a.tables = h->d_tables; a.n = n; a.n_steps = n_steps;
+    a.flags_valid = flags_valid; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg; a.keys = make_keys(seed);
+    const int grid = grid_for(n, 1024, h->num_sms, 1);
+    cudaStream_t s = (cudaStream_t)stream;
+#define B2_LAUNCH_N(A)                                                                                      \
+    do {                                                                                                    \
+        if (all_track) step_fast_n_kernel<A, true><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);                \
+        else step_fast_n_kernel<A, false><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);                         \
+    } while (0)
+    if (cfg->action_mode == B2048_ACT_RANDOM_LEGAL) B2_LAUNCH_N(B2048_ACT_RANDOM_LEGAL);
+    else if (cfg->action_mode == B2048_ACT_PRIORITY) B2_LAUNCH_N(B2048_ACT_PRIORITY);
+    else B2_LAUNCH_N(B2048_ACT_RANDOM_ANY);
+#undef B2_LAUNCH_N
     B2_CUDA(cudaGetLastError());
     return B2048_OK;
 }

@@ -397,3 +397,39 @@ def test_priority_policy_statistics(b2048, prio, doc_avg):
     mean_score = float(final_score.float().mean())
     print("priority", prio, "mean score", mean_score, "docstring", doc_avg)
     assert abs(mean_score - doc_avg) / doc_avg < 0.05, (mean_score, doc_avg)
+
+
+@pytest.mark.parametrize("mode,auto_reset,track", [("random_legal", True, True), ("priority", False, True),
+                                                   ("random_any", True, False), ("random_legal", False, False)])
+def test_step_many_n_equals_single_steps(b2048, mode, auto_reset, track):
+    """b2048_step_many_n (n_steps in one launch, state in registers) == n_steps single-step launches, bit for bit:
+    boards, counters, flags and reward of the last step, float32 reward sum in step order, episode count."""
+    n, K, seed = 70001, 37, 99
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 25
+    cfg = b2048.Game2048EnvConfig(**kw)
+    a = b2048.Batched2048Env(n, cfg, seed=seed, gid0=11, track_state=track)
+    b = b2048.Batched2048Env(n, cfg, seed=seed, gid0=11, track_state=track)
+    a.reset_many(); b.reset_many()
+    for _ in range(3):                                   # both start from the same non-trivial state
+        a.step_many(action_mode="random_legal", auto_reset=True)
+        b.step_many(action_mode="random_legal", auto_reset=True)
+    rsum = torch.zeros(n, dtype=torch.float32, device="cuda")
+    eps = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ref_sum = torch.zeros(n, dtype=torch.float32, device="cuda")
+    ref_eps = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for _ in range(K):
+        rew, fl = a.step_many(action_mode=mode, auto_reset=auto_reset, action_priority=(0, 1, 3, 2))
+        ref_sum += rew
+        ref_eps += ((fl & 0x60) != 0).int()
+    rew_n, fl_n = b.step_many_n(K, action_mode=mode, auto_reset=auto_reset, action_priority=(0, 1, 3, 2),
+                                reward_sum_out=rsum, episodes_out=eps)
+    torch.cuda.synchronize()
+    assert torch.equal(a.board, b.board) and torch.equal(a.flags, fl_n) and torch.equal(a.reward, rew_n)
+    if track:
+        assert torch.equal(a.score, b.score) and torch.equal(a.step_count, b.step_count) and torch.equal(a.max_exp, b.max_exp)
+    assert torch.equal(ref_sum, rsum) and torch.equal(ref_eps, eps)
+    assert a.t == b.t
+    # and the two stay in lock-step afterwards
+    a.step_many(action_mode="random_legal", auto_reset=True)
+    b.step_many(action_mode="random_legal", auto_reset=True)
+    assert torch.equal(a.board, b.board)
