@@ -216,35 +216,62 @@ def run_b200(args):
     value = world * n * K / (kernel_ms * 1e-3)
     clocks = clk.summary()
 
-    # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region
+    # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region.  Per step the actions go
+    #      host -> device and board / reward / flags come back device -> host (13 B per board: PCIe-bound).  The step
+    #      writes into one of two output slots (step_many's board_out / reward_out / flags_out), so the copy-back of
+    #      step k runs on a second stream under the H2D + kernel of step k + 1.
     Ke = min(K, 100)
     h_act = torch.randint(0, 4, (n,), dtype=torch.uint8).pin_memory()
     d_act = torch.empty(n, dtype=torch.uint8, device=dev)
-    h_board = torch.empty(n, dtype=torch.int64).pin_memory()
-    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_flags = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_board = [torch.empty(n, dtype=torch.int64).pin_memory() for _ in range(2)]
+    h_rew = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_flags = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    d_board = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_rew = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+    d_flags = [torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    step_done = [torch.cuda.Event() for _ in range(2)]
+    d2h_done = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream(dev)
+    for ev in d2h_done:
+        ev.record(main)
+    e2e_k = [0]
 
     def e2e_step():
+        slot = e2e_k[0] & 1
+        e2e_k[0] += 1
         d_act.copy_(h_act, non_blocking=True)
-        rew, fl = env.step_many(d_act, auto_reset=True)
-        h_board.copy_(env.board, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_flags.copy_(fl, non_blocking=True)
+        main.wait_event(d2h_done[slot])              # the slot's previous copy-back has read its device buffers
+        env.step_many(d_act, auto_reset=True, board_out=d_board[slot], reward_out=d_rew[slot], flags_out=d_flags[slot])
+        step_done[slot].record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(step_done[slot])
+            h_board[slot].copy_(d_board[slot], non_blocking=True)
+            h_rew[slot].copy_(d_rew[slot], non_blocking=True)
+            h_flags[slot].copy_(d_flags[slot], non_blocking=True)
+            d2h_done[slot].record(copy_stream)
+
+    def e2e_drain():
+        main.wait_event(d2h_done[0])
+        main.wait_event(d2h_done[1])
 
     for _ in range(3):
         e2e_step()
+    e2e_drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(Ke):
         e2e_step()
+    e2e_drain()                                      # the last results are on the host before the clock stops
     e1.record()
     barrier()
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * Ke / (float(te.item()) * 1e-3)
-    checksum = int(h_board.sum().item()) ^ int(h_flags.sum().item())
+    last = (e2e_k[0] - 1) & 1
+    checksum = int(h_board[last].sum().item()) ^ int(h_flags[last].sum().item())
 
     if rank == 0:
         peak, peak_src = measured_peaks()
