@@ -466,8 +466,9 @@ class ReinforceAgent:
         n_live = int(length.sum().item())
         if n_live < int(0.9 * n):
             tgrid = torch.arange(T, device=dev, dtype=torch.int32).unsqueeze(1)
-            live = (tgrid < length.unsqueeze(0)).reshape(-1)
-            boards, mflags, acts = boards[live], mflags[live], acts[live]
+            # ONE stream compaction (nonzero) of the live mask; everything per-sample is then an index_select by it
+            live = torch.nonzero((tgrid < length.unsqueeze(0)).reshape(-1)).reshape(-1)
+            boards, mflags, acts = boards.index_select(0, live), mflags.index_select(0, live), acts.index_select(0, live)
             n = n_live
         stats = self._buf("stats", (4,), torch.float64)
         ep_mean = self._buf("ep_mean", (B,), torch.float32)
@@ -492,7 +493,7 @@ class ReinforceAgent:
 
         def backward(net: DeviceMLP, cf: torch.Tensor, head_mode: int):
             if live is not None:
-                cf = cf[live]
+                cf = cf.index_select(0, live)
             net.grad.zero_()
             ws_floats = int(lib.b2048_backward_workspace_floats(C.byref(net.desc), min(chunk, n)))
             ws = self._buf("bwd_ws", (ws_floats,), torch.float32)
