@@ -300,7 +300,7 @@ class ReinforceAgent:
 
     # ------------------------------------------------------------------ batched rollouts
     def rollout_many(self, benv: Batched2048Env, max_steps: int | None = None, horizon: int | None = None,
-                     greedy: bool = False, precision: int | str = 0, reset: bool = True, check_every: int = 32) -> Rollout:
+                     greedy: bool = False, precision: int | str = 0, reset: bool = True, check_every: int = 48) -> Rollout:
         """Rolls the whole batch with the current policy.
         horizon=None: every board plays to termination / truncation like run_episode (finished boards are
         frozen by the step kernel); horizon=H: fixed H steps with reset-on-done (all lanes always live)."""
