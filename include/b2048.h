@@ -219,12 +219,21 @@ int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mas
  * persistent kernel (tcgen05 policy + env step); anything else is a policy-kernel / step-kernel loop.
  * slot_map (device int32[n_slots], may be NULL): play only the listed boards — run-to-termination callers pass the
  * boards still alive at the start of the chunk, so finished episodes cost nothing; slices t > ep_len[b] of a board
- * that is not listed are left untouched.  Fused kernel only. */
+ * that is not listed are left untouched.  Fused kernel only.
+ * n_slots_dev (device int32[1], may be NULL): the number of listed boards is read from device memory (as written by
+ * b2048_compact_live) and n_slots is only an upper bound for the launch — the host can then enqueue the next chunk
+ * without waiting for the count. */
 int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* flags, uint8_t* actions, float* rewards,
                        uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                        const b2048_env_cfg* cfg /* host */, const b2048_mlp_desc* mlp /* host */, int64_t B,
                        int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
-                       int32_t greedy, int32_t precision, const int32_t* slot_map, int64_t n_slots, void* stream);
+                       int32_t greedy, int32_t precision, const int32_t* slot_map, int64_t n_slots,
+                       const int32_t* n_slots_dev, void* stream);
+
+/* slot_map[0 .. *count) = the boards with ep_len[b] == 0 (episode still running), for b2048_rollout_many's slot_map;
+ * count is a device int32 (zeroed by the call).  Order is unspecified (a board's results do not depend on its slot). */
+int b2048_compact_live(b2048_handle* h, const int32_t* ep_len, int64_t B, int32_t* slot_map, int32_t* count,
+                       void* stream);
 
 /* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1).
  *   precision : 0 = fp32 CUDA cores; 1 = bf16 tcgen05 (16-256-256-(<=4) ReLU, raw / log2 observations, n >= 4096,

@@ -65,7 +65,8 @@ SIGNATURES = {
     "b2048_symmetries": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "b2048_policy_step": [_vp, _vp, _vp, C.POINTER(MlpDesc), _vp, _vp, _vp, _i64, _u64, _u64, _u32, _i32, _i32, _vp],
     "b2048_rollout_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(EnvCfg), C.POINTER(MlpDesc), _i64, _i32, _i32,
-                           _u64, _u64, _u32, _i32, _i32, _i32, _vp, _i64, _vp],
+                           _u64, _u64, _u32, _i32, _i32, _i32, _vp, _i64, _vp, _vp],
+    "b2048_compact_live": [_vp, _vp, _i64, _vp, _vp, _vp],
     "b2048_mlp_forward": [_vp, _vp, C.POINTER(MlpDesc), _vp, _i64, _i32, _vp],
     "b2048_dense_forward": [_vp, _vp, C.POINTER(MlpDesc), _vp, _vp, _i64, _vp],
     "b2048_reverse_scan": [_vp, _vp, _vp, _f32, _i32, _i64, _vp],

@@ -153,7 +153,8 @@ int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
                       float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                       const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
-                      uint32_t t0, int use_mask, int greedy, const int32_t* slot_map, int64_t n_slots, cudaStream_t stream);
+                      uint32_t t0, int use_mask, int greedy, const int32_t* slot_map, int64_t n_slots, const int32_t* n_slots_dev,
+                      cudaStream_t stream);
 
 int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int smem_optin, const char* who) {
     if (!d) return fail(B2048_ERR_INVALID, std::string(who) + ": mlp descriptor is NULL");
@@ -198,6 +199,34 @@ extern "C" int b2048_policy_step(b2048_handle* h, const uint64_t* board, const u
                             true);
 }
 
+// Live-board list of a run-to-termination rollout: slot_map[0 .. *count) = the boards whose episode is still running
+// (ep_len[b] == 0), in no particular order (a board's results do not depend on its slot).  *count must be zero on entry.
+__global__ void __launch_bounds__(256) compact_live_kernel(const int32_t* __restrict__ ep_len, int64_t B,
+                                                            int32_t* __restrict__ slot_map, int32_t* __restrict__ count) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = b < B && ep_len[b] == 0;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, live);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs((int)m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (live) slot_map[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)b;
+}
+
+extern "C" int b2048_compact_live(b2048_handle* h, const int32_t* ep_len, int64_t B, int32_t* slot_map, int32_t* count,
+                                  void* stream) {
+    B2_REQUIRE(h != nullptr, "b2048_compact_live: handle is NULL");
+    B2_REQUIRE(B >= 0 && B < ((int64_t)1 << 31), "b2048_compact_live: B out of range");
+    B2_REQUIRE(ep_len && slot_map && count, "b2048_compact_live: NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), s));
+    if (B == 0) return B2048_OK;
+    compact_live_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(ep_len, B, slot_map, count);
+    B2_CUDA(cudaGetLastError());
+    return B2048_OK;
+}
+
 // The rollout loop of ReinforceAgent.run_episode (reference src/reinforce_agent.py:221-236) for a whole batch, issued
 // from C so that a rollout step costs two kernel launches and no interpreter time: for k in [0, n_steps):
 //   t = t_begin + k;  actions[t] = policy(boards[t], flags[t]);  (boards[t+1], flags[t+1], rewards[t]) = step(...)
@@ -206,7 +235,7 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
                                   const b2048_env_cfg* cfg, const b2048_mlp_desc* mlp, int64_t B, int32_t t_begin,
                                   int32_t n_steps, uint64_t seed, uint64_t gid0, uint32_t t0, int32_t use_mask,
                                   int32_t greedy, int32_t precision, const int32_t* slot_map, int64_t n_slots,
-                                  void* stream) {
+                                  const int32_t* n_slots_dev, void* stream) {
     B2_REQUIRE(h != nullptr, "b2048_rollout_many: handle is NULL");
     B2_REQUIRE(B >= 0 && n_steps >= 0 && t_begin >= 0, "b2048_rollout_many: negative size");
     if (B == 0 || n_steps == 0) return B2048_OK;
@@ -216,7 +245,7 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
     if (precision == 1) {
         // one persistent launch for the whole horizon (policy on tcgen05 + env step in the same kernel)
         int st = launch_rollout_tc(h, mlp, boards, flags, actions, rewards, score, step, max_exp, ep_len, &c, B, t_begin, n_steps,
-                                   seed, gid0, t0, use_mask, greedy, slot_map, n_slots, (cudaStream_t)stream);
+                                   seed, gid0, t0, use_mask, greedy, slot_map, n_slots, n_slots_dev, (cudaStream_t)stream);
         if (st != B2048_ERR_UNSUPPORTED) return st;
     }
     B2_REQUIRE(slot_map == nullptr, "b2048_rollout_many: slot_map needs the fused tensor-core rollout kernel (precision 1, "

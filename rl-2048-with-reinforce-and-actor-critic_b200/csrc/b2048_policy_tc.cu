@@ -103,6 +103,8 @@ struct PolicyTcArgs {
     const uint8_t* tables;    // row tables + small tables (global memory; read through L1 / L2)
     const int32_t* slot_map;  // nullable: slot s of the launch is board slot_map[s] (run-to-termination rollouts launch
                               // the live boards only); n = number of slots, ro_stride = boards per record slice
+    const int32_t* n_dev;     // nullable: the number of slots is read from device memory (b2048_compact_live wrote it),
+                              // so the host can enqueue the next chunk without waiting for the count; n = upper bound
     int64_t ro_stride;
     uint64_t seed;
     int32_t t_begin, n_steps;
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
+    const int64_t n_slots = (kRollout && args.n_dev) ? (int64_t)*args.n_dev : args.n;   // uniform over the grid
+    const int64_t n_tiles = (n_slots + TC_M - 1) / TC_M;
     const int64_t first = blockIdx.x;
     // items of this CTA: its tiles, times the number of rollout steps
     const int n_owned = first < n_tiles ? (int)((n_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
             auto encode_a1 = [&](int j, int r) {   // this thread's board -> 16 bf16 in the A1 core matrices
                 const int64_t s = tile_of(j) * TC_M + row;
                 uint64_t bd = 0ull;
-                if (s < args.n) {
+                if (s < n_slots) {
                     const int64_t b = (kRollout && args.slot_map) ? args.slot_map[s] : s;
                     bd = board_base[slice_of(r) * (kRollout ? args.ro_stride : args.n) + b];
                 }
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 if (jn == n_owned) { jn = 0; ++rn; }
                 const int64_t s = tile_of(j) * TC_M + row;
                 const int64_t slice = slice_of(r);
-                const bool valid = s < args.n;
+                const bool valid = s < n_slots;
                 const int64_t b = (kRollout && valid && args.slot_map) ? args.slot_map[s] : s;   // board behind the slot
                 const int64_t stride = kRollout ? args.ro_stride : args.n;
                 const bool use_mask = args.mask_flags != nullptr;               // rollout: non-NULL iff the policy is masked
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
             auto load_in = [&](int j, int r) {
                 EnvIn e = {0ull, 0u, 0u, 2u, 0u, 0};
                 const int64_t s = tile_of(j) * TC_M + row;
-                if (s < args.n) {
+                if (s < n_slots) {
                     const int64_t b = args.slot_map ? args.slot_map[s] : s;
                     const int64_t i = slice_of(r) * args.ro_stride + b;
                     e.bd = args.ro_boards[i]; e.fin = args.ro_flags[i];
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 const int item = r * n_owned + j;
                 const int64_t s = tile_of(j) * TC_M + row;
                 const int64_t slice = slice_of(r);
-                const bool valid = s < args.n;
+                const bool valid = s < n_slots;
                 const int64_t b = (valid && args.slot_map) ? args.slot_map[s] : s;
                 const uint32_t t_env = args.t0 + (uint32_t)slice + 1u;
                 FastIO io;
@@ -639,7 +642,7 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     a.debug_clock = nullptr;
     a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
     a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = seed; a.t_begin = 0; a.n_steps = 1;
-    a.t0 = 0; a.slot_map = nullptr; a.ro_stride = n;
+    a.t0 = 0; a.slot_map = nullptr; a.n_dev = nullptr; a.ro_stride = n;
     a.debug_clock = debug_clock_buffer();
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
@@ -664,7 +667,7 @@ int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
     a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
     a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
     a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = 0; a.t_begin = 0; a.n_steps = 1;
-    a.t0 = 0; a.slot_map = nullptr; a.ro_stride = n;
+    a.t0 = 0; a.slot_map = nullptr; a.n_dev = nullptr; a.ro_stride = n;
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     policy_tc_kernel<false><<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
@@ -677,7 +680,8 @@ int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
                       float* rewards, uint32_t* score, uint32_t* step, uint8_t* max_exp, int32_t* ep_len,
                       const b2048_env_cfg* cfg, int64_t B, int32_t t_begin, int32_t n_steps, uint64_t seed, uint64_t gid0,
-                      uint32_t t0, int use_mask, int greedy, const int32_t* slot_map, int64_t n_slots, cudaStream_t stream) {
+                      uint32_t t0, int use_mask, int greedy, const int32_t* slot_map, int64_t n_slots, const int32_t* n_slots_dev,
+                      cudaStream_t stream) {
     const bool net_ok = mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H &&
                         mlp->dims[3] == 4 && mlp->activation == B2048_ACTV_RELU &&
                         (mlp->obs_mode == B2048_OBS_RAW || mlp->obs_mode == B2048_OBS_LOG2) && h->smem_optin >= SM_TOTAL_RO;
@@ -698,7 +702,8 @@ int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boar
     a.obs_mode = mlp->obs_mode; a.obs_scale = mlp->obs_log2_scale; a.debug_clock = nullptr;
     a.ro_boards = boards; a.ro_flags = flags; a.ro_actions = actions; a.ro_rewards = rewards; a.score = score; a.step = step;
     a.max_exp = max_exp; a.ep_len = ep_len; a.tables = h->d_tables; a.seed = seed; a.t_begin = t_begin; a.n_steps = n_steps;
-    a.t0 = t0; a.cfg = *cfg; a.cfg.action_mode = B2048_ACT_BUFFER; a.slot_map = slot_map; a.ro_stride = B;
+    a.t0 = t0; a.cfg = *cfg; a.cfg.action_mode = B2048_ACT_BUFFER; a.slot_map = slot_map; a.n_dev = slot_map ? n_slots_dev : nullptr;
+    a.ro_stride = B;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     a.debug_clock = debug_clock_buffer();
     policy_tc_kernel<true><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);

@@ -327,26 +327,54 @@ class ReinforceAgent:
         # rewards buffer is zeroed first (total_reward sums whole columns) and the final state is gathered below.
         compact = (not fixed) and int(precision) == 1 and B >= 4096 and self.tc_supported() and \
             os.environ.get("B2048_NO_FUSED_ROLLOUT") is None and os.environ.get("B2048_NO_COMPACT_ROLLOUT") is None
-        slot_map, n_slots = None, 0
         if compact:
             rewards.zero_()
-        while T < cap:
+            # Live-board bookkeeping stays on the device: after every chunk b2048_compact_live rebuilds the list and its
+            # count, the next chunk's kernel reads the count from device memory, and the host only looks at the count
+            # of the chunk BEFORE the one it has just enqueued (pinned copy + event) — the GPU never waits for the host.
+            slot_buf = self._buf("ro_slot_map", (B,), torch.int32)
+            count_dev = self._buf("ro_live_count", (1,), torch.int32)
+            n_max = (cap + check_every - 1) // check_every + 1
+            count_host = getattr(self, "_ro_count_host", None)
+            if count_host is None or count_host.numel() < n_max:
+                count_host = self._ro_count_host = torch.zeros(n_max, dtype=torch.int32).pin_memory()
+            events: list[torch.cuda.Event] = []
+            upper, k = B, 0
+            while T < cap:
+                chunk = min(check_every, cap - T)
+                with torch.cuda.device(self.device):
+                    _lib.check(self._lib.b2048_rollout_many(
+                        self._h, _ptr(boards), _ptr(flags), _ptr(actions), _ptr(rewards), _ptr(benv.score),
+                        _ptr(benv.step_count), _ptr(benv.max_exp), _ptr(length), C.byref(cfg), C.byref(self._actor.desc), B, T,
+                        chunk, benv.seed, benv.gid0, t0, int(self._use_mask), int(greedy), 1,
+                        _ptr(slot_buf) if k > 0 else None, upper, _ptr(count_dev) if k > 0 else None, _stream()),
+                        "b2048_rollout_many")
+                    _lib.check(self._lib.b2048_compact_live(self._h, _ptr(length), B, _ptr(slot_buf), _ptr(count_dev), _stream()),
+                               "b2048_compact_live")
+                count_host[k: k + 1].copy_(count_dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+                T += chunk
+                if k >= 1:                      # boards alive after chunk k - 1 (that copy finished before chunk k started)
+                    events[k - 1].synchronize()
+                    alive = int(count_host[k - 1])
+                    if alive == 0:              # chunk k found nothing to play
+                        T -= chunk
+                        break
+                    upper = alive
+                k += 1
+        while not compact and T < cap:
             chunk = min(check_every if not fixed else 256, cap - T)
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.b2048_rollout_many(
                     self._h, _ptr(boards), _ptr(flags), _ptr(actions), _ptr(rewards), _ptr(benv.score), _ptr(benv.step_count),
                     _ptr(benv.max_exp), None if fixed else _ptr(length), C.byref(cfg), C.byref(self._actor.desc), B, T,
                     chunk, benv.seed, benv.gid0, t0, int(self._use_mask), int(greedy), int(precision),
-                    _ptr(slot_map), n_slots, _stream()), "b2048_rollout_many")
+                    None, 0, None, _stream()), "b2048_rollout_many")
             T += chunk
-            if not fixed:
-                if compact:
-                    slot_map = torch.nonzero(length == 0).reshape(-1).to(torch.int32)   # boards still playing
-                    n_slots = int(slot_map.numel())
-                    if n_slots == 0:
-                        break
-                elif bool((length != 0).all()):
-                    break
+            if not fixed and bool((length != 0).all()):
+                break
         benv.t = t0 + T
         if fixed:
             length.fill_(T)
