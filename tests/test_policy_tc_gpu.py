@@ -144,3 +144,32 @@ def test_fused_rollout_kernel_equals_two_kernel_loop(b2048, n, horizon, max_step
         for k in ("boards", "flags", "actions", "rewards"):
             assert (a[k] == b[k]).all(), k
     assert a["rewards"][live].sum() > 0
+
+
+def test_fused_rollout_greedy_equals_two_kernel_loop(b2048):
+    """Greedy (evaluation) rollouts: fused persistent kernel == policy-kernel / step-kernel loop, raw observations."""
+    import os
+    from helpers import full_env_kwargs
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 60; kw["obs_mode"] = "raw"; kw["obs_log2_scale"] = 1.0
+    outs = []
+    for fused in (False, True):
+        if not fused:
+            os.environ["B2048_NO_FUSED_ROLLOUT"] = "1"
+        try:
+            benv = b2048.Batched2048Env(20000, b2048.Game2048EnvConfig(**kw), seed=5, gid0=0)
+            agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                         b2048.ReinforceAgentConfig())
+            p = b2048.init_model_params(16, [256, 256], 4, np.random.default_rng(8), "HeNormal")
+            p["W"][0] = p["W"][0] * 0.05                 # raw tile values are large: keep the logits moderate
+            agent.params = p
+            ro = agent.rollout_many(benv, greedy=True, precision=1)
+            torch.cuda.synchronize()
+            outs.append((ro.T, ro.length.cpu().numpy(), ro.actions.cpu().numpy(), ro.rewards.cpu().numpy(),
+                         benv.score.cpu().numpy(), benv.board.cpu().numpy()))
+        finally:
+            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+    (Ta, La, Aa, Ra, Sa, Ba), (Tb, Lb, Ab, Rb, Sb, Bb) = outs
+    assert (La == Lb).all() and (Sa == Sb).all() and (Ba == Bb).all()
+    T = min(Ta, Tb)
+    live = np.arange(T)[:, None] < La[None, :]
+    assert (Aa[:T][live] == Ab[:T][live]).all() and (Ra[:T][live] == Rb[:T][live]).all()
