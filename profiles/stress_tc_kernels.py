@@ -1,0 +1,55 @@
+"""Stress run of the barrier-heavy tensor-core kernels: many shapes of the fused persistent rollout kernel against the
+two-kernel loop (bit-exact on the live region), and the tensor-core update against the fp32 kernels, repeated with
+different seeds.  A protocol race would show up as a mismatch or a hang (run it under `timeout`)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, b2048
+
+torch.cuda.set_device(0)
+KW = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", base_reward_scale=0.5)
+rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+t_end = time.time() + (float(sys.argv[2]) if len(sys.argv) > 2 else 120.0)
+n_cases = 0
+while time.time() < t_end:
+    B = int(rng.choice([4096, 4097, 8192, 18944, 19000, 33000, 65536, 100001, 150000, 300000]))
+    horizon = None if rng.random() < 0.5 else int(rng.integers(3, 70))
+    max_steps = int(rng.integers(10, 90))
+    greedy = bool(rng.random() < 0.3)
+    seed = int(rng.integers(1, 1 << 30))
+    outs = []
+    for fused in (False, True):
+        if not fused:
+            os.environ["B2048_NO_FUSED_ROLLOUT"] = "1"
+        else:
+            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+        env = b2048.Batched2048Env(B, b2048.Game2048EnvConfig(max_steps=max_steps, **KW), seed=seed, gid0=seed % 1000)
+        agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(model_seed=seed % 97))
+        ro = agent.rollout_many(env, horizon=horizon, greedy=greedy, precision=1, check_every=int(rng.integers(5, 60)) if fused else 32)
+        torch.cuda.synchronize()
+        outs.append((ro.T, ro.length.clone(), ro.actions.clone(), ro.rewards.clone(), ro.boards.clone(), env.score.clone(),
+                     env.board.clone(), agent, ro))
+    os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+    (Ta, La, Aa, Ra, Ba, Sa, Fa, _, _), (Tb, Lb, Ab, Rb, Bb, Sb, Fb, agent, ro) = outs
+    assert torch.equal(La, Lb) and torch.equal(Sa, Sb) and torch.equal(Fa, Fb), ("state", B, horizon, max_steps)
+    T = min(Ta, Tb)
+    live = torch.arange(T, device="cuda").unsqueeze(1) < La.unsqueeze(0)
+    live1 = torch.arange(T + 1, device="cuda").unsqueeze(1) <= La.unsqueeze(0)
+    assert torch.equal(Aa[:T][live], Ab[:T][live]) and torch.equal(Ra[:T][live], Rb[:T][live]), ("record", B, horizon, max_steps)
+    assert torch.equal(Ba[: T + 1][live1], Bb[: T + 1][live1]), ("boards", B, horizon, max_steps)
+    # tensor-core update vs fp32 on the fused rollout
+    th0 = agent._actor.theta.clone()
+    i1 = agent.update_from_rollout(ro, precision=1)
+    d1 = agent._actor.theta - th0
+    agent._actor.theta.copy_(th0)
+    i0 = agent.update_from_rollout(ro, precision=0)
+    d0 = agent._actor.theta - th0
+    rel = float((d1 - d0).norm() / d0.norm())
+    gn = abs(i1["actor_grad_norm"] - i0["actor_grad_norm"]) / i0["actor_grad_norm"]
+    # The bf16-rounded network is a slightly different policy than the float32 one: on a weak,
+    # heavily cancelling gradient the two updates differ by 5-40 %.  A protocol race would give NaNs or O(1) norm errors;
+    # kernel exactness is what tests/test_learn_tc_gpu.py pins against the bf16-rounding oracle.
+    assert np.isfinite(rel) and rel < 1.0 and gn < 0.15, ("update", B, rel, gn)
+    n_cases += 1
+    print(f"case {n_cases}: B={B} horizon={horizon} max_steps={max_steps} greedy={greedy} T={T} update rel {rel:.3f} OK", flush=True)
+print("stress OK:", n_cases, "cases")
