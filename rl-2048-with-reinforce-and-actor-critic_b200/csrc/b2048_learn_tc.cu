@@ -709,7 +709,6 @@ int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         g.tiles64 = tiles * 2;
         // dW2 = H1^T DL2, db2 = column sums of DL2
         g.A = a.h1; g.B = a.dl2; g.C = gW2; g.ldm = TC_H; g.ldn = 1; g.n_valid = TC_H; g.colsum = gb2; g.colsum_of_b = 1;
-        if (getenv("B2048_ATB_NOCOLSUM")) g.colsum = nullptr;   // timing experiment only (db2 is then missing)
         if ((st = launch_atb<256>(h, g, stream)) != B2048_OK) return st;
         // dW3 = H2^T d3
         g.A = a.h2; g.B = a.d3t; g.C = gW3; g.ldm = n_out; g.ldn = 1; g.n_valid = n_out; g.colsum = nullptr; g.colsum_of_b = 0;
