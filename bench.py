@@ -335,7 +335,8 @@ def run_b200(args):
     if not args.no_rollout:
         try:
             for key, prec in (("rollout", 1), ("rollout_fp32", 0)):
-                r = b2048.bench_rollout(dev, gid0=rank * 65536, precision=prec)
+                # tensor-core leg: 256 steps = one persistent launch; fp32 leg: 64 steps (two launches per step)
+                r = b2048.bench_rollout(dev, gid0=rank * 65536, precision=prec, steps=256 if prec == 1 else 64)
                 v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(v, op=dist.ReduceOp.SUM)
