@@ -632,6 +632,7 @@ extern "C" int b2048_create(b2048_handle** out) {
     B2_REQUIRE(out != nullptr, "b2048_create: out is NULL");
     b2048_handle* h = new b2048_handle();
     h->tc_image = nullptr;
+    h->attrs = 0u;
     B2_CUDA(cudaGetDevice(&h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));

@@ -628,11 +628,11 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
 
 template <int NB>
 static int launch_atb(b2048_handle* h, const AtbArgs& a, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    constexpr unsigned kBit = NB == 256 ? 4u : 8u;
+    if (!(h->attrs & kBit)) {
         cudaError_t e = cudaFuncSetAttribute(atb_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtbCfg<NB>::kSmem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(atb_tc_kernel)");
-        attr_set = true;
+        h->attrs |= kBit;
     }
     int grid = (int)(a.tiles64 < h->num_sms ? a.tiles64 : h->num_sms);
     atb_tc_kernel<NB><<<grid, ATB_THREADS, AtbCfg<NB>::kSmem, stream>>>(a);
@@ -652,12 +652,11 @@ int64_t backward_tc_workspace_bytes(int64_t chunk) { return tc_workspace(chunk).
 int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                        uint8_t* workspace, int64_t chunk, cudaStream_t stream) {
-    static bool attr_set = false;
     { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
-    if (!attr_set) {
+    if (!(h->attrs & 2u)) {
         cudaError_t e = cudaFuncSetAttribute(fb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_TOTAL);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(fb_tc_kernel)");
-        attr_set = true;
+        h->attrs |= 2u;
     }
     launch_tc_prepare(mlp, h->tc_image, stream);
     const int n_out = mlp->dims[3];

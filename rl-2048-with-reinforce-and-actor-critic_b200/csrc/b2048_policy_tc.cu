@@ -585,17 +585,16 @@ void launch_tc_prepare(const b2048_mlp_desc* mlp, uint8_t* img, cudaStream_t str
 // Allocates the handle's weight-image buffer (shared by the policy, rollout and training kernels; also used by
 // b2048_learn_tc.cu) and opts the kernels of this file into their dynamic shared memory sizes.
 int ensure_tc_image(b2048_handle* h) {
-    static bool attrs_set = false;
     if (!h->tc_image) {
         cudaError_t e = cudaMalloc(&h->tc_image, IMG_BYTES);
         if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(tc_image)");
     }
-    if (!attrs_set) {
+    if (!(h->attrs & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
         e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
-        attrs_set = true;
+        h->attrs |= 1u;
     }
     return B2048_OK;
 }
