@@ -130,6 +130,17 @@ def cpu_baseline(seconds: float = 10.0):
                       f"{cores} processes of oracle/pyport.py (per-env Python+NumPy restatement of the reference)"}
 
 
+def cpu_rollout_baseline(seconds: float = 5.0):
+    """north_star: "the reference's CPU env + rollout timed on the box's own host cores" — the rollout half: the
+    reference's run_episode loop (NumPy MLP forward + sampling + env step) per environment, one process per core."""
+    from oracle import pyport
+    cores = len(os.sched_getaffinity(0))
+    rate, nsteps = pyport.time_rollout_multiprocess(seconds, cores)
+    return {"value": rate, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{nsteps} policy-rollout steps (16-256-256-4 NumPy MLP + masked sampling + env step, runner-default env) in "
+                      f"~{seconds:.0f} s, {cores} processes of oracle/pyport.py"}
+
+
 def cpu_native_baseline(n=1 << 18, steps=20):
     """Extra context: the C oracle (same rules, compiled, multi-threaded) — a much stronger CPU baseline."""
     import oracle
@@ -303,6 +314,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            line["cpu_baseline_rollout"] = cpu_rollout_baseline(min(5.0, args.cpu_seconds))
             try:
                 line["cpu_baseline_native"] = cpu_native_baseline()
             except Exception as e:  # the native leg is context only

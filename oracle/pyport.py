@@ -231,3 +231,55 @@ def time_multiprocess_series(seconds: float, procs: int, count: int) -> list[tup
             res = pool.map(_worker, [(seconds, 1000 + 131 * k + i) for i in range(procs)])
             out.append((sum(n / dt for n, dt in res), sum(n for n, _ in res)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- policy rollout
+def time_policy_rollout_steps(seconds: float, seed: int = 0) -> tuple[int, float]:
+    """ReinforceAgent.run_episode restated at the reference's granularity (src/reinforce_agent.py:126-252,
+    src/MLP.py:22-196): per step encode_observation -> three float32 `a @ W + b` products with ReLU -> masked
+    max-subtracted softmax -> rng.choice(4, p=probs) -> env.step, trajectory lists appended, on one environment with the
+    runner-default 16-256-256-4 network.  (Without the reference's eager debug strings and ANSI renders, which are
+    logging: this port is therefore a slightly faster baseline than the reference itself.)"""
+    rng = np.random.default_rng(seed)
+    sizes = [16, 256, 256, 4]
+    W = [(rng.normal(size=(i, o)) * np.sqrt(2.0 / i)).astype(np.float32) for i, o in zip(sizes[:-1], sizes[1:])]
+    b = [np.zeros(o, np.float32) for o in sizes[1:]]
+    env = PyEnv(**RUNNER_DEFAULT_ENV)
+    obs = env.reset(seed)
+    n = 0
+    obs_list, act_list, rew_list = [], [], []
+    t0 = time.perf_counter()
+    while True:
+        x = obs["board"].astype(np.float32).flatten()
+        mask = obs["action_mask"]
+        a = x
+        for l in range(3):
+            z = a @ W[l] + b[l]
+            a = np.maximum(z, 0.0) if l < 2 else z
+        logits = np.where(mask.astype(bool), a, -1e9)
+        e = np.exp(logits - np.max(logits))
+        probs = e / np.sum(e)
+        action = int(rng.choice(4, p=probs))
+        nobs, r, done, trunc = env.step(action)
+        obs_list.append(obs); act_list.append(action); rew_list.append(float(r))
+        obs = nobs
+        n += 1
+        if done or trunc:
+            obs = env.reset(seed + n)
+            obs_list, act_list, rew_list = [], [], []
+        if (n & 31) == 0 and time.perf_counter() - t0 >= seconds:
+            break
+    return n, time.perf_counter() - t0
+
+
+def _rollout_worker(args):
+    seconds, seed = args
+    return time_policy_rollout_steps(seconds, seed)
+
+
+def time_rollout_multiprocess(seconds: float, procs: int) -> tuple[float, int]:
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_rollout_worker, [(seconds, 5000 + i) for i in range(procs)])
+    return sum(n / dt for n, dt in res), sum(n for n, _ in res)

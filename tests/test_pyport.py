@@ -55,3 +55,10 @@ def test_pyport_replays_golden(name):
                 ob = obs["board"] if mask_on else obs
                 assert (np.asarray(ob, np.float32).reshape(-1) == g[f"{name}/obs"][t - 1][i]).all()
         alive = g[f"{name}/alive"][t - 1][:n]
+
+
+def test_policy_rollout_port_runs():
+    """The CPU rollout baseline (run_episode restated per environment) steps and resets."""
+    from oracle import pyport
+    n, dt = pyport.time_policy_rollout_steps(0.3, seed=3)
+    assert n >= 32 and dt > 0
