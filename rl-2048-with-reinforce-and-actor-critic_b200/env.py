@@ -69,9 +69,9 @@ class Game2048Env(_EnvBase):
             self._logger.addHandler(logging.NullHandler())
         self.action_space = spaces.Discrete(4)
         self.observation_space = self._build_observation_space()
-        dev = self._benv.device
-        self._obs_buf = torch.zeros((1, self._benv.obs_width), dtype=torch.float32, device=dev)
-        self._r64 = torch.zeros(1, dtype=torch.float64, device=dev)
+        # observation and float64 reward live in the game's packed device buffer (one read-back per step)
+        self._obs_buf = self.game._obs_dev[: self._benv.obs_width].view(1, self._benv.obs_width)
+        self._r64 = self.game._r64
 
     @property
     def state(self) -> list[list[int]]:
@@ -104,6 +104,9 @@ class Game2048Env(_EnvBase):
     def _get_obs(self):
         return self._shape_obs(self._benv.encode_obs().cpu().numpy()[0])
 
+    def _obs_from_host(self):
+        return self._shape_obs(self.game._host_obs(self._benv.obs_width))
+
     def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None):
         super().reset(seed=seed)
         self._step_count = 0
@@ -128,19 +131,20 @@ class Game2048Env(_EnvBase):
         if is_changed:
             n_empty = sum(1 for i in range(16) if not (moved >> (4 * i)) & 0xF)
             replay = g._draw_spawn(n_empty)
-        g._replay[0] = replay
-        g._act.fill_(int(action))
+        g._ctl_host[0] = int(action)
+        g._ctl_host[1] = replay
+        g._ctl.copy_(g._ctl_host, non_blocking=True)
         # the fused kernel: move, spawn, reward (float64, env.py:197-261), done / truncated, mask, observation
         self._benv.step_many(g._act, spawn_replay=g._replay[:1], reward64_out=self._r64, obs_out=self._obs_buf)
-        g._sync_from_device()
-        g.score = int(self._benv.score.cpu()[0])
+        g._sync_from_device()                                   # the step's only read-back
+        g.score = g._host_score()
         flags = g._flags
-        reward = float(self._r64.cpu()[0])
-        self.max_tile_seen = 1 << int(self._benv.max_exp.cpu()[0])
+        reward = g._host_reward64()
+        self.max_tile_seen = 1 << g._host_max_exp()
         terminated = bool(flags & _lib.F_DONE)
         truncated = bool(flags & _lib.F_TRUNC)
         invalid_action = (not is_changed) and (not terminated)
-        obs = self._shape_obs(self._obs_buf.cpu().numpy()[0])
+        obs = self._obs_from_host()
         info_d = {"score": g.score, "raw_state": g.state, "merged": merged, "invalid_action": invalid_action,
                   "step_index": self._step_count}
         return obs, reward, terminated, truncated, info_d

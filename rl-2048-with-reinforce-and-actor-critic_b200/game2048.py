@@ -57,11 +57,33 @@ class Game2048:
         self._new_merged: list[int] = []
         self._logger = logging.getLogger(__name__ + ".Game2048")
         self._packed: int = 0
-        self._replay = torch.zeros(2, dtype=torch.uint8, device=self._dev)
-        self._act = torch.zeros(1, dtype=torch.uint8, device=self._dev)
-        self._tmp_board = torch.zeros(1, dtype=torch.int64, device=self._dev)
-        self._tmp_info = torch.zeros(4, dtype=torch.uint8, device=self._dev)
-        self._tmp_flags = torch.zeros(1, dtype=torch.uint8, device=self._dev)
+        # The single-env drop-in pays one host round trip per kernel call, so everything a call returns lives in ONE
+        # device buffer read back with ONE copy (the Batched2048Env tensors of this env are views into it), and
+        # everything a call takes (action, spawn replay) goes up with one copy from a pinned host buffer.
+        #   _pack: board i64 @0 | reward f64 @8 | score i32 @16 | step i32 @20 | reward f32 @24 | max_exp u8 @28 |
+        #          flags u8 @29 | observation f32[272] @32
+        be = self._benv
+        self._pack = torch.zeros(32 + 4 * 272, dtype=torch.uint8, device=self._dev)
+        be.board = self._pack[0:8].view(torch.int64)
+        self._r64 = self._pack[8:16].view(torch.float64)
+        be.score = self._pack[16:20].view(torch.int32)
+        be.step_count = self._pack[20:24].view(torch.int32)
+        be.reward = self._pack[24:28].view(torch.float32)
+        be.max_exp = self._pack[28:29]
+        be.flags = self._pack[29:30]
+        be.max_exp.fill_(2)
+        self._obs_dev = self._pack[32:].view(torch.float32)
+        self._host = np.zeros(32 + 4 * 272, dtype=np.uint8)
+        #   _pre: preview outputs  moved board i64 @0 | merge info u8[4] @8 | flags u8 @12
+        self._pre = torch.zeros(16, dtype=torch.uint8, device=self._dev)
+        self._tmp_board = self._pre[0:8].view(torch.int64)
+        self._tmp_info = self._pre[8:12]
+        self._tmp_flags = self._pre[12:13]
+        #   _ctl: action u8 @0 | spawn replay u8[2] @1
+        self._ctl = torch.zeros(3, dtype=torch.uint8, device=self._dev)
+        self._ctl_host = torch.zeros(3, dtype=torch.uint8).pin_memory()
+        self._act = self._ctl[0:1]
+        self._replay = self._ctl[1:3]
 
     # ------------------------------------------------------------------ state views
     @property
@@ -96,27 +118,45 @@ class Game2048:
         self._set_seed(seed)
         self.step_count = 0
         self.score = 0
-        r = np.array([self._draw_spawn(16), self._draw_spawn(15)], dtype=np.uint8)
-        self._replay.copy_(torch.from_numpy(r))
+        self._ctl_host[1] = self._draw_spawn(16)
+        self._ctl_host[2] = self._draw_spawn(15)
+        self._ctl.copy_(self._ctl_host, non_blocking=True)
         self._benv.reset_many(spawn_replay=self._replay)
         self._sync_from_device()
         return self.state
 
     def _sync_from_device(self) -> None:
-        self._packed = int(self._benv.board.cpu().numpy().view(np.uint64)[0])
-        self._flags = int(self._benv.flags.cpu()[0])
+        """ONE device -> host copy of everything the last call produced."""
+        self._host = self._pack.cpu().numpy()
+        self._packed = int(self._host[0:8].view(np.uint64)[0])
+        self._flags = int(self._host[29])
+
+    # host views of the last synchronised state (Game2048Env reads them instead of touching the device again)
+    def _host_reward64(self) -> float:
+        return float(self._host[8:16].view(np.float64)[0])
+
+    def _host_score(self) -> int:
+        return int(self._host[16:20].view(np.int32)[0])
+
+    def _host_max_exp(self) -> int:
+        return int(self._host[28])
+
+    def _host_obs(self, width: int) -> np.ndarray:
+        return self._host[32: 32 + 4 * width].view(np.float32).copy()
 
     def _preview(self, action: int):
         """Game2048._move on a copy: (moved packed board, merged exponents per line, flags)."""
         lib = self._benv._lib
-        self._act.fill_(int(action))
+        self._ctl_host[0] = int(action)
+        self._ctl.copy_(self._ctl_host, non_blocking=True)
         with torch.cuda.device(self._dev):
             _lib.check(lib.b2048_move_many(self._benv._h, _ptr(self._benv.board), _ptr(self._tmp_board), _ptr(self._act),
                                            None, _ptr(self._tmp_info), _ptr(self._tmp_flags), 1, _stream()),
                        "b2048_move_many")
-        moved = int(self._tmp_board.cpu().numpy().view(np.uint64)[0])
-        info = self._tmp_info.cpu().numpy()
-        flags = int(self._tmp_flags.cpu()[0])
+        pre = self._pre.cpu().numpy()                       # one copy: moved board, merge info, flags
+        moved = int(pre[0:8].view(np.uint64)[0])
+        info = pre[8:12].copy()
+        flags = int(pre[12])
         return moved, info, flags
 
     def step(self, action: Action) -> tuple[bool, list[list[int]], list[int], bool]:
@@ -135,7 +175,7 @@ class Game2048:
         if is_changed:
             n_empty = sum(1 for i in range(16) if not (moved >> (4 * i)) & 0xF)
             replay = self._draw_spawn(n_empty)
-        self._replay[0] = replay
+        self._ctl_host[1] = replay
         self._commit(action)
         self.score += sum(merged)
         is_done = bool(self._flags & _lib.F_DONE)
@@ -143,7 +183,8 @@ class Game2048:
 
     def _commit(self, action: int) -> None:
         """Committed step through the fused kernel (raw rules: no reward shaping, no truncation)."""
-        self._act.fill_(int(action))
+        self._ctl_host[0] = int(action)
+        self._ctl.copy_(self._ctl_host, non_blocking=True)
         self._benv.step_many(self._act, spawn_replay=self._replay[:1])
         self._sync_from_device()
 

@@ -253,8 +253,15 @@ class ReinforceAgent:
         ``policy_seed`` reproduces the reference's episode.  Returns (action, probs, activations, pre_activations)."""
         packed, mask = self._obs_to_packed(obs)
         action_mask = obs["action_mask"] if isinstance(obs, dict) else None
-        b = torch.tensor([np.uint64(packed).astype(np.int64)], dtype=torch.int64, device=self.device)
-        f = torch.tensor([mask], dtype=torch.uint8, device=self.device)
+        # one pinned-host -> device copy carries the board and its mask (single-env path: every copy is a round trip)
+        if getattr(self, "_sa_dev", None) is None:
+            self._sa_host = torch.zeros(16, dtype=torch.uint8).pin_memory()
+            self._sa_dev = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        self._sa_host[0:8] = torch.from_numpy(np.array([packed], dtype=np.uint64).view(np.uint8))
+        self._sa_host[8] = mask
+        self._sa_dev.copy_(self._sa_host, non_blocking=True)
+        b = self._sa_dev[0:8].view(torch.int64)
+        f = self._sa_dev[8:9]
         probs_d = self._buf("sa_probs", (1, 4), torch.float32)
         self.policy_step(b, f if action_mask is not None else None, None, 0, 0, 0, probs_out=probs_d)
         probs = probs_d.cpu().numpy()[0].copy()
