@@ -307,7 +307,7 @@ def run_b200(args):
             # the profiled launch ends, so they do not show up as DRAM writes)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": 19089152 if (n == BOARDS_PER_GPU and not args.lean) else None,
+                         "traffic": 19086080 if (n == BOARDS_PER_GPU and not args.lean) else None,
                          "traffic_source": "profiles/r01_ncu_step_fast_kernel.csv (bytes per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "b2::step_fast_kernel<RANDOM_LEGAL, %s, plain>" % ("false" if args.lean else "true"),
                          "avg_launch_us": per_launch_s * 1e6},
