@@ -43,6 +43,16 @@ RUNNER_ENV = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", ba
                   bonus_mode="off", max_steps=1024)
 
 
+def measured_tensor_peaks():
+    """(burst, sustained) dense bf16 TFLOP/s from MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -353,6 +363,12 @@ def run_b200(args):
                 if world > 1:
                     dist.all_reduce(v, op=dist.ReduceOp.SUM)
                 r["value_all_gpus"] = float(v.item())
+                if prec == 1:   # tensor-core roofline of the fused policy + env kernel (a multi-millisecond launch: sustained peak)
+                    burst, sustained, src = measured_tensor_peaks()
+                    r["roofline"] = {"bound": "tensor", "achieved": r["achieved_tflops"], "peak": sustained, "unit": "TFLOP/s",
+                                     "frac": r["achieved_tflops"] / sustained, "peak_burst": burst, "peak_source": src,
+                                     "algorithmic_flops_per_rollout_step": r["flops_per_step"],
+                                     "kernel": "b2::policy_tc_kernel<rollout>", "traffic": None}
                 extra[key] = r
             r = b2048.bench_env_trained_boards(dev, boards=n, gid0=rank * n)
             v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
