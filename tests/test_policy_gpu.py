@@ -406,6 +406,14 @@ def test_trainer_smoke(b2048, tmp_path):
     cfg["eval"]["model_path"] = os.path.join(tmp_path, "final.npz")
     res = trainer.evaluation(cfg)
     assert res["avg_reward"] > 0 and sum(res["max_tile_counts"].values()) <= 256
+    # resume from the full checkpoint (actor + Adam moments + counters) and continue the batch numbering
+    assert "final_checkpoint.npz" in files
+    cfg2 = trainer.merge_config({"mlp": {"hidden_sizes": [32, 32]},
+                                 "agent": {"optimizer": "adam", "learning_rate": 1e-3, "baseline_mode": "batch_norm"},
+                                 "train": {"batch_size": 512, "num_batches": 37, "start_batch": 34, "out_dir": None,
+                                           "resume": os.path.join(tmp_path, "final_checkpoint.npz")}})
+    more = trainer.training(cfg2)
+    assert [r["batch"] for r in more] == [34, 35, 36] and all(np.isfinite(r["avg_reward"]) for r in more)
 
 
 def test_checkpoint_round_trip_and_rank_weights(b2048, tmp_path):
