@@ -103,6 +103,17 @@ int b2048_destroy(b2048_handle* h);
 const char* b2048_last_error(void);
 int b2048_version(void);
 
+/* Test / profiling switches of one handle (all off by default; production code never sets them).  They replace
+ * process-wide environment variables: the parity tests use them to reach the non-fused fall-back kernels so that
+ * the fused ones can be compared with them bit for bit. */
+enum { B2048_DBG_NO_FUSED_ROLLOUT = 0, /* b2048_rollout_many: always the policy-kernel / step-kernel loop */
+       B2048_DBG_NO_FAST_STEP = 1,     /* b2048_step_many: always the generic step_kernel */
+       B2048_DBG_TC_CLOCKS = 2,        /* tensor-core kernels record in-kernel phase clocks and print them to stderr */
+       B2048_DBG_STEP_CLOCKS = 3,      /* the fast step kernel records per-iteration clocks and prints them to stderr */
+       B2048_DBG_NO_PDL = 4,           /* launch without programmatic dependent launch (plain stream order) */
+       B2048_DBG_COUNT = 5 };
+int b2048_debug_set(b2048_handle* h, int32_t option, int32_t value);
+
 /* Copies the device tables back (host pointers; either may be NULL):
  * lut_left[65536]  : row after a left move (4 nibbles);
  * lut_merge[65536] : two nibbles = exponents of the (<= 2) merged tiles,
@@ -146,8 +157,6 @@ int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_o
                     int32_t* ep_len, uint32_t ep_t,
                     int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, void* stream);
 
-/* Move preview without spawn (Game2048._move, game2048.py:158-165): used by the
- * differential tests and by get_action_mask-style callers. */
 /* n_steps consecutive b2048_step_many calls (step indices t, t + 1, ..., t + n_steps - 1) of a DEVICE-SIDE action mode
  * (random legal / random any / priority) in ONE launch, in place: every thread keeps its board, counters and legal
  * mask in registers across the steps, so the steps cost no HBM traffic, no launches and no table staging — random or
@@ -163,11 +172,12 @@ int b2048_step_many_n(b2048_handle* h, uint64_t* board, uint32_t* score, uint32_
                       float* reward_sum, int32_t* episodes, int64_t n, int32_t n_steps, uint64_t seed,
                       uint64_t gid0, uint32_t t, void* stream);
 
+/* Move preview without spawn (Game2048._move, game2048.py:158-165): used by the
+ * differential tests and by get_action_mask-style callers. */
 int b2048_move_many(b2048_handle* h, const uint64_t* board_in, uint64_t* board_out,
                     const uint8_t* action, int32_t* merge_sum, uint8_t* merge_info /* [n,4] per line */,
                     uint8_t* flags, int64_t n, void* stream);
 
-/* Observation encode only (Game2048Env._preprocess_board, env.py:131-150). */
 /* The 8 dihedral variants of (board, action, legal mask): Game2048Env.get_symmetries (env.py:317-397) and
  * ReinforceAgent._augment_trajectories (reinforce_agent.py:773-808) on packed boards.  Inputs are [rows][n]
  * (any of the three may be NULL together with its output); outputs are [rows][8 n], variant v of element (r, i) at
@@ -177,6 +187,7 @@ int b2048_symmetries(b2048_handle* h, const uint64_t* board, const uint8_t* flag
                      uint64_t* board_out, uint8_t* flags_out, uint8_t* action_out, int64_t rows, int64_t n,
                      void* stream);
 
+/* Observation encode only (Game2048Env._preprocess_board, env.py:131-150). */
 int b2048_encode_obs(const uint64_t* board, float* obs, int32_t obs_mode, float obs_log2_scale,
                      int64_t n, void* stream);
 

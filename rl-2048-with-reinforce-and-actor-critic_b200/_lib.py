@@ -44,6 +44,9 @@ class MlpDesc(C.Structure):
     ]
 
 
+DEBUG_OPTIONS = {"no_fused_rollout": 0, "no_fast_step": 1, "tc_clocks": 2, "step_clocks": 3, "no_pdl": 4}
+
+
 class B2048Error(RuntimeError):
     pass
 
@@ -55,6 +58,7 @@ SIGNATURES = {
     "b2048_create": [C.POINTER(_vp)],
     "b2048_destroy": [_vp],
     "b2048_version": [],
+    "b2048_debug_set": [_vp, _i32, _i32],
     "b2048_get_row_lut": [_vp, _vp, _vp],
     "b2048_reset_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _u32, _vp],
     "b2048_step_many": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp,
@@ -91,6 +95,7 @@ def load():
         raise B2048Error(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback.")
+    import torch  # noqa: F401  (libb2048 links the shared CUDA runtime; torch has already mapped libcudart.so.12)
     lib = C.CDLL(LIB_PATH)
     lib.b2048_last_error.restype = C.c_char_p
     lib.b2048_last_error.argtypes = []

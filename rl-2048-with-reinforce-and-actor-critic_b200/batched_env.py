@@ -72,6 +72,26 @@ def get_handle(device: torch.device) -> C.c_void_p:
     return _handles[idx]
 
 
+_debug: dict[str, bool] = {}
+
+
+def debug_set(option: str, value: bool = True, device: torch.device | str | None = None) -> None:
+    """Test / profiling switch of the library handle of `device` (b2048_debug_set, include/b2048.h): "no_fused_rollout",
+    "no_fast_step", "tc_clocks", "step_clocks", "no_pdl"; plus the host-side "no_compact_rollout" (rollout_many plays all
+    boards of every chunk instead of the live list).  All off by default."""
+    if option == "no_compact_rollout":
+        _debug[option] = bool(value)
+        return
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().b2048_debug_set(get_handle(dev), _lib.DEBUG_OPTIONS[option], int(bool(value))), "b2048_debug_set")
+    _debug[option] = bool(value)
+
+
+def debug_get(option: str) -> bool:
+    return _debug.get(option, False)
+
+
 def _ptr(t: torch.Tensor | None):
     return None if t is None else C.c_void_p(t.data_ptr())
 

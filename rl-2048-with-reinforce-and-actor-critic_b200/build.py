@@ -11,8 +11,11 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libb2048.so")
 SOURCES = ["b2048_capi.cu", "b2048_env.cu", "b2048_policy.cu", "b2048_policy_tc.cu", "b2048_learn.cu", "b2048_learn_tc.cu"]
+# -cudart shared: torch already loads libcudart; a statically linked runtime would also embed every runtime entry-point
+# name in the shipped binary.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-cudart", "shared"]
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 
 def _nvcc() -> str:
@@ -37,13 +40,33 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + sources()
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    # one nvcc -c per translation unit, in parallel (the units are independent: no relocatable device code), then a link
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_time = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    hdr_time = max(hdr_time, os.path.getmtime(os.path.join(PKG_DIR, "..", "include", "b2048.h")))
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
+            continue
+        procs.append((src, subprocess.Popen([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src], cwd=CSRC, stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(f"---- {os.path.basename(src)}\n{out}")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed building libb2048.so")
+    res = subprocess.run([nvcc, "-shared", "-cudart", "shared", "-o", LIB_PATH] + objs, cwd=CSRC, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libb2048.so")
+        raise RuntimeError("nvcc failed linking libb2048.so")
     return LIB_PATH
 
 

@@ -23,3 +23,11 @@ int check_cuda(cudaError_t e, const char* what) {
 extern "C" const char* b2048_last_error(void) { return b2::g_last_error.c_str(); }
 
 extern "C" int b2048_version(void) { return 100; }
+
+extern "C" int b2048_debug_set(b2048_handle* h, int32_t option, int32_t value) {
+    B2_REQUIRE(h != nullptr, "b2048_debug_set: handle is NULL");
+    B2_REQUIRE(option >= 0 && option < B2048_DBG_COUNT, "b2048_debug_set: unknown option");
+    if (value) h->debug |= 1u << option;
+    else h->debug &= ~(1u << option);
+    return B2048_OK;
+}

@@ -633,6 +633,7 @@ extern "C" int b2048_create(b2048_handle** out) {
     b2048_handle* h = new b2048_handle();
     h->tc_image = nullptr;
     h->attrs = 0u;
+    h->debug = 0u;
     B2_CUDA(cudaGetDevice(&h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -723,7 +724,7 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
     a.n = n; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg; a.keys = make_keys(seed);
     a.debug_clock = nullptr;
     static long long* dbg_buf = nullptr;
-    if (getenv("B2048_STEP_DEBUG_CLOCK")) {
+    if (h->debug & (1u << B2048_DBG_STEP_CLOCKS)) {
         if (!dbg_buf) cudaMalloc(&dbg_buf, 32 * sizeof(long long));
         a.debug_clock = dbg_buf;
     }
@@ -736,7 +737,7 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
                       cfg->use_action_mask && cfg->empty_tile_reward == 0.0 && cfg->merge_reward == 0.0 &&
                       cfg->bonus_mode == B2048_BONUS_OFF && cfg->endgame_penalty == 0.0 && reward != nullptr &&
                       reward64 == nullptr && spawn_replay == nullptr && (obs == nullptr || cfg->obs_mode == B2048_OBS_NONE) &&
-                      getenv("B2048_NO_FAST_STEP") == nullptr;
+                      !(h->debug & (1u << B2048_DBG_NO_FAST_STEP));
     if (fast) {
         int grid = grid_for(n, 1024, h->num_sms, 1);
         if (cfg->action_mode == B2048_ACT_BUFFER) launch_fast<B2048_ACT_BUFFER>(all_track, grid, B2048_TABLES_BYTES, s, a);

@@ -685,7 +685,7 @@ int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(d3t)");
         int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
         a.debug_clock = nullptr;
-        if (getenv("B2048_TC_DEBUG_CLOCK")) {
+        if (h->debug & (1u << B2048_DBG_TC_CLOCKS)) {
             static long long* dbg_buf = nullptr;
             if (!dbg_buf) cudaMalloc(&dbg_buf, 80 * sizeof(long long));
             a.debug_clock = dbg_buf;

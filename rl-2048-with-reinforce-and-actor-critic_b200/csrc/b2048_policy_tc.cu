@@ -599,9 +599,9 @@ int ensure_tc_image(b2048_handle* h) {
     return B2048_OK;
 }
 
-static long long* debug_clock_buffer() {
+static long long* debug_clock_buffer(const b2048_handle* h) {
     static long long* dbg_buf = nullptr;
-    if (!getenv("B2048_TC_DEBUG_CLOCK")) return nullptr;
+    if (!(h->debug & (1u << B2048_DBG_TC_CLOCKS))) return nullptr;
     if (!dbg_buf) { cudaMalloc(&dbg_buf, 80 * sizeof(long long)); cudaMemset(dbg_buf, 0, 80 * sizeof(long long)); }
     return dbg_buf;
 }
@@ -642,7 +642,7 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
     a.ro_boards = nullptr; a.ro_flags = nullptr; a.ro_actions = nullptr; a.ro_rewards = nullptr; a.score = nullptr;
     a.step = nullptr; a.max_exp = nullptr; a.ep_len = nullptr; a.tables = nullptr; a.seed = seed; a.t_begin = 0; a.n_steps = 1;
     a.t0 = 0; a.slot_map = nullptr; a.n_dev = nullptr; a.ro_stride = n;
-    a.debug_clock = debug_clock_buffer();
+    a.debug_clock = debug_clock_buffer(h);
     int64_t tiles = (n + TC_M - 1) / TC_M;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     policy_tc_kernel<false><<<grid, TC_THREADS, SM_TOTAL2, stream>>>(a);
@@ -690,7 +690,7 @@ int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boar
     // slot_map: only the listed boards are played (n_slots of them); without it all B boards
     const int64_t n = slot_map ? n_slots : B;
     const int64_t tiles = (n + TC_M - 1) / TC_M;
-    if (!net_ok || !env_ok || B < 4096 || tiles * (int64_t)n_steps > 0x7FFFFFFF || getenv("B2048_NO_FUSED_ROLLOUT") != nullptr)
+    if (!net_ok || !env_ok || B < 4096 || tiles * (int64_t)n_steps > 0x7FFFFFFF || (h->debug & (1u << B2048_DBG_NO_FUSED_ROLLOUT)))
         return B2048_ERR_UNSUPPORTED;
     if (n == 0) return B2048_OK;
     { int st = ensure_tc_image(h); if (st != B2048_OK) return st; }
@@ -704,7 +704,7 @@ int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boar
     a.t0 = t0; a.cfg = *cfg; a.cfg.action_mode = B2048_ACT_BUFFER; a.slot_map = slot_map; a.n_dev = slot_map ? n_slots_dev : nullptr;
     a.ro_stride = B;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
-    a.debug_clock = debug_clock_buffer();
+    a.debug_clock = debug_clock_buffer(h);
     policy_tc_kernel<true><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);
     if (a.debug_clock) print_debug_clock(a.debug_clock, stream);
     return check_cuda(cudaGetLastError(), "policy_tc_kernel<rollout> launch");

@@ -25,7 +25,7 @@ import torch
 from . import _lib
 from .MLP import (DeviceMLP, MLPConfig, encode_observation, init_model_params, load_model_params,  # noqa: F401
                   save_model_params, forward_logits, logits_to_probs)
-from .batched_env import Batched2048Env, _ptr, _stream, get_handle
+from .batched_env import Batched2048Env, _ptr, _stream, debug_get, get_handle
 from .env import Game2048Env
 
 if not hasattr(logging, "VERBOSE"):  # the reference's custom level (src/utils/logging_ext.py)
@@ -72,6 +72,7 @@ class Rollout:
     T: int
     ep_weight: torch.Tensor | None = None   # float32 [B] episode rank weights (None = 1)
     n_traj: int | None = None               # divisor of the per-episode weight (defaults to B)
+    auto_reset: bool = False                # fixed-horizon rollout with reset-on-done: a lane holds SEVERAL episodes
 
     @property
     def B(self) -> int:
@@ -190,11 +191,14 @@ class ReinforceAgent:
             net.adam_m.copy_(torch.from_numpy(ck[prefix + "_adam_m"]).to(self.device))
             net.adam_v.copy_(torch.from_numpy(ck[prefix + "_adam_v"]).to(self.device))
 
+        if bool(int(ck["has_critic"])) != (self._critic is not None):
+            raise ValueError(f"checkpoint has_critic={int(ck['has_critic'])} but the agent was built with "
+                             f"use_critic={self._critic is not None}")
         restore(self._actor, "actor")
-        if int(ck["has_critic"]) and self._critic is not None:
+        if self._critic is not None:
             restore(self._critic, "critic")
+            self._adam_t_c = int(ck["adam_t_c"])
         self._adam_t = int(ck["adam_t"])
-        self._adam_t_c = int(ck["adam_t_c"])
 
     # ------------------------------------------------------------------ kernels
     def _buf(self, name: str, shape, dtype) -> torch.Tensor:
@@ -246,11 +250,30 @@ class ReinforceAgent:
             mask = sum(int(v) << a for a, v in enumerate(obs["action_mask"]))
         return packed, mask
 
+    def _forward_cache(self, obs) -> tuple[list[np.ndarray], list[np.ndarray]]:
+        """forward_logits' cached activations [a_0 .. a_L] and pre-activations [z_0 .. z_{L-1}] of the actor for one
+        observation (src/MLP.py:159-196), computed by b2048_dense_forward on the device parameters."""
+        x, _ = encode_observation(obs)
+        net = self._actor
+        L = net.n_layers
+        xd = torch.from_numpy(np.ascontiguousarray(x.reshape(1, -1), dtype=np.float32)).to(self.device)
+        acts = [torch.empty((1, net.dims[l + 1]), dtype=torch.float32, device=self.device) for l in range(L)]
+        pres = [torch.empty((1, net.dims[l + 1]), dtype=torch.float32, device=self.device) for l in range(L)]
+        act_ptrs = (C.c_void_p * (L + 1))(None, *[a.data_ptr() for a in acts])
+        pre_ptrs = (C.c_void_p * L)(*[p.data_ptr() for p in pres])
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.b2048_dense_forward(self._h, _ptr(xd), C.byref(net.desc), act_ptrs, pre_ptrs, 1, _stream()),
+                       "b2048_dense_forward")
+        return [x] + [a.cpu().numpy()[0] for a in acts], [p.cpu().numpy()[0] for p in pres]
+
     def select_action(self, obs, rng: np.random.Generator, action_fn: Callable[[Any, np.ndarray | None], int] | None = None,
-                      use_greedy: bool = False):
+                      use_greedy: bool = False, return_cache: bool = True):
         """Same contract as reinforce_agent.py:126-192.  Probabilities come from the fused policy kernel; the
         final draw uses the caller's NumPy generator (``rng.choice``) exactly like the reference, so a given
-        ``policy_seed`` reproduces the reference's episode.  Returns (action, probs, activations, pre_activations)."""
+        ``policy_seed`` reproduces the reference's episode.  Returns (action, probs, activations, pre_activations)
+        with the reference's cached layer outputs (forward_logits' second / third return values); ``return_cache=False``
+        (what run_episode passes: it discards them, reinforce_agent.py:222-227) skips that extra forward and returns
+        two empty lists."""
         packed, mask = self._obs_to_packed(obs)
         action_mask = obs["action_mask"] if isinstance(obs, dict) else None
         # one pinned-host -> device copy carries the board and its mask (single-env path: every copy is a round trip)
@@ -284,7 +307,10 @@ class ReinforceAgent:
                 action = int(np.argmax(p))
             else:
                 action = int(rng.choice(len(probs), p=probs))
-        return action, probs, [], []
+        if not return_cache:
+            return action, probs, [], []
+        activations, pre_activations = self._forward_cache(obs)
+        return action, probs, activations, pre_activations
 
     def run_episode(self, env_seed: int, policy_seed: int, action_gen=None, use_greedy: bool = False) -> dict[str, Any]:
         """One episode on the single-env drop-in (reinforce_agent.py:195-252); same trajectory dict."""
@@ -294,7 +320,7 @@ class ReinforceAgent:
         obs_list, action_list, reward_list, states_list = [], [], [], []
         done, total_reward = False, 0.0
         while not done:
-            action, _, _, _ = self.select_action(obs, policy_rng, action_gen, use_greedy=use_greedy)
+            action, _, _, _ = self.select_action(obs, policy_rng, action_gen, use_greedy=use_greedy, return_cache=False)
             next_obs, reward, terminated, truncated, info = self.env.step(action)
             reward = float(reward)
             obs_list.append(obs); action_list.append(action); reward_list.append(reward); states_list.append(state)
@@ -333,7 +359,7 @@ class ReinforceAgent:
         # (slot_map), so finished episodes cost nothing.  Slices beyond an episode's end are then never written: the
         # rewards buffer is zeroed first (total_reward sums whole columns) and the final state is gathered below.
         compact = (not fixed) and int(precision) == 1 and B >= 4096 and self.tc_supported() and \
-            os.environ.get("B2048_NO_FUSED_ROLLOUT") is None and os.environ.get("B2048_NO_COMPACT_ROLLOUT") is None
+            not debug_get("no_fused_rollout") and not debug_get("no_compact_rollout")
         if compact:
             rewards.zero_()
             # Live-board bookkeeping stays on the device: after every chunk b2048_compact_live rebuilds the list and its
@@ -397,7 +423,7 @@ class ReinforceAgent:
             return Rollout(boards[: T + 1], flags[: T + 1], actions[:T], rewards[:T], length, T)
         benv.board = boards[T]
         benv.flags = flags[T]
-        return Rollout(boards[: T + 1], flags[: T + 1], actions[:T], rewards[:T], length, T)
+        return Rollout(boards[: T + 1], flags[: T + 1], actions[:T], rewards[:T], length, T, auto_reset=fixed)
 
     # ------------------------------------------------------------------ reference API: learning
     def compute_returns(self, rewards: list[float]) -> np.ndarray:
@@ -475,17 +501,25 @@ class ReinforceAgent:
             raise ValueError(f"Unknown optimizer: {cfg.optimizer}")                  # reinforce_agent.py:582
         if cfg.use_critic and cfg.critic_loss_type not in ("mse", "huber"):
             raise ValueError(f"Unknown critic loss type: {cfg.critic_loss_type}")    # reinforce_agent.py:908
-        if cfg.augmentation:
-            ro = self._augment_rollout(ro)
-        T, B = ro.T, ro.B
-        if B == 0 or T == 0:
+        if ro.B == 0 or ro.T == 0:
             return {}
+        if ro.auto_reset:
+            # The learner kernels see one episode per lane (returns scan, TD shift and the 1/(T_ep n_traj) weight mask on
+            # len[b] only, like update_batch's per-episode arrays, reinforce_agent.py:403-555).  A reset-on-done lane
+            # holds several episodes: returns would run across the resets and TD targets would bootstrap from the
+            # reset board.  Roll out to termination / truncation instead (horizon=None; max_steps bounds the length).
+            raise ValueError("update_from_rollout: fixed-horizon rollouts with reset-on-done hold several episodes per "
+                             "lane and are not a reference-equivalent update batch; use rollout_many(horizon=None)")
         if ro.ep_weight is None and cfg.reward_rank_weights:
-            # global reward ranks on the device (all-gathered over ranks when the episodes are sharded)
+            # global reward ranks on the device (all-gathered over ranks when the episodes are sharded), computed on
+            # the ORIGINAL episodes and repeated by the augmentation like the reference (reinforce_agent.py:369-384, :806)
             from . import dist as bd
             dinfo = bd.DistInfo(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
                                 int(os.environ.get("LOCAL_RANK", "0"))) if allreduce is not None else None
             ro.ep_weight = bd.episode_rank_weights(ro.total_reward(), cfg.reward_rank_weights, dinfo)
+        if cfg.augmentation:
+            ro = self._augment_rollout(ro)
+        T, B = ro.T, ro.B
         n_traj = float(ro.n_traj if ro.n_traj is not None else B)
         lib, h, dev = self._lib, self._h, self.device
         n = T * B

@@ -51,7 +51,8 @@ def transform_flags(flags: torch.Tensor, variant: int) -> torch.Tensor:
 
 
 def augment_rollout(ro):
-    """Rollout with 8x the episodes (every dihedral variant), weights repeated, n_traj = 8 B."""
+    """Rollout with 8x the episodes (every dihedral variant), weights repeated, n_traj = 8 x the caller's n_traj (the
+    GLOBAL episode count when the episodes are sharded over ranks; B when it was not set)."""
     import ctypes as C
     from . import _lib
     from .batched_env import get_handle
@@ -73,4 +74,4 @@ def augment_rollout(ro):
     rewards = ro.rewards.repeat(1, 8)
     length = ro.length.repeat(8)
     w = None if ro.ep_weight is None else ro.ep_weight.repeat(8)
-    return Rollout(boards, flags, actions, rewards.contiguous(), length, T, w, 8 * B)
+    return Rollout(boards, flags, actions, rewards.contiguous(), length, T, w, 8 * (ro.n_traj if ro.n_traj is not None else B))

@@ -3,7 +3,8 @@
 Accepts the reference's JSON schema (sections ``env`` / ``mlp`` / ``agent`` / ``train`` / ``eval`` / ``run_mode``,
 runner.py:10-63, defaults runner.py:116-173) and writes the same artefacts (``config.json``,
 ``training_stats.csv`` with columns ``batch,avg_reward,max_reward,min_reward,max_tile_counts``, best-average
-``.npz`` checkpoints taken BEFORE the update once ``global_step > 30``, runner.py:526-673).  One training batch =
+``.npz`` checkpoints taken BEFORE the update once the 1-based ``global_step > 30``, runner.py:526-673; ``checkpoint.npz``
+with the full optimiser state every ``train.checkpoint_every`` batches).  One training batch =
 ``train.batch_size`` episodes played in parallel on the GPU (``rollout_many``) followed by one
 ``update_from_rollout``; evaluation = greedy rollouts with the max-tile histogram (runner.py:737-828).
 Extra keys: ``train.precision`` ("auto" | 0 | 1), ``seed``.  Under torchrun the episodes are sharded over ranks.
@@ -53,9 +54,15 @@ def merge_config(user: dict[str, Any] | None) -> dict[str, Any]:
     return cfg
 
 
-def tile_histogram(max_exp: torch.Tensor) -> dict[str, int]:
-    tiles = (1 << max_exp.to(torch.int64)).cpu().numpy()
-    return {str(b): int((tiles == b).sum()) for b in TILE_BINS}
+def tile_histogram(max_exp: torch.Tensor, info: bd.DistInfo | None = None) -> list[int]:
+    """Episodes per max tile, a list in TILE_BINS order like the reference's CSV column (runner.py:557, :617-624, :669);
+    summed over ranks when the episodes are sharded."""
+    tiles = 1 << max_exp.to(torch.int64)
+    bins = torch.as_tensor(TILE_BINS, dtype=torch.int64, device=tiles.device)
+    counts = (tiles.unsqueeze(1) == bins.unsqueeze(0)).sum(0)
+    if info is not None and info.is_distributed:
+        bd.allreduce_sum_(counts)
+    return [int(c) for c in counts.tolist()]
 
 
 def build(cfg: dict[str, Any], num_envs: int, info: bd.DistInfo, device=None):
@@ -80,39 +87,50 @@ def training(cfg: dict[str, Any], info: bd.DistInfo | None = None, device=None, 
     out_dir = tr.get("out_dir")
     rows: list[dict[str, Any]] = []
     writer = None
+    # resume: ``train.resume`` = path of a checkpoint written by an earlier run (actor, critic, Adam moments, step
+    # counters — everything the reference's actor-only save_model loses); ``train.start_batch`` continues the seeds
+    # and the CSV (rows are appended, like the reference's safe_append_csv_row, runner.py:662-671)
+    start = int(tr.get("start_batch", 0))
+    resuming = bool(tr.get("resume")) or start > 0
     if info.rank == 0 and out_dir:
         os.makedirs(out_dir, exist_ok=True)
         with open(os.path.join(out_dir, "config.json"), "w") as f:
             json.dump(cfg, f, indent=1)
-        fcsv = open(os.path.join(out_dir, "training_stats.csv"), "w", newline="")
+        csv_path = os.path.join(out_dir, "training_stats.csv")
+        append = resuming and os.path.exists(csv_path)
+        fcsv = open(csv_path, "a" if append else "w", newline="")
         writer = csv.DictWriter(fcsv, fieldnames=["batch", "avg_reward", "max_reward", "min_reward", "max_tile_counts"])
-        writer.writeheader()
+        if not append:
+            writer.writeheader()
     best = -float("inf")
-    # resume: ``train.resume`` = path of a checkpoint written by an earlier run (actor, critic, Adam moments, step
-    # counters — everything the reference's actor-only save_model loses); ``train.start_batch`` continues the seeds
-    start = int(tr.get("start_batch", 0))
     if tr.get("resume"):
         agent.load_checkpoint(tr["resume"])
+    ckpt_every = int(tr.get("checkpoint_every", 50))
     for step in range(start, int(tr["num_batches"])):
         t0 = time.perf_counter()
+        global_step = step + 1                                                             # 1-based like runner.py:610
         env.seed = (int(cfg["seed"]) + 0x9E3779B97F4A7C15 * (step + 1)) & (2**64 - 1)      # fresh episodes every batch
         ro = agent.rollout_many(env, precision=tr.get("precision", "auto"))
         total = ro.total_reward()
         avg, mx, mn = _global_stats(total, info)
-        hist = tile_histogram(env.max_exp)
-        if avg > best and step > 30 and info.rank == 0 and out_dir:                        # runner.py:643-660
+        hist = tile_histogram(env.max_exp, info)
+        is_record = avg > best                                                             # runner.py:643-660
+        if is_record:
             best = avg
-            agent.save_model(os.path.join(out_dir, f"best_avg_{avg:.2f}_step_{step}.npz"))
-        best = max(best, avg) if step > 30 else best
+        if global_step > 30 and is_record and info.rank == 0 and out_dir:
+            agent.save_model(os.path.join(out_dir, f"best_avg_{avg:.2f}_step_{global_step}.npz"))
         upd = bd.sharded_update(agent, ro, info, total_episodes=int(tr["batch_size"]))
-        row = {"batch": step, "avg_reward": avg, "max_reward": mx, "min_reward": mn, "max_tile_counts": json.dumps(hist)}
+        row = {"batch": global_step, "avg_reward": avg, "max_reward": mx, "min_reward": mn, "max_tile_counts": json.dumps(hist)}
         rows.append(dict(row, steps=int(ro.length.sum().item()), seconds=time.perf_counter() - t0,
                          grad_norm=upd.get("actor_grad_norm")))
         if writer:
             writer.writerow(row)
             fcsv.flush()
+        if info.rank == 0 and out_dir and ckpt_every > 0 and global_step % ckpt_every == 0:
+            # a crashed run resumes from here: train.resume = this file, train.start_batch = global_step
+            agent.save_checkpoint(os.path.join(out_dir, "checkpoint.npz"))
         if info.rank == 0 and (step % max(1, int(tr["num_batches"]) // 20) == 0 or step == int(tr["num_batches"]) - 1):
-            log(f"batch {step}: avg_reward={avg:.2f} max={mx:.1f} min={mn:.1f} steps={rows[-1]['steps']} "
+            log(f"batch {global_step}: avg_reward={avg:.2f} max={mx:.1f} min={mn:.1f} steps={rows[-1]['steps']} "
                 f"sec={rows[-1]['seconds']:.3f}")
     if writer:
         fcsv.close()
@@ -133,7 +151,7 @@ def evaluation(cfg: dict[str, Any], info: bd.DistInfo | None = None, device=None
             agent.load_model(ev["model_path"])
     ro = agent.rollout_many(env, greedy=bool(ev.get("use_greedy", True)), precision=cfg["train"].get("precision", "auto"))
     avg, mx, mn = _global_stats(ro.total_reward(), info)
-    return {"avg_reward": avg, "max_reward": mx, "min_reward": mn, "max_tile_counts": tile_histogram(env.max_exp),
+    return {"avg_reward": avg, "max_reward": mx, "min_reward": mn, "max_tile_counts": tile_histogram(env.max_exp, info),
             "mean_len": float(ro.length.float().mean())}
 
 

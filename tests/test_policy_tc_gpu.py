@@ -107,10 +107,7 @@ def test_fused_rollout_kernel_equals_two_kernel_loop(b2048, n, horizon, max_step
     kw = full_env_kwargs("runner_default"); kw["max_steps"] = max_steps
     outs = []
     for fused in (False, True):
-        if fused:
-            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
-        else:
-            os.environ["B2048_NO_FUSED_ROLLOUT"] = "1"
+        b2048.debug_set("no_fused_rollout", not fused)
         try:
             benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=77, gid0=5)
             agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
@@ -125,7 +122,7 @@ def test_fused_rollout_kernel_equals_two_kernel_loop(b2048, n, horizon, max_step
                              max_exp=benv.max_exp.cpu().numpy(), final_board=benv.board.cpu().numpy(),
                              final_flags=benv.flags.cpu().numpy()))
         finally:
-            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+            b2048.debug_set("no_fused_rollout", False)
     a, b = outs
     assert a["T"] == b["T"]
     T, L = a["T"], a["length"]
@@ -153,8 +150,7 @@ def test_fused_rollout_greedy_equals_two_kernel_loop(b2048):
     kw = full_env_kwargs("runner_default"); kw["max_steps"] = 60; kw["obs_mode"] = "raw"; kw["obs_log2_scale"] = 1.0
     outs = []
     for fused in (False, True):
-        if not fused:
-            os.environ["B2048_NO_FUSED_ROLLOUT"] = "1"
+        b2048.debug_set("no_fused_rollout", not fused)
         try:
             benv = b2048.Batched2048Env(20000, b2048.Game2048EnvConfig(**kw), seed=5, gid0=0)
             agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
@@ -167,9 +163,62 @@ def test_fused_rollout_greedy_equals_two_kernel_loop(b2048):
             outs.append((ro.T, ro.length.cpu().numpy(), ro.actions.cpu().numpy(), ro.rewards.cpu().numpy(),
                          benv.score.cpu().numpy(), benv.board.cpu().numpy()))
         finally:
-            os.environ.pop("B2048_NO_FUSED_ROLLOUT", None)
+            b2048.debug_set("no_fused_rollout", False)
     (Ta, La, Aa, Ra, Sa, Ba), (Tb, Lb, Ab, Rb, Sb, Bb) = outs
     assert (La == Lb).all() and (Sa == Sb).all() and (Ba == Bb).all()
     T = min(Ta, Tb)
     live = np.arange(T)[:, None] < La[None, :]
     assert (Aa[:T][live] == Ab[:T][live]).all() and (Ra[:T][live] == Rb[:T][live]).all()
+
+
+@pytest.mark.parametrize("n,horizon,max_steps", [(65536, None, 150), (262144, None, 40), (65536, 48, 30), (262144, 20, 1024)])
+def test_fused_tc_rollout_replays_in_oracle(b2048, n, horizon, max_steps):
+    """The fused persistent tcgen05 rollout kernel (policy_tc_kernel<rollout>, 16-256-256-4) against the CPU ORACLE
+    directly (not against the repo's other path): the recorded actions replayed through oracle.step_many reproduce
+    every live board, reward and flags byte, the episode lengths, and the final score / step / max-tile counters —
+    run to termination (live-board compaction between chunks) and fixed horizon with reset-on-done."""
+    from helpers import full_env_kwargs
+    seed, gid0 = 4242, 17
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = max_steps
+    benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=gid0)
+    agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                 b2048.ReinforceAgentConfig(model_seed=3))
+    assert agent.tc_supported()
+    ro = agent.rollout_many(benv, horizon=horizon, precision=1)
+    torch.cuda.synchronize()
+    T = ro.T
+    boards = ro.boards.cpu().numpy().view(np.uint64); flags = ro.flags.cpu().numpy()
+    actions = ro.actions.cpu().numpy(); rewards = ro.rewards.cpu().numpy(); length = ro.length.cpu().numpy()
+    okw = dict(kw); okw.pop("size")
+    fixed = horizon is not None
+    cfg = oracle.make_cfg(action_mode="buffer", auto_reset=fixed, **okw)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    assert (st["board"] == boards[0]).all() and ((st["flags"] & 0xF) == (flags[0] & 0xF)).all()
+    if fixed:
+        assert T == horizon and (length == T).all()
+    else:
+        assert length.min() >= 1 and length.max() == T <= max_steps
+    frozen = {k: st[k].copy() for k in ("score", "step", "max_exp")}
+    for t in range(T):
+        live = length > t
+        prev = {k: st[k].copy() for k in ("board", "score", "step", "max_exp")}
+        o = oracle.step_many(st, cfg, seed, gid0, t + 1, action=actions[t])
+        assert (st["board"][live] == boards[t + 1][live]).all(), t
+        assert (o["reward"][live] == rewards[t][live]).all(), t
+        assert (o["flags"][live] == flags[t + 1][live]).all(), t
+        ended = length == t + 1
+        if not fixed:
+            assert ((flags[t + 1][ended] & 0x60) != 0).all() and ((flags[t + 1][live & ~ended] & 0x60) == 0).all()
+            # finished episodes are frozen on the device: keep the oracle's copy of them untouched too
+            dead = ~live
+            for k in prev:
+                st[k][dead] = prev[k][dead]
+    # final env state of every board (counters included) as the oracle left it
+    assert (benv.board.cpu().numpy().view(np.uint64) == st["board"]).all()
+    assert (benv.score.cpu().numpy() == st["score"]).all()
+    assert (benv.step_count.cpu().numpy() == st["step"]).all()
+    assert (benv.max_exp.cpu().numpy() == st["max_exp"]).all()
+    # sampled actions are legal wherever a legal move exists
+    m = flags[:T] & 0xF
+    livem = np.arange(T)[:, None] < length[None, :]
+    assert ((((m >> actions) & 1) == 1) | (m == 0))[livem].all()
