@@ -7,7 +7,11 @@ Workload at every N (weak scaling): BASELINE.json configs[1] per GPU — random-
 stepping on 1,048,576 packed boards (uniform over the legal moves from the Philox action word,
 reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards of the rank.
 
-  value      env-steps/s, whole job, boards resident in HBM, CUDA-event time of the K launches (max over ranks)
+  value      env-steps/s, whole job, boards resident in HBM: ONE CUDA-event pair around K back-to-back launches that
+             rotate over 12 resident 1 M-board batches (276 MB of state > the 126 MB L2, so no launch finds its inputs
+             in L2 and no flush kernel sits between the launches); max over ranks.  Consecutive step launches overlap
+             through programmatic dependent launch.  `env_flushed` repeats the round-1 protocol (one batch, a 256 MiB
+             memset and an event pair around every launch) for continuity.
   e2e        the same metric through the host-facing API with HOST (pinned) buffers: per step the actions
              are copied host->device and board/reward/flags device->host inside the timed region
   roofline   HBM: 22 algorithmic bytes per env-step over the measured kernel time
@@ -17,6 +21,8 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
   rollout    secondary: policy-rollout steps/s (MLP 16-256-256-4 forward + masked sampling + env step), 65,536 boards
   train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
              one update; 65,536 / 262,144 boards per GPU)
+  sharded_sweep  secondary, N >= 2 only: BASELINE.json configs[4] — 64 M boards in total, 16-step episodes, one update
+  summary    the key numbers of every leg once more, LAST in the line (a truncated tail still shows them)
 
 `--impl reference` times the CPU side alone (the reference is pure Python and cannot travel to the GPU
 box; oracle/pyport.py restates it at the same per-environment granularity).
@@ -60,6 +66,35 @@ def measured_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def profile_traffic(candidates, launch_filter=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed ncu summary (profiles/*.csv written by
+    profiles/summarize_ncu.py): the first candidate file that exists; the mean over its launch columns whose header
+    contains `launch_filter`.  Returns (bytes or None, file name or None)."""
+    import csv
+    for name in candidates:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            with open(path) as f:
+                rows = list(csv.reader(f))
+            hdr = rows[0]
+            cols = [i for i in range(2, len(hdr)) if launch_filter is None or launch_filter in hdr[i]]
+            tot = None
+            for r in rows[1:]:
+                if r and r[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and cols:
+                    v = sum(float(r[i]) for i in cols) / len(cols) * _UNIT.get(r[1], 1.0)
+                    tot = v if tot is None else tot + v
+            if tot is not None:
+                return tot, "profiles/" + name
+        except Exception:
+            continue
+    return None, None
 
 
 class ClockSampler:
@@ -202,13 +237,14 @@ def run_b200(args):
     n = args.boards
     K, W = args.steps, max(3, args.warmup)
 
-    env = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=0xB200, gid0=rank * n,
-                               track_state=not args.lean)
-    env.reset_many()
-    # spread the boards over the episode distribution before timing (64 untimed steps)
-    for _ in range(64):
-        env.step_many(action_mode="random_legal", auto_reset=True)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    R = args.batches                    # resident batches the launches rotate over: R x 23 MB of state > the 126 MB L2
+    envs = [b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=0xB200 + r, gid0=rank * n,
+                                 track_state=not args.lean) for r in range(R)]
+    for e in envs:
+        e.reset_many()
+        # spread the boards over the episode distribution before timing (64 untimed steps)
+        e.step_many_n(64, action_mode="random_legal", auto_reset=True)
+    env = envs[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,26 +252,45 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(W):
-        flush.zero_()
-        env.step_many(action_mode="random_legal", auto_reset=True)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for k in range(max(W, R)):
+        envs[k % R].step_many(action_mode="random_legal", auto_reset=True)
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local_rank) as clk:
+        # a short spin kernel in front lets the host enqueue ahead of the device, so the K launches run back to back
+        torch.cuda._sleep(2_000_000)
+        t0e.record()
         for k in range(K):
-            flush.zero_()                      # evict boards from L2 between timed launches
-            starts[k].record()
-            env.step_many(action_mode="random_legal", auto_reset=True)
-            ends[k].record()
+            envs[k % R].step_many(action_mode="random_legal", auto_reset=True)
+        t1e.record()
         barrier()
-    kernel_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    kernel_ms = t0e.elapsed_time(t1e)
     t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     kernel_ms = float(t.item())
     value = world * n * K / (kernel_ms * 1e-3)
     clocks = clk.summary()
+
+    # ---- the round-1 protocol for continuity: one batch, L2 flushed by a 256 MiB memset and an event pair around every launch
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    Kf = min(K, 50)
+    for _ in range(3):
+        flush.zero_()
+        env.step_many(action_mode="random_legal", auto_reset=True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(Kf)]
+    barrier()
+    for k in range(Kf):
+        flush.zero_()                      # evict boards from L2 between timed launches
+        starts[k].record()
+        env.step_many(action_mode="random_legal", auto_reset=True)
+        ends[k].record()
+    barrier()
+    tf = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(starts, ends))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+    flushed_ms = float(tf.item()) / Kf
 
     # ---- e2e: host (pinned) buffers through the public API, copies inside the timed region.  Per step the actions go
     #      host -> device and board / reward / flags come back device -> host (13 B per board: PCIe-bound).  The step
@@ -294,33 +349,46 @@ def run_b200(args):
     last = (e2e_k[0] - 1) & 1
     checksum = int(h_board[last].sum().item()) ^ int(h_flags[last].sum().item())
 
+    e2e_ms = float(te.item()) / Ke
     if rank == 0:
         peak, peak_src = measured_peaks()
         per_launch_s = kernel_ms * 1e-3 / K
         achieved = n * ALGO_BYTES_PER_STEP / per_launch_s / 1e9
+        kname = "b2::step_fast_kernel<RANDOM_LEGAL, %s, plain>" % ("false" if args.lean else "true")
+        traffic, traffic_src = (None, None)
+        if n == BOARDS_PER_GPU and not args.lean:
+            traffic, traffic_src = profile_traffic(["r02_ncu_step_fast_kernel.csv", "r01_ncu_step_fast_kernel.csv"], "step_fast")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, R),
             "ms_per_step": kernel_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"random-legal batched env stepping, {n} packed boards per GPU "
                                    f"(BASELINE.json configs[1]), runner-default env, reset-on-done",
-                       "boards_per_gpu": n, "l2": "flushed between timed launches (256 MiB memset)",
+                       "boards_per_gpu": n,
+                       "l2": f"inputs larger than L2: the launches rotate over {R} resident {n}-board batches "
+                             f"({R * n * (22 if args.lean else 23) / 1e6:.0f} MB of state vs 126 MB L2), no flush kernel between them; "
+                             "one CUDA-event pair around the K back-to-back launches",
                        "state": "board only (22 B/step variant)" if args.lean else
                                 "board + score/step/max_tile counters kept per step (+18 B/step, not counted)"},
             "clocks": clocks,
+            # pcie_gbs: bytes that cross PCIe per GPU per step (both directions) over the e2e step time — the e2e figure
+            # is bound by the host link / host memory system, not by the kernel (14 B per board per step)
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 1, "d2h_bytes_per_step": n * 13,
-                    "steps": Ke, "checksum": checksum},
+                    "steps": Ke, "checksum": checksum, "ms_per_step": e2e_ms,
+                    "pcie_gbs_per_gpu": n * 14 / (e2e_ms * 1e-3) / 1e9, "pcie_gbs_all_gpus": world * n * 14 / (e2e_ms * 1e-3) / 1e9,
+                    "bound": "host link (PCIe) per GPU; the host memory system when several GPUs copy at once"},
             "gpu_launches": K,
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on 1,048,576 boards
-            # from the `ncu --set full` capture summarised in profiles/r01_ncu_step_fast_kernel.csv (19.09 MB read: the
-            # boards, masks, counters and the row tables; the 14 MB of outputs are still in the 126 MB L2 when
-            # the profiled launch ends, so they do not show up as DRAM writes)
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on 1,048,576 boards, read
+            # from the committed `ncu --set full` summary named in traffic_source (the outputs of a profiled single launch
+            # are still dirty in the 126 MB L2 when it ends, so they do not all show up as DRAM writes)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": 19086080 if (n == BOARDS_PER_GPU and not args.lean) else None,
-                         "traffic_source": "profiles/r01_ncu_step_fast_kernel.csv (bytes per launch)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": "b2::step_fast_kernel<RANDOM_LEGAL, %s, plain>" % ("false" if args.lean else "true"),
-                         "avg_launch_us": per_launch_s * 1e6},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_STEP, "kernel": kname,
+                         "avg_launch_us": per_launch_s * 1e6,
+                         "limiter": "integer (ALU) issue, not HBM: see profiles/ and DESIGN.md section 3"},
+            "env_flushed": {"value": world * n / (flushed_ms * 1e-3), "unit": UNIT, "ms_per_step": flushed_ms, "steps": Kf,
+                            "frac": n * ALGO_BYTES_PER_STEP / (flushed_ms * 1e-3) / 1e9 / peak,
+                            "protocol": "round-1 protocol: one batch, 256 MiB memset + an event pair around every launch"},
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
@@ -329,6 +397,7 @@ def run_b200(args):
                 line["cpu_baseline_native"] = cpu_native_baseline()
             except Exception as e:  # the native leg is context only
                 line["cpu_baseline_native"] = {"error": str(e)}
+    del envs[1:]
     # ---- secondary: the same stepping with 64 steps per launch (b2048_step_many_n: state in registers across steps)
     multi = None
     if not args.lean:
@@ -365,10 +434,12 @@ def run_b200(args):
                 r["value_all_gpus"] = float(v.item())
                 if prec == 1:   # tensor-core roofline of the fused policy + env kernel (a multi-millisecond launch: sustained peak)
                     burst, sustained, src = measured_tensor_peaks()
+                    tr, tr_src = profile_traffic(["r02_ncu_rollout_tc_kernel_65k.csv", "r01_ncu_rollout_tc_kernel_65k.csv"], "policy_tc")
                     r["roofline"] = {"bound": "tensor", "achieved": r["achieved_tflops"], "peak": sustained, "unit": "TFLOP/s",
                                      "frac": r["achieved_tflops"] / sustained, "peak_burst": burst, "peak_source": src,
                                      "algorithmic_flops_per_rollout_step": r["flops_per_step"],
-                                     "kernel": "b2::policy_tc_kernel<rollout>", "traffic": None}
+                                     "kernel": "b2::policy_tc_kernel<rollout>", "traffic": tr,
+                                     "traffic_source": (tr_src + " (DRAM bytes of the profiled 16-step launch on 65,536 boards)") if tr_src else None}
                 extra[key] = r
             r = b2048.bench_env_trained_boards(dev, boards=n, gid0=rank * n)
             v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
@@ -376,13 +447,30 @@ def run_b200(args):
                 dist.all_reduce(v, op=dist.ReduceOp.SUM)
             r["value_all_gpus"] = float(v.item())
             extra["env_trained_boards"] = r
-            extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision=1)
-            extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision=1,
+            extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision="auto")
+            extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision="auto",
                                                                       use_critic=True, iters=3)
+            if world > 1 and not args.no_sweep:
+                extra["sharded_sweep"] = b2048.bench_sharded_sweep(dev, total_boards=args.sweep_boards, info=info)
         except Exception as e:
             extra["rollout_error"] = repr(e)
     if rank == 0:
         line.update(extra)
+        # the key numbers once more, LAST in the line
+        g = lambda d, *ks: (g(d.get(ks[0], {}), *ks[1:]) if len(ks) > 1 else d.get(ks[0])) if isinstance(d, dict) else None
+        line["summary"] = {
+            "env_steps_per_s": value, "env_ms_per_step": kernel_ms / K, "env_hbm_frac": line["roofline"]["frac"],
+            "env_flushed_ms_per_step": flushed_ms, "e2e_env_steps_per_s": e2e_value,
+            "e2e_pcie_gbs_per_gpu": line["e2e"]["pcie_gbs_per_gpu"],
+            "env_multi_step_per_s": g(extra, "env_multi_step", "value"),
+            "rollout_steps_per_s": g(extra, "rollout", "value_all_gpus"), "rollout_tensor_frac": g(extra, "rollout", "roofline", "frac"),
+            "train_iter_rollout_ms": g(extra, "train_iter", "rollout_ms"), "train_iter_update_ms": g(extra, "train_iter", "update_ms"),
+            "train_iter_update_mode": g(extra, "train_iter", "update_precision"),
+            "train_iter_update_ms_bf16": g(extra, "train_iter", "update_ms_bf16"),
+            "ac_rollout_ms": g(extra, "train_iter_actor_critic", "rollout_ms"), "ac_update_ms": g(extra, "train_iter_actor_critic", "update_ms"),
+            "sweep_rollout_steps_per_s": g(extra, "sharded_sweep", "rollout_steps_per_s"),
+            "sweep_update_samples_per_s": g(extra, "sharded_sweep", "update_samples_per_s"),
+            "error": extra.get("rollout_error")}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -413,6 +501,9 @@ def main():
     ap.add_argument("--lean", action="store_true", help="board-only state (no score/step/max_tile arrays)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the BASELINE.json configs[4] leg (runs at N >= 2)")
+    ap.add_argument("--sweep-boards", type=int, default=64 << 20, help="total boards of the configs[4] leg")
+    ap.add_argument("--batches", type=int, default=12, help="resident 1 M-board batches the timed launches rotate over")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--train-boards", type=int, default=65536)
     ap.add_argument("--ac-boards", type=int, default=262144, help="actor-critic leg (BASELINE.json configs[3])")

@@ -13,7 +13,7 @@ from .env import Game2048Env
 from .MLP import (MLPConfig, DeviceMLP, encode_observation, init_model_params, load_model_params, save_model_params,
                   forward_logits, logits_to_probs)
 from .reinforce_agent import ReinforceAgent, ReinforceAgentConfig, Rollout
-from .rollout_bench import bench_env_trained_boards, bench_rollout, bench_train_iter
+from .rollout_bench import bench_env_trained_boards, bench_rollout, bench_sharded_sweep, bench_train_iter
 from . import dist
 
 __all__ = ["B2048Error", "Batched2048Env", "Game2048EnvConfig", "debug_set", "get_handle", "make_env_cfg", "Game2048",

@@ -279,6 +279,10 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
     long long* dc = dbg ? args.debug_clock + (blockIdx.x == 0 ? 0 : 16) : nullptr;
     int dci = 0;
     if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dc[dci++] = (long long)gt; dc[dci++] = clock64(); }
+    // Programmatic dependent launch (no-ops when the launch does not carry the attribute): the NEXT launch in the
+    // stream may start placing its CTAs as soon as SMs free up, so its barrier set-up and its 194 KB table staging run
+    // under this launch's tail; it reads or writes nothing a previous launch touched before its own griddepcontrol.wait.
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -308,6 +312,8 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
     T.agg = reinterpret_cast<const AggEntry*>(smem + B2048_LUT_BYTES + B2048_SMALL_AGG_OFF);
     T.sel = reinterpret_cast<const SelEntry*>(smem + B2048_LUT_BYTES + B2048_SMALL_SEL_OFF);
     T.act = smem + B2048_LUT_BYTES + B2048_SMALL_ACT_OFF;
+    // everything above touched only the static tables; the boards may have been written by the previous launch
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const b2048_env_cfg& cfg = args.cfg;
     if constexpr (kPlain) {
@@ -323,6 +329,9 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
             if (kTrack) { score_next = args.score[k]; step_next = args.step[k]; max_next = args.max_exp[k]; }
         };
         if (i < n) request(i);
+        // the Philox block of the first board is computed while the tables arrive; later ones at the end of the
+        // previous iteration (same instruction count, the first one is off the staging's critical path)
+        Rand4 rnd = stream_keyed(args.keys, args.gid0 + (uint64_t)i, args.t, B2048_DOM_STEP);
         {   // the tables have to be in shared memory before the first lookup
             uint32_t ok = 0;
             while (!ok) {
@@ -342,11 +351,12 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
             io.action = act_next; io.mask_in = fin_next;
             const uint32_t inext = i + stride;
             if (inext < n) request(inext);
-            step_fast<kAct, kTrack>(io, cfg, args.keys, args.seed, args.gid0 + (uint64_t)i, args.t, T);
+            step_fast_rnd<kAct, kTrack>(io, cfg, rnd, args.seed, args.gid0 + (uint64_t)i, args.t, T);
             *reinterpret_cast<uint2*>(args.board_out + i) = make_uint2(io.lo, io.hi);
             if (kTrack) { args.score[i] = io.score; args.step[i] = io.step; args.max_exp[i] = (uint8_t)io.max_exp; }
             args.reward[i] = io.reward;
             args.flags[i] = (uint8_t)io.flags;
+            if (inext < n) rnd = stream_keyed(args.keys, args.gid0 + (uint64_t)inext, args.t, B2048_DOM_STEP);
         }
         return;
     }
@@ -417,18 +427,27 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
     if (dbg) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); dc[14] = clock64(); dc[15] = (long long)gt; }
 }
 
+// Launched with cudaLaunchAttributeProgrammaticStreamSerialization (programmatic dependent launch): when the previous
+// kernel in the stream is another step launch, this one's prologue (barrier set-up, table staging) overlaps its tail
+// instead of waiting for the grid to drain and the launch to travel; after any other kernel it degrades to plain
+// stream order (griddepcontrol.wait returns once that kernel has completed).
+template <int kAct, bool kTrack, bool kPlain>
+static cudaError_t launch_fast_one(int grid, size_t smem, cudaStream_t s, const StepArgs& a, bool pdl) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(1024); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&lc, step_fast_kernel<kAct, kTrack, kPlain>, a);
+}
 template <int kAct>
-static void launch_fast(bool track, int grid, size_t smem, cudaStream_t s, const StepArgs& a) {
+static cudaError_t launch_fast(bool track, int grid, size_t smem, cudaStream_t s, const StepArgs& a, bool pdl) {
     const bool plain = a.ep_len == nullptr && a.action_out == nullptr && a.merge_sum == nullptr && a.debug_clock == nullptr &&
                        (kAct == B2048_ACT_BUFFER || kAct == B2048_ACT_RANDOM_ANY || a.flags_in != nullptr) &&
                        a.n < ((int64_t)1 << 31) - (int64_t)grid * 1024;
-    if (plain) {
-        if (track) step_fast_kernel<kAct, true, true><<<grid, 1024, smem, s>>>(a);
-        else step_fast_kernel<kAct, false, true><<<grid, 1024, smem, s>>>(a);
-    } else {
-        if (track) step_fast_kernel<kAct, true, false><<<grid, 1024, smem, s>>>(a);
-        else step_fast_kernel<kAct, false, false><<<grid, 1024, smem, s>>>(a);
-    }
+    if (plain) return track ? launch_fast_one<kAct, true, true>(grid, smem, s, a, pdl) : launch_fast_one<kAct, false, true>(grid, smem, s, a, pdl);
+    return track ? launch_fast_one<kAct, true, false>(grid, smem, s, a, pdl) : launch_fast_one<kAct, false, false>(grid, smem, s, a, pdl);
 }
 
 // ------------------------------------------------------------------------------------------------ multi-step
@@ -740,10 +759,13 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
                       !(h->debug & (1u << B2048_DBG_NO_FAST_STEP));
     if (fast) {
         int grid = grid_for(n, 1024, h->num_sms, 1);
-        if (cfg->action_mode == B2048_ACT_BUFFER) launch_fast<B2048_ACT_BUFFER>(all_track, grid, B2048_TABLES_BYTES, s, a);
-        else if (cfg->action_mode == B2048_ACT_RANDOM_LEGAL) launch_fast<B2048_ACT_RANDOM_LEGAL>(all_track, grid, B2048_TABLES_BYTES, s, a);
-        else if (cfg->action_mode == B2048_ACT_PRIORITY) launch_fast<B2048_ACT_PRIORITY>(all_track, grid, B2048_TABLES_BYTES, s, a);
-        else launch_fast<B2048_ACT_RANDOM_ANY>(all_track, grid, B2048_TABLES_BYTES, s, a);
+        const bool pdl = !(h->debug & (1u << B2048_DBG_NO_PDL));
+        cudaError_t e;
+        if (cfg->action_mode == B2048_ACT_BUFFER) e = launch_fast<B2048_ACT_BUFFER>(all_track, grid, B2048_TABLES_BYTES, s, a, pdl);
+        else if (cfg->action_mode == B2048_ACT_RANDOM_LEGAL) e = launch_fast<B2048_ACT_RANDOM_LEGAL>(all_track, grid, B2048_TABLES_BYTES, s, a, pdl);
+        else if (cfg->action_mode == B2048_ACT_PRIORITY) e = launch_fast<B2048_ACT_PRIORITY>(all_track, grid, B2048_TABLES_BYTES, s, a, pdl);
+        else e = launch_fast<B2048_ACT_RANDOM_ANY>(all_track, grid, B2048_TABLES_BYTES, s, a, pdl);
+        B2_CUDA(e);
     } else if (use_smem) {
         int grid = grid_for(n, 1024, h->num_sms, 1);
         step_kernel<true, 1024><<<grid, 1024, B2048_LUT_BYTES, s>>>(a);

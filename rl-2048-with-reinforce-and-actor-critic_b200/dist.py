@@ -2,9 +2,11 @@
 the CPU tests).  The path shards by construction — every board / episode is independent (reference
 src/reinforce_agent.py:195-252 touches no cross-environment state) — so ranks own contiguous ranges of the
 GLOBAL board id, the Philox streams are keyed on that id (results are independent of the world size) and
-nothing is exchanged during rollouts.  Per update the only exchange is one all-reduce(SUM) of the flat
-gradient per network (285 KB for the runner-default MLP) plus the four float64 baseline sums when the
-baseline is "batch" / "batch_norm"."""
+nothing is exchanged during rollouts.  Per update the only exchange is ONE all-reduce(SUM) of the flat
+gradient buffer [actor | critic] (285 KB per network for the runner-default MLP), preceded by a 32-byte
+all-reduce of the four float64 baseline sums when the baseline is "batch" / "batch_norm" (the global mean / std
+enter every sample's coefficient, so they have to exist before the gradient; folding them into the gradient
+message as g = g_A - mu g_B would need a second dW accumulation, +40 % of the update, to save a 32-byte message)."""
 from __future__ import annotations
 
 import os

@@ -122,6 +122,7 @@ class ReinforceAgent:
                                         self.mlp_config.init_distribution, self.mlp_config.last_init_normal)
             self._critic = self._make_net(cparams)
             self._adam_t_c = 0
+        self._bind_grads()
         self._scratch: dict[str, torch.Tensor] = {}
         self.last_update_info: dict[str, Any] = {}
 
@@ -132,6 +133,16 @@ class ReinforceAgent:
         net.adam_v = torch.zeros_like(net.theta)
         net.grad = torch.zeros_like(net.theta)
         return net
+
+    def _bind_grads(self) -> None:
+        """The gradients of the actor and (when present) the critic are views into ONE flat float32 buffer
+        [actor | critic], so a sharded update exchanges them with a single all-reduce."""
+        nets = [self._actor] + ([self._critic] if self._critic is not None else [])
+        self._grad_all = torch.zeros(sum(n.n_params for n in nets), dtype=torch.float32, device=self.device)
+        off = 0
+        for n in nets:
+            n.grad = self._grad_all[off: off + n.n_params]
+            off += n.n_params
 
     @property
     def params(self) -> dict[str, Any]:
@@ -145,6 +156,7 @@ class ReinforceAgent:
             self._actor.load_params(value)
         else:
             self._actor = self._make_net(value)
+            self._bind_grads()
 
     @property
     def critic_params(self):
@@ -154,11 +166,13 @@ class ReinforceAgent:
     def critic_params(self, value) -> None:
         if value is None:
             self._critic = None
+            self._bind_grads()
         elif self._critic is not None and [np.asarray(W).shape for W in value["W"]] == \
                 [(self._critic.dims[l], self._critic.dims[l + 1]) for l in range(self._critic.n_layers)]:
             self._critic.load_params(value)
         else:
             self._critic = self._make_net(value)
+            self._bind_grads()
 
     def load_model(self, file_path: str | None = "params.npz") -> None:
         self.params = load_model_params(file_path)
@@ -180,6 +194,23 @@ class ReinforceAgent:
             out.update(critic_theta=self._critic.theta.cpu().numpy(), critic_dims=np.asarray(self._critic.dims, np.int64),
                        critic_adam_m=self._critic.adam_m.cpu().numpy(), critic_adam_v=self._critic.adam_v.cpu().numpy())
         np.savez(file_path, **out)
+
+    def save_state(self) -> dict[str, Any]:
+        """Device-side snapshot of everything an update mutates (see save_checkpoint), for load_state."""
+        st = {"adam_t": self._adam_t, "adam_t_c": getattr(self, "_adam_t_c", 0)}
+        for name, net in (("actor", self._actor), ("critic", self._critic)):
+            if net is not None:
+                st[name] = (net.theta.clone(), net.adam_m.clone(), net.adam_v.clone())
+        return st
+
+    def load_state(self, st: dict[str, Any]) -> None:
+        self._adam_t = st["adam_t"]
+        if self._critic is not None:
+            self._adam_t_c = st["adam_t_c"]
+        for name, net in (("actor", self._actor), ("critic", self._critic)):
+            if net is not None:
+                for dst, src in zip((net.theta, net.adam_m, net.adam_v), st[name]):
+                    dst.copy_(src)
 
     def load_checkpoint(self, file_path: str) -> None:
         ck = np.load(file_path if str(file_path).endswith(".npz") else str(file_path) + ".npz")
@@ -222,6 +253,13 @@ class ReinforceAgent:
                 self._h, _ptr(boards), _ptr(flags) if self._use_mask else None, C.byref(self._actor.desc),
                 _ptr(actions_out), _ptr(probs_out), _ptr(logits_out), boards.numel(), seed & (2**64 - 1), gid0, t,
                 int(greedy), precision, _stream()), "b2048_policy_step")
+
+    def _update_mode_name(self, prec: int, n: int) -> str:
+        """Which arithmetic b2048_mlp_backward ran for `prec` on n samples (include/b2048.h)."""
+        tc_ok = self.tc_supported() and n >= 4096
+        if prec == 0 or not tc_ok:
+            return "fp32 CUDA cores"
+        return {1: "bf16 tcgen05", 2: "bf16 tcgen05", 3: "fp16 split tcgen05 (fp32-grade forward)"}.get(prec, str(prec))
 
     def tc_supported(self) -> bool:
         a = self._actor
@@ -570,8 +608,6 @@ class ReinforceAgent:
                 _lib.check(lib.b2048_mlp_backward(h, _ptr(boards), _ptr(mflags) if self._use_mask else None, _ptr(acts),
                                                   _ptr(cf), C.byref(net.desc), _ptr(net.grad), n, head_mode, _ptr(ws),
                                                   ws_floats, min(chunk, n), prec, _stream()), "b2048_mlp_backward")
-            if allreduce is not None:
-                allreduce(net.grad)
 
         def apply(net: DeviceMLP, lr: float, sign: float, t_adam: int) -> float:
             sumsq = self._buf("sumsq_" + str(sign), (1,), torch.float64)
@@ -610,6 +646,8 @@ class ReinforceAgent:
             advantages(returns)
             info["returns"] = returns
         backward(self._actor, coef.reshape(-1), 0)
+        if allreduce is not None:
+            allreduce(self._grad_all)        # ONE message per update: [actor gradient | critic gradient]
 
         if cfg.optimizer == "adam":
             self._adam_t += 1
@@ -620,6 +658,7 @@ class ReinforceAgent:
                 self._adam_t_c += 1
             ss_c = apply(self._critic, cfg.critic_learning_rate, -1.0, getattr(self, "_adam_t_c", 0))
         info["advantages"] = adv
+        info["precision"] = self._update_mode_name(prec, n)
         info["actor_grad_norm"] = float(ss_a.cpu()[0]) ** 0.5
         if ss_c is not None:
             info["critic_grad_norm"] = float(ss_c.cpu()[0]) ** 0.5

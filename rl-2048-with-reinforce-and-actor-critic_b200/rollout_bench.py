@@ -37,11 +37,15 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
             "gpu_launches": 2 * steps if precision == 0 else 2 * ((steps + 255) // 256)}
 
 
-def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision=0, use_critic: bool = False):
+def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision="auto", use_critic: bool = False,
+                     update_precisions=("auto",)):
     """BASELINE.json configs[2]: REINFORCE rollout (to termination, max_steps 1024) + one update (gamma 0.99,
     baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks.
     use_critic=True is configs[3]: actor + separate critic (reference semantics, reinforce_agent.py:403-498), TD(0)
-    advantages, Adam, both networks 16-256-256-{4,1} ReLU."""
+    advantages, Adam, both networks 16-256-256-{4,1} ReLU.
+    update_precisions: the update of the LAST iteration is also timed (on a restored copy of the parameters) in these
+    other modes of update_from_rollout, e.g. ("auto", 1) reports the default mode and the single-bf16 opt-in."""
+    import sys
     from . import dist as bd
     info = info or bd.DistInfo()
     env = bd.make_sharded_env(boards * info.world_size, Game2048EnvConfig(**RUNNER_ENV), info, seed=0xB200, device=dev)
@@ -49,14 +53,18 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
                                  use_critic=True, optimizer="adam", model_seed=0) if use_critic else
             ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
     agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"), acfg)
-    out = []
+    allreduce = bd.allreduce_sum_ if info.is_distributed else None
+    out, alt = [], {}
     for it in range(iters):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         torch.cuda.synchronize()
         e[0].record()
         ro = agent.rollout_many(env, precision=precision)
         e[1].record()
-        upd = bd.sharded_update(agent, ro, info, total_episodes=boards * info.world_size)
+        ro.n_traj = boards * info.world_size
+        if it == iters - 1:
+            saved = agent.save_state()
+        upd = agent.update_from_rollout(ro, allreduce=allreduce, precision=update_precisions[0])
         e[2].record()
         torch.cuda.synchronize()
         live_steps = int(ro.length.sum().item())
@@ -68,15 +76,77 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
         out.append({"rollout_ms": float(tm[0]), "update_ms": float(tm[1]), "episode_steps": int(ts[2].item()),
                     "T": ro.T, "mean_len": float(ro.length.float().mean().item()),
                     "mean_return": float(ro.total_reward().mean().item()), "actor_grad_norm": upd["actor_grad_norm"]})
+        if it == iters - 1:
+            after = agent.save_state()
+            for prec in update_precisions[1:]:
+                agent.load_state(saved)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a0.record()
+                u2 = agent.update_from_rollout(ro, allreduce=allreduce, precision=prec)
+                a1.record()
+                torch.cuda.synchronize()
+                ta = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+                bd.allreduce_max_(ta)
+                alt[str(prec)] = {"update_ms": float(ta[0]), "actor_grad_norm": u2["actor_grad_norm"]}
+            agent.load_state(after)
+    print("[bench_train_iter] " + ("actor-critic" if use_critic else "REINFORCE") + " iterations: " + repr(out), file=sys.stderr)
     last = out[-1]
     tot_ms = last["rollout_ms"] + last["update_ms"]
-    return {"metric": ("actor-critic" if use_critic else "REINFORCE") + " iteration (rollout to termination + update)",
-            "boards_per_gpu": boards,
-            "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],
-            "update_ms": last["update_ms"], "T": last["T"], "mean_len": last["mean_len"], "mean_return": last["mean_return"],
-            "actor_grad_norm": last["actor_grad_norm"], "iters": out,
-            "exchange": ("1 all-reduce per network of the flat fp32 gradient (71,172 / 70,401 floats)" if use_critic else
-                         "1 all-reduce of the flat fp32 gradient (71,172 floats)") + " + 4 float64 baseline sums per update"}
+    res = {"metric": ("actor-critic" if use_critic else "REINFORCE") + " iteration (rollout to termination + update)",
+           "boards_per_gpu": boards, "network": "16-256-256-4 ReLU actor" + (" + 16-256-256-1 critic" if use_critic else ""),
+           "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],
+           "update_ms": last["update_ms"], "update_precision": agent.last_update_info.get("precision"),
+           "T": last["T"], "mean_len": last["mean_len"], "mean_return": last["mean_return"],
+           "actor_grad_norm": last["actor_grad_norm"], "episode_steps": last["episode_steps"],
+           "exchange": "1 all-reduce of the flat fp32 gradient buffer [actor | critic] + 4 float64 baseline sums per update"}
+    for k, v in alt.items():
+        res["update_ms_precision_" + k] = v["update_ms"]
+    return res
+
+
+def bench_sharded_sweep(dev, total_boards: int = 64 << 20, info=None, horizon: int = 16, iters: int = 2):
+    """BASELINE.json configs[4]: sharded rollout sweep, `total_boards` boards in total over the ranks (32 M / 16 M / 8 M per
+    GPU at 2 / 4 / 8 GPUs), a fixed 16-step horizon expressed the reference's way — Game2048EnvConfig.max_steps = 16, so
+    every episode is truncated after 16 steps (env.py:279-286) and each lane holds exactly one episode — then ONE
+    REINFORCE update with a single gradient all-reduce over NVLink (tensor-core rollout and update kernels)."""
+    import sys
+    from . import dist as bd
+    info = info or bd.DistInfo()
+    kw = dict(RUNNER_ENV, max_steps=horizon)
+    env = bd.make_sharded_env(total_boards, Game2048EnvConfig(**kw), info, seed=0xB200, device=dev)
+    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                           ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
+    allreduce = bd.allreduce_sum_ if info.is_distributed else None
+    out = []
+    for it in range(iters):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        if info.is_distributed:
+            torch.distributed.barrier()
+        e[0].record()
+        ro = agent.rollout_many(env, precision="auto", check_every=horizon)
+        e[1].record()
+        ro.n_traj = total_boards
+        upd = agent.update_from_rollout(ro, allreduce=allreduce)
+        e[2].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], dtype=torch.float64, device=dev)
+        bd.allreduce_max_(t)
+        s = torch.tensor([float(ro.length.sum().item())], dtype=torch.float64, device=dev)
+        bd.allreduce_sum_(s)
+        out.append({"rollout_ms": float(t[0]), "update_ms": float(t[1]), "samples": int(s.item()),
+                    "actor_grad_norm": upd["actor_grad_norm"]})
+    print("[bench_sharded_sweep] iterations: " + repr(out), file=sys.stderr)
+    last = out[-1]
+    return {"metric": "BASELINE.json configs[4]: sharded rollout sweep + one all-reduced update", "boards_total": total_boards,
+            "boards_per_gpu": env.num_envs, "n_gpus": info.world_size, "horizon": horizon,
+            "horizon_semantics": "max_steps = 16 truncation (one episode per lane, run-to-termination rollout)",
+            "rollout_ms": last["rollout_ms"], "update_ms": last["update_ms"], "samples": last["samples"],
+            "rollout_steps_per_s": last["samples"] / (last["rollout_ms"] * 1e-3),
+            "update_samples_per_s": last["samples"] / (last["update_ms"] * 1e-3),
+            "update_precision": agent.last_update_info.get("precision"), "actor_grad_norm": last["actor_grad_norm"],
+            "exchange": "1 all-reduce of the flat fp32 gradient (71,172 floats) + 4 float64 baseline sums"}
 
 
 def bench_env_trained_boards(dev, boards: int = 1 << 20, train_batches: int = 100, harvest_steps: int = 256, steps: int = 200,

@@ -101,6 +101,47 @@ def main():
         gn = abs(upd["actor_grad_norm"] - u1["actor_grad_norm"]) / u1["actor_grad_norm"]
         print(f"tensor-core path: fused rollout sharding invariance OK; update rel err {rel:.2e}, grad-norm rel err {gn:.2e}")
         assert rel < 1e-3 and gn < 1e-3
+    # ---- 4. x8 symmetry augmentation and the actor-critic update under sharding: every rank applies exactly the update
+    #         of one process holding all episodes (n_traj stays the GLOBAL episode count x 8), and an update issues one
+    #         gradient all-reduce ([actor | critic] in one flat message) plus, for the batch baselines, the 4-double
+    #         statistics message that has to precede the gradient
+    calls = []
+    real_allreduce = bd.allreduce_sum_
+
+    def counting_allreduce(t):
+        calls.append(int(t.numel()))
+        return real_allreduce(t)
+
+    for name, kw, expect_calls in (("augmentation", dict(augmentation=True, baseline_mode="batch"), 2),
+                                   ("actor-critic", dict(use_critic=True, baseline_mode="batch_norm", optimizer="adam",
+                                                         critic_learning_rate=1e-3), 2),
+                                   ("actor-critic, baseline off", dict(use_critic=True, baseline_mode="off"), 1)):
+        acfg = b2048.ReinforceAgentConfig(gamma=0.99, learning_rate=1e-2, model_seed=3, **kw)
+        mlp = b2048.MLPConfig(hidden_sizes=[64, 64], activation="ReLU", init_distribution="HeNormal")
+        n_ep = 6000 + 1
+        env = bd.make_sharded_env(n_ep, cfg, info, seed=seed + 3)
+        agent = b2048.ReinforceAgent(env, mlp, acfg)
+        th0 = agent._actor.theta.clone()
+        ro = agent.rollout_many(env)
+        ro.n_traj = n_ep
+        calls.clear()
+        upd = agent.update_from_rollout(ro, allreduce=counting_allreduce)
+        assert len(calls) == expect_calls, (name, calls)
+        theta = agent._actor.theta.clone()
+        ctheta = None if agent._critic is None else agent._critic.theta.clone()
+        if info.rank == 0:
+            env1 = b2048.Batched2048Env(n_ep, cfg, device=dev, seed=seed + 3)
+            a1 = b2048.ReinforceAgent(env1, mlp, acfg)
+            c0 = None if a1._critic is None else a1._critic.theta.clone()
+            u1 = a1.update_from_rollout(a1.rollout_many(env1))
+            rel = float(((theta - th0) - (a1._actor.theta - th0)).norm() / (a1._actor.theta - th0).norm())
+            msg = f"{name}: {len(calls)} all-reduce(s) per update {calls}; actor update rel err {rel:.2e}"
+            assert rel < 1e-3, msg
+            if ctheta is not None:
+                relc = float(((ctheta - c0) - (a1._critic.theta - c0)).norm() / (a1._critic.theta - c0).norm())
+                msg += f", critic {relc:.2e}"
+                assert relc < 1e-3, msg
+            print(msg)
     dist.barrier()
     if info.rank == 0:
         print("multi-GPU check OK")
