@@ -247,8 +247,10 @@ int b2048_compact_live(b2048_handle* h, const int32_t* ep_len, int64_t B, int32_
                        void* stream);
 
 /* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1).
- *   precision : 0 = fp32 CUDA cores; 1 = bf16 tcgen05 (16-256-256-(<=4) ReLU, raw / log2 observations, n >= 4096,
- *               else B2048_ERR_UNSUPPORTED); 2 = tensor cores when they apply, else fp32. */
+ *   precision : 0 = fp32 CUDA cores; 1 = single-bf16 tcgen05 (16-256-256-(<=4) ReLU, raw / log2 observations, n >= 4096,
+ *               else B2048_ERR_UNSUPPORTED; 1e-2 class); 3 = split-fp16 tcgen05 (every operand as fp16 hi + lo, three
+ *               MMAs per product: 1e-5 of the float64 result; same shapes, log2 observations, else
+ *               B2048_ERR_UNSUPPORTED); 2 = precision 3 when it applies, else fp32. */
 int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
                       int64_t n, int32_t precision, void* stream);
 
@@ -299,10 +301,14 @@ int b2048_td_errors(b2048_handle* h, const float* reward, const float* value, co
  *   head_mode 1: += d/dtheta sum_s coef[s] V(board[s])
  * workspace: device floats, at least b2048_backward_workspace_floats(mlp, chunk); samples are processed
  * `chunk` at a time.
- *   precision : 0 = fp32 CUDA cores (parity path); 1 = bf16 tcgen05 tensor cores (16-256-256-(<=4) ReLU network,
- *               raw / log2 observations, n >= 4096; anything else returns B2048_ERR_UNSUPPORTED); 2 = tensor cores
- *               when they apply, else fp32.  The tensor-core path rounds activations and deltas to bf16 and
- *               accumulates in fp32 (1e-2 relative parity bar). */
+ *   precision : 0 = fp32 CUDA cores;
+ *               3 = float32-grade tensor-core path (16-256-256-(<=4) ReLU network, log2 observations, n >= 4096; anything
+ *                   else returns B2048_ERR_UNSUPPORTED): forward with split-fp16 operands (hi + lo, three tcgen05.mma
+ *                   per product), backward deltas and dW GEMMs in fp16 with a power-of-two loss scale, fp32 accumulation.
+ *                   Within 1e-2 of the float32 gradient also on heavily cancelling (zero-mean advantage) batches;
+ *               2 = precision 3 when it applies, else fp32 (what the host layer's "auto" passes);
+ *               1 = single-bf16 tensor cores (raw / log2 observations), an explicit opt-in: its forward pass flips ReLU
+ *                   units whose pre-activation is within bf16 rounding of zero, a 3-30 % error on cancelling gradients. */
 int64_t b2048_backward_workspace_floats(const b2048_mlp_desc* mlp, int64_t chunk);
 int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
                        const uint8_t* action, const float* coef, const b2048_mlp_desc* mlp, float* grads,

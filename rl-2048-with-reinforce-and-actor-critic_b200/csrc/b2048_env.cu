@@ -651,6 +651,7 @@ extern "C" int b2048_create(b2048_handle** out) {
     B2_REQUIRE(out != nullptr, "b2048_create: out is NULL");
     b2048_handle* h = new b2048_handle();
     h->tc_image = nullptr;
+    h->hp_image = nullptr;
     h->attrs = 0u;
     h->debug = 0u;
     B2_CUDA(cudaGetDevice(&h->device));
@@ -688,6 +689,7 @@ extern "C" int b2048_destroy(b2048_handle* h) {
     if (!h) return B2048_OK;
     cudaFree(h->d_tables);
     if (h->tc_image) cudaFree(h->tc_image);
+    if (h->hp_image) cudaFree(h->hp_image);
     delete h;
     return B2048_OK;
 }

@@ -23,6 +23,11 @@ int validate_mlp(const b2048_mlp_desc* d, MlpDev* out, size_t* smem_bytes, int s
 // b2048_learn_tc.cu
 bool backward_tc_supported(const b2048_handle* h, const b2048_mlp_desc* mlp);
 int64_t backward_tc_workspace_bytes(int64_t chunk);
+bool backward_hp_supported(const b2048_handle* h, const b2048_mlp_desc* mlp);
+int64_t backward_hp_workspace_bytes(int64_t chunk);
+int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
+                       const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
+                       uint8_t* workspace, int64_t chunk, cudaStream_t stream);
 int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                        uint8_t* workspace, int64_t chunk, cudaStream_t stream);
@@ -488,7 +493,14 @@ extern "C" int64_t b2048_backward_workspace_floats(const b2048_mlp_desc* mlp, in
     per += mlp->dims[mlp->n_layers];                                            // d_{L-1}
     int64_t wt = 0;
     for (int l = 1; l + 1 < mlp->n_layers; ++l) wt += (int64_t)mlp->dims[l] * mlp->dims[l + 1];
-    return per * chunk + wt + 64;
+    int64_t floats = per * chunk + wt + 64;
+    // the tensor-core paths carve their images out of the same workspace
+    if (mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == 256 && mlp->dims[2] == 256) {
+        const int64_t tc = (backward_tc_workspace_bytes(chunk) + 3) / 4, hp = (backward_hp_workspace_bytes(chunk) + 3) / 4;
+        floats = floats > tc ? floats : tc;
+        floats = floats > hp ? floats : hp;
+    }
+    return floats;
 }
 
 // Accumulates into grads (flat, same layout as the flat parameter vector: W_0, b_0, W_1, b_1, ...):
@@ -504,17 +516,28 @@ extern "C" int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const 
     B2_REQUIRE(board && coef && grads && workspace, "b2048_mlp_backward: NULL buffer");
     B2_REQUIRE(head_mode == 1 || action != nullptr, "b2048_mlp_backward: action required for the policy head");
     B2_REQUIRE(chunk > 0, "b2048_mlp_backward: chunk must be positive");
-    B2_REQUIRE(precision >= 0 && precision <= 2, "b2048_mlp_backward: precision must be 0 (fp32), 1 (bf16 tcgen05) or 2 (auto)");
-    if (precision != 0) {
+    B2_REQUIRE(precision >= 0 && precision <= 3,
+               "b2048_mlp_backward: precision must be 0 (fp32), 1 (bf16 tcgen05), 2 (auto) or 3 (split-fp16 tcgen05)");
+    if (precision == 2 || precision == 3) {   // float32-grade tensor-core path (what "auto" selects)
+        const bool ok = backward_hp_supported(h, mlp) && n >= 4096 &&
+                        workspace_floats * 4 >= backward_hp_workspace_bytes(chunk < n ? chunk : n);
+        if (ok)
+            return launch_backward_hp(h, board, mask_flags, action, coef, mlp, grads, n, head_mode,
+                                      reinterpret_cast<uint8_t*>(workspace), chunk < n ? chunk : n, (cudaStream_t)stream);
+        if (precision == 3)
+            return fail(B2048_ERR_UNSUPPORTED,
+                        "b2048_mlp_backward: the split-fp16 tcgen05 path needs a 16-256-256-(<=4) ReLU network, log2 "
+                        "observations, n >= 4096 and a workspace of b2048_backward_workspace_floats()");
+    }
+    if (precision == 1) {                     // single-bf16 tensor cores: an explicit opt-in (5 % class gradient error)
         const bool ok = backward_tc_supported(h, mlp) && n >= 4096 &&
                         workspace_floats * 4 >= backward_tc_workspace_bytes(chunk < n ? chunk : n);
         if (ok)
             return launch_backward_tc(h, board, mask_flags, action, coef, mlp, grads, n, head_mode,
                                       reinterpret_cast<uint8_t*>(workspace), chunk < n ? chunk : n, (cudaStream_t)stream);
-        if (precision == 1)
-            return fail(B2048_ERR_UNSUPPORTED,
-                        "b2048_mlp_backward: the tcgen05 path needs a 16-256-256-(<=4) ReLU network, raw/log2 observations, "
-                        "n >= 4096 and a workspace of b2048_backward_workspace_floats()");
+        return fail(B2048_ERR_UNSUPPORTED,
+                    "b2048_mlp_backward: the tcgen05 path needs a 16-256-256-(<=4) ReLU network, raw/log2 observations, "
+                    "n >= 4096 and a workspace of b2048_backward_workspace_floats()");
     }
     BackwardArgs a;
     size_t smem = 0;

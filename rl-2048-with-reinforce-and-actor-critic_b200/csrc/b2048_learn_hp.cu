@@ -1,0 +1,825 @@
+// b2048_learn_hp.cu — K6 on the tensor cores at float32-grade accuracy (precision 3, what "auto" selects).
+//
+// Why: the gradient of update_batch (src/reinforce_agent.py:403-555, _backpropagation :639-678) is a heavily cancelling
+// sum over samples, and a ReLU unit whose pre-activation is within the forward pass's rounding error of zero switches
+// on / off relative to the float32 arithmetic of the reference.  The relative error of the summed gradient therefore
+// scales with the SQUARE ROOT of the forward rounding error (measured on rollout-derived batches: bf16 operands 5 %,
+// fp16 1.5 %, float32 itself 0.06 % against float64).  Single-bf16 tensor-core arithmetic (b2048_learn_tc.cu) cannot
+// meet the 1e-2 parity bar; this path does:
+//
+//  fwd_hp_kernel   forward pass with every operand split into fp16 hi + lo (x = hi + lo to 22 bits) and three
+//                  tcgen05.mma per product (hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM): pre-activations accurate
+//                  to ~1e-6 relative.  The 256 KB of split W2 do not fit in shared memory next to the activations, so
+//                  the weights STREAM through a 3-slot ring of 32 KB K-slab units (bulk async copies from the L2-resident
+//                  image), and the split activations go through a 2-stage ring that the epilogues fill slab by slab.
+//                  Outputs: head outputs (logits / V), the ReLU masks of both layers (64 bits per thread, bit-packed),
+//                  and the fp16 activation images H1, H2 for the dW GEMMs.
+//  bwd_tc_kernel   backward deltas only (no forward): d3 from the float32 logits, D5 = d3 W3^T, DL2 = D5 . mask2,
+//                  D4 = DL2 W2 (the resident fp16 W2 image read MN-major), DL1 = D4 . mask1, fp16 operands with a
+//                  power-of-two loss scale (the coefficients are ~1e-8).  Rounding the backward operands perturbs the
+//                  gradient linearly (no mask flips): 0.04 % at fp16.
+//  atb_tc_kernel   (b2048_learn_tc.cu) the dW GEMMs on the fp16 images, un-scaled on the way out.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "b2048_device.cuh"
+#include "b2048_internal.h"
+#include "b2048_tc.cuh"
+#include "b2048_learn_tc.cuh"
+
+namespace b2 {
+
+int ensure_tc_image(b2048_handle* h);
+
+// ------------------------------------------------------------------------------------------------ split-weight image
+constexpr int HP_UNIT = 32768;                  // one streamed unit: a 64-wide K slab of W2 hi or lo, [256 rows x 128 B]
+constexpr int HP_RES = 8 * HP_UNIT;             // units in streaming order hi0, lo0, hi1, lo1, ...; then the resident part
+constexpr int RES_W1H = 0;                      // [32 row-groups][2 k-chunks][8 rows][16 B] (no swizzle), as IMG_W1
+constexpr int RES_W1L = 8192;
+constexpr int RES_BIAS = 16384;                 // k = 0: b1 hi, 1: b2 hi, 2: b1 lo, 3: b2 lo
+constexpr int RES_W3H = 24576;                  // 4 slabs [16 rows x 128 B] (SWIZZLE_128B), as IMG_W3
+constexpr int RES_W3L = 32768;
+constexpr int RES_B3 = 40960;                   // float [4]
+constexpr int RES_ONES1 = 41216;                // every row = e0 + e2
+constexpr int RES_ONES2 = 41472;                // every row = e1 + e3
+constexpr int RES_BYTES = 41728;
+constexpr int HP_BYTES = HP_RES + RES_BYTES;
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+__global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                          const float* __restrict__ W2, const float* __restrict__ b2,
+                                                          const float* __restrict__ W3, const float* __restrict__ b3,
+                                                          int n_out, uint8_t* __restrict__ img) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    auto put2 = [&](size_t off_hi, size_t off_lo, float v) {
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        *reinterpret_cast<__half*>(img + off_hi) = hi;
+        *reinterpret_cast<__half*>(img + off_lo) = lo;
+    };
+    for (int idx = tid; idx < TC_H * TC_H; idx += nth) {
+        int k = idx / TC_H, n = idx - k * TC_H;
+        int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
+        size_t off = (size_t)n * 128 + (size_t)((kc ^ (n & 7)) * 16) + ke * 2;
+        put2((size_t)(2 * slab) * HP_UNIT + off, (size_t)(2 * slab + 1) * HP_UNIT + off, W2[idx]);
+    }
+    uint8_t* res = img + HP_RES;
+    for (int idx = tid; idx < TC_K1 * TC_H; idx += nth) {
+        int k = idx / TC_H, n = idx - k * TC_H;
+        size_t off = (size_t)(n >> 3) * 256 + (size_t)(k >> 3) * 128 + (size_t)(n & 7) * 16 + (k & 7) * 2;
+        __half hi, lo;
+        split_f16(W1[idx], hi, lo);
+        *reinterpret_cast<__half*>(res + RES_W1H + off) = hi;
+        *reinterpret_cast<__half*>(res + RES_W1L + off) = lo;
+        __half bh1, bl1, bh2, bl2;
+        split_f16(b1[n], bh1, bl1);
+        split_f16(b2[n], bh2, bl2);
+        __half bv = k == 0 ? bh1 : (k == 1 ? bh2 : (k == 2 ? bl1 : (k == 3 ? bl2 : __float2half_rn(0.0f))));
+        *reinterpret_cast<__half*>(res + RES_BIAS + off) = bv;
+    }
+    for (int idx = tid; idx < TC_N3 * TC_H; idx += nth) {
+        int j = idx / TC_H, k = idx - j * TC_H;
+        int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
+        size_t off = (size_t)slab * 2048 + (size_t)j * 128 + (size_t)((kc ^ (j & 7)) * 16) + ke * 2;
+        __half hi, lo;
+        split_f16(j < n_out ? W3[k * n_out + j] : 0.0f, hi, lo);
+        *reinterpret_cast<__half*>(res + RES_W3H + off) = hi;
+        *reinterpret_cast<__half*>(res + RES_W3L + off) = lo;
+    }
+    if (tid < 4) reinterpret_cast<float*>(res + RES_B3)[tid] = tid < n_out ? b3[tid] : 0.0f;
+    for (int idx = tid; idx < 2 * 8 * 8; idx += nth) {
+        int e = idx & 7, chunk = idx >> 6;
+        *reinterpret_cast<__half*>(res + RES_ONES1 + idx * 2) = __float2half_rn((chunk == 0 && (e == 0 || e == 2)) ? 1.0f : 0.0f);
+        *reinterpret_cast<__half*>(res + RES_ONES2 + idx * 2) = __float2half_rn((chunk == 0 && (e == 1 || e == 3)) ? 1.0f : 0.0f);
+    }
+}
+
+// fp16 copy of the single-precision image layout of b2048_tc.cuh (W2 / W3 only are read): the backward kernel's B operands
+__global__ void __launch_bounds__(256) bwd_prepare_kernel(const float* __restrict__ W2, const float* __restrict__ W3, int n_out,
+                                                           uint8_t* __restrict__ img) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nth = gridDim.x * blockDim.x;
+    for (int idx = tid; idx < TC_H * TC_H; idx += nth) {
+        int k = idx / TC_H, n = idx - k * TC_H;
+        int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
+        *reinterpret_cast<__half*>(img + (size_t)IMG_W2 + (size_t)slab * 32768 + (size_t)n * 128 + (size_t)((kc ^ (n & 7)) * 16) + ke * 2) =
+            __float2half_rn(W2[idx]);
+    }
+    for (int idx = tid; idx < TC_N3 * TC_H; idx += nth) {
+        int j = idx / TC_H, k = idx - j * TC_H;
+        int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
+        *reinterpret_cast<__half*>(img + (size_t)IMG_W3 + (size_t)slab * 2048 + (size_t)j * 128 + (size_t)((kc ^ (j & 7)) * 16) + ke * 2) =
+            __float2half_rn(j < n_out ? W3[k * n_out + j] : 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ precise forward
+constexpr int FS_W = 0;                               // W ring: 3 slots x 32 KB
+constexpr int FS_A = 3 * HP_UNIT;                     // A ring: 2 stages x [16 KB hi slab | 16 KB lo slab]
+constexpr int FS_ASTAGE = 32768;
+constexpr int FS_RES = FS_A + 2 * FS_ASTAGE;          // resident part of the image
+constexpr int FS_A1 = FS_RES + RES_BYTES;             // [16 row-groups][2][8][16 B] = 4096 B
+constexpr int FS_BAR = FS_A1 + 4096;
+constexpr int FS_TOTAL = FS_BAR + 512;
+static_assert(FS_RES % 1024 == 0 && (FS_RES + RES_W3H) % 1024 == 0 && (FS_RES + RES_W3L) % 1024 == 0 && FS_A1 % 128 == 0,
+              "operand alignment");
+static_assert(FS_TOTAL <= 232448, "fwd_hp_kernel exceeds the shared memory of an sm_100 CTA");
+
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(TC_H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);       // A/B fp16
+constexpr uint32_t kIdescHeadF16 = (1u << 4) | ((uint32_t)(TC_N3 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+struct FwdHpArgs {
+    const uint8_t* img;       // split-weight image (global)
+    const uint64_t* board;
+    float* out;               // [n][n_out] head outputs, bias included
+    uint8_t *h1, *h2;         // nullable: fp16 activation images (layout of b2048_learn_tc.cuh)
+    uint8_t* a1t;             // nullable: small K-major image of the encoded inputs (B operand of dW1^T = DL1^T A1)
+    uint64_t *m1, *m2;        // nullable: ReLU masks, entry (tile * 4 + g) * 128 + row = 64 bits of thread (row, g)
+    int64_t n;
+    int n_out, obs_mode;
+    float obs_scale;
+};
+
+constexpr int FH_THREADS = 512 + 3 * 32 + 128;   // 16 epilogue warps, MMA warp, weight loader, image storer, 4 I/O warps
+
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    __half2 p = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+// hi = fp16x2(relu(a), relu(b)) in one instruction; lo = fp16x2(relu(x) - float(hi))
+__device__ __forceinline__ void relu_split(uint32_t a_bits, uint32_t b_bits, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(__uint_as_float(b_bits)), "f"(__uint_as_float(a_bits)));
+    const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
+    const float ra = fmaxf(__uint_as_float(a_bits), 0.0f), rb = fmaxf(__uint_as_float(b_bits), 0.0f);
+    lo = pack_f16(ra - hf.x, rb - hf.y);
+}
+
+__global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_constant__ FwdHpArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FS_BAR);
+    const uint32_t bar_res = s_u32(&bars[0]), bar_a1 = s_u32(&bars[1]), bar_d1 = s_u32(&bars[2]), bar_d2 = s_u32(&bars[3]),
+                   bar_d3 = s_u32(&bars[4]), bar_d3r = s_u32(&bars[5]);
+    const uint32_t w_full0 = s_u32(&bars[6]), w_empty0 = s_u32(&bars[9]);
+    const uint32_t a_full0 = s_u32(&bars[12]), a_free0 = s_u32(&bars[14]);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FS_BAR + 256);
+
+    if (tid == 0) {
+        mbar_init(bar_res, 1);
+        mbar_init(bar_a1, 4);
+        mbar_init(bar_d1, 1);
+        mbar_init(bar_d2, 1);
+        mbar_init(bar_d3, 1);
+        mbar_init(bar_d3r, 4);
+        for (int i = 0; i < 3; ++i) { mbar_init(w_full0 + 8u * i, 1); mbar_init(w_empty0 + 8u * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(a_full0 + 8u * i, 16); mbar_init(a_free0 + 8u * i, 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {   // D1 = columns 0..255, D2 = 256..511, D3 = 256..271 (over the drained first columns of D2)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
+    const int64_t first = blockIdx.x;
+
+    if (warp == 16) {
+        // ============================ MMA warp ============================
+        if (lane == 0) {
+            const uint8_t* gres = args.img + HP_RES;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_res), "r"((uint32_t)RES_BYTES) : "memory");
+            for (uint32_t off = 0; off < (uint32_t)RES_BYTES; off += 16384u) {
+                uint32_t sz = (uint32_t)RES_BYTES - off < 16384u ? (uint32_t)RES_BYTES - off : 16384u;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 s_u32(smem + FS_RES + off)),
+                             "l"(gres + off), "r"(sz), "r"(bar_res)
+                             : "memory");
+            }
+            mbar_wait(bar_res, 0);
+            const uint32_t sA1 = s_u32(smem + FS_A1), sW = s_u32(smem + FS_W), sA = s_u32(smem + FS_A);
+            const uint32_t sRes = s_u32(smem + FS_RES);
+            const uint64_t dBias = desc_nosw_k16(sRes + RES_BIAS);
+            const uint64_t dOnes1 = desc_ones(sRes + RES_ONES1), dOnes2 = desc_ones(sRes + RES_ONES2);
+            auto issue_layer1 = [&](uint32_t ph) {
+                mbar_wait(bar_a1, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sRes + RES_W1H), kIdescF16, 0u);
+                umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sRes + RES_W1L), kIdescF16, 1u);
+                umma_f16(tmem_base, dOnes1, dBias, kIdescF16, 1u);
+                umma_commit(bar_d1);
+            };
+            uint32_t ph = 0, U = 0, F = 0;     // tile parity, streamed weight units consumed, activation ring fills consumed
+            if (first < n_tiles) issue_layer1(0u);
+            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+                if (tile != first) mbar_wait(bar_d3r, ph ^ 1u);     // the previous tile's head outputs have left D3 (inside D2)
+                // ---- layer 2: per 64-wide K slab  D2 += H1hi W2hi + H1lo W2hi + H1hi W2lo
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t st = F & 1u, au = F >> 1;
+                    mbar_wait(a_full0 + 8u * st, au & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ahi = sA + st * FS_ASTAGE, alo = ahi + 16384u;
+                    uint32_t slot = U % 3u, use = U / 3u;
+                    mbar_wait(w_full0 + 8u * slot, use & 1u);
+                    uint32_t wb = sW + slot * HP_UNIT;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), kIdescF16,
+                                 (s | q) ? 1u : 0u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(alo + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), kIdescF16, 1u);
+                    umma_commit(w_empty0 + 8u * slot);
+                    ++U;
+                    slot = U % 3u; use = U / 3u;
+                    mbar_wait(w_full0 + 8u * slot, use & 1u);
+                    wb = sW + slot * HP_UNIT;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), kIdescF16, 1u);
+                    umma_commit(w_empty0 + 8u * slot);
+                    ++U;
+                    umma_commit(a_free0 + 8u * st);
+                    ++F;
+                }
+                umma_f16(tmem_base + 256u, dOnes2, dBias, kIdescF16, 1u);
+                umma_commit(bar_d2);
+                // ---- the next tile's layer 1 (D1 was drained before the last H1 slab arrival waited for above)
+                if (tile + gridDim.x < n_tiles) issue_layer1(ph ^ 1u);
+                // ---- head: D3 (columns 256..271: that part of D2 is drained before the first H2 slab arrives)
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t st = F & 1u, au = F >> 1;
+                    mbar_wait(a_full0 + 8u * st, au & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ahi = sA + st * FS_ASTAGE, alo = ahi + 16384u;
+                    const uint32_t w3h = sRes + RES_W3H + (uint32_t)s * 2048u, w3l = sRes + RES_W3L + (uint32_t)s * 2048u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(w3h + (uint32_t)q * 32u), kIdescHeadF16,
+                                 (s | q) ? 1u : 0u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(alo + (uint32_t)q * 32u), desc_sw128(w3h + (uint32_t)q * 32u), kIdescHeadF16, 1u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(w3l + (uint32_t)q * 32u), kIdescHeadF16, 1u);
+                    umma_commit(a_free0 + 8u * st);
+                    ++F;
+                }
+                umma_commit(bar_d3);
+                ph ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 17) {
+        // ============================ weight loader: streams the 8 split-W2 units of every tile through the ring
+        if (lane == 0) {
+            uint32_t U = 0;
+            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+                for (int j = 0; j < 8; ++j, ++U) {
+                    const uint32_t slot = U % 3u, use = U / 3u;
+                    if (use > 0) mbar_wait(w_empty0 + 8u * slot, (use - 1u) & 1u);
+                    const uint32_t bar = w_full0 + 8u * slot;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)HP_UNIT) : "memory");
+                    const uint8_t* g = args.img + (size_t)j * HP_UNIT;
+                    const uint32_t d = s_u32(smem + FS_W) + slot * HP_UNIT;
+#pragma unroll
+                    for (uint32_t off = 0; off < (uint32_t)HP_UNIT; off += 16384u)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d + off),
+                                     "l"(g + off), "r"(16384u), "r"(bar)
+                                     : "memory");
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 18) {
+        // ============================ image storer: the hi half of every activation slab leaves as a global image
+        if (lane == 0) {
+            uint32_t F = 0;
+            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+                for (int layer = 0; layer < 2; ++layer) {
+                    uint8_t* img = layer == 0 ? args.h1 : args.h2;
+                    for (int s = 0; s < 4; ++s, ++F) {
+                        const uint32_t st = F & 1u, au = F >> 1;
+                        mbar_wait(a_full0 + 8u * st, au & 1u);
+                        if (img != nullptr) {
+                            const uint32_t src = s_u32(smem + FS_A) + st * FS_ASTAGE;
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                uint8_t* dst = img + (size_t)(tile * 2 + half) * ACT_TILE_BYTES + (size_t)s * ACT_SLAB_BYTES;
+                                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                                             "r"(src + (uint32_t)half * 8192u), "r"((uint32_t)ACT_SLAB_BYTES)
+                                             : "memory");
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                        mbar_arrive(a_free0 + 8u * st);
+                    }
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+    } else if (warp < 16) {
+        // ============================ epilogue warps ============================
+        const int q = warp & 3, g = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t ph = 0, F = 0;
+        auto epilogue = [&](uint32_t tcol0) -> uint64_t {
+            uint32_t mw[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s, ++F) {
+                const uint32_t st = F & 1u, au = F >> 1;
+                uint32_t r[16];
+                tmem_ld16(tcol0 + (uint32_t)(s * 64 + g * 16), r);
+                uint32_t m = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) m = __funnelshift_l(0u - r[i], m, 1);   // z > 0  <=>  sign bit of -bits(z)
+                mw[s] = m;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) relu_split(r[2 * k], r[2 * k + 1], hi[k], lo[k]);
+                if (au > 0) mbar_wait(a_free0 + 8u * st, (au - 1u) & 1u);          // the ring stage has been consumed
+                uint8_t* base = smem + FS_A + st * FS_ASTAGE + row * 128;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(base + sw) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(base + 16384 + sw) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full0 + 8u * st);
+            }
+            return (uint64_t)(mw[0] | (mw[1] << 16)) | ((uint64_t)(mw[2] | (mw[3] << 16)) << 32);
+        };
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(bar_d1, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t m1 = epilogue(tlane);
+            if (args.m1) args.m1[(size_t)(tile * 4 + g) * TC_M + row] = m1;
+            mbar_wait(bar_d2, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t m2 = epilogue(tlane + 256u);
+            if (args.m2) args.m2[(size_t)(tile * 4 + g) * TC_M + row] = m2;
+            ph ^= 1u;
+        }
+    } else {
+        // ============================ I/O warps (19..22), one thread per sample ============================
+        const int q = warp & 3;   // warps 19, 20, 21, 22 -> lane quarters 3, 0, 1, 2: a TMEM load may only touch the quarter warp % 4
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float* sB3 = reinterpret_cast<const float*>(smem + FS_RES + RES_B3);
+        uint32_t ph = 0;
+        auto encode_a1 = [&](int64_t tile) {
+            const int64_t s = tile * TC_M + row;
+            uint64_t bd = (s < args.n) ? args.board[s] : 0ull;
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t e0 = (uint32_t)(bd >> (8 * j)) & 0xFu, e1 = (uint32_t)(bd >> (8 * j + 4)) & 0xFu;
+                float v0, v1;
+                if (args.obs_mode == B2048_OBS_RAW) { v0 = e0 ? (float)(1u << e0) : 0.0f; v1 = e1 ? (float)(1u << e1) : 0.0f; }
+                else { v0 = (float)e0 * args.obs_scale; v1 = (float)e1 * args.obs_scale; }
+                packed[j] = pack_f16(v0, v1);
+                if (args.a1t) {
+                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(s, 2 * j)) = (uint16_t)(packed[j] & 0xFFFFu);
+                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(s, 2 * j + 1)) = (uint16_t)(packed[j] >> 16);
+                }
+            }
+            uint8_t* a1 = smem + FS_A1 + (row >> 3) * 256 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a1);
+        };
+        if (first < n_tiles) encode_a1(first);
+        mbar_wait(bar_res, 0);
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            const int64_t s = tile * TC_M + row;
+            mbar_wait(bar_d1, ph);                                               // A1 is free
+            const int64_t next = tile + gridDim.x;
+            if (next < n_tiles) encode_a1(next);
+            mbar_wait(bar_d3, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r4[4];
+            tmem_ld4(tlane + 256u, r4);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_d3r);
+            if (s < args.n) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < args.n_out) args.out[s * args.n_out + j] = __uint_as_float(r4[j]) + sB3[j];
+            }
+            ph ^= 1u;
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 16) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward deltas
+constexpr int BW_D3A = SM_BAR + 256;     // head deltas of the tile in flight as an fp16 A operand [128 x 16], A1's layout
+constexpr int BW_TOTAL = BW_D3A + 4096;
+static_assert(BW_TOTAL <= 232448, "bwd_tc_kernel exceeds the shared memory of an sm_100 CTA");
+
+struct BwdArgs {
+    const uint8_t* img;           // fp16 image, layout of b2048_tc.cuh (W2 and W3 are read)
+    const float* logits;          // [n][n_out] from fwd_hp_kernel (head_mode 0)
+    const uint64_t *m1, *m2;      // ReLU masks from fwd_hp_kernel
+    const uint8_t* mask_flags;
+    const uint8_t* action;
+    const float* coef;
+    const float* scale;           // device float[2]: loss scale S (a power of two) and 1 / S
+    uint8_t *dl2, *dl1, *d3t;
+    float* gb3;
+    int64_t n;
+    int head_mode, n_out;
+};
+
+constexpr int BW_THREADS = 512 + 32 + 128;
+
+__device__ __forceinline__ void bw_store_slab(uint8_t* img, int64_t tile, uint32_t sA2, int g) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint8_t* dst = img + (size_t)(tile * 2 + half) * ACT_TILE_BYTES + (size_t)g * ACT_SLAB_BYTES;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                     "r"(sA2 + (uint32_t)g * 16384u + (uint32_t)half * 8192u), "r"((uint32_t)ACT_SLAB_BYTES)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void bw_stores_read_done() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_constant__ BwdArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    const uint32_t bar_img = s_u32(&bars[0]), bar_dl3 = s_u32(&bars[1]), bar_d5 = s_u32(&bars[2]), bar_d4 = s_u32(&bars[3]),
+                   bar_free = s_u32(&bars[4]);
+    const uint32_t bar_bslab0 = s_u32(&bars[8]);    // [8..11]  DL2 slab written (D5 drained for that slab)
+    const uint32_t bar_dslab0 = s_u32(&bars[12]);   // [12..15] DL1 slab written (D4 drained for that slab)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 208);
+
+    if (tid == 0) {
+        mbar_init(bar_img, 1);
+        mbar_init(bar_dl3, 4);
+        mbar_init(bar_d5, 1);
+        mbar_init(bar_d4, 1);
+        mbar_init(bar_free, 1);
+        for (int g = 0; g < 4; ++g) {
+            mbar_init(bar_bslab0 + 8u * g, 16);
+            mbar_init(bar_dslab0 + 8u * g, 16);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {   // D5 = columns 0..255, D4 = columns 256..511
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
+    const int64_t first = blockIdx.x;
+
+    if (warp == 16) {
+        // ============================ MMA / copy warp ============================
+        if (lane == 0) {
+            const uint32_t sA2 = s_u32(smem + SM_A2), sW2 = s_u32(smem + IMG_W2), sW3 = s_u32(smem + IMG_W3);
+            constexpr uint32_t kIdescBwd = kIdescF16 | kIdescBMn;
+            // only W2 and W3 of the image are read by this kernel
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)(131072 + 8192)) : "memory");
+            for (uint32_t off = 0; off < 131072u; off += 16384u)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 s_u32(smem + IMG_W2 + off)),
+                             "l"(args.img + IMG_W2 + off), "r"(16384u), "r"(bar_img)
+                             : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             s_u32(smem + IMG_W3)),
+                         "l"(args.img + IMG_W3), "r"(8192u), "r"(bar_img)
+                         : "memory");
+            mbar_wait(bar_img, 0);
+            auto issue_d5 = [&](uint32_t ph) {
+                // backward through the head: D5 = d3 . W3^T.  A = d3 as fp16 [128 x 16] (K-major, A1's layout); B = the
+                // head's W3 image [j][f] read MN-major (N = f contiguous: 64-wide slabs 2048 B apart, 8 K rows = 1024 B)
+                mbar_wait(bar_dl3, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                umma_f16(tmem_base, desc_nosw_k16(s_u32(smem + BW_D3A)), desc_sw128_mn(sW3, 2048u), kIdescBwd, 0u);
+                umma_commit(bar_d5);
+            };
+            uint32_t ph = 0;
+            if (first < n_tiles) issue_d5(0u);
+            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+                // ---- backward through layer 2: D4 = DL2 . W2 over K = out features; B = the W2 image [out][in] read
+                //      MN-major (N = in contiguous: 64-wide slabs 32768 B apart, 8 K rows = 1024 B)
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(bar_bslab0 + 8u * g, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        umma_f16(tmem_base + 256u, desc_sw128(sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u),
+                                 desc_sw128_mn(sW2 + (uint32_t)(g * 64 + q * 16) * 128u, 32768u), kIdescBwd, (g | q) ? 1u : 0u);
+                    bw_store_slab(args.dl2, tile, sA2, g);
+                }
+                bw_stores_read_done();                   // epilogue 4 overwrites DL2 once bar_d4 completes
+                umma_commit(bar_d4);
+                // ---- the next tile's D5 (this tile's D5 was drained by every warp before the DL2 slab arrivals)
+                if (tile + gridDim.x < n_tiles) issue_d5(ph ^ 1u);
+                for (int g = 0; g < 4; ++g) {
+                    mbar_wait(bar_dslab0 + 8u * g, ph);
+                    bw_store_slab(args.dl1, tile, sA2, g);
+                }
+                bw_stores_read_done();
+                mbar_arrive(bar_free);                   // A2 free: the DL1 image of the tile has been streamed out
+                ph ^= 1u;
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+    } else if (warp < 16) {
+        // ============================ epilogue warps ============================
+        const int q = warp & 3, g = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint8_t* a2_row = smem + SM_A2 + row * 128;
+        uint32_t ph = 0;
+        auto masked_store = [&](uint32_t tcol0, uint64_t mask, uint32_t bar0) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                uint32_t rr[16];
+                tmem_ld16(tcol0 + (uint32_t)(s * 64 + g * 16), rr);
+                const uint32_t mb = (uint32_t)(mask >> (16 * s)) & 0xFFFFu;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t out[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i0 = c * 8 + 2 * k;
+                        float lo = (mb >> (15 - i0)) & 1u ? __uint_as_float(rr[i0]) : 0.0f;
+                        float hi = (mb >> (14 - i0)) & 1u ? __uint_as_float(rr[i0 + 1]) : 0.0f;
+                        out[k] = pack_f16(lo, hi);
+                    }
+                    const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                    *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = make_uint4(out[0], out[1], out[2], out[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8u * s);
+            }
+        };
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            const uint64_t m2 = args.m2[(size_t)(tile * 4 + g) * TC_M + row];
+            const uint64_t m1 = args.m1[(size_t)(tile * 4 + g) * TC_M + row];
+            // ---- DL2 = D5 [z2 > 0]  (the A2 buffer is free once the previous tile's DL1 image has been streamed out)
+            mbar_wait(bar_d5, ph);
+            if (tile != first) mbar_wait(bar_free, ph ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            masked_store(tlane, m2, bar_bslab0);
+            // ---- DL1 = D4 [z1 > 0] over DL2 (the backward MMAs have completed), streamed out by the MMA warp
+            mbar_wait(bar_d4, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            masked_store(tlane + 256u, m1, bar_dslab0);
+            ph ^= 1u;
+        }
+    } else {
+        // ============================ I/O warps (17..20), one thread per sample ============================
+        const int row = (warp & 3) * 32 + lane;
+        uint8_t* d3a = smem + BW_D3A + (row >> 3) * 256 + (row & 7) * 16;   // this row's two 16-byte K chunks
+        *reinterpret_cast<uint4*>(d3a + 128) = make_uint4(0u, 0u, 0u, 0u);    // k = 8..15 stay zero
+        const float S = args.scale[0];
+        uint32_t ph = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            const int64_t s = tile * TC_M + row;
+            const bool valid = s < args.n;
+            const bool use_mask = args.mask_flags != nullptr;
+            uint32_t fl = 0xFu, act = 0;
+            float cf = 0.0f, lg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (valid) {
+                if (use_mask) fl = args.mask_flags[s];
+                if (args.action) act = args.action[s];
+                cf = args.coef[s];
+                if (args.head_mode == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < args.n_out) lg[j] = args.logits[s * args.n_out + j];
+                }
+            }
+            float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (args.head_mode == 0) {
+                float m[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = (use_mask && !((fl >> j) & 1u)) ? -1e9f : lg[j];   // MLP.py:144-146
+                const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+                float e[4], sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { e[j] = expf(m[j] - mx); sum += e[j]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = cf * ((act == (uint32_t)j ? 1.0f : 0.0f) - e[j] / sum);   // reinforce_agent.py:340-344
+            } else {
+                d[0] = cf;                                                        // value head: dLoss/dV * weight
+            }
+            if (tile != first) mbar_wait(bar_d5, ph ^ 1u);                        // the previous tile's D5 has read d3a
+            const uint32_t p01 = pack_f16(d[0] * S, d[1] * S), p23 = pack_f16(d[2] * S, d[3] * S);
+            *reinterpret_cast<uint4*>(d3a) = make_uint4(p01, p23, 0u, 0u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_dl3);
+            // off the critical path: transposed fp16 copy for dW3 = H2^T d3 (rows >= n_out of the small image stay zero)
+            // and the head bias gradient (unscaled float32 sum over the warp's 32 samples)
+            const uint32_t pk[2] = {p01, p23};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < args.n_out)
+                    *reinterpret_cast<uint16_t*>(args.d3t + small_off(s, j)) = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v = d[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                if (lane == 0 && j < args.n_out && v != 0.0f) atomicAdd(args.gb3 + j, v);
+            }
+            ph ^= 1u;
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 16) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ loss scale
+// S = the power of two that brings max |coef| into [32, 64): fp16 deltas keep their precision (they are ~1e-8 otherwise)
+// with a factor 1000 of head-room for the growth through W3 and W2.  scale[0] = S, scale[1] = 1 / S, scale[2] = bits of max.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f && isfinite(m)) atomicMax(out_bits, __float_as_uint(m));
+}
+__global__ void scale_from_max_kernel(float* __restrict__ scale) {
+    const float m = __uint_as_float(reinterpret_cast<uint32_t*>(scale)[2]);
+    int e = 0;
+    if (m > 0.0f) frexpf(m, &e);                   // m = f 2^e, f in [0.5, 1)
+    int sh = 6 - e;
+    sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+    scale[0] = ldexpf(1.0f, sh);
+    scale[1] = ldexpf(1.0f, -sh);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct HpWorkspace {       // byte offsets inside the caller's workspace for a chunk padded to `np` samples
+    int64_t h1, h2, dl2, dl1, a1t, d3t, m1, m2, logits, scale, img, bimg, total;
+};
+static HpWorkspace hp_workspace(int64_t chunk) {
+    HpWorkspace w;
+    const int64_t np = (chunk + TC_M - 1) / TC_M * TC_M;
+    const int64_t act = np / 64 * ACT_TILE_BYTES, small = np / 64 * SMALL_TILE_BYTES;
+    int64_t o = 0;
+    w.h1 = o; o += act; w.h2 = o; o += act; w.dl2 = o; o += act; w.dl1 = o; o += act;
+    w.a1t = o; o += small; w.d3t = o; o += small;
+    w.m1 = o; o += np * 32; w.m2 = o; o += np * 32;
+    w.logits = o; o += np * 16;
+    w.scale = o; o += 1024;
+    w.img = o; o += (HP_BYTES + 1023) / 1024 * 1024;
+    w.bimg = o; o += (IMG_BYTES + 1023) / 1024 * 1024;
+    w.total = o;
+    return w;
+}
+
+bool backward_hp_supported(const b2048_handle* h, const b2048_mlp_desc* mlp) {
+    // log2 observations only: fp16 holds them exactly and the hidden activations stay far below 65504; raw tile values
+    // (up to 32768 per input) could overflow the fp16 activations
+    return mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H && mlp->dims[3] >= 1 &&
+           mlp->dims[3] <= 4 && mlp->activation == B2048_ACTV_RELU && mlp->obs_mode == B2048_OBS_LOG2 &&
+           h->smem_optin >= FS_TOTAL && h->smem_optin >= BW_TOTAL && h->smem_optin >= AtbCfg<256>::kSmem;
+}
+
+int64_t backward_hp_workspace_bytes(int64_t chunk) { return hp_workspace(chunk).total + 1024; }
+int64_t forward_hp_workspace_bytes() { return (HP_BYTES + 1023) / 1024 * 1024 + 1024; }
+
+static int hp_attrs(b2048_handle* h) {
+    if (!(h->attrs & 16u)) {
+        cudaError_t e = cudaFuncSetAttribute(fwd_hp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_TOTAL);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(fwd_hp_kernel)");
+        e = cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(bwd_tc_kernel)");
+        h->attrs |= 16u;
+    }
+    return B2048_OK;
+}
+
+static int ensure_hp_image(b2048_handle* h) {
+    if (!h->hp_image) {
+        cudaError_t e = cudaMalloc(&h->hp_image, (HP_BYTES + 1023) / 1024 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(hp_image)");
+    }
+    return B2048_OK;
+}
+
+// b2048_mlp_forward at float32-grade accuracy on the tensor cores: out[n][n_out].  B2048_ERR_UNSUPPORTED (silent) for
+// other shapes.
+int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n, cudaStream_t stream) {
+    if (!backward_hp_supported(h, mlp) || n < 4096) return B2048_ERR_UNSUPPORTED;
+    { int st = hp_attrs(h); if (st != B2048_OK) return st; }
+    { int st = ensure_hp_image(h); if (st != B2048_OK) return st; }
+    hp_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[0], mlp->b[0], mlp->W[1], mlp->b[1], mlp->W[2], mlp->b[2], mlp->dims[3], h->hp_image);
+    FwdHpArgs f;
+    f.img = h->hp_image; f.board = board; f.out = out; f.h1 = nullptr; f.h2 = nullptr; f.a1t = nullptr; f.m1 = nullptr; f.m2 = nullptr;
+    f.n = n; f.n_out = mlp->dims[3]; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale;
+    const int64_t tiles = (n + TC_M - 1) / TC_M;
+    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    fwd_hp_kernel<<<grid, FH_THREADS, FS_TOTAL, stream>>>(f);
+    return check_cuda(cudaGetLastError(), "fwd_hp_kernel launch");
+}
+
+// Same contract as the fp32 body of b2048_mlp_backward (grads accumulated, flat layout W_0, b_0, W_1, b_1, ...).
+int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
+                       const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
+                       uint8_t* workspace, int64_t chunk, cudaStream_t stream) {
+    { int st = hp_attrs(h); if (st != B2048_OK) return st; }
+    const int n_out = mlp->dims[3];
+    float* gW1 = grads;
+    float* gb1 = gW1 + 16 * TC_H;
+    float* gW2 = gb1 + TC_H;
+    float* gb2 = gW2 + TC_H * TC_H;
+    float* gW3 = gb2 + TC_H;
+    float* gb3 = gW3 + TC_H * n_out;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    const HpWorkspace w = hp_workspace(chunk);
+    uint8_t* img = ws + w.img;
+    uint8_t* bimg = ws + w.bimg;
+    float* scale = reinterpret_cast<float*>(ws + w.scale);
+    hp_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[0], mlp->b[0], mlp->W[1], mlp->b[1], mlp->W[2], mlp->b[2], n_out, img);
+    bwd_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[1], mlp->W[2], n_out, bimg);
+    cudaError_t e = cudaMemsetAsync(scale, 0, 16, stream);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(scale)");
+    absmax_kernel<<<h->num_sms * 4, 256, 0, stream>>>(coef, n, reinterpret_cast<uint32_t*>(scale) + 2);
+    scale_from_max_kernel<<<1, 1, 0, stream>>>(scale);
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t cn = (n - c0) < chunk ? (n - c0) : chunk;
+        const int64_t tiles = (cn + TC_M - 1) / TC_M;
+        const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+        FwdHpArgs f;
+        f.img = img; f.board = board + c0; f.out = reinterpret_cast<float*>(ws + w.logits);
+        f.h1 = ws + w.h1; f.h2 = ws + w.h2; f.a1t = ws + w.a1t;
+        f.m1 = reinterpret_cast<uint64_t*>(ws + w.m1); f.m2 = reinterpret_cast<uint64_t*>(ws + w.m2);
+        f.n = cn; f.n_out = n_out; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale;
+        fwd_hp_kernel<<<grid, FH_THREADS, FS_TOTAL, stream>>>(f);
+        int st = check_cuda(cudaGetLastError(), "fwd_hp_kernel launch");
+        if (st != B2048_OK) return st;
+        BwdArgs b;
+        b.img = bimg; b.logits = f.out; b.m1 = f.m1; b.m2 = f.m2;
+        b.mask_flags = mask_flags ? mask_flags + c0 : nullptr;
+        b.action = action ? action + c0 : nullptr;
+        b.coef = coef + c0; b.scale = scale;
+        b.dl2 = ws + w.dl2; b.dl1 = ws + w.dl1; b.d3t = ws + w.d3t; b.gb3 = gb3;
+        b.n = cn; b.head_mode = head_mode; b.n_out = n_out;
+        e = cudaMemsetAsync(b.d3t, 0, (size_t)tiles * 2 * SMALL_TILE_BYTES, stream);
+        if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(d3t)");
+        bwd_tc_kernel<<<grid, BW_THREADS, BW_TOTAL, stream>>>(b);
+        st = check_cuda(cudaGetLastError(), "bwd_tc_kernel launch");
+        if (st != B2048_OK) return st;
+        AtbArgs g;
+        g.tiles64 = tiles * 2; g.f16 = 1; g.inv_scale = scale + 1;
+        // dW2 = H1^T DL2, db2 = column sums of DL2
+        g.A = f.h1; g.B = b.dl2; g.C = gW2; g.ldm = TC_H; g.ldn = 1; g.n_valid = TC_H; g.colsum = gb2; g.colsum_of_b = 1;
+        if ((st = launch_atb<256>(h, g, stream)) != B2048_OK) return st;
+        // dW3 = H2^T d3
+        g.A = f.h2; g.B = b.d3t; g.C = gW3; g.ldm = n_out; g.ldn = 1; g.n_valid = n_out; g.colsum = nullptr; g.colsum_of_b = 0;
+        if ((st = launch_atb<16>(h, g, stream)) != B2048_OK) return st;
+        // dW1^T = DL1^T A1, db1 = column sums of DL1
+        g.A = b.dl1; g.B = f.a1t; g.C = gW1; g.ldm = 1; g.ldn = TC_H; g.n_valid = 16; g.colsum = gb1; g.colsum_of_b = 0;
+        if ((st = launch_atb<16>(h, g, stream)) != B2048_OK) return st;
+    }
+    return B2048_OK;
+}
+
+}  // namespace b2

@@ -24,6 +24,7 @@
 //      whole sample range of the CTA and are added into the gradient with float atomics at the end.  Idle
 //      warps add up the columns of the staged DL tiles for the bias gradients (no extra HBM pass).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -32,6 +33,7 @@
 #include "b2048_device.cuh"
 #include "b2048_internal.h"
 #include "b2048_tc.cuh"
+#include "b2048_learn_tc.cuh"
 
 namespace b2 {
 
@@ -39,10 +41,6 @@ void launch_tc_prepare(const b2048_mlp_desc* mlp, uint8_t* img, cudaStream_t str
 int ensure_tc_image(b2048_handle* h);
 
 // ------------------------------------------------------------------------------------------------ layouts
-constexpr int ACT_TILE_BYTES = 32768;     // activation image of 64 samples: 4 slabs x [64 rows x 128 B]
-constexpr int ACT_SLAB_BYTES = 8192;
-constexpr int SMALL_TILE_BYTES = 2048;    // small K-major image of 64 samples: [16 rows x 128 B]
-
 constexpr int FB_D3A = SM_BAR + 256;      // head deltas of the tile in flight as a bf16 A operand [128 x 16], A1's layout
 constexpr int FB_TOTAL = FB_D3A + 4096;
 static_assert(FB_TOTAL <= 232448, "fb_tc_kernel exceeds the shared memory of an sm_100 CTA");
@@ -72,17 +70,6 @@ struct FbArgs {
     float obs_scale;
     long long* debug_clock;   // optional phase timestamps of CTA 0's first epilogue thread (B2048_TC_DEBUG_CLOCK)
 };
-
-// byte offset of (sample row r of the chunk, slab, 16-byte chunk) inside an activation image
-__device__ __forceinline__ size_t act_off(int64_t r, int slab, int chunk) {
-    return (size_t)(r >> 6) * ACT_TILE_BYTES + (size_t)slab * ACT_SLAB_BYTES + (size_t)(r & 63) * 128 +
-           (size_t)((chunk ^ (int)(r & 7)) << 4);
-}
-// byte offset of element (row j, sample r) inside a small K-major image
-__device__ __forceinline__ size_t small_off(int64_t r, int j) {
-    return (size_t)(r >> 6) * SMALL_TILE_BYTES + (size_t)j * 128 + (size_t)(((int)((r & 63) >> 3) ^ (j & 7)) << 4) +
-           (size_t)(r & 7) * 2;
-}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
@@ -463,25 +450,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) fb_tc_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ dW GEMM
-struct AtbArgs {
-    const uint8_t* A;       // activation image (MN-major A operand: M = 256 features, K = samples)
-    const uint8_t* B;       // NB == 256: activation image (MN-major B); NB == 16: small K-major image
-    int64_t tiles64;
-    float* C;               // C[m * ldm + n * ldn] += sum_s A[s][m] B[s][n]   for n < n_valid
-    int ldm, ldn, n_valid;
-    float* colsum;          // optional [256]: += column sums of the staged A (colsum_of_b == 0) or B image
-    int colsum_of_b;
-};
-
-template <int NB>
-struct AtbCfg {
-    static constexpr int kBBytes = NB == 256 ? ACT_TILE_BYTES : SMALL_TILE_BYTES;
-    static constexpr int kStageBytes = ACT_TILE_BYTES + kBBytes;
-    static constexpr int kStages = NB == 256 ? 3 : 4;
-    static constexpr int kBar = kStages * kStageBytes;
-    static constexpr int kSmem = kBar + 128;
-    static constexpr uint32_t kTmemCols = NB == 256 ? 512u : 32u;
-};
 constexpr int ATB_THREADS = 192;   // warp 0 copies, warp 1 issues the MMAs, warps 2..5 column sums + final read-out
 
 template <int NB>
@@ -493,6 +461,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
     const uint32_t bar_full0 = s_u32(&bars[0]), bar_empty0 = s_u32(&bars[4]), bar_done = s_u32(&bars[8]);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kBar + 96);
     const bool want_colsum = args.colsum != nullptr;
+    const float out_scale = args.inv_scale ? *args.inv_scale : 1.0f;
 
     if (tid == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) {
@@ -544,7 +513,8 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_f16(128, NB) | kIdescAMn | (NB == 256 ? kIdescBMn : 0u);
+            // kind::f16 operand format bits (7-9: A, 10-12: B): 1 = bf16, 0 = fp16
+            const uint32_t idesc = (idesc_f16(128, NB) & ~(args.f16 ? ((1u << 7) | (1u << 10)) : 0u)) | kIdescAMn | (NB == 256 ? kIdescBMn : 0u);
             for (int it = 0; it < n_it; ++it) {
                 const int st = it % Cfg::kStages, use = it / Cfg::kStages;
                 mbar_wait(bar_full0 + 8u * st, (uint32_t)use & 1u);
@@ -579,8 +549,14 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
 #pragma unroll 4
                 for (int r = rsub; r < 64; r += 4) {
                     const uint4 v = *reinterpret_cast<const uint4*>(x + r * 128 + ((chunk ^ (r & 7)) << 4));
-                    acc[0] += bf_lo(v.x); acc[1] += bf_hi(v.x); acc[2] += bf_lo(v.y); acc[3] += bf_hi(v.y);
-                    acc[4] += bf_lo(v.z); acc[5] += bf_hi(v.z); acc[6] += bf_lo(v.w); acc[7] += bf_hi(v.w);
+                    if (args.f16) {
+                        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+                        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+                        acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+                    } else {
+                        acc[0] += bf_lo(v.x); acc[1] += bf_hi(v.x); acc[2] += bf_lo(v.y); acc[3] += bf_hi(v.y);
+                        acc[4] += bf_lo(v.z); acc[5] += bf_hi(v.z); acc[6] += bf_lo(v.w); acc[7] += bf_hi(v.w);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_empty0 + 8u * st);
@@ -593,7 +569,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
             if (lane < 8 && n_it > 0) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                    if (acc[e] != 0.0f) atomicAdd(args.colsum + cw * 64 + chunk * 8 + e, acc[e]);
+                    if (acc[e] != 0.0f) atomicAdd(args.colsum + cw * 64 + chunk * 8 + e, acc[e] * out_scale);
             }
         }
         // ---- read-out: TMEM lane quarter = warp % 4
@@ -611,7 +587,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int n = c0 + i;
-                        const float v = __uint_as_float(r[i]);
+                        const float v = __uint_as_float(r[i]) * out_scale;
                         if (n < args.n_valid && v != 0.0f) atomicAdd(args.C + (size_t)m * args.ldm + (size_t)n * args.ldn, v);
                     }
                 }
@@ -627,7 +603,7 @@ __global__ void __launch_bounds__(ATB_THREADS, 1) atb_tc_kernel(const __grid_con
 }
 
 template <int NB>
-static int launch_atb(b2048_handle* h, const AtbArgs& a, cudaStream_t stream) {
+int launch_atb(b2048_handle* h, const AtbArgs& a, cudaStream_t stream) {
     constexpr unsigned kBit = NB == 256 ? 4u : 8u;
     if (!(h->attrs & kBit)) {
         cudaError_t e = cudaFuncSetAttribute(atb_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtbCfg<NB>::kSmem);
@@ -638,6 +614,9 @@ static int launch_atb(b2048_handle* h, const AtbArgs& a, cudaStream_t stream) {
     atb_tc_kernel<NB><<<grid, ATB_THREADS, AtbCfg<NB>::kSmem, stream>>>(a);
     return check_cuda(cudaGetLastError(), "atb_tc_kernel launch");
 }
+
+template int launch_atb<256>(b2048_handle*, const AtbArgs&, cudaStream_t);
+template int launch_atb<16>(b2048_handle*, const AtbArgs&, cudaStream_t);
 
 bool backward_tc_supported(const b2048_handle* h, const b2048_mlp_desc* mlp) {
     return mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H && mlp->dims[3] >= 1 &&
@@ -705,7 +684,7 @@ int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* ma
             }
         }
         AtbArgs g;
-        g.tiles64 = tiles * 2;
+        g.tiles64 = tiles * 2; g.f16 = 0; g.inv_scale = nullptr;
         // dW2 = H1^T DL2, db2 = column sums of DL2
         g.A = a.h1; g.B = a.dl2; g.C = gW2; g.ldm = TC_H; g.ldn = 1; g.n_valid = TC_H; g.colsum = gb2; g.colsum_of_b = 1;
         if ((st = launch_atb<256>(h, g, stream)) != B2048_OK) return st;

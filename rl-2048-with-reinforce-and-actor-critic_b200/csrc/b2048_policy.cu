@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) dense_forward_kernel(const __g
 int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags,
                      uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
                      int greedy, cudaStream_t stream, bool rebuild_image);
+int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n, cudaStream_t stream);
 int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n,
                       cudaStream_t stream);
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
@@ -303,14 +304,22 @@ extern "C" int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b
     B2_REQUIRE(n >= 0, "b2048_mlp_forward: n < 0");
     if (n == 0) return B2048_OK;
     B2_REQUIRE(board != nullptr && out != nullptr && mlp != nullptr, "b2048_mlp_forward: board/out/mlp is NULL");
-    B2_REQUIRE(precision >= 0 && precision <= 2, "b2048_mlp_forward: precision must be 0 (fp32), 1 (bf16 tcgen05) or 2 (auto)");
-    if (precision != 0) {
+    B2_REQUIRE(precision >= 0 && precision <= 3,
+               "b2048_mlp_forward: precision must be 0 (fp32), 1 (bf16 tcgen05), 2 (auto) or 3 (split-fp16 tcgen05)");
+    if (precision == 2 || precision == 3) {   // float32-grade tensor-core forward (what "auto" selects)
+        int st = launch_forward_hp(h, mlp, board, out, n, (cudaStream_t)stream);
+        if (st != B2048_ERR_UNSUPPORTED) return st;
+        if (precision == 3)
+            return fail(B2048_ERR_UNSUPPORTED,
+                        "b2048_mlp_forward: precision 3 (split-fp16 tcgen05) implements 16-256-256-(<=4) ReLU networks on log2 "
+                        "observations with n >= 4096 only");
+    }
+    if (precision == 1) {
         int st = launch_forward_tc(h, mlp, board, out, n, (cudaStream_t)stream);
         if (st != B2048_ERR_UNSUPPORTED) return st;
-        if (precision == 1)
-            return fail(B2048_ERR_UNSUPPORTED,
-                        "b2048_mlp_forward: precision 1 (bf16 tcgen05) implements 16-256-256-(<=4) ReLU networks on raw/log2 "
-                        "observations with n >= 4096 only");
+        return fail(B2048_ERR_UNSUPPORTED,
+                    "b2048_mlp_forward: precision 1 (bf16 tcgen05) implements 16-256-256-(<=4) ReLU networks on raw/log2 "
+                    "observations with n >= 4096 only");
     }
     ForwardArgs a;
     size_t smem = 0;

@@ -257,9 +257,11 @@ class ReinforceAgent:
     def _update_mode_name(self, prec: int, n: int) -> str:
         """Which arithmetic b2048_mlp_backward ran for `prec` on n samples (include/b2048.h)."""
         tc_ok = self.tc_supported() and n >= 4096
-        if prec == 0 or not tc_ok:
-            return "fp32 CUDA cores"
-        return {1: "bf16 tcgen05", 2: "bf16 tcgen05", 3: "fp16 split tcgen05 (fp32-grade forward)"}.get(prec, str(prec))
+        if prec in (2, 3) and tc_ok and self._actor.obs_mode == "log2":
+            return "fp16 split tcgen05 (float32-grade forward, fp16 backward with loss scale)"
+        if prec == 1 and tc_ok:
+            return "bf16 tcgen05"
+        return "fp32 CUDA cores"
 
     def tc_supported(self) -> bool:
         a = self._actor
@@ -529,8 +531,10 @@ class ReinforceAgent:
                             precision: int | str = "auto") -> dict[str, Any]:
         """One policy-gradient update from device-resident rollout buffers.  `allreduce(tensor)` (optional) sums
         a tensor over ranks in place: the flat gradients and the advantage statistics are the only exchange.
-        precision: 0 = fp32 CUDA cores (parity path), 1 = bf16 tcgen05 tensor cores (forward + backward + dW GEMMs),
-        "auto" = tensor cores whenever the network shape / batch allow it (b2048_mlp_backward, include/b2048.h)."""
+        precision: 0 = fp32 CUDA cores, "auto" (default) = the float32-grade tensor-core path (split-fp16 forward, fp16
+        backward; within 1e-2 of the reference's float32 gradient) whenever the network shape / batch allow it, else fp32;
+        3 = that path or an error; 1 = single-bf16 tensor cores, an explicit opt-in (its forward flips ReLU units near zero:
+        3-30 % error on cancelling gradients; b2048_mlp_backward, include/b2048.h)."""
         prec = 2 if precision == "auto" else int(precision)
         cfg = self.agent_config
         if cfg.baseline_mode not in BASELINE:

@@ -1,0 +1,199 @@
+"""Float32-grade tensor-core gradient path (b2048_mlp_backward precision 3, what "auto" selects: fwd_hp_kernel with
+split-fp16 operands + bwd_tc_kernel + atb_tc_kernel on fp16 images) against the float32 restatement of the reference's
+forward_logits / _backpropagation (oracle/learner.py; src/MLP.py:159-196, src/reinforce_agent.py:502-555, :639-678),
+against float64, and against the fp32 CUDA-core kernels.  Bar: 1e-2 relative per gradient tensor (north_star's
+tensor-core tolerance) on coherent AND zero-mean / rollout-derived (heavily cancelling) gradients; the forward pass itself
+is held to 1e-5."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from oracle import learner  # noqa: E402
+from helpers import full_env_kwargs, random_boards, rel_err  # noqa: E402
+from test_learn_tc_gpu import call_backward, dev64, make_agent, make_case, oracle_grads, split_grads  # noqa: E402
+
+HP = 3
+
+
+@pytest.fixture(scope="module")
+def b2048():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import b2048 as m
+    return m
+
+
+def forward64(params, X):
+    a = X.astype(np.float64)
+    L = len(params["W"])
+    pres = []
+    for i in range(L):
+        z = a @ params["W"][i].astype(np.float64) + params["b"][i].astype(np.float64)
+        pres.append(z)
+        a = np.maximum(z, 0.0) if i < L - 1 else z
+    return a, pres
+
+
+@pytest.mark.parametrize("n,head", [(128 * 70 + 37, "actor"), (4096, "critic"), (200000 + 5, "actor")])
+def test_hp_forward_vs_float64(b2048, n, head):
+    """b2048_mlp_forward precision 3: head outputs within 1e-5 of the float64 forward (split-fp16 operands carry 22 bits;
+    single bf16 is at 4e-3, single fp16 at 5e-4)."""
+    import ctypes as C
+    from b2048 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    boards = random_boards(rng, n)
+    agent = make_agent(b2048, use_critic=(head == "critic"), seed=6)
+    if head == "critic":
+        p = agent.critic_params
+        p["b"] = [rng.normal(size=b.shape).astype(np.float32) * 0.1 for b in p["b"]]
+        agent.critic_params = p
+        net, params = agent._critic, agent.critic_params
+    else:
+        net, params = agent._actor, agent.params
+    n_out = net.dims[-1]
+    out = torch.zeros((n, n_out), dtype=torch.float32, device="cuda")
+    bd = dev64(boards)
+    _lib.check(lib.b2048_mlp_forward(agent._h, C.c_void_p(bd.data_ptr()), C.byref(net.desc), C.c_void_p(out.data_ptr()), n, HP,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "b2048_mlp_forward")
+    torch.cuda.synchronize()
+    ref, _ = forward64(params, learner.encode(boards, "log2", 0.0625))
+    err = rel_err(out.cpu().numpy(), ref)
+    print(f"split-fp16 forward vs float64 ({head}, n = {n}): {err:.2e}")
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("head_mode,n,chunk,zero_mean", [(0, 50000, 16384, False), (1, 20000, 1 << 20, False),
+                                                         (0, 4096, 4096, False), (0, 30000, 1 << 20, True),
+                                                         (0, 128 * 70 + 37, 1 << 20, True), (1, 33000, 8192, True)])
+def test_hp_backward_vs_fp32(b2048, head_mode, n, chunk, zero_mean):
+    """Every gradient tensor within 1e-2 of the float32 restatement of the reference AND of the fp32 kernels — on
+    coherent and on zero-mean (noise-like, heavily cancelling) coefficient sets, one chunk and several, ragged tiles."""
+    rng = np.random.default_rng(5 + head_mode)
+    boards, masks, actions, coef = make_case(rng, n, zero_mean=zero_mean, scale=1e-4)
+    agent = make_agent(b2048, use_critic=(head_mode == 1), seed=3)
+    if head_mode == 1:
+        p = agent.critic_params
+        p["b"] = [rng.normal(size=b.shape).astype(np.float32) * 0.1 for b in p["b"]]
+        agent.critic_params = p
+        net, n_out, params = agent._critic, 1, agent.critic_params
+    else:
+        net, n_out, params = agent._actor, 4, agent.params
+    args = (boards, masks if head_mode == 0 else None, actions if head_mode == 0 else None, coef, head_mode)
+    g_hp, _ = call_backward(b2048, agent, net, *args, HP, chunk)
+    g_32, _ = call_backward(b2048, agent, net, *args, 0, chunk)
+    gW, gb, _, _, _ = oracle_grads(params, boards, masks if head_mode == 0 else None, actions, coef, head_mode, "log2", 0.0625)
+    a, b = split_grads(g_hp, n_out), split_grads(g_32, n_out)
+    errs = {}
+    for l in range(3):
+        errs[f"dW{l} vs fp32 kernels"] = rel_err(a[l][0], b[l][0])
+        errs[f"db{l} vs fp32 kernels"] = rel_err(a[l][1], b[l][1])
+        errs[f"dW{l} vs oracle"] = rel_err(a[l][0], gW[l])
+        errs[f"db{l} vs oracle"] = rel_err(a[l][1], gb[l])
+    print("split-fp16 gradient errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < 1e-2, (k, v, errs)
+
+
+def test_hp_gradient_on_rollout_within_1e2_of_fp32(b2048):
+    """A ROLLOUT-derived policy gradient (advantage-weighted, zero-mean: the case single-bf16 arithmetic misses by
+    5-30 %): the default tensor-core mode is within 1e-2 of the fp32 kernels and of the float64 gradient."""
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 24
+    B = 8192
+    env = b2048.Batched2048Env(B, b2048.Game2048EnvConfig(**kw), seed=123, gid0=5)
+    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                 b2048.ReinforceAgentConfig(model_seed=11, baseline_mode="batch"))
+    ro = agent.rollout_many(env, precision=1)
+    T = ro.T
+    agent.update_from_rollout(ro, precision=0)                      # fills the per-slot coefficient buffer
+    coef = agent._scratch["coef"][: T * B].clone()
+    live = (torch.arange(T, device="cuda").unsqueeze(1) < ro.length.unsqueeze(0)).reshape(-1)
+    boards = ro.boards[:T].reshape(-1)[live].cpu().numpy().view(np.uint64)
+    flags = ro.flags[:T].reshape(-1)[live].cpu().numpy()
+    acts = ro.actions[:T].reshape(-1)[live].cpu().numpy()
+    cf = coef[live].cpu().numpy()
+    n = len(boards)
+    assert n >= 4096
+    g_hp, _ = call_backward(b2048, agent, agent._actor, boards, flags, acts, cf, 0, HP, n)
+    g_bf, _ = call_backward(b2048, agent, agent._actor, boards, flags, acts, cf, 0, 1, n)
+    g_32, _ = call_backward(b2048, agent, agent._actor, boards, flags, acts, cf, 0, 0, n)
+    # float64 gradient of the same batch
+    params = agent.params
+    X = learner.encode(boards, "log2", 0.0625)
+    out, pres = forward64(params, X)
+    p = learner.probs_from_logits(out.astype(np.float32), flags & 0xF).astype(np.float64)
+    d = cf[:, None].astype(np.float64) * (np.eye(4)[acts.astype(np.int64)] - p)
+    h1, h2 = np.maximum(pres[0], 0), np.maximum(pres[1], 0)
+    dl2 = (d @ params["W"][2].astype(np.float64).T) * (pres[1] > 0)
+    dl1 = (dl2 @ params["W"][1].astype(np.float64).T) * (pres[0] > 0)
+    g_64 = np.concatenate([np.concatenate([w.reshape(-1), b.reshape(-1)]) for w, b in
+                           ((X.astype(np.float64).T @ dl1, dl1.sum(0)), (h1.T @ dl2, dl2.sum(0)), (h2.T @ d, d.sum(0)))])
+    e_32, e_64, e_bf, e_3264 = rel_err(g_hp, g_32), rel_err(g_hp, g_64), rel_err(g_bf, g_32), rel_err(g_32, g_64)
+    print(f"rollout gradient, {n} samples: split-fp16 vs fp32 kernels {e_32:.2e}, vs float64 {e_64:.2e}; "
+          f"single bf16 vs fp32 {e_bf:.2e}; fp32 kernels vs float64 {e_3264:.2e}")
+    assert e_32 < 1e-2 and e_64 < 1e-2, (e_32, e_64)
+
+
+def test_update_from_rollout_auto_matches_fp32(b2048):
+    """Whole update (returns scan -> advantages -> gradients -> clip -> SGD) with precision "auto" (tensor cores) vs the
+    fp32 kernels: gradient norm and parameter step within 1e-2."""
+    n, seed = 8192, 21
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 48
+    outs = []
+    for prec in (0, "auto"):
+        benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=0)
+        agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode="batch", learning_rate=1e-2))
+        agent.params = b2048.init_model_params(16, [256, 256], 4, np.random.default_rng(1), "HeNormal")
+        before = agent._actor.theta.cpu().numpy().copy()
+        ro = agent.rollout_many(benv, precision=0)
+        info = agent.update_from_rollout(ro, precision=prec)
+        outs.append((agent._actor.theta.cpu().numpy() - before, info["actor_grad_norm"], info["precision"]))
+    (d0, g0, m0), (d1, g1, m1) = outs
+    print(f"update {m1} vs {m0}: grad norms {g0} {g1}, step rel err {rel_err(d1, d0):.2e}")
+    assert m1.startswith("fp16 split tcgen05") and m0.startswith("fp32")
+    assert abs(g0 - g1) / g0 < 1e-2, (g0, g1)
+    assert rel_err(d1, d0) < 1e-2, rel_err(d1, d0)
+
+
+def test_actor_critic_update_auto_matches_fp32(b2048):
+    """Actor-critic update (critic forward -> TD errors -> critic grads -> baseline-processed TD advantages -> actor grads
+    -> Adam on both networks) with every GEMM on the tensor cores in the default mode vs the fp32 kernels: TD errors,
+    both gradient norms within 1e-2 (the value forward is float32-grade too, so the TD differences do not amplify it)."""
+    n, seed = 8192, 33
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 40
+    outs = []
+    for prec in (0, "auto"):
+        benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=0)
+        agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode="batch_norm", learning_rate=1e-3,
+                                                                critic_learning_rate=5e-4, use_critic=True, optimizer="sgd",
+                                                                model_seed=5))
+        a0 = agent._actor.theta.cpu().numpy().copy(); c0 = agent._critic.theta.cpu().numpy().copy()
+        ro = agent.rollout_many(benv, precision=0)
+        info = agent.update_from_rollout(ro, precision=prec)
+        outs.append((agent._actor.theta.cpu().numpy() - a0, agent._critic.theta.cpu().numpy() - c0,
+                     info["actor_grad_norm"], info["critic_grad_norm"], info["td"].cpu().numpy().copy()))
+    (da0, dc0, ga0, gc0, td0), (da1, dc1, ga1, gc1, td1) = outs
+    print("actor-critic auto vs fp32: grad norms", (ga0, ga1), (gc0, gc1), "td rel err", rel_err(td1, td0),
+          "steps", rel_err(da1, da0), rel_err(dc1, dc0))
+    assert rel_err(td1, td0) < 1e-4
+    assert abs(ga0 - ga1) / ga0 < 1e-2 and abs(gc0 - gc1) / gc0 < 1e-2
+    assert rel_err(da1, da0) < 1e-2 and rel_err(dc1, dc0) < 1e-2
+
+
+def test_hp_refuses_raw_observations_and_auto_falls_back(b2048):
+    """fp16 activations could overflow on raw tile values: precision 3 is refused loudly, "auto" runs the fp32 kernels."""
+    from b2048 import _lib
+    agent = make_agent(b2048, obs_mode="raw", scale=1.0)
+    n = 5000
+    rng = np.random.default_rng(0)
+    boards, masks, actions, coef = make_case(rng, n)
+    with pytest.raises(_lib.B2048Error):
+        call_backward(b2048, agent, agent._actor, boards, masks, actions, coef, 0, HP, n)
+    g2, _ = call_backward(b2048, agent, agent._actor, boards, masks, actions, coef, 0, 2, n)
+    g0, _ = call_backward(b2048, agent, agent._actor, boards, masks, actions, coef, 0, 0, n)
+    assert rel_err(g2, g0) < 1e-5          # same fp32 kernels (atomic summation order differs run to run)

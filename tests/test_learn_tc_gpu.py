@@ -1,6 +1,7 @@
-"""bf16 tcgen05 gradient path (b2048_mlp_backward precision=1: fb_tc_kernel + atb_tc_kernel) against the NumPy
-restatement of the reference's _backpropagation (oracle/learner.py; src/reinforce_agent.py:639-678) and against
-the fp32 CUDA-core path.  Bar: 1e-2 relative (north_star's bf16 tolerance), per gradient tensor.
+"""Single-bf16 tcgen05 gradient path (b2048_mlp_backward precision=1, an explicit OPT-IN since round 2: fb_tc_kernel +
+atb_tc_kernel) against the NumPy restatement of the same bf16 roundings (tight: the kernels are exact) and against the
+float32 arithmetic of the reference (loose: a bf16 forward flips ReLU units near zero, a 3-30 % error on cancelling
+gradients — which is why the DEFAULT tensor-core mode is the split-fp16 path of tests/test_learn_hp_gpu.py, held to 1e-2).
 
 The first test also un-swizzles the intermediate bf16 images the two kernels exchange (H1, H2, DL2, DL1, A1^T,
 d3^T) so that a layout bug is localised to one stage."""
