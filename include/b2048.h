@@ -111,7 +111,10 @@ enum { B2048_DBG_NO_FUSED_ROLLOUT = 0, /* b2048_rollout_many: always the policy-
        B2048_DBG_TC_CLOCKS = 2,        /* tensor-core kernels record in-kernel phase clocks and print them to stderr */
        B2048_DBG_STEP_CLOCKS = 3,      /* the fast step kernel records per-iteration clocks and prints them to stderr */
        B2048_DBG_NO_PDL = 4,           /* launch without programmatic dependent launch (plain stream order) */
-       B2048_DBG_COUNT = 5 };
+       B2048_DBG_NO_UPDATE_PIPE = 5,   /* b2048_mlp_backward precision 3: always the chunked kernel sequence, never the persistent pipeline */
+       B2048_DBG_COUNT = 6,
+       B2048_DBG_PARAM_PIPE_SPLIT = 16 /* integer parameter, not a flag: CTAs per role of the persistent update pipeline,
+                                          value = backward | dW2 << 8 | dW1/dW3 << 16 (a zero field = default share) */ };
 int b2048_debug_set(b2048_handle* h, int32_t option, int32_t value);
 
 /* Copies the device tables back (host pointers; either may be NULL):

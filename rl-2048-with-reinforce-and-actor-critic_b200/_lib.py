@@ -44,7 +44,8 @@ class MlpDesc(C.Structure):
     ]
 
 
-DEBUG_OPTIONS = {"no_fused_rollout": 0, "no_fast_step": 1, "tc_clocks": 2, "step_clocks": 3, "no_pdl": 4}
+DEBUG_OPTIONS = {"no_fused_rollout": 0, "no_fast_step": 1, "tc_clocks": 2, "step_clocks": 3, "no_pdl": 4, "no_update_pipe": 5,
+                 "pipe_split": 16}
 
 
 class B2048Error(RuntimeError):

@@ -77,14 +77,15 @@ _debug: dict[str, bool] = {}
 
 def debug_set(option: str, value: bool = True, device: torch.device | str | None = None) -> None:
     """Test / profiling switch of the library handle of `device` (b2048_debug_set, include/b2048.h): "no_fused_rollout",
-    "no_fast_step", "tc_clocks", "step_clocks", "no_pdl"; plus the host-side "no_compact_rollout" (rollout_many plays all
+    "no_fast_step", "tc_clocks", "step_clocks", "no_pdl", "no_update_pipe", the integer "pipe_split"; plus the host-side "no_compact_rollout" (rollout_many plays all
     boards of every chunk instead of the live list).  All off by default."""
     if option == "no_compact_rollout":
         _debug[option] = bool(value)
         return
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().b2048_debug_set(get_handle(dev), _lib.DEBUG_OPTIONS[option], int(bool(value))), "b2048_debug_set")
+        v = int(value) if option == "pipe_split" else int(bool(value))
+        _lib.check(_lib.load().b2048_debug_set(get_handle(dev), _lib.DEBUG_OPTIONS[option], v), "b2048_debug_set")
     _debug[option] = bool(value)
 
 

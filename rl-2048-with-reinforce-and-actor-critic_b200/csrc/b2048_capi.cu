@@ -26,6 +26,10 @@ extern "C" int b2048_version(void) { return 100; }
 
 extern "C" int b2048_debug_set(b2048_handle* h, int32_t option, int32_t value) {
     B2_REQUIRE(h != nullptr, "b2048_debug_set: handle is NULL");
+    if (option == B2048_DBG_PARAM_PIPE_SPLIT) {
+        h->pipe_split = (unsigned)value;
+        return B2048_OK;
+    }
     B2_REQUIRE(option >= 0 && option < B2048_DBG_COUNT, "b2048_debug_set: unknown option");
     if (value) h->debug |= 1u << option;
     else h->debug &= ~(1u << option);

@@ -654,6 +654,7 @@ extern "C" int b2048_create(b2048_handle** out) {
     h->hp_image = nullptr;
     h->attrs = 0u;
     h->debug = 0u;
+    h->pipe_split = 0u;
     B2_CUDA(cudaGetDevice(&h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device));
     B2_CUDA(cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));

@@ -27,7 +27,7 @@ bool backward_hp_supported(const b2048_handle* h, const b2048_mlp_desc* mlp);
 int64_t backward_hp_workspace_bytes(int64_t chunk);
 int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
-                       uint8_t* workspace, int64_t chunk, cudaStream_t stream);
+                       uint8_t* workspace, int64_t workspace_bytes, int64_t chunk, cudaStream_t stream);
 int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                        uint8_t* workspace, int64_t chunk, cudaStream_t stream);
@@ -523,7 +523,8 @@ extern "C" int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const 
                         workspace_floats * 4 >= backward_hp_workspace_bytes(chunk < n ? chunk : n);
         if (ok)
             return launch_backward_hp(h, board, mask_flags, action, coef, mlp, grads, n, head_mode,
-                                      reinterpret_cast<uint8_t*>(workspace), chunk < n ? chunk : n, (cudaStream_t)stream);
+                                      reinterpret_cast<uint8_t*>(workspace), workspace_floats * 4 - 1024, chunk < n ? chunk : n,
+                                      (cudaStream_t)stream);
         if (precision == 3)
             return fail(B2048_ERR_UNSUPPORTED,
                         "b2048_mlp_backward: the split-fp16 tcgen05 path needs a 16-256-256-(<=4) ReLU network, log2 "

@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <ctime>
+#include <unistd.h>
 
 #include "b2048_device.cuh"
 #include "b2048_internal.h"
@@ -120,6 +122,39 @@ __global__ void __launch_bounds__(256) bwd_prepare_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------ pipeline context
+// The three stages (forward, backward deltas, dW GEMMs) run either as separate launches over a chunk of samples (the
+// images of the whole chunk go through HBM), or as ROLES of one persistent launch (update_pipe_kernel): every CTA of
+// the grid is a forward, a backward or a dW CTA for the whole call, tiles of 128 samples travel from role to role
+// through a ring of `R` tile slots that stays resident in the 126 MB L2, and per-tile flags (release / acquire at GPU
+// scope) order the hand-offs.  The dW accumulators then live in TMEM for the whole call and the images never reach HBM.
+struct PipeCtx {
+    uint32_t* f_done;     // [n_tiles] forward outputs of tile t are in slot t % R      (NULL: stand-alone launch, slot == tile)
+    uint32_t* b_done;     // [n_tiles] backward outputs of tile t are in its slot
+    uint32_t* c2_done;    // [n_tiles] the dW2 role has consumed tile t
+    uint32_t* c13_done;   // [n_tiles] the dW1 / dW3 role has consumed tile t
+    int64_t R;            // ring slots
+    volatile int* progress;   // debug (B2048_DBG_TC_CLOCKS): mapped host memory, 8 ints per CTA, else NULL
+};
+__device__ __forceinline__ void prog(const PipeCtx& px, int idx, int64_t v) {
+    if (px.progress) px.progress[blockIdx.x * 8 + idx] = (int)v;
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flag_wait(const uint32_t* p) {
+    while (ld_acquire(p) == 0u) __nanosleep(100);
+}
+// everything this thread (and, through the mbarriers it waited on, this CTA) wrote before becomes visible to a thread that
+// acquires the flag; bulk-copy (async proxy) writes must have completed (cp.async.bulk.wait_group 0) before the call
+__device__ __forceinline__ void flag_set(uint32_t* p) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ precise forward
 constexpr int FS_W = 0;                               // W ring: 3 slots x 32 KB
 constexpr int FS_A = 3 * HP_UNIT;                     // A ring: 2 stages x [16 KB hi slab | 16 KB lo slab]
@@ -145,6 +180,7 @@ struct FwdHpArgs {
     int64_t n;
     int n_out, obs_mode;
     float obs_scale;
+    long long* debug_clock;   // optional phase timestamps of CTA 0 (B2048_DBG_TC_CLOCKS), else NULL
 };
 
 constexpr int FH_THREADS = 512 + 3 * 32 + 128;   // 16 epilogue warps, MMA warp, weight loader, image storer, 4 I/O warps
@@ -161,12 +197,12 @@ __device__ __forceinline__ void relu_split(uint32_t a_bits, uint32_t b_bits, uin
     lo = pack_f16(ra - hf.x, rb - hf.y);
 }
 
-__global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_constant__ FwdHpArgs args) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+__device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& px, const int rank, const int nranks, uint8_t* smem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool piped = px.f_done != nullptr;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FS_BAR);
     const uint32_t bar_res = s_u32(&bars[0]), bar_a1 = s_u32(&bars[1]), bar_d1 = s_u32(&bars[2]), bar_d2 = s_u32(&bars[3]),
-                   bar_d3 = s_u32(&bars[4]), bar_d3r = s_u32(&bars[5]);
+                   bar_d3 = s_u32(&bars[4]), bar_d3r = s_u32(&bars[5]), bar_out = s_u32(&bars[16]), bar_slot = s_u32(&bars[17]);
     const uint32_t w_full0 = s_u32(&bars[6]), w_empty0 = s_u32(&bars[9]);
     const uint32_t a_full0 = s_u32(&bars[12]), a_free0 = s_u32(&bars[14]);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FS_BAR + 256);
@@ -178,6 +214,8 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
         mbar_init(bar_d2, 1);
         mbar_init(bar_d3, 1);
         mbar_init(bar_d3r, 4);
+        mbar_init(bar_slot, 4);          // pipeline mode: the tile's ring slot is free (its previous tile has been consumed)
+        mbar_init(bar_out, 20);          // pipeline mode: every epilogue / I/O warp has written its global outputs of the tile
         for (int i = 0; i < 3; ++i) { mbar_init(w_full0 + 8u * i, 1); mbar_init(w_empty0 + 8u * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(a_full0 + 8u * i, 16); mbar_init(a_free0 + 8u * i, 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -192,7 +230,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
-    const int64_t first = blockIdx.x;
+    const int64_t first = rank;
 
     if (warp == 16) {
         // ============================ MMA warp ============================
@@ -221,16 +259,27 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
             };
             uint32_t ph = 0, U = 0, F = 0;     // tile parity, streamed weight units consumed, activation ring fills consumed
             if (first < n_tiles) issue_layer1(0u);
-            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            const bool dbg = args.debug_clock != nullptr && rank == 0;
+            long long wa = 0, ww = 0, t_prev = dbg ? clock64() : 0;
+            int lt = 0;
+            for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
+                if (dbg && lt < 6) {
+                    const long long now = clock64();
+                    args.debug_clock[40 + 4 * lt] = now - t_prev; args.debug_clock[41 + 4 * lt] = wa; args.debug_clock[42 + 4 * lt] = ww;
+                    t_prev = now; wa = 0; ww = 0;
+                }
                 if (tile != first) mbar_wait(bar_d3r, ph ^ 1u);     // the previous tile's head outputs have left D3 (inside D2)
                 // ---- layer 2: per 64-wide K slab  D2 += H1hi W2hi + H1lo W2hi + H1hi W2lo
                 for (int s = 0; s < 4; ++s) {
                     const uint32_t st = F & 1u, au = F >> 1;
+                    long long c0 = dbg ? clock64() : 0;
                     mbar_wait(a_full0 + 8u * st, au & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ahi = sA + st * FS_ASTAGE, alo = ahi + 16384u;
                     uint32_t slot = U % 3u, use = U / 3u;
+                    long long c1 = dbg ? clock64() : 0;
                     mbar_wait(w_full0 + 8u * slot, use & 1u);
+                    if (dbg) { const long long c2 = clock64(); wa += c1 - c0; ww += c2 - c1; }
                     uint32_t wb = sW + slot * HP_UNIT;
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -255,7 +304,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
                 umma_f16(tmem_base + 256u, dOnes2, dBias, kIdescF16, 1u);
                 umma_commit(bar_d2);
                 // ---- the next tile's layer 1 (D1 was drained before the last H1 slab arrival waited for above)
-                if (tile + gridDim.x < n_tiles) issue_layer1(ph ^ 1u);
+                if (tile + nranks < n_tiles) issue_layer1(ph ^ 1u);
                 // ---- head: D3 (columns 256..271: that part of D2 is drained before the first H2 slab arrives)
                 for (int s = 0; s < 4; ++s) {
                     const uint32_t st = F & 1u, au = F >> 1;
@@ -285,7 +334,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
         // ============================ weight loader: streams the 8 split-W2 units of every tile through the ring
         if (lane == 0) {
             uint32_t U = 0;
-            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t tile = first; tile < n_tiles; tile += nranks) {
                 for (int j = 0; j < 8; ++j, ++U) {
                     const uint32_t slot = U % 3u, use = U / 3u;
                     if (use > 0) mbar_wait(w_empty0 + 8u * slot, (use - 1u) & 1u);
@@ -306,7 +355,8 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
         // ============================ image storer: the hi half of every activation slab leaves as a global image
         if (lane == 0) {
             uint32_t F = 0;
-            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t tile = first; tile < n_tiles; tile += nranks) {
+                if (piped) mbar_wait(bar_slot, (uint32_t)((tile - first) / nranks) & 1u);
                 for (int layer = 0; layer < 2; ++layer) {
                     uint8_t* img = layer == 0 ? args.h1 : args.h2;
                     for (int s = 0; s < 4; ++s, ++F) {
@@ -316,7 +366,7 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
                             const uint32_t src = s_u32(smem + FS_A) + st * FS_ASTAGE;
 #pragma unroll
                             for (int half = 0; half < 2; ++half) {
-                                uint8_t* dst = img + (size_t)(tile * 2 + half) * ACT_TILE_BYTES + (size_t)s * ACT_SLAB_BYTES;
+                                uint8_t* dst = img + (size_t)((tile % px.R) * 2 + half) * ACT_TILE_BYTES + (size_t)s * ACT_SLAB_BYTES;
                                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                                              "r"(src + (uint32_t)half * 8192u), "r"((uint32_t)ACT_SLAB_BYTES)
                                              : "memory");
@@ -326,6 +376,13 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
                         }
                         mbar_arrive(a_free0 + 8u * st);
                     }
+                }
+                if (piped) {    // publish the tile: masks / head outputs / A1^T written (bar_out), image writes complete
+                    prog(px, 4, tile);
+                    mbar_wait(bar_out, (uint32_t)((tile - first) / nranks) & 1u);
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    flag_set(px.f_done + tile);
+                    prog(px, 5, tile);
                 }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -366,53 +423,86 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
             }
             return (uint64_t)(mw[0] | (mw[1] << 16)) | ((uint64_t)(mw[2] | (mw[3] << 16)) << 32);
         };
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+        int lt = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
+            const bool dbg = args.debug_clock != nullptr && rank == 0 && tid == 0 && lt < 6;
+            long long* dc = dbg ? args.debug_clock + 6 * lt : nullptr;
+            if (dbg) dc[0] = clock64();
             mbar_wait(bar_d1, ph);
+            if (dbg) dc[1] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t m1 = epilogue(tlane);
-            if (args.m1) args.m1[(size_t)(tile * 4 + g) * TC_M + row] = m1;
+            if (dbg) dc[2] = clock64();
+            if (piped) mbar_wait(bar_slot, ph);
+            if (args.m1) args.m1[(size_t)((tile % px.R) * 4 + g) * TC_M + row] = m1;
             mbar_wait(bar_d2, ph);
+            if (dbg) dc[3] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t m2 = epilogue(tlane + 256u);
-            if (args.m2) args.m2[(size_t)(tile * 4 + g) * TC_M + row] = m2;
+            if (dbg) dc[4] = clock64();
+            if (args.m2) args.m2[(size_t)((tile % px.R) * 4 + g) * TC_M + row] = m2;
+            if (piped) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_out);
+            }
             ph ^= 1u;
         }
-    } else {
+    } else if (warp < 23) {
         // ============================ I/O warps (19..22), one thread per sample ============================
         const int q = warp & 3;   // warps 19, 20, 21, 22 -> lane quarters 3, 0, 1, 2: a TMEM load may only touch the quarter warp % 4
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float* sB3 = reinterpret_cast<const float*>(smem + FS_RES + RES_B3);
         uint32_t ph = 0;
+        uint32_t pk_next[8], pk_cur[8];      // encoded inputs of the tile being prefetched / of the current tile (for A1^T)
         auto encode_a1 = [&](int64_t tile) {
             const int64_t s = tile * TC_M + row;
             uint64_t bd = (s < args.n) ? args.board[s] : 0ull;
-            uint32_t packed[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 uint32_t e0 = (uint32_t)(bd >> (8 * j)) & 0xFu, e1 = (uint32_t)(bd >> (8 * j + 4)) & 0xFu;
                 float v0, v1;
                 if (args.obs_mode == B2048_OBS_RAW) { v0 = e0 ? (float)(1u << e0) : 0.0f; v1 = e1 ? (float)(1u << e1) : 0.0f; }
                 else { v0 = (float)e0 * args.obs_scale; v1 = (float)e1 * args.obs_scale; }
-                packed[j] = pack_f16(v0, v1);
-                if (args.a1t) {
-                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(s, 2 * j)) = (uint16_t)(packed[j] & 0xFFFFu);
-                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(s, 2 * j + 1)) = (uint16_t)(packed[j] >> 16);
-                }
+                pk_next[j] = pack_f16(v0, v1);
             }
             uint8_t* a1 = smem + FS_A1 + (row >> 3) * 256 + (row & 7) * 16;
-            *reinterpret_cast<uint4*>(a1) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            *reinterpret_cast<uint4*>(a1) = make_uint4(pk_next[0], pk_next[1], pk_next[2], pk_next[3]);
+            *reinterpret_cast<uint4*>(a1 + 128) = make_uint4(pk_next[4], pk_next[5], pk_next[6], pk_next[7]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a1);
         };
         if (first < n_tiles) encode_a1(first);
         mbar_wait(bar_res, 0);
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t tile = first; tile < n_tiles; tile += nranks) {
             const int64_t s = tile * TC_M + row;
+            const int64_t srow = (tile % px.R) * TC_M + row;                      // row inside the ring of tile slots
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk_cur[j] = pk_next[j];
             mbar_wait(bar_d1, ph);                                               // A1 is free
-            const int64_t next = tile + gridDim.x;
+            if (piped) {
+                // The tile's slot is taken only now (not when its inputs were prefetched): its previous tile has been
+                // consumed by both dW roles (hence by the backward role).  The storer and the epilogue warps write
+                // into the slot after bar_slot.
+                if (tile >= px.R && lane == 0) {
+                    if (warp == 19) prog(px, 1, tile);
+                    flag_wait(px.c2_done + (tile - px.R));
+                    flag_wait(px.c13_done + (tile - px.R));
+                    if (warp == 19) prog(px, 3, tile);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_slot);
+            }
+            if (args.a1t) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(srow, 2 * j)) = (uint16_t)(pk_cur[j] & 0xFFFFu);
+                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(srow, 2 * j + 1)) = (uint16_t)(pk_cur[j] >> 16);
+                }
+            }
+            const int64_t next = tile + nranks;
             if (next < n_tiles) encode_a1(next);
             mbar_wait(bar_d3, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -424,7 +514,12 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
             if (s < args.n) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (j < args.n_out) args.out[s * args.n_out + j] = __uint_as_float(r4[j]) + sB3[j];
+                    if (j < args.n_out) args.out[srow * args.n_out + j] = __uint_as_float(r4[j]) + sB3[j];
+            }
+            if (piped) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_out);
             }
             ph ^= 1u;
         }
@@ -435,6 +530,14 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
     if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+__global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_constant__ FwdHpArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    PipeCtx px;
+    px.f_done = nullptr; px.b_done = nullptr; px.c2_done = nullptr; px.c13_done = nullptr;
+    px.R = (args.n + TC_M - 1) / TC_M + 1;      // stand-alone: slot == tile
+    fwd_role(args, px, (int)blockIdx.x, (int)gridDim.x, smem);
 }
 
 // ------------------------------------------------------------------------------------------------ backward deltas
@@ -454,6 +557,7 @@ struct BwdArgs {
     float* gb3;
     int64_t n;
     int head_mode, n_out;
+    long long* debug_clock;   // optional phase timestamps of CTA 0 (B2048_DBG_TC_CLOCKS), else NULL
 };
 
 constexpr int BW_THREADS = 512 + 32 + 128;
@@ -472,9 +576,9 @@ __device__ __forceinline__ void bw_stores_read_done() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_constant__ BwdArgs args) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+__device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px, const int rank, const int nranks, uint8_t* smem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool piped = px.f_done != nullptr;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
     const uint32_t bar_img = s_u32(&bars[0]), bar_dl3 = s_u32(&bars[1]), bar_d5 = s_u32(&bars[2]), bar_d4 = s_u32(&bars[3]),
                    bar_free = s_u32(&bars[4]);
@@ -504,7 +608,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
-    const int64_t first = blockIdx.x;
+    const int64_t first = rank;
 
     if (warp == 16) {
         // ============================ MMA / copy warp ============================
@@ -533,7 +637,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
             };
             uint32_t ph = 0;
             if (first < n_tiles) issue_d5(0u);
-            for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+            for (int64_t tile = first; tile < n_tiles; tile += nranks) {
                 // ---- backward through layer 2: D4 = DL2 . W2 over K = out features; B = the W2 image [out][in] read
                 //      MN-major (N = in contiguous: 64-wide slabs 32768 B apart, 8 K rows = 1024 B)
                 for (int g = 0; g < 4; ++g) {
@@ -543,18 +647,24 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
                     for (int q = 0; q < 4; ++q)
                         umma_f16(tmem_base + 256u, desc_sw128(sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u),
                                  desc_sw128_mn(sW2 + (uint32_t)(g * 64 + q * 16) * 128u, 32768u), kIdescBwd, (g | q) ? 1u : 0u);
-                    bw_store_slab(args.dl2, tile, sA2, g);
+                    bw_store_slab(args.dl2, tile % px.R, sA2, g);
                 }
                 bw_stores_read_done();                   // epilogue 4 overwrites DL2 once bar_d4 completes
                 umma_commit(bar_d4);
                 // ---- the next tile's D5 (this tile's D5 was drained by every warp before the DL2 slab arrivals)
-                if (tile + gridDim.x < n_tiles) issue_d5(ph ^ 1u);
+                if (tile + nranks < n_tiles) issue_d5(ph ^ 1u);
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_dslab0 + 8u * g, ph);
-                    bw_store_slab(args.dl1, tile, sA2, g);
+                    bw_store_slab(args.dl1, tile % px.R, sA2, g);
                 }
                 bw_stores_read_done();
                 mbar_arrive(bar_free);                   // A2 free: the DL1 image of the tile has been streamed out
+                if (piped) {                             // publish the tile: d3^T written, DL2 / DL1 image writes complete
+                    prog(px, 4, tile);
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    flag_set(px.b_done + tile);
+                    prog(px, 5, tile);
+                }
                 ph ^= 1u;
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -592,33 +702,55 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
                 if (lane == 0) mbar_arrive(bar0 + 8u * s);
             }
         };
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
-            const uint64_t m2 = args.m2[(size_t)(tile * 4 + g) * TC_M + row];
-            const uint64_t m1 = args.m1[(size_t)(tile * 4 + g) * TC_M + row];
+        int lt = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
+            const bool dbg = args.debug_clock != nullptr && rank == 0 && tid == 0 && lt < 6;
+            long long* dc = dbg ? args.debug_clock + 8 * lt : nullptr;
+            if (dbg) dc[0] = clock64();
+            if (piped) {
+                if (lane == 0) {
+                    if (warp == 0) prog(px, 1, tile);
+                    flag_wait(px.f_done + tile);
+                    if (warp == 0) prog(px, 2, tile);
+                }
+                __syncwarp();
+            }
+            const uint64_t m2 = args.m2[(size_t)((tile % px.R) * 4 + g) * TC_M + row];
+            const uint64_t m1 = args.m1[(size_t)((tile % px.R) * 4 + g) * TC_M + row];
             // ---- DL2 = D5 [z2 > 0]  (the A2 buffer is free once the previous tile's DL1 image has been streamed out)
             mbar_wait(bar_d5, ph);
+            if (dbg) dc[1] = clock64();
             if (tile != first) mbar_wait(bar_free, ph ^ 1u);
+            if (dbg) dc[2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             masked_store(tlane, m2, bar_bslab0);
+            if (dbg) dc[3] = clock64();
             // ---- DL1 = D4 [z1 > 0] over DL2 (the backward MMAs have completed), streamed out by the MMA warp
             mbar_wait(bar_d4, ph);
+            if (dbg) dc[4] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             masked_store(tlane + 256u, m1, bar_dslab0);
+            if (dbg) dc[5] = clock64();
             ph ^= 1u;
         }
-    } else {
+    } else if (warp < 21) {
         // ============================ I/O warps (17..20), one thread per sample ============================
         const int row = (warp & 3) * 32 + lane;
         uint8_t* d3a = smem + BW_D3A + (row >> 3) * 256 + (row & 7) * 16;   // this row's two 16-byte K chunks
         *reinterpret_cast<uint4*>(d3a + 128) = make_uint4(0u, 0u, 0u, 0u);    // k = 8..15 stay zero
         const float S = args.scale[0];
         uint32_t ph = 0;
-        for (int64_t tile = first; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t tile = first; tile < n_tiles; tile += nranks) {
             const int64_t s = tile * TC_M + row;
+            const int64_t srow = (tile % px.R) * TC_M + row;                      // row inside the ring of tile slots
             const bool valid = s < args.n;
             const bool use_mask = args.mask_flags != nullptr;
             uint32_t fl = 0xFu, act = 0;
             float cf = 0.0f, lg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (piped) {
+                if (lane == 0) flag_wait(px.f_done + tile);
+                __syncwarp();
+            }
             if (valid) {
                 if (use_mask) fl = args.mask_flags[s];
                 if (args.action) act = args.action[s];
@@ -626,7 +758,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
                 if (args.head_mode == 0) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (j < args.n_out) lg[j] = args.logits[s * args.n_out + j];
+                        if (j < args.n_out) lg[j] = args.logits[srow * args.n_out + j];
                 }
             }
             float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -643,19 +775,30 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
             } else {
                 d[0] = cf;                                                        // value head: dLoss/dV * weight
             }
-            if (tile != first) mbar_wait(bar_d5, ph ^ 1u);                        // the previous tile's D5 has read d3a
             const uint32_t p01 = pack_f16(d[0] * S, d[1] * S), p23 = pack_f16(d[2] * S, d[3] * S);
+            const uint32_t pk[2] = {p01, p23};
+            // transposed fp16 copy for dW3 = H2^T d3 (rows >= n_out of the small image stay zero).  Pipeline mode: written
+            // BEFORE the arrival that lets the MMA lane issue this tile's D5, so the lane's later publication of the tile
+            // (which follows that wait in program order) covers it; stand-alone it stays off the critical path.
+            if (piped) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < args.n_out)
+                        *reinterpret_cast<uint16_t*>(args.d3t + small_off(srow, j)) = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
+                __threadfence();
+            }
+            if (tile != first) mbar_wait(bar_d5, ph ^ 1u);                        // the previous tile's D5 has read d3a
             *reinterpret_cast<uint4*>(d3a) = make_uint4(p01, p23, 0u, 0u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_dl3);
-            // off the critical path: transposed fp16 copy for dW3 = H2^T d3 (rows >= n_out of the small image stay zero)
-            // and the head bias gradient (unscaled float32 sum over the warp's 32 samples)
-            const uint32_t pk[2] = {p01, p23};
+            if (!piped) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (j < args.n_out)
-                    *reinterpret_cast<uint16_t*>(args.d3t + small_off(s, j)) = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
+                for (int j = 0; j < 4; ++j)
+                    if (j < args.n_out)
+                        *reinterpret_cast<uint16_t*>(args.d3t + small_off(srow, j)) = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
+            }
+            // the head bias gradient (unscaled float32 sum over the warp's 32 samples)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float v = d[j];
@@ -672,6 +815,244 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
     if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_constant__ BwdArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    PipeCtx px;
+    px.f_done = nullptr; px.b_done = nullptr; px.c2_done = nullptr; px.c13_done = nullptr;
+    px.R = (args.n + TC_M - 1) / TC_M + 1;      // stand-alone: slot == tile
+    bwd_role(args, px, (int)blockIdx.x, (int)gridDim.x, smem);
+}
+
+// ------------------------------------------------------------------------------------------------ dW roles
+// The dW GEMMs of atb_tc_kernel (b2048_learn_tc.cu) as roles of the persistent pipeline: a CTA takes the tiles rank,
+// rank + nranks, ... as the backward role publishes them, pulls the two 64-sample halves of the tile's images from the L2-resident
+// ring with bulk copies (3-stage ring) and accumulates in TMEM for the WHOLE call — one read-out + atomic add per CTA and call.
+//   kWhich == 2  : dW2 = H1^T DL2 (2 x 256 TMEM columns), db2 = column sums of DL2
+//   kWhich == 13 : dW3 = H2^T d3 and dW1^T = DL1^T A1 (4 x 16 TMEM columns), db1 = column sums of DL1
+struct DwArgs {
+    const uint8_t *h1, *h2, *dl2, *dl1, *a1t, *d3t;   // the ring's images
+    float *gW1, *gb1, *gW2, *gb2, *gW3;
+    const float* inv_scale;                           // device float: 1 / loss scale
+    int64_t n_tiles;
+    int n_out;
+};
+template <int kWhich>
+struct DwCfg {
+    static constexpr int kStageBytes = kWhich == 2 ? 2 * ACT_TILE_BYTES : 2 * ACT_TILE_BYTES + 2 * SMALL_TILE_BYTES;
+    static constexpr int kStages = 3;
+    static constexpr int kBar = kStages * kStageBytes;
+    static constexpr int kSmem = kBar + 128;
+    static constexpr uint32_t kTmemCols = kWhich == 2 ? 512u : 64u;
+};
+static_assert(DwCfg<13>::kSmem <= 232448 && DwCfg<2>::kStageBytes % 1024 == 0 && DwCfg<13>::kStageBytes % 1024 == 0, "dW role stages");
+
+__device__ __forceinline__ float2 h2f(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+
+template <int kWhich>
+__device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, const int rank, const int nranks, uint8_t* smem) {
+    using Cfg = DwCfg<kWhich>;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBar);
+    const uint32_t bar_full0 = s_u32(&bars[0]), bar_empty0 = s_u32(&bars[4]), bar_done = s_u32(&bars[8]);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kBar + 96);
+    if (tid == 0) {
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(bar_full0 + 8u * i, 1);
+            mbar_init(bar_empty0 + 8u * i, 5);        // the MMA commit + the four column-sum warps
+        }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_my = rank < args.n_tiles ? (args.n_tiles - rank + nranks - 1) / nranks : 0;
+    const int64_t n_it = 2 * n_my;                          // 64-sample half tiles
+    uint32_t* c_done = kWhich == 2 ? px.c2_done : px.c13_done;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int64_t it = 0; it < n_it; ++it) {
+                const int st = (int)(it % Cfg::kStages);
+                const int64_t use = it / Cfg::kStages;
+                const int64_t tile = rank + (it >> 1) * nranks;
+                const int64_t half = (tile % px.R) * 2 + (it & 1);
+                if (use > 0) mbar_wait(bar_empty0 + 8u * st, (uint32_t)(use - 1) & 1u);
+                if ((it & 1) == 0) {
+                    prog(px, 1, tile);
+                    flag_wait(px.b_done + tile);             // forward and backward outputs of the tile are in its slot
+                    prog(px, 2, tile);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                const uint32_t bar = bar_full0 + 8u * st;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)Cfg::kStageBytes) : "memory");
+                const uint32_t sa = s_u32(smem + st * Cfg::kStageBytes);
+                const uint8_t* ga = (kWhich == 2 ? args.h1 : args.h2) + (size_t)half * ACT_TILE_BYTES;
+                const uint8_t* gb = (kWhich == 2 ? args.dl2 : args.dl1) + (size_t)half * ACT_TILE_BYTES;
+#pragma unroll
+                for (uint32_t off = 0; off < (uint32_t)ACT_TILE_BYTES; off += 16384u) {
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + off),
+                                 "l"(ga + off), "r"(16384u), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sa + (uint32_t)ACT_TILE_BYTES + off),
+                                 "l"(gb + off), "r"(16384u), "r"(bar) : "memory");
+                }
+                if (kWhich == 13) {
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sa + 2u * ACT_TILE_BYTES),
+                                 "l"(args.d3t + (size_t)half * SMALL_TILE_BYTES), "r"((uint32_t)SMALL_TILE_BYTES), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     sa + 2u * ACT_TILE_BYTES + (uint32_t)SMALL_TILE_BYTES),
+                                 "l"(args.a1t + (size_t)half * SMALL_TILE_BYTES), "r"((uint32_t)SMALL_TILE_BYTES), "r"(bar) : "memory");
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 6) {
+        // ---- releaser: a tile's slot is handed back as soon as the MMAs (and column sums) of its second half have completed
+        if (lane == 0) {
+            for (int64_t j = 0; j < n_it; ++j) {
+                mbar_wait(bar_empty0 + 8u * (uint32_t)(j % Cfg::kStages), (uint32_t)(j / Cfg::kStages) & 1u);
+                if (j & 1) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c_done + rank + (j >> 1) * nranks), "r"(1u) : "memory");
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc2 = ((1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) | kIdescAMn | kIdescBMn;
+            constexpr uint32_t idesc16 = ((1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) | kIdescAMn;
+            for (int64_t it = 0; it < n_it; ++it) {
+                const int st = (int)(it % Cfg::kStages);
+                const int64_t use = it / Cfg::kStages;
+                mbar_wait(bar_full0 + 8u * st, (uint32_t)use & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = s_u32(smem + st * Cfg::kStageBytes), sb = sa + (uint32_t)ACT_TILE_BYTES;
+                const uint32_t acc = it ? 1u : 0u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {                                   // 16 samples per MMA
+                    if (kWhich == 2) {
+                        const uint64_t db = desc_sw128_mn(sb + (uint32_t)kk * 2048u, ACT_SLAB_BYTES);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf)
+                            umma_f16(tmem_base + (uint32_t)(hf * 256), desc_sw128_mn(sa + (uint32_t)hf * 16384u + (uint32_t)kk * 2048u, ACT_SLAB_BYTES),
+                                     db, idesc2, (acc | (uint32_t)kk) ? 1u : 0u);
+                    } else {
+                        const uint32_t s3 = sa + 2u * ACT_TILE_BYTES, s1 = s3 + (uint32_t)SMALL_TILE_BYTES;
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            umma_f16(tmem_base + (uint32_t)(hf * 16), desc_sw128_mn(sa + (uint32_t)hf * 16384u + (uint32_t)kk * 2048u, ACT_SLAB_BYTES),
+                                     desc_sw128(s3 + (uint32_t)kk * 32u), idesc16, (acc | (uint32_t)kk) ? 1u : 0u);
+                            umma_f16(tmem_base + 32u + (uint32_t)(hf * 16), desc_sw128_mn(sb + (uint32_t)hf * 16384u + (uint32_t)kk * 2048u, ACT_SLAB_BYTES),
+                                     desc_sw128(s1 + (uint32_t)kk * 32u), idesc16, (acc | (uint32_t)kk) ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(bar_empty0 + 8u * st);
+            }
+            umma_commit(bar_done);
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ---- column sums of the staged DL image (DL2 is the second image of a dW2 stage, DL1 the second of a dW1/dW3 stage)
+        const int cw = warp - 2, chunk = lane & 7, rsub = lane >> 3;
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+        for (int64_t it = 0; it < n_it; ++it) {
+            const int st = (int)(it % Cfg::kStages);
+            const int64_t use = it / Cfg::kStages;
+            mbar_wait(bar_full0 + 8u * st, (uint32_t)use & 1u);
+            const uint8_t* x = smem + st * Cfg::kStageBytes + ACT_TILE_BYTES + cw * ACT_SLAB_BYTES;
+#pragma unroll 4
+            for (int r = rsub; r < 64; r += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(x + r * 128 + ((chunk ^ (r & 7)) << 4));
+                const float2 f0 = h2f(v.x), f1 = h2f(v.y), f2 = h2f(v.z), f3 = h2f(v.w);
+                acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty0 + 8u * st);
+        }
+        const float out_scale = *args.inv_scale;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xFFFFFFFFu, acc[e], 8);
+            acc[e] += __shfl_xor_sync(0xFFFFFFFFu, acc[e], 16);
+        }
+        float* gb = kWhich == 2 ? args.gb2 : args.gb1;
+        if (lane < 8 && n_it > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (acc[e] != 0.0f) atomicAdd(gb + cw * 64 + chunk * 8 + e, acc[e] * out_scale);
+        }
+        // ---- read-out: TMEM lane quarter = warp % 4
+        if (n_it > 0) {
+            mbar_wait(bar_done, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int m = hf * 128 + q * 32 + lane;                        // feature index
+                if (kWhich == 2) {
+                    for (int c0 = 0; c0 < 256; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(tlane + (uint32_t)(hf * 256 + c0), r);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float v = __uint_as_float(r[i]) * out_scale;
+                            if (v != 0.0f) atomicAdd(args.gW2 + (size_t)m * TC_H + (c0 + i), v);
+                        }
+                    }
+                } else {
+                    uint32_t r3[16], r1[16];
+                    tmem_ld16(tlane + (uint32_t)(hf * 16), r3);
+                    tmem_ld16(tlane + 32u + (uint32_t)(hf * 16), r1);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float v3 = __uint_as_float(r3[i]) * out_scale, v1 = __uint_as_float(r1[i]) * out_scale;
+                        if (i < args.n_out && v3 != 0.0f) atomicAdd(args.gW3 + (size_t)m * args.n_out + i, v3);       // dW3[m][j]
+                        if (v1 != 0.0f) atomicAdd(args.gW1 + (size_t)i * TC_H + m, v1);                                // dW1[k][m]
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the persistent update pipeline
+struct PipeArgs {
+    FwdHpArgs f;
+    BwdArgs b;
+    DwArgs d;
+    PipeCtx px;
+    int nF, nB, nC2, nC13;     // CTAs per role (sum == gridDim.x)
+};
+constexpr int PIPE_SMEM = FS_TOTAL > BW_TOTAL ? (FS_TOTAL > DwCfg<13>::kSmem ? FS_TOTAL : DwCfg<13>::kSmem)
+                                              : (BW_TOTAL > DwCfg<13>::kSmem ? BW_TOTAL : DwCfg<13>::kSmem);
+static_assert(PIPE_SMEM <= 232448 && DwCfg<2>::kSmem <= PIPE_SMEM, "update_pipe_kernel shared memory");
+
+__global__ void __launch_bounds__(FH_THREADS, 1) update_pipe_kernel(const __grid_constant__ PipeArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    int r = (int)blockIdx.x;
+    if (threadIdx.x == 0) prog(a.px, 0, r < a.nF ? 100 : (r < a.nF + a.nB ? 200 : (r < a.nF + a.nB + a.nC2 ? 300 : 400)));
+    if (r < a.nF) { fwd_role(a.f, a.px, r, a.nF, smem); if (threadIdx.x == 0) prog(a.px, 7, 1); return; }
+    r -= a.nF;
+    if (r < a.nB) { bwd_role(a.b, a.px, r, a.nB, smem); return; }
+    r -= a.nB;
+    if (r < a.nC2) { dw_role<2>(a.d, a.px, r, a.nC2, smem); return; }
+    dw_role<13>(a.d, a.px, r - a.nC2, a.nC13, smem);
 }
 
 // ------------------------------------------------------------------------------------------------ loss scale
@@ -719,7 +1100,7 @@ bool backward_hp_supported(const b2048_handle* h, const b2048_mlp_desc* mlp) {
     // (up to 32768 per input) could overflow the fp16 activations
     return mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H && mlp->dims[3] >= 1 &&
            mlp->dims[3] <= 4 && mlp->activation == B2048_ACTV_RELU && mlp->obs_mode == B2048_OBS_LOG2 &&
-           h->smem_optin >= FS_TOTAL && h->smem_optin >= BW_TOTAL && h->smem_optin >= AtbCfg<256>::kSmem;
+           h->smem_optin >= PIPE_SMEM && h->smem_optin >= AtbCfg<256>::kSmem;
 }
 
 int64_t backward_hp_workspace_bytes(int64_t chunk) { return hp_workspace(chunk).total + 1024; }
@@ -731,6 +1112,8 @@ static int hp_attrs(b2048_handle* h) {
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(fwd_hp_kernel)");
         e = cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_TOTAL);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(bwd_tc_kernel)");
+        e = cudaFuncSetAttribute(update_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(update_pipe_kernel)");
         h->attrs |= 16u;
     }
     return B2048_OK;
@@ -754,16 +1137,113 @@ int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
     FwdHpArgs f;
     f.img = h->hp_image; f.board = board; f.out = out; f.h1 = nullptr; f.h2 = nullptr; f.a1t = nullptr; f.m1 = nullptr; f.m2 = nullptr;
     f.n = n; f.n_out = mlp->dims[3]; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale;
+    f.debug_clock = nullptr;
+    static long long* dbg_buf = nullptr;
+    if (h->debug & (1u << B2048_DBG_TC_CLOCKS)) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 80 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 80 * sizeof(long long), stream);
+        f.debug_clock = dbg_buf;
+    }
     const int64_t tiles = (n + TC_M - 1) / TC_M;
     const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     fwd_hp_kernel<<<grid, FH_THREADS, FS_TOTAL, stream>>>(f);
+    if (f.debug_clock) {
+        long long hb[80];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 5; ++k) {
+            long long* d = hb + 6 * k;
+            fprintf(stderr, "[fwd_hp clock] tile %d: wait_d1 %lld epi1 %lld wait_d2 %lld epi2 %lld | to next %lld || mma lane: period %lld, "
+                            "layer-2 waits: activations %lld weights %lld\n",
+                    k, d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[6] - d[0], hb[40 + 4 * (k + 1)], hb[41 + 4 * (k + 1)],
+                    hb[42 + 4 * (k + 1)]);
+        }
+    }
     return check_cuda(cudaGetLastError(), "fwd_hp_kernel launch");
 }
 
 // Same contract as the fp32 body of b2048_mlp_backward (grads accumulated, flat layout W_0, b_0, W_1, b_1, ...).
+// The whole update of n samples as ONE persistent cooperative launch (see PipeCtx): the SMs are split into forward,
+// backward and dW roles; R tile slots of images (R x 276 KB, L2-resident) connect them.
+static int launch_backward_hp_piped(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
+                                    const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
+                                    uint8_t* ws, int64_t R, cudaStream_t stream) {
+    const int n_out = mlp->dims[3];
+    const int64_t n_tiles = (n + TC_M - 1) / TC_M;
+    const HpWorkspace w = hp_workspace(R * TC_M);
+    uint32_t* flags = reinterpret_cast<uint32_t*>(ws + w.total);
+    float* scale = reinterpret_cast<float*>(ws + w.scale);
+    hp_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[0], mlp->b[0], mlp->W[1], mlp->b[1], mlp->W[2], mlp->b[2], n_out, ws + w.img);
+    bwd_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[1], mlp->W[2], n_out, ws + w.bimg);
+    cudaError_t e = cudaMemsetAsync(scale, 0, 16, stream);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(scale)");
+    absmax_kernel<<<h->num_sms * 4, 256, 0, stream>>>(coef, n, reinterpret_cast<uint32_t*>(scale) + 2);
+    scale_from_max_kernel<<<1, 1, 0, stream>>>(scale);
+    e = cudaMemsetAsync(flags, 0, (size_t)n_tiles * 16, stream);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(flags)");
+    e = cudaMemsetAsync(ws + w.d3t, 0, (size_t)R * 2 * SMALL_TILE_BYTES, stream);     // rows >= n_out of d3^T stay zero
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(d3t)");
+    PipeArgs a;
+    a.px.f_done = flags; a.px.b_done = flags + n_tiles; a.px.c2_done = flags + 2 * n_tiles; a.px.c13_done = flags + 3 * n_tiles;
+    a.px.R = R;
+    a.px.progress = nullptr;
+    static int* prog_host = nullptr;
+    if (h->debug & (1u << B2048_DBG_TC_CLOCKS)) {
+        if (!prog_host) cudaHostAlloc(&prog_host, 256 * 8 * sizeof(int), cudaHostAllocMapped);
+        for (int i = 0; i < 256 * 8; ++i) prog_host[i] = -1;
+        int* dptr = nullptr;
+        cudaHostGetDevicePointer(&dptr, prog_host, 0);
+        a.px.progress = dptr;
+    }
+    a.f.img = ws + w.img; a.f.board = board; a.f.out = reinterpret_cast<float*>(ws + w.logits);
+    a.f.h1 = ws + w.h1; a.f.h2 = ws + w.h2; a.f.a1t = ws + w.a1t;
+    a.f.m1 = reinterpret_cast<uint64_t*>(ws + w.m1); a.f.m2 = reinterpret_cast<uint64_t*>(ws + w.m2);
+    a.f.n = n; a.f.n_out = n_out; a.f.obs_mode = mlp->obs_mode; a.f.obs_scale = mlp->obs_log2_scale; a.f.debug_clock = nullptr;
+    a.b.img = ws + w.bimg; a.b.logits = a.f.out; a.b.m1 = a.f.m1; a.b.m2 = a.f.m2;
+    a.b.mask_flags = mask_flags; a.b.action = action; a.b.coef = coef; a.b.scale = scale;
+    a.b.dl2 = ws + w.dl2; a.b.dl1 = ws + w.dl1; a.b.d3t = ws + w.d3t;
+    a.b.n = n; a.b.head_mode = head_mode; a.b.n_out = n_out; a.b.debug_clock = nullptr;
+    float* gW1 = grads;
+    float* gb1 = gW1 + 16 * TC_H;
+    float* gW2 = gb1 + TC_H;
+    float* gb2 = gW2 + TC_H * TC_H;
+    float* gW3 = gb2 + TC_H;
+    a.b.gb3 = gW3 + TC_H * n_out;
+    a.d.h1 = a.f.h1; a.d.h2 = a.f.h2; a.d.dl2 = a.b.dl2; a.d.dl1 = a.b.dl1; a.d.a1t = a.f.a1t; a.d.d3t = a.b.d3t;
+    a.d.gW1 = gW1; a.d.gb1 = gb1; a.d.gW2 = gW2; a.d.gb2 = gb2; a.d.gW3 = gW3; a.d.inv_scale = scale + 1;
+    a.d.n_tiles = n_tiles; a.d.n_out = n_out;
+    // role split: per tile the forward role needs ~14 K cycles, the backward role ~7.5 K, each dW role ~3 K
+    const int S = h->num_sms;
+    a.nB = (h->pipe_split & 0xFF) ? (h->pipe_split & 0xFF) : (S * 27 + 50) / 100;
+    a.nC2 = ((h->pipe_split >> 8) & 0xFF) ? ((h->pipe_split >> 8) & 0xFF) : (S * 11 + 50) / 100;
+    a.nC13 = ((h->pipe_split >> 16) & 0xFF) ? ((h->pipe_split >> 16) & 0xFF) : (S * 11 + 50) / 100;
+    a.nF = S - a.nB - a.nC2 - a.nC13;
+    if (a.nF < 1 || a.nB < 1 || a.nC2 < 1 || a.nC13 < 1) return fail(B2048_ERR_INVALID, "update pipeline: bad role split");
+    void* params[] = {&a};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(update_pipe_kernel), dim3((unsigned)S), dim3(FH_THREADS), params,
+                                    (size_t)PIPE_SMEM, stream);
+    if (e == cudaSuccess && a.px.progress) {      // debug watchdog: a stuck pipeline is reported and the process ends
+        for (int ms = 0; ms < 3000 && cudaStreamQuery(stream) == cudaErrorNotReady; ++ms) {
+            struct timespec ts = {0, 1000000};
+            nanosleep(&ts, nullptr);
+        }
+        if (cudaStreamQuery(stream) == cudaErrorNotReady) {
+            fprintf(stderr, "[update pipeline] stuck after 3 s; n_tiles %lld R %lld roles F %d B %d dW2 %d dW13 %d\n", (long long)n_tiles,
+                    (long long)R, a.nF, a.nB, a.nC2, a.nC13);
+            for (int b = 0; b < S; ++b) {
+                const int* q = prog_host + b * 8;
+                fprintf(stderr, "  cta %3d role %d: [1] %d [2] %d [3] %d [4] %d [5] %d done %d\n", b, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
+            }
+            fflush(stderr);
+            _exit(3);
+        }
+    }
+    return check_cuda(e, "update_pipe_kernel launch");
+}
+
 int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
-                       uint8_t* workspace, int64_t chunk, cudaStream_t stream) {
+                       uint8_t* workspace, int64_t workspace_bytes, int64_t chunk, cudaStream_t stream) {
     { int st = hp_attrs(h); if (st != B2048_OK) return st; }
     const int n_out = mlp->dims[3];
     float* gW1 = grads;
@@ -773,6 +1253,14 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
     float* gW3 = gb2 + TC_H;
     float* gb3 = gW3 + TC_H * n_out;
     uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    {   // large batches: the persistent pipeline with an L2-resident ring of tile slots
+        const int64_t n_tiles = (n + TC_M - 1) / TC_M;
+        const int64_t Rmax = (h->pipe_split >> 24) ? (int64_t)(h->pipe_split >> 24) * 16 : 288;   // 288 slots x 276 KB = 80 MB of the 126 MB L2
+        const int64_t R = n_tiles < Rmax ? n_tiles : Rmax;
+        const int64_t need = hp_workspace(R * TC_M).total + n_tiles * 16 + 2048;
+        if (!(h->debug & (1u << B2048_DBG_NO_UPDATE_PIPE)) && n_tiles >= 4 * (int64_t)h->num_sms && need <= workspace_bytes)
+            return launch_backward_hp_piped(h, board, mask_flags, action, coef, mlp, grads, n, head_mode, ws, R, stream);
+    }
     const HpWorkspace w = hp_workspace(chunk);
     uint8_t* img = ws + w.img;
     uint8_t* bimg = ws + w.bimg;
@@ -791,7 +1279,7 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         f.img = img; f.board = board + c0; f.out = reinterpret_cast<float*>(ws + w.logits);
         f.h1 = ws + w.h1; f.h2 = ws + w.h2; f.a1t = ws + w.a1t;
         f.m1 = reinterpret_cast<uint64_t*>(ws + w.m1); f.m2 = reinterpret_cast<uint64_t*>(ws + w.m2);
-        f.n = cn; f.n_out = n_out; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale;
+        f.n = cn; f.n_out = n_out; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale; f.debug_clock = nullptr;
         fwd_hp_kernel<<<grid, FH_THREADS, FS_TOTAL, stream>>>(f);
         int st = check_cuda(cudaGetLastError(), "fwd_hp_kernel launch");
         if (st != B2048_OK) return st;
@@ -801,12 +1289,28 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         b.action = action ? action + c0 : nullptr;
         b.coef = coef + c0; b.scale = scale;
         b.dl2 = ws + w.dl2; b.dl1 = ws + w.dl1; b.d3t = ws + w.d3t; b.gb3 = gb3;
-        b.n = cn; b.head_mode = head_mode; b.n_out = n_out;
+        b.n = cn; b.head_mode = head_mode; b.n_out = n_out; b.debug_clock = nullptr;
+        static long long* dbg_buf = nullptr;
+        if ((h->debug & (1u << B2048_DBG_TC_CLOCKS)) && c0 == 0) {
+            if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
+            cudaMemsetAsync(dbg_buf, 0, 64 * sizeof(long long), stream);
+            b.debug_clock = dbg_buf;
+        }
         e = cudaMemsetAsync(b.d3t, 0, (size_t)tiles * 2 * SMALL_TILE_BYTES, stream);
         if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(d3t)");
         bwd_tc_kernel<<<grid, BW_THREADS, BW_TOTAL, stream>>>(b);
         st = check_cuda(cudaGetLastError(), "bwd_tc_kernel launch");
         if (st != B2048_OK) return st;
+        if (b.debug_clock) {
+            long long hb[64];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(hb, dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost);
+            for (int k = 0; k < 5; ++k) {
+                long long* d = hb + 8 * k;
+                fprintf(stderr, "[bwd_tc clock] tile %d: wait_d5 %lld wait_free %lld epi3 %lld wait_d4 %lld epi4 %lld | to next %lld\n", k,
+                        d[1] - d[0], d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], d[8] - d[0]);
+            }
+        }
         AtbArgs g;
         g.tiles64 = tiles * 2; g.f16 = 1; g.inv_scale = scale + 1;
         // dW2 = H1^T DL2, db2 = column sums of DL2

@@ -197,3 +197,36 @@ def test_hp_refuses_raw_observations_and_auto_falls_back(b2048):
     g2, _ = call_backward(b2048, agent, agent._actor, boards, masks, actions, coef, 0, 2, n)
     g0, _ = call_backward(b2048, agent, agent._actor, boards, masks, actions, coef, 0, 0, n)
     assert rel_err(g2, g0) < 1e-5          # same fp32 kernels (atomic summation order differs run to run)
+
+
+@pytest.mark.parametrize("head_mode,n", [(0, 128 * 700 + 37), (1, 128 * 600), (0, 300000)])
+def test_hp_update_pipeline_matches_chunked_kernels_and_oracle(b2048, head_mode, n):
+    """Large batches run as ONE persistent launch (update_pipe_kernel: forward / backward / dW roles exchanging tiles through
+    an L2-resident ring of 288 slots with acquire / release flags; more tiles than slots, so slots are recycled).  Same
+    gradient as the chunked kernel sequence (fp32 atomic order only) and within 1e-2 of the float32 restatement."""
+    rng = np.random.default_rng(50 + head_mode)
+    boards, masks, actions, coef = make_case(rng, n, zero_mean=True, scale=1e-5)
+    agent = make_agent(b2048, use_critic=(head_mode == 1), seed=8)
+    if head_mode == 1:
+        p = agent.critic_params
+        p["b"] = [rng.normal(size=b.shape).astype(np.float32) * 0.1 for b in p["b"]]
+        agent.critic_params = p
+        net, n_out, params = agent._critic, 1, agent.critic_params
+    else:
+        net, n_out, params = agent._actor, 4, agent.params
+    args = (boards, masks if head_mode == 0 else None, actions if head_mode == 0 else None, coef, head_mode)
+    g_pipe, _ = call_backward(b2048, agent, net, *args, HP, 1 << 20)
+    g_pipe2, _ = call_backward(b2048, agent, net, *args, HP, 1 << 20)          # run-to-run: atomic summation order only
+    b2048.debug_set("no_update_pipe", True)
+    try:
+        g_chunk, _ = call_backward(b2048, agent, net, *args, HP, 65536)
+    finally:
+        b2048.debug_set("no_update_pipe", False)
+    gW, gb, _, _, _ = oracle_grads(params, boards, masks if head_mode == 0 else None, actions, coef, head_mode, "log2", 0.0625)
+    g_or = np.concatenate([np.concatenate([w.reshape(-1), b.reshape(-1)]) for w, b in zip(gW, gb)])
+    e_rr, e_ck, e_or = rel_err(g_pipe2, g_pipe), rel_err(g_pipe, g_chunk), rel_err(g_pipe, g_or)
+    print(f"update pipeline, {n} samples: run-to-run {e_rr:.1e}, vs chunked kernels {e_ck:.1e}, vs float32 oracle {e_or:.1e}")
+    assert e_rr < 1e-5 and e_ck < 1e-4, (e_rr, e_ck)
+    a, b = split_grads(g_pipe, n_out), split_grads(g_or, n_out)
+    for l in range(3):
+        assert rel_err(a[l][0], b[l][0]) < 1e-2 and rel_err(a[l][1], b[l][1]) < 1e-2, (l, rel_err(a[l][0], b[l][0]), rel_err(a[l][1], b[l][1]))
