@@ -396,25 +396,28 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
         uint32_t ph = 0, F = 0;
         auto epilogue = [&](uint32_t tcol0) -> uint64_t {
             uint32_t mw[4];
+            uint32_t r[2][16];
+            tmem_ld16_issue(tcol0 + (uint32_t)(g * 16), r[0]);      // the TMEM load of slab s + 1 is in flight while slab s is converted
 #pragma unroll
             for (int s = 0; s < 4; ++s, ++F) {
                 const uint32_t st = F & 1u, au = F >> 1;
-                uint32_t r[16];
-                tmem_ld16(tcol0 + (uint32_t)(s * 64 + g * 16), r);
+                uint32_t (&rc)[16] = r[s & 1];
+                tmem_ld_wait(rc);
+                if (s < 3) tmem_ld16_issue(tcol0 + (uint32_t)((s + 1) * 64 + g * 16), r[(s + 1) & 1]);
                 uint32_t m = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) m = __funnelshift_l(0u - r[i], m, 1);   // z > 0  <=>  sign bit of -bits(z)
+                for (int i = 0; i < 16; ++i) m = __funnelshift_l(0u - rc[i], m, 1);   // z > 0  <=>  sign bit of -bits(z)
                 mw[s] = m;
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) relu_split(r[2 * k], r[2 * k + 1], hi[k], lo[k]);
                 if (au > 0) mbar_wait(a_free0 + 8u * st, (au - 1u) & 1u);          // the ring stage has been consumed
                 uint8_t* base = smem + FS_A + st * FS_ASTAGE + row * 128;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) relu_split(rc[8 * c + 2 * k], rc[8 * c + 2 * k + 1], hi[k], lo[k]);
                     const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(base + sw) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(base + 16384 + sw) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(base + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(base + 16384 + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -37,8 +37,14 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
             "gpu_launches": 2 * steps if precision == 0 else 2 * ((steps + 255) // 256)}
 
 
+# the reference's documented configuration (runner.py:10-63): one-hot observations,
+# hidden [256, 128, 64], Adam lr 0.01, critic lr 5e-4, empty-tile reward 0.05
+ONEHOT_ENV = dict(obs_mode="onehot", obs_log2_scale=1.0, reward_mode="log2", base_reward_scale=1.0, bonus_mode="off",
+                  empty_tile_reward=0.05, max_steps=1024)
+
+
 def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision="auto", use_critic: bool = False,
-                     update_precisions=("auto",)):
+                     update_precisions=("auto",), network: str = "default"):
     """BASELINE.json configs[2]: REINFORCE rollout (to termination, max_steps 1024) + one update (gamma 0.99,
     baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks.
     use_critic=True is configs[3]: actor + separate critic (reference semantics, reinforce_agent.py:403-498), TD(0)
@@ -48,11 +54,19 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
     import sys
     from . import dist as bd
     info = info or bd.DistInfo()
-    env = bd.make_sharded_env(boards * info.world_size, Game2048EnvConfig(**RUNNER_ENV), info, seed=0xB200, device=dev)
-    acfg = (ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, critic_learning_rate=5e-4, baseline_mode="batch_norm",
-                                 use_critic=True, optimizer="adam", model_seed=0) if use_critic else
-            ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
-    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"), acfg)
+    onehot = network == "onehot"
+    env = bd.make_sharded_env(boards * info.world_size, Game2048EnvConfig(**(ONEHOT_ENV if onehot else RUNNER_ENV)), info,
+                              seed=0xB200, device=dev)
+    if onehot:      # runner.py:27-47
+        acfg = ReinforceAgentConfig(gamma=0.99, learning_rate=0.01, critic_learning_rate=5e-4, baseline_mode="batch",
+                                    use_critic=True, optimizer="adam", model_seed=0)
+    else:
+        acfg = (ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, critic_learning_rate=5e-4, baseline_mode="batch_norm",
+                                     use_critic=True, optimizer="adam", model_seed=0) if use_critic else
+                ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
+    hidden = [256, 128, 64] if onehot else [256, 256]
+    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=hidden, activation="ReLU", init_distribution="HeNormal"), acfg)
+    use_critic = use_critic or onehot
     allreduce = bd.allreduce_sum_ if info.is_distributed else None
     out, alt = [], {}
     for it in range(iters):
@@ -94,7 +108,10 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
     last = out[-1]
     tot_ms = last["rollout_ms"] + last["update_ms"]
     res = {"metric": ("actor-critic" if use_critic else "REINFORCE") + " iteration (rollout to termination + update)",
-           "boards_per_gpu": boards, "network": "16-256-256-4 ReLU actor" + (" + 16-256-256-1 critic" if use_critic else ""),
+           "boards_per_gpu": boards,
+           "network": ("272-256-128-64-4 ReLU actor + 272-256-128-64-1 critic, one-hot observations (runner.py:27-47)" if onehot else
+                       "16-256-256-4 ReLU actor" + (" + 16-256-256-1 critic" if use_critic else "")),
+           "rollout_precision": "bf16 tcgen05 (fused persistent kernel)" if (agent.tc_supported() and precision != 0) else "fp32 CUDA cores",
            "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],
            "update_ms": last["update_ms"], "update_precision": agent.last_update_info.get("precision"),
            "T": last["T"], "mean_len": last["mean_len"], "mean_return": last["mean_return"],
