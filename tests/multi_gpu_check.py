@@ -95,11 +95,11 @@ def main():
         assert torch.equal(r1.length, lens), "fused rollout: episode lengths differ between sharded and single-GPU runs"
         live = torch.arange(r1.T, device=dev).unsqueeze(1) < r1.length.unsqueeze(0)
         assert torch.equal((r1.actions.int() * live)[:Tm], acts[: r1.T]), "fused rollout: actions differ"
-        u1 = a1.update_from_rollout(r1, precision=1)
+        u1 = a1.update_from_rollout(r1)      # same mode as the sharded update: "auto" = the float32-grade tensor-core path
         d_ref, d_got = a1._actor.theta - th0, theta - th0
         rel = float((d_got - d_ref).norm() / d_ref.norm())
         gn = abs(upd["actor_grad_norm"] - u1["actor_grad_norm"]) / u1["actor_grad_norm"]
-        print(f"tensor-core path: fused rollout sharding invariance OK; update rel err {rel:.2e}, grad-norm rel err {gn:.2e}")
+        print(f"tensor-core path ({upd['precision']}): fused rollout sharding invariance OK; update rel err {rel:.2e}, grad-norm rel err {gn:.2e}")
         assert rel < 1e-3 and gn < 1e-3
     # ---- 4. x8 symmetry augmentation and the actor-critic update under sharding: every rank applies exactly the update
     #         of one process holding all episodes (n_traj stays the GLOBAL episode count x 8), and an update issues one
