@@ -175,7 +175,6 @@ struct FwdHpArgs {
     const uint64_t* board;
     float* out;               // [n][n_out] head outputs, bias included
     uint8_t *h1, *h2;         // nullable: fp16 activation images (layout of b2048_learn_tc.cuh)
-    uint8_t* a1t;             // nullable: small K-major image of the encoded inputs (B operand of dW1^T = DL1^T A1)
     uint64_t *m1, *m2;        // nullable: ReLU masks, entry (tile * 4 + g) * 128 + row = 64 bits of thread (row, g)
     int64_t n;
     int n_out, obs_mode;
@@ -458,7 +457,8 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float* sB3 = reinterpret_cast<const float*>(smem + FS_RES + RES_B3);
         uint32_t ph = 0;
-        uint32_t pk_next[8], pk_cur[8];      // encoded inputs of the tile being prefetched / of the current tile (for A1^T)
+        uint32_t pk_next[8];
+        long long wait_cycles = 0;
         auto encode_a1 = [&](int64_t tile) {
             const int64_t s = tile * TC_M + row;
             uint64_t bd = (s < args.n) ? args.board[s] : 0ull;
@@ -482,28 +482,19 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
         for (int64_t tile = first; tile < n_tiles; tile += nranks) {
             const int64_t s = tile * TC_M + row;
             const int64_t srow = (tile % px.R) * TC_M + row;                      // row inside the ring of tile slots
-#pragma unroll
-            for (int j = 0; j < 8; ++j) pk_cur[j] = pk_next[j];
             mbar_wait(bar_d1, ph);                                               // A1 is free
             if (piped) {
                 // The tile's slot is taken only now (not when its inputs were prefetched): its previous tile has been
                 // consumed by both dW roles (hence by the backward role).  The storer and the epilogue warps write
                 // into the slot after bar_slot.
                 if (tile >= px.R && lane == 0) {
-                    if (warp == 19) prog(px, 1, tile);
+                    const long long w0 = clock64();
                     flag_wait(px.c2_done + (tile - px.R));
                     flag_wait(px.c13_done + (tile - px.R));
-                    if (warp == 19) prog(px, 3, tile);
+                    if (warp == 19) { wait_cycles += clock64() - w0; prog(px, 6, wait_cycles >> 10); }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_slot);
-            }
-            if (args.a1t) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(srow, 2 * j)) = (uint16_t)(pk_cur[j] & 0xFFFFu);
-                    *reinterpret_cast<uint16_t*>(args.a1t + small_off(srow, 2 * j + 1)) = (uint16_t)(pk_cur[j] >> 16);
-                }
             }
             const int64_t next = tile + nranks;
             if (next < n_tiles) encode_a1(next);
@@ -546,20 +537,25 @@ __global__ void __launch_bounds__(FH_THREADS, 1) fwd_hp_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------ backward deltas
 constexpr int BW_D3A = SM_BAR + 256;     // head deltas of the tile in flight as an fp16 A operand [128 x 16], A1's layout
 constexpr int BW_TOTAL = BW_D3A + 4096;
+constexpr int BW_A1T = IMG_W1;           // 2 buffers x 2 half-tiles x [32 rows x 128 B]: inputs^T (+ a ones row) of the tile, K-major
+                                         // B operand of dW1^T = DL1^T A1; lives in the W1 / BIAS part of the image area (not loaded)
 static_assert(BW_TOTAL <= 232448, "bwd_tc_kernel exceeds the shared memory of an sm_100 CTA");
+static_assert(IMG_W3 - IMG_W1 >= 2 * 8192 && BW_A1T % 1024 == 0, "A1^T buffers");
 
 struct BwdArgs {
     const uint8_t* img;           // fp16 image, layout of b2048_tc.cuh (W2 and W3 are read)
     const float* logits;          // [n][n_out] from fwd_hp_kernel (head_mode 0)
     const uint64_t *m1, *m2;      // ReLU masks from fwd_hp_kernel
+    const uint64_t* board;        // packed boards (inputs of dW1)
     const uint8_t* mask_flags;
     const uint8_t* action;
     const float* coef;
     const float* scale;           // device float[2]: loss scale S (a power of two) and 1 / S
-    uint8_t *dl2, *dl1, *d3t;
-    float* gb3;
+    uint8_t *dl2, *d3t;
+    float *gW1, *gb1, *gb3;
     int64_t n;
-    int head_mode, n_out;
+    int head_mode, n_out, obs_mode;
+    float obs_scale;
     long long* debug_clock;   // optional phase timestamps of CTA 0 (B2048_DBG_TC_CLOCKS), else NULL
 };
 
@@ -579,12 +575,18 @@ __device__ __forceinline__ void bw_stores_read_done() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// Backward deltas of one 128-sample tile at a time, and the input-layer gradient:
+//   D5 = d3 W3^T in two N = 128 halves (TMEM columns 0..127, the second half once the first is drained)
+//   DL2 = D5 . [z2 > 0]  -> A2 (fp16, the A operand of D4) and the global DL2 image (dW2 is another kernel / role)
+//   D4 = DL2 W2 (TMEM columns 256..511)  ->  DL1 = D4 . [z1 > 0]  -> A2
+//   dW1^T += DL1^T [A1 | 1]  (TMEM columns 128..191, N = 32: columns 0..15 = the 16 inputs, column 16 = the bias gradient);
+//   DL1 never leaves the SM; the accumulators stay in TMEM for all tiles of the CTA and are added to the gradient once.
 __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px, const int rank, const int nranks, uint8_t* smem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool piped = px.f_done != nullptr;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
     const uint32_t bar_img = s_u32(&bars[0]), bar_dl3 = s_u32(&bars[1]), bar_d5 = s_u32(&bars[2]), bar_d4 = s_u32(&bars[3]),
-                   bar_free = s_u32(&bars[4]);
+                   bar_free = s_u32(&bars[4]), bar_d5b = s_u32(&bars[5]);
     const uint32_t bar_bslab0 = s_u32(&bars[8]);    // [8..11]  DL2 slab written (D5 drained for that slab)
     const uint32_t bar_dslab0 = s_u32(&bars[12]);   // [12..15] DL1 slab written (D4 drained for that slab)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 208);
@@ -593,15 +595,16 @@ __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px,
         mbar_init(bar_img, 1);
         mbar_init(bar_dl3, 4);
         mbar_init(bar_d5, 1);
+        mbar_init(bar_d5b, 1);
         mbar_init(bar_d4, 1);
-        mbar_init(bar_free, 1);
+        mbar_init(bar_free, 1);          // the dW1 MMAs of the tile have completed: A2 and the tile's A1^T buffer are free
         for (int g = 0; g < 4; ++g) {
             mbar_init(bar_bslab0 + 8u * g, 16);
             mbar_init(bar_dslab0 + 8u * g, 16);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {   // D5 = columns 0..255, D4 = columns 256..511
+    if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -612,12 +615,16 @@ __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px,
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (args.n + TC_M - 1) / TC_M;
     const int64_t first = rank;
+    const int64_t n_local = first < n_tiles ? (n_tiles - first + nranks - 1) / nranks : 0;
 
     if (warp == 16) {
         // ============================ MMA / copy warp ============================
         if (lane == 0) {
             const uint32_t sA2 = s_u32(smem + SM_A2), sW2 = s_u32(smem + IMG_W2), sW3 = s_u32(smem + IMG_W3);
-            constexpr uint32_t kIdescBwd = kIdescF16 | kIdescBMn;
+            const uint32_t sA1T = s_u32(smem + BW_A1T);
+            constexpr uint32_t kIdescBwd = kIdescF16 | kIdescBMn;                                                          // M128 N256
+            constexpr uint32_t kIdescD5 = ((1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24)) | kIdescBMn;   // M128 N128
+            constexpr uint32_t kIdescDw1 = ((1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24)) | kIdescAMn;   // M128 N32
             // only W2 and W3 of the image are read by this kernel
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)(131072 + 8192)) : "memory");
             for (uint32_t off = 0; off < 131072u; off += 16384u)
@@ -630,22 +637,27 @@ __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px,
                          "l"(args.img + IMG_W3), "r"(8192u), "r"(bar_img)
                          : "memory");
             mbar_wait(bar_img, 0);
-            auto issue_d5 = [&](uint32_t ph) {
-                // backward through the head: D5 = d3 . W3^T.  A = d3 as fp16 [128 x 16] (K-major, A1's layout); B = the
-                // head's W3 image [j][f] read MN-major (N = f contiguous: 64-wide slabs 2048 B apart, 8 K rows = 1024 B)
+            auto issue_d5a = [&](uint32_t ph) {
+                // backward through the head, features 0..127: D5 = d3 . W3^T.  A = d3 as fp16 [128 x 16] (K-major, A1's layout);
+                // B = the head's W3 image [j][f] read MN-major (N = f contiguous: 64-wide slabs 2048 B apart, 8 K rows = 1024 B)
                 mbar_wait(bar_dl3, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_f16(tmem_base, desc_nosw_k16(s_u32(smem + BW_D3A)), desc_sw128_mn(sW3, 2048u), kIdescBwd, 0u);
+                umma_f16(tmem_base, desc_nosw_k16(s_u32(smem + BW_D3A)), desc_sw128_mn(sW3, 2048u), kIdescD5, 0u);
                 umma_commit(bar_d5);
             };
             uint32_t ph = 0;
-            if (first < n_tiles) issue_d5(0u);
-            for (int64_t tile = first; tile < n_tiles; tile += nranks) {
+            int64_t lt = 0;
+            if (first < n_tiles) issue_d5a(0u);
+            for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
                 // ---- backward through layer 2: D4 = DL2 . W2 over K = out features; B = the W2 image [out][in] read
                 //      MN-major (N = in contiguous: 64-wide slabs 32768 B apart, 8 K rows = 1024 B)
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_bslab0 + 8u * g, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (g == 1) {   // slabs 0 and 1 of DL2 are written, i.e. the first half of D5 is drained: features 128..255
+                        umma_f16(tmem_base, desc_nosw_k16(s_u32(smem + BW_D3A)), desc_sw128_mn(sW3 + 2u * 2048u, 2048u), kIdescD5, 0u);
+                        umma_commit(bar_d5b);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         umma_f16(tmem_base + 256u, desc_sw128(sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u),
@@ -655,14 +667,22 @@ __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px,
                 bw_stores_read_done();                   // epilogue 4 overwrites DL2 once bar_d4 completes
                 umma_commit(bar_d4);
                 // ---- the next tile's D5 (this tile's D5 was drained by every warp before the DL2 slab arrivals)
-                if (tile + nranks < n_tiles) issue_d5(ph ^ 1u);
-                for (int g = 0; g < 4; ++g) {
-                    mbar_wait(bar_dslab0 + 8u * g, ph);
-                    bw_store_slab(args.dl1, tile % px.R, sA2, g);
+                if (tile + nranks < n_tiles) issue_d5a(ph ^ 1u);
+                // ---- dW1^T += DL1^T [A1 | 1]: A = DL1 in A2 read MN-major (M = features: 64-wide slabs 16384 B apart,
+                //      K = samples: 8 rows = 1024 B), B = the tile's A1^T buffer (K-major, 32 rows: 16 inputs, the ones row, zeros)
+                for (int g = 0; g < 4; ++g) mbar_wait(bar_dslab0 + 8u * g, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sB = sA1T + (uint32_t)(lt & 1) * 8192u;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {         // 16 samples per MMA
+                    const uint64_t db = desc_sw128(sB + (uint32_t)(kk >> 2) * 4096u + (uint32_t)(kk & 3) * 32u);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        umma_f16(tmem_base + 128u + (uint32_t)(hf * 32), desc_sw128_mn(sA2 + (uint32_t)hf * 32768u + (uint32_t)kk * 2048u, 16384u),
+                                 db, kIdescDw1, (lt | kk) ? 1u : 0u);
                 }
-                bw_stores_read_done();
-                mbar_arrive(bar_free);                   // A2 free: the DL1 image of the tile has been streamed out
-                if (piped) {                             // publish the tile: d3^T written, DL2 / DL1 image writes complete
+                umma_commit(bar_free);
+                if (piped) {                             // publish the tile: d3^T written, DL2 image writes complete
                     prog(px, 4, tile);
                     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                     flag_set(px.b_done + tile);
@@ -680,76 +700,113 @@ __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px,
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint8_t* a2_row = smem + SM_A2 + row * 128;
         uint32_t ph = 0;
-        auto masked_store = [&](uint32_t tcol0, uint64_t mask, uint32_t bar0) {
+        // slab s of the [128 x 256] delta tile: columns tcol .. tcol + 15 of this warp's lanes, masked, as fp16 into A2
+        auto masked_slab = [&](uint32_t tcol, int s, uint64_t mask, uint32_t bar0) {
+            uint32_t rr[16];
+            tmem_ld16(tcol, rr);
+            const uint32_t mb = (uint32_t)(mask >> (16 * s)) & 0xFFFFu;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                uint32_t rr[16];
-                tmem_ld16(tcol0 + (uint32_t)(s * 64 + g * 16), rr);
-                const uint32_t mb = (uint32_t)(mask >> (16 * s)) & 0xFFFFu;
+            for (int c = 0; c < 2; ++c) {
+                uint32_t out[4];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t out[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i0 = c * 8 + 2 * k;
-                        float lo = (mb >> (15 - i0)) & 1u ? __uint_as_float(rr[i0]) : 0.0f;
-                        float hi = (mb >> (14 - i0)) & 1u ? __uint_as_float(rr[i0 + 1]) : 0.0f;
-                        out[k] = pack_f16(lo, hi);
-                    }
-                    const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
-                    *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = make_uint4(out[0], out[1], out[2], out[3]);
+                for (int k = 0; k < 4; ++k) {
+                    const int i0 = c * 8 + 2 * k;
+                    float lo = (mb >> (15 - i0)) & 1u ? __uint_as_float(rr[i0]) : 0.0f;
+                    float hi = (mb >> (14 - i0)) & 1u ? __uint_as_float(rr[i0 + 1]) : 0.0f;
+                    out[k] = pack_f16(lo, hi);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 8u * s);
+                const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                *reinterpret_cast<uint4*>(a2_row + s * 16384 + sw) = make_uint4(out[0], out[1], out[2], out[3]);
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8u * s);
         };
         int lt = 0;
+        long long wait_cycles = 0;
         for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
             const bool dbg = args.debug_clock != nullptr && rank == 0 && tid == 0 && lt < 6;
             long long* dc = dbg ? args.debug_clock + 8 * lt : nullptr;
             if (dbg) dc[0] = clock64();
             if (piped) {
                 if (lane == 0) {
-                    if (warp == 0) prog(px, 1, tile);
+                    const long long w0 = clock64();
                     flag_wait(px.f_done + tile);
-                    if (warp == 0) prog(px, 2, tile);
+                    if (warp == 0) { wait_cycles += clock64() - w0; prog(px, 6, wait_cycles >> 10); }
                 }
                 __syncwarp();
             }
             const uint64_t m2 = args.m2[(size_t)((tile % px.R) * 4 + g) * TC_M + row];
             const uint64_t m1 = args.m1[(size_t)((tile % px.R) * 4 + g) * TC_M + row];
-            // ---- DL2 = D5 [z2 > 0]  (the A2 buffer is free once the previous tile's DL1 image has been streamed out)
+            // ---- DL2 = D5 [z2 > 0]  (A2 is free once the previous tile's dW1 MMAs have read DL1)
             mbar_wait(bar_d5, ph);
             if (dbg) dc[1] = clock64();
             if (tile != first) mbar_wait(bar_free, ph ^ 1u);
             if (dbg) dc[2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            masked_store(tlane, m2, bar_bslab0);
+            masked_slab(tlane + (uint32_t)(g * 16), 0, m2, bar_bslab0);
+            masked_slab(tlane + (uint32_t)(64 + g * 16), 1, m2, bar_bslab0);
+            mbar_wait(bar_d5b, ph);                      // features 128..255 of D5 (same TMEM columns)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            masked_slab(tlane + (uint32_t)(g * 16), 2, m2, bar_bslab0);
+            masked_slab(tlane + (uint32_t)(64 + g * 16), 3, m2, bar_bslab0);
             if (dbg) dc[3] = clock64();
-            // ---- DL1 = D4 [z1 > 0] over DL2 (the backward MMAs have completed), streamed out by the MMA warp
+            // ---- DL1 = D4 [z1 > 0] over DL2 (the backward MMAs have completed); read by the dW1 MMAs
             mbar_wait(bar_d4, ph);
             if (dbg) dc[4] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            masked_store(tlane + 256u, m1, bar_dslab0);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) masked_slab(tlane + 256u + (uint32_t)(s * 64 + g * 16), s, m1, bar_dslab0);
             if (dbg) dc[5] = clock64();
             ph ^= 1u;
+        }
+        // ---- read-out of dW1^T (columns 0..15) and db1 (column 16): lane quarter q, features hf * 128 + q * 32 + lane
+        if (g == 0 && n_local > 0) {
+            mbar_wait(bar_free, ph ^ 1u);                // the last tile's dW1 MMAs
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float inv = args.scale[1];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int m = hf * 128 + row;
+                uint32_t r0[16], r1[16];
+                tmem_ld16(tlane + 128u + (uint32_t)(hf * 32), r0);
+                tmem_ld16(tlane + 128u + (uint32_t)(hf * 32 + 16), r1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float v = __uint_as_float(r0[i]) * inv;
+                    if (v != 0.0f) atomicAdd(args.gW1 + (size_t)i * TC_H + m, v);          // dW1[k][m]
+                }
+                const float vb = __uint_as_float(r1[0]) * inv;
+                if (vb != 0.0f) atomicAdd(args.gb1 + m, vb);
+            }
         }
     } else if (warp < 21) {
         // ============================ I/O warps (17..20), one thread per sample ============================
         const int row = (warp & 3) * 32 + lane;
         uint8_t* d3a = smem + BW_D3A + (row >> 3) * 256 + (row & 7) * 16;   // this row's two 16-byte K chunks
         *reinterpret_cast<uint4*>(d3a + 128) = make_uint4(0u, 0u, 0u, 0u);    // k = 8..15 stay zero
+        // A1^T buffers: rows 17..31 stay zero, row 16 = 1 (the bias-gradient column), rows 0..15 are rewritten per tile
+        {
+            const int tq = tid - 17 * 32;                                      // 0..127
+            for (int i = tq; i < 2 * 8192 / 16; i += 128) {
+                const int off = i * 16, rowj = (off & 4095) >> 7;
+                const uint32_t v = rowj == 16 ? 0x3C003C00u : 0u;              // fp16 1.0 pairs
+                *reinterpret_cast<uint4*>(smem + BW_A1T + off) = make_uint4(v, v, v, v);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four I/O warps only
+        }
         const float S = args.scale[0];
         uint32_t ph = 0;
-        for (int64_t tile = first; tile < n_tiles; tile += nranks) {
+        int64_t lt = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
             const int64_t s = tile * TC_M + row;
             const int64_t srow = (tile % px.R) * TC_M + row;                      // row inside the ring of tile slots
             const bool valid = s < args.n;
             const bool use_mask = args.mask_flags != nullptr;
             uint32_t fl = 0xFu, act = 0;
             float cf = 0.0f, lg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const uint64_t bd = valid ? args.board[s] : 0ull;
             if (piped) {
                 if (lane == 0) flag_wait(px.f_done + tile);
                 __syncwarp();
@@ -790,7 +847,20 @@ __device__ __forceinline__ void bwd_role(const BwdArgs& args, const PipeCtx& px,
                         *reinterpret_cast<uint16_t*>(args.d3t + small_off(srow, j)) = (uint16_t)(pk[j >> 1] >> (16 * (j & 1)));
                 __threadfence();
             }
-            if (tile != first) mbar_wait(bar_d5, ph ^ 1u);                        // the previous tile's D5 has read d3a
+            // the tile's inputs, transposed, into its A1^T buffer (two tiles back used the same buffer: its dW1 MMAs are done)
+            if (lt >= 2) mbar_wait(bar_free, ph);
+            {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t e = (uint32_t)(bd >> (4 * j)) & 0xFu;
+                    const float v = args.obs_mode == B2048_OBS_RAW ? (e ? (float)(1u << e) : 0.0f) : (float)e * args.obs_scale;
+                    // element (row j, sample r): j * 128 + (((r >> 3) ^ (j & 7)) << 4) + (r & 7) * 2
+                    uint8_t* pz = smem + BW_A1T + (lt & 1) * 8192 + (row >> 6) * 4096 + j * 128 +
+                                  ((((row & 63) >> 3) ^ (j & 7)) << 4) + (row & 7) * 2;
+                    *reinterpret_cast<__half*>(pz) = __float2half_rn(v);
+                }
+            }
+            if (tile != first) mbar_wait(bar_d5b, ph ^ 1u);                       // the previous tile's D5 (both halves) has read d3a
             *reinterpret_cast<uint4*>(d3a) = make_uint4(p01, p23, 0u, 0u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -832,24 +902,25 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_tc_kernel(const __grid_cons
 // The dW GEMMs of atb_tc_kernel (b2048_learn_tc.cu) as roles of the persistent pipeline: a CTA takes the tiles rank,
 // rank + nranks, ... as the backward role publishes them, pulls the two 64-sample halves of the tile's images from the L2-resident
 // ring with bulk copies (3-stage ring) and accumulates in TMEM for the WHOLE call — one read-out + atomic add per CTA and call.
-//   kWhich == 2  : dW2 = H1^T DL2 (2 x 256 TMEM columns), db2 = column sums of DL2
-//   kWhich == 13 : dW3 = H2^T d3 and dW1^T = DL1^T A1 (4 x 16 TMEM columns), db1 = column sums of DL1
+//   kWhich == 2 : dW2 = H1^T DL2 (2 x 256 TMEM columns), db2 = column sums of DL2
+//   kWhich == 3 : dW3 = H2^T d3 (2 x 16 TMEM columns)
+// (dW1 and db1 are accumulated by the backward role itself: DL1 never leaves its SM.)
 struct DwArgs {
-    const uint8_t *h1, *h2, *dl2, *dl1, *a1t, *d3t;   // the ring's images
-    float *gW1, *gb1, *gW2, *gb2, *gW3;
+    const uint8_t *h1, *h2, *dl2, *d3t;   // the ring's images
+    float *gW2, *gb2, *gW3;
     const float* inv_scale;                           // device float: 1 / loss scale
     int64_t n_tiles;
     int n_out;
 };
 template <int kWhich>
 struct DwCfg {
-    static constexpr int kStageBytes = kWhich == 2 ? 2 * ACT_TILE_BYTES : 2 * ACT_TILE_BYTES + 2 * SMALL_TILE_BYTES;
-    static constexpr int kStages = 3;
+    static constexpr int kStageBytes = kWhich == 2 ? 2 * ACT_TILE_BYTES : ACT_TILE_BYTES + SMALL_TILE_BYTES;
+    static constexpr int kStages = kWhich == 2 ? 3 : 6;
     static constexpr int kBar = kStages * kStageBytes;
-    static constexpr int kSmem = kBar + 128;
-    static constexpr uint32_t kTmemCols = kWhich == 2 ? 512u : 64u;
+    static constexpr int kSmem = kBar + 256;
+    static constexpr uint32_t kTmemCols = kWhich == 2 ? 512u : 32u;
 };
-static_assert(DwCfg<13>::kSmem <= 232448 && DwCfg<2>::kStageBytes % 1024 == 0 && DwCfg<13>::kStageBytes % 1024 == 0, "dW role stages");
+static_assert(DwCfg<2>::kSmem <= 232448 && DwCfg<2>::kStageBytes % 1024 == 0 && DwCfg<3>::kStageBytes % 1024 == 0, "dW role stages");
 
 __device__ __forceinline__ float2 h2f(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 
@@ -858,12 +929,12 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
     using Cfg = DwCfg<kWhich>;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBar);
-    const uint32_t bar_full0 = s_u32(&bars[0]), bar_empty0 = s_u32(&bars[4]), bar_done = s_u32(&bars[8]);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kBar + 96);
+    const uint32_t bar_full0 = s_u32(&bars[0]), bar_empty0 = s_u32(&bars[8]), bar_done = s_u32(&bars[16]);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kBar + 160);
     if (tid == 0) {
         for (int i = 0; i < Cfg::kStages; ++i) {
             mbar_init(bar_full0 + 8u * i, 1);
-            mbar_init(bar_empty0 + 8u * i, 5);        // the MMA commit + the four column-sum warps
+            mbar_init(bar_empty0 + 8u * i, kWhich == 2 ? 5 : 1);   // the MMA commit (+ the four column-sum warps of the dW2 role)
         }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -878,10 +949,11 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_my = rank < args.n_tiles ? (args.n_tiles - rank + nranks - 1) / nranks : 0;
     const int64_t n_it = 2 * n_my;                          // 64-sample half tiles
-    uint32_t* c_done = kWhich == 2 ? px.c2_done : px.c13_done;
+    uint32_t* c_done = kWhich == 2 ? px.c2_done : px.c13_done;      // (c13_done: the dW3 role)
 
     if (warp == 0) {
         if (lane == 0) {
+            long long wait_cycles = 0;
             for (int64_t it = 0; it < n_it; ++it) {
                 const int st = (int)(it % Cfg::kStages);
                 const int64_t use = it / Cfg::kStages;
@@ -889,31 +961,31 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
                 const int64_t half = (tile % px.R) * 2 + (it & 1);
                 if (use > 0) mbar_wait(bar_empty0 + 8u * st, (uint32_t)(use - 1) & 1u);
                 if ((it & 1) == 0) {
-                    prog(px, 1, tile);
+                    const long long w0 = clock64();
                     flag_wait(px.b_done + tile);             // forward and backward outputs of the tile are in its slot
-                    prog(px, 2, tile);
+                    wait_cycles += clock64() - w0;
+                    prog(px, 6, wait_cycles >> 10);
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 const uint32_t bar = bar_full0 + 8u * st;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)Cfg::kStageBytes) : "memory");
                 const uint32_t sa = s_u32(smem + st * Cfg::kStageBytes);
                 const uint8_t* ga = (kWhich == 2 ? args.h1 : args.h2) + (size_t)half * ACT_TILE_BYTES;
-                const uint8_t* gb = (kWhich == 2 ? args.dl2 : args.dl1) + (size_t)half * ACT_TILE_BYTES;
 #pragma unroll
-                for (uint32_t off = 0; off < (uint32_t)ACT_TILE_BYTES; off += 16384u) {
+                for (uint32_t off = 0; off < (uint32_t)ACT_TILE_BYTES; off += 16384u)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa + off),
                                  "l"(ga + off), "r"(16384u), "r"(bar) : "memory");
+                if (kWhich == 2) {
+                    const uint8_t* gb = args.dl2 + (size_t)half * ACT_TILE_BYTES;
+#pragma unroll
+                    for (uint32_t off = 0; off < (uint32_t)ACT_TILE_BYTES; off += 16384u)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         sa + (uint32_t)ACT_TILE_BYTES + off),
+                                     "l"(gb + off), "r"(16384u), "r"(bar) : "memory");
+                } else {
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     sa + (uint32_t)ACT_TILE_BYTES + off),
-                                 "l"(gb + off), "r"(16384u), "r"(bar) : "memory");
-                }
-                if (kWhich == 13) {
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     sa + 2u * ACT_TILE_BYTES),
+                                     sa + (uint32_t)ACT_TILE_BYTES),
                                  "l"(args.d3t + (size_t)half * SMALL_TILE_BYTES), "r"((uint32_t)SMALL_TILE_BYTES), "r"(bar) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     sa + 2u * ACT_TILE_BYTES + (uint32_t)SMALL_TILE_BYTES),
-                                 "l"(args.a1t + (size_t)half * SMALL_TILE_BYTES), "r"((uint32_t)SMALL_TILE_BYTES), "r"(bar) : "memory");
                 }
             }
         }
@@ -947,14 +1019,10 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
                             umma_f16(tmem_base + (uint32_t)(hf * 256), desc_sw128_mn(sa + (uint32_t)hf * 16384u + (uint32_t)kk * 2048u, ACT_SLAB_BYTES),
                                      db, idesc2, (acc | (uint32_t)kk) ? 1u : 0u);
                     } else {
-                        const uint32_t s3 = sa + 2u * ACT_TILE_BYTES, s1 = s3 + (uint32_t)SMALL_TILE_BYTES;
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
+                        for (int hf = 0; hf < 2; ++hf)
                             umma_f16(tmem_base + (uint32_t)(hf * 16), desc_sw128_mn(sa + (uint32_t)hf * 16384u + (uint32_t)kk * 2048u, ACT_SLAB_BYTES),
-                                     desc_sw128(s3 + (uint32_t)kk * 32u), idesc16, (acc | (uint32_t)kk) ? 1u : 0u);
-                            umma_f16(tmem_base + 32u + (uint32_t)(hf * 16), desc_sw128_mn(sb + (uint32_t)hf * 16384u + (uint32_t)kk * 2048u, ACT_SLAB_BYTES),
-                                     desc_sw128(s1 + (uint32_t)kk * 32u), idesc16, (acc | (uint32_t)kk) ? 1u : 0u);
-                        }
+                                     desc_sw128(sb + (uint32_t)kk * 32u), idesc16, (acc | (uint32_t)kk) ? 1u : 0u);
                     }
                 }
                 umma_commit(bar_empty0 + 8u * st);
@@ -968,7 +1036,7 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-        for (int64_t it = 0; it < n_it; ++it) {
+        for (int64_t it = 0; kWhich == 2 && it < n_it; ++it) {
             const int st = (int)(it % Cfg::kStages);
             const int64_t use = it / Cfg::kStages;
             mbar_wait(bar_full0 + 8u * st, (uint32_t)use & 1u);
@@ -988,8 +1056,8 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
             acc[e] += __shfl_xor_sync(0xFFFFFFFFu, acc[e], 8);
             acc[e] += __shfl_xor_sync(0xFFFFFFFFu, acc[e], 16);
         }
-        float* gb = kWhich == 2 ? args.gb2 : args.gb1;
-        if (lane < 8 && n_it > 0) {
+        float* gb = args.gb2;
+        if (kWhich == 2 && lane < 8 && n_it > 0) {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
                 if (acc[e] != 0.0f) atomicAdd(gb + cw * 64 + chunk * 8 + e, acc[e] * out_scale);
@@ -1014,14 +1082,12 @@ __device__ __forceinline__ void dw_role(const DwArgs& args, const PipeCtx& px, c
                         }
                     }
                 } else {
-                    uint32_t r3[16], r1[16];
+                    uint32_t r3[16];
                     tmem_ld16(tlane + (uint32_t)(hf * 16), r3);
-                    tmem_ld16(tlane + 32u + (uint32_t)(hf * 16), r1);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float v3 = __uint_as_float(r3[i]) * out_scale, v1 = __uint_as_float(r1[i]) * out_scale;
+                        const float v3 = __uint_as_float(r3[i]) * out_scale;
                         if (i < args.n_out && v3 != 0.0f) atomicAdd(args.gW3 + (size_t)m * args.n_out + i, v3);       // dW3[m][j]
-                        if (v1 != 0.0f) atomicAdd(args.gW1 + (size_t)i * TC_H + m, v1);                                // dW1[k][m]
                     }
                 }
             }
@@ -1040,22 +1106,22 @@ struct PipeArgs {
     BwdArgs b;
     DwArgs d;
     PipeCtx px;
-    int nF, nB, nC2, nC13;     // CTAs per role (sum == gridDim.x)
+    int nF, nB, nC2, nC13;     // CTAs per role: forward, backward (+ dW1), dW2, dW3 (sum == gridDim.x)
 };
-constexpr int PIPE_SMEM = FS_TOTAL > BW_TOTAL ? (FS_TOTAL > DwCfg<13>::kSmem ? FS_TOTAL : DwCfg<13>::kSmem)
-                                              : (BW_TOTAL > DwCfg<13>::kSmem ? BW_TOTAL : DwCfg<13>::kSmem);
+constexpr int PIPE_SMEM = FS_TOTAL > BW_TOTAL ? (FS_TOTAL > DwCfg<3>::kSmem ? FS_TOTAL : DwCfg<3>::kSmem)
+                                              : (BW_TOTAL > DwCfg<3>::kSmem ? BW_TOTAL : DwCfg<3>::kSmem);
 static_assert(PIPE_SMEM <= 232448 && DwCfg<2>::kSmem <= PIPE_SMEM, "update_pipe_kernel shared memory");
 
 __global__ void __launch_bounds__(FH_THREADS, 1) update_pipe_kernel(const __grid_constant__ PipeArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     int r = (int)blockIdx.x;
+    const long long t0 = clock64();
     if (threadIdx.x == 0) prog(a.px, 0, r < a.nF ? 100 : (r < a.nF + a.nB ? 200 : (r < a.nF + a.nB + a.nC2 ? 300 : 400)));
-    if (r < a.nF) { fwd_role(a.f, a.px, r, a.nF, smem); if (threadIdx.x == 0) prog(a.px, 7, 1); return; }
-    r -= a.nF;
-    if (r < a.nB) { bwd_role(a.b, a.px, r, a.nB, smem); return; }
-    r -= a.nB;
-    if (r < a.nC2) { dw_role<2>(a.d, a.px, r, a.nC2, smem); return; }
-    dw_role<13>(a.d, a.px, r - a.nC2, a.nC13, smem);
+    if (r < a.nF) fwd_role(a.f, a.px, r, a.nF, smem);
+    else if (r < a.nF + a.nB) bwd_role(a.b, a.px, r - a.nF, a.nB, smem);
+    else if (r < a.nF + a.nB + a.nC2) dw_role<2>(a.d, a.px, r - a.nF - a.nB, a.nC2, smem);
+    else dw_role<3>(a.d, a.px, r - a.nF - a.nB - a.nC2, a.nC13, smem);
+    if (threadIdx.x == 0) prog(a.px, 7, (clock64() - t0) >> 10);
 }
 
 // ------------------------------------------------------------------------------------------------ loss scale
@@ -1080,15 +1146,15 @@ __global__ void scale_from_max_kernel(float* __restrict__ scale) {
 
 // ------------------------------------------------------------------------------------------------ host side
 struct HpWorkspace {       // byte offsets inside the caller's workspace for a chunk padded to `np` samples
-    int64_t h1, h2, dl2, dl1, a1t, d3t, m1, m2, logits, scale, img, bimg, total;
+    int64_t h1, h2, dl2, d3t, m1, m2, logits, scale, img, bimg, total;
 };
 static HpWorkspace hp_workspace(int64_t chunk) {
     HpWorkspace w;
     const int64_t np = (chunk + TC_M - 1) / TC_M * TC_M;
     const int64_t act = np / 64 * ACT_TILE_BYTES, small = np / 64 * SMALL_TILE_BYTES;
     int64_t o = 0;
-    w.h1 = o; o += act; w.h2 = o; o += act; w.dl2 = o; o += act; w.dl1 = o; o += act;
-    w.a1t = o; o += small; w.d3t = o; o += small;
+    w.h1 = o; o += act; w.h2 = o; o += act; w.dl2 = o; o += act;
+    w.d3t = o; o += small;
     w.m1 = o; o += np * 32; w.m2 = o; o += np * 32;
     w.logits = o; o += np * 16;
     w.scale = o; o += 1024;
@@ -1138,7 +1204,7 @@ int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
     { int st = ensure_hp_image(h); if (st != B2048_OK) return st; }
     hp_prepare_kernel<<<64, 256, 0, stream>>>(mlp->W[0], mlp->b[0], mlp->W[1], mlp->b[1], mlp->W[2], mlp->b[2], mlp->dims[3], h->hp_image);
     FwdHpArgs f;
-    f.img = h->hp_image; f.board = board; f.out = out; f.h1 = nullptr; f.h2 = nullptr; f.a1t = nullptr; f.m1 = nullptr; f.m2 = nullptr;
+    f.img = h->hp_image; f.board = board; f.out = out; f.h1 = nullptr; f.h2 = nullptr; f.m1 = nullptr; f.m2 = nullptr;
     f.n = n; f.n_out = mlp->dims[3]; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale;
     f.debug_clock = nullptr;
     static long long* dbg_buf = nullptr;
@@ -1167,7 +1233,7 @@ int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t
 
 // Same contract as the fp32 body of b2048_mlp_backward (grads accumulated, flat layout W_0, b_0, W_1, b_1, ...).
 // The whole update of n samples as ONE persistent cooperative launch (see PipeCtx): the SMs are split into forward,
-// backward and dW roles; R tile slots of images (R x 276 KB, L2-resident) connect them.
+// backward and dW roles; R tile slots of images (R x 206 KB, L2-resident) connect them.
 static int launch_backward_hp_piped(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                                     const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                                     uint8_t* ws, int64_t R, cudaStream_t stream) {
@@ -1199,27 +1265,28 @@ static int launch_backward_hp_piped(b2048_handle* h, const uint64_t* board, cons
         a.px.progress = dptr;
     }
     a.f.img = ws + w.img; a.f.board = board; a.f.out = reinterpret_cast<float*>(ws + w.logits);
-    a.f.h1 = ws + w.h1; a.f.h2 = ws + w.h2; a.f.a1t = ws + w.a1t;
+    a.f.h1 = ws + w.h1; a.f.h2 = ws + w.h2;
     a.f.m1 = reinterpret_cast<uint64_t*>(ws + w.m1); a.f.m2 = reinterpret_cast<uint64_t*>(ws + w.m2);
     a.f.n = n; a.f.n_out = n_out; a.f.obs_mode = mlp->obs_mode; a.f.obs_scale = mlp->obs_log2_scale; a.f.debug_clock = nullptr;
     a.b.img = ws + w.bimg; a.b.logits = a.f.out; a.b.m1 = a.f.m1; a.b.m2 = a.f.m2;
-    a.b.mask_flags = mask_flags; a.b.action = action; a.b.coef = coef; a.b.scale = scale;
-    a.b.dl2 = ws + w.dl2; a.b.dl1 = ws + w.dl1; a.b.d3t = ws + w.d3t;
-    a.b.n = n; a.b.head_mode = head_mode; a.b.n_out = n_out; a.b.debug_clock = nullptr;
+    a.b.board = board; a.b.mask_flags = mask_flags; a.b.action = action; a.b.coef = coef; a.b.scale = scale;
+    a.b.dl2 = ws + w.dl2; a.b.d3t = ws + w.d3t;
+    a.b.n = n; a.b.head_mode = head_mode; a.b.n_out = n_out; a.b.obs_mode = mlp->obs_mode; a.b.obs_scale = mlp->obs_log2_scale;
+    a.b.debug_clock = nullptr;
     float* gW1 = grads;
     float* gb1 = gW1 + 16 * TC_H;
     float* gW2 = gb1 + TC_H;
     float* gb2 = gW2 + TC_H * TC_H;
     float* gW3 = gb2 + TC_H;
-    a.b.gb3 = gW3 + TC_H * n_out;
-    a.d.h1 = a.f.h1; a.d.h2 = a.f.h2; a.d.dl2 = a.b.dl2; a.d.dl1 = a.b.dl1; a.d.a1t = a.f.a1t; a.d.d3t = a.b.d3t;
-    a.d.gW1 = gW1; a.d.gb1 = gb1; a.d.gW2 = gW2; a.d.gb2 = gb2; a.d.gW3 = gW3; a.d.inv_scale = scale + 1;
+    a.b.gb3 = gW3 + TC_H * n_out; a.b.gW1 = gW1; a.b.gb1 = gb1;
+    a.d.h1 = a.f.h1; a.d.h2 = a.f.h2; a.d.dl2 = a.b.dl2; a.d.d3t = a.b.d3t;
+    a.d.gW2 = gW2; a.d.gb2 = gb2; a.d.gW3 = gW3; a.d.inv_scale = scale + 1;
     a.d.n_tiles = n_tiles; a.d.n_out = n_out;
-    // role split: per tile the forward role needs ~14 K cycles, the backward role ~7.5 K, each dW role ~3 K
+    // role split: per tile the forward role needs ~14 K cycles, the backward role ~7.5 K, the dW2 role ~4.5 K, the dW3 role ~2.5 K (both bound by ~30 B/clk of L2 -> shared-memory bulk copies per SM)
     const int S = h->num_sms;
     a.nB = (h->pipe_split & 0xFF) ? (h->pipe_split & 0xFF) : (S * 27 + 50) / 100;
     a.nC2 = ((h->pipe_split >> 8) & 0xFF) ? ((h->pipe_split >> 8) & 0xFF) : (S * 11 + 50) / 100;
-    a.nC13 = ((h->pipe_split >> 16) & 0xFF) ? ((h->pipe_split >> 16) & 0xFF) : (S * 11 + 50) / 100;
+    a.nC13 = ((h->pipe_split >> 16) & 0xFF) ? ((h->pipe_split >> 16) & 0xFF) : (S * 8 + 50) / 100;
     a.nF = S - a.nB - a.nC2 - a.nC13;
     if (a.nF < 1 || a.nB < 1 || a.nC2 < 1 || a.nC13 < 1) return fail(B2048_ERR_INVALID, "update pipeline: bad role split");
     void* params[] = {&a};
@@ -1240,6 +1307,19 @@ static int launch_backward_hp_piped(b2048_handle* h, const uint64_t* board, cons
             fflush(stderr);
             _exit(3);
         }
+        cudaStreamSynchronize(stream);
+        long long tot[4] = {0, 0, 0, 0}, wt[4] = {0, 0, 0, 0};
+        int cnt[4] = {0, 0, 0, 0};
+        for (int b = 0; b < S; ++b) {
+            const int* q = prog_host + b * 8;
+            const int role = q[0] / 100 - 1;
+            if (role < 0 || role > 3) continue;
+            cnt[role]++; tot[role] += q[7]; wt[role] += q[6] > 0 ? q[6] : 0;
+        }
+        const char* nm[4] = {"forward", "backward+dW1", "dW2", "dW3"};
+        for (int r = 0; r < 4; ++r)
+            if (cnt[r]) fprintf(stderr, "[update pipeline] %-13s %3d CTAs: %lld K cycles in the kernel, %lld K of them waiting for flags (per CTA)\n",
+                                nm[r], cnt[r], tot[r] / cnt[r], wt[r] / cnt[r]);
     }
     return check_cuda(e, "update_pipe_kernel launch");
 }
@@ -1258,7 +1338,7 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
     uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
     {   // large batches: the persistent pipeline with an L2-resident ring of tile slots
         const int64_t n_tiles = (n + TC_M - 1) / TC_M;
-        const int64_t Rmax = (h->pipe_split >> 24) ? (int64_t)(h->pipe_split >> 24) * 16 : 288;   // 288 slots x 276 KB = 80 MB of the 126 MB L2
+        const int64_t Rmax = (h->pipe_split >> 24) ? (int64_t)(h->pipe_split >> 24) * 16 : 288;   // 288 slots x 206 KB = 59 MB of the 126 MB L2
         const int64_t R = n_tiles < Rmax ? n_tiles : Rmax;
         const int64_t need = hp_workspace(R * TC_M).total + n_tiles * 16 + 2048;
         if (!(h->debug & (1u << B2048_DBG_NO_UPDATE_PIPE)) && n_tiles >= 4 * (int64_t)h->num_sms && need <= workspace_bytes)
@@ -1280,7 +1360,7 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
         FwdHpArgs f;
         f.img = img; f.board = board + c0; f.out = reinterpret_cast<float*>(ws + w.logits);
-        f.h1 = ws + w.h1; f.h2 = ws + w.h2; f.a1t = ws + w.a1t;
+        f.h1 = ws + w.h1; f.h2 = ws + w.h2;
         f.m1 = reinterpret_cast<uint64_t*>(ws + w.m1); f.m2 = reinterpret_cast<uint64_t*>(ws + w.m2);
         f.n = cn; f.n_out = n_out; f.obs_mode = mlp->obs_mode; f.obs_scale = mlp->obs_log2_scale; f.debug_clock = nullptr;
         fwd_hp_kernel<<<grid, FH_THREADS, FS_TOTAL, stream>>>(f);
@@ -1291,8 +1371,10 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         b.mask_flags = mask_flags ? mask_flags + c0 : nullptr;
         b.action = action ? action + c0 : nullptr;
         b.coef = coef + c0; b.scale = scale;
-        b.dl2 = ws + w.dl2; b.dl1 = ws + w.dl1; b.d3t = ws + w.d3t; b.gb3 = gb3;
-        b.n = cn; b.head_mode = head_mode; b.n_out = n_out; b.debug_clock = nullptr;
+        b.board = board + c0;
+        b.dl2 = ws + w.dl2; b.d3t = ws + w.d3t; b.gb3 = gb3; b.gW1 = gW1; b.gb1 = gb1;
+        b.n = cn; b.head_mode = head_mode; b.n_out = n_out; b.obs_mode = mlp->obs_mode; b.obs_scale = mlp->obs_log2_scale;
+        b.debug_clock = nullptr;
         static long long* dbg_buf = nullptr;
         if ((h->debug & (1u << B2048_DBG_TC_CLOCKS)) && c0 == 0) {
             if (!dbg_buf) cudaMalloc(&dbg_buf, 64 * sizeof(long long));
@@ -1321,9 +1403,6 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         if ((st = launch_atb<256>(h, g, stream)) != B2048_OK) return st;
         // dW3 = H2^T d3
         g.A = f.h2; g.B = b.d3t; g.C = gW3; g.ldm = n_out; g.ldn = 1; g.n_valid = n_out; g.colsum = nullptr; g.colsum_of_b = 0;
-        if ((st = launch_atb<16>(h, g, stream)) != B2048_OK) return st;
-        // dW1^T = DL1^T A1, db1 = column sums of DL1
-        g.A = b.dl1; g.B = f.a1t; g.C = gW1; g.ldm = 1; g.ldn = TC_H; g.n_valid = 16; g.colsum = gb1; g.colsum_of_b = 0;
         if ((st = launch_atb<16>(h, g, stream)) != B2048_OK) return st;
     }
     return B2048_OK;
