@@ -1,6 +1,6 @@
 """Stress run of the barrier-heavy tensor-core kernels: many shapes of the fused persistent rollout kernel against the
-two-kernel loop (bit-exact on the live region), and the tensor-core update against the fp32 kernels, repeated with
-different seeds.  A protocol race would show up as a mismatch or a hang (run it under `timeout`)."""
+two-kernel loop (bit-exact on the live region), and the default tensor-core update (split-fp16 forward; one persistent
+pipeline launch for large batches) against the fp32 kernels at the 1e-2 bar, repeated with different seeds.  A protocol race would show up as a mismatch or a hang (run it under `timeout`)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, b2048
@@ -38,48 +38,18 @@ while time.time() < t_end:
         n_cases += 1
         print(f"case {n_cases}: B={B} horizon={horizon} max_steps={max_steps} greedy={greedy} T={T} rollout OK", flush=True)
         continue
-    # tensor-core update vs fp32 on the fused rollout
+    # default tensor-core update (float32-grade forward, the persistent pipeline for large batches) vs the fp32 kernels on the
+    # fused rollout: within the 1e-2 parity bar on every case (round 1's single-bf16 path was at 0.1-0.3 here)
     th0 = agent._actor.theta.clone()
-    i1 = agent.update_from_rollout(ro, precision=1)
+    i1 = agent.update_from_rollout(ro, precision="auto")
     d1 = agent._actor.theta - th0
     agent._actor.theta.copy_(th0)
     i0 = agent.update_from_rollout(ro, precision=0)
     d0 = agent._actor.theta - th0
     rel = float((d1 - d0).norm() / d0.norm())
     gn = abs(i1["actor_grad_norm"] - i0["actor_grad_norm"]) / i0["actor_grad_norm"]
-    # The bf16-rounded network is a slightly different policy than the float32 one: on a weak,
-    # heavily cancelling gradient the two updates differ by 5-40 %.  A protocol race would give NaNs or O(1) norm errors;
-    # kernel exactness is what tests/test_learn_tc_gpu.py pins against the bf16-rounding oracle.
     assert np.isfinite(rel) and np.isfinite(gn), ("update", B, rel, gn)
-    if gn > 0.08 or rel > 0.3:
-        # an unusually large bf16-vs-fp32 gap: make sure it is the arithmetic, i.e. that the bf16-rounding oracle
-        # reproduces the tensor-core gradient of exactly this case
-        import ctypes as C
-        from oracle import learner
-        from b2048 import _lib
-        T_ = ro.T
-        cfc = agent._scratch["coef"][: T_ * B]
-        lv = (torch.arange(T_, device="cuda").unsqueeze(1) < ro.length.unsqueeze(0)).reshape(-1)
-        bd = ro.boards[:T_].reshape(-1)[lv]; fl = ro.flags[:T_].reshape(-1)[lv]; ac = ro.actions[:T_].reshape(-1)[lv]; cf = cfc[lv].clone()
-        n = int(bd.numel())
-        if n <= 1_500_000:
-            agent._actor.theta.copy_(th0)
-            net = agent._actor
-            lib = _lib.load()
-            net.grad.zero_()
-            wsf = int(lib.b2048_backward_workspace_floats(C.byref(net.desc), n))
-            ws = torch.zeros(wsf, dtype=torch.float32, device="cuda")
-            p = lambda t: C.c_void_p(t.data_ptr())
-            _lib.check(lib.b2048_mlp_backward(agent._h, p(bd), p(fl), p(ac), p(cf), C.byref(net.desc), p(net.grad), n, 0, p(ws), wsf,
-                                              n, 1, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bwd")
-            torch.cuda.synchronize()
-            g_tc = net.grad.cpu().numpy()
-            X = learner.encode(bd.cpu().numpy().view(np.uint64), "log2", 0.0625)
-            gW, gb, _ = learner.backprop_bf16(agent.params, X, fl.cpu().numpy() & 0xF, ac.cpu().numpy().astype(np.int64), cf.cpu().numpy(), 0)
-            g_or = np.concatenate([np.concatenate([w.reshape(-1), b.reshape(-1)]) for w, b in zip(gW, gb)])
-            e = float(np.linalg.norm(g_tc - g_or) / np.linalg.norm(g_or))
-            print(f"   large gap (rel {rel:.3f}, grad-norm {gn:.3f}) on {n} samples: tc vs bf16-rounding oracle {e:.2e}", flush=True)
-            assert e < 5e-3, ("tc vs bf16 oracle", e)
+    assert rel < 1e-2 and gn < 1e-2, ("update vs fp32", B, max_steps, rel, gn, i1["precision"])
     n_cases += 1
     print(f"case {n_cases}: B={B} horizon={horizon} max_steps={max_steps} greedy={greedy} T={T} update rel {rel:.3f} OK", flush=True)
 print("stress OK:", n_cases, "cases")
