@@ -8,6 +8,54 @@ import numpy as np, torch, b2048
 torch.cuda.set_device(0)
 KW = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", base_reward_scale=0.5)
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+
+
+def _samples(agent, ro):
+    T, B = ro.T, ro.B
+    lv = (torch.arange(T, device="cuda").unsqueeze(1) < ro.length.unsqueeze(0)).reshape(-1)
+    cf = agent._scratch["coef"][: T * B][lv]
+    return ro.boards[:T].reshape(-1)[lv], ro.flags[:T].reshape(-1)[lv], ro.actions[:T].reshape(-1)[lv].long(), cf
+
+
+def grad_of(agent, ro, th0, prec):
+    """flat actor gradient (before clipping) of update_from_rollout in the given precision, parameters restored"""
+    agent._actor.theta.copy_(th0)
+    agent.agent_config.max_grad_norm, keep = 1e30, agent.agent_config.max_grad_norm
+    agent.update_from_rollout(ro, precision=prec)
+    agent.agent_config.max_grad_norm = keep
+    g = agent._actor.grad.clone().double()
+    agent._actor.theta.copy_(th0)
+    return g
+
+
+def grad_float64(agent, ro, th0):
+    """the same gradient in float64 (torch on the device, chunked): sum_s coef_s d log pi(a_s | s_s) / d theta"""
+    agent._actor.theta.copy_(th0)
+    agent.update_from_rollout(ro, precision=0)          # fills the coefficient buffer
+    agent._actor.theta.copy_(th0)
+    bd, fl, ac, cf = _samples(agent, ro)
+    P = agent.params
+    W = [torch.from_numpy(w).cuda().double() for w in P["W"]]
+    b = [torch.from_numpy(x).cuda().double() for x in P["b"]]
+    sh = torch.arange(16, device="cuda", dtype=torch.int64) * 4
+    gW = [torch.zeros_like(w) for w in W]; gb = [torch.zeros_like(x) for x in b]
+    for c0 in range(0, bd.numel(), 1 << 20):
+        sl = slice(c0, c0 + (1 << 20))
+        X = (((bd[sl].unsqueeze(1) >> sh) & 15).float() * 0.0625).double()     # log2 observations x 0.0625 (exact)
+        z1 = X @ W[0] + b[0]; h1 = z1.clamp_min(0)
+        z2 = h1 @ W[1] + b[1]; h2 = z2.clamp_min(0)
+        lg = (h2 @ W[2] + b[2]).float()                                        # softmax in float32 like the reference
+        legal = ((fl[sl].long().unsqueeze(1) >> torch.arange(4, device="cuda")) & 1).bool()
+        lg = torch.where(legal, lg, torch.full_like(lg, -1e9))
+        p = torch.softmax(lg, dim=1).double()
+        d3 = cf[sl].double().unsqueeze(1) * (torch.nn.functional.one_hot(ac[sl], 4).double() - p)
+        d2 = (d3 @ W[2].T) * (z2 > 0)
+        d1 = (d2 @ W[1].T) * (z1 > 0)
+        for l, (a, d) in enumerate(((X, d1), (h1, d2), (h2, d3))):
+            gW[l] += a.T @ d; gb[l] += d.sum(0)
+    return torch.cat([torch.cat([w.reshape(-1), x]) for w, x in zip(gW, gb)])
+
+
 t_end = time.time() + (float(sys.argv[2]) if len(sys.argv) > 2 else 120.0)
 n_cases = 0
 while time.time() < t_end:
@@ -39,17 +87,20 @@ while time.time() < t_end:
         print(f"case {n_cases}: B={B} horizon={horizon} max_steps={max_steps} greedy={greedy} T={T} rollout OK", flush=True)
         continue
     # default tensor-core update (float32-grade forward, the persistent pipeline for large batches) vs the fp32 kernels on the
-    # fused rollout: within the 1e-2 parity bar on every case (round 1's single-bf16 path was at 0.1-0.3 here)
+    # fused rollout: the unclipped GRADIENT within the 1e-2 parity bar on every case (round 1's single-bf16 path was at
+    # 0.1-0.3 here).  (The parameter step theta' - theta is not compared: at lr 1e-3 it is ~1e-6 per element against
+    # theta ~ 0.1, so its own float32 representation carries ~0.5 % of noise.)
     th0 = agent._actor.theta.clone()
-    i1 = agent.update_from_rollout(ro, precision="auto")
-    d1 = agent._actor.theta - th0
-    agent._actor.theta.copy_(th0)
-    i0 = agent.update_from_rollout(ro, precision=0)
-    d0 = agent._actor.theta - th0
-    rel = float((d1 - d0).norm() / d0.norm())
-    gn = abs(i1["actor_grad_norm"] - i0["actor_grad_norm"]) / i0["actor_grad_norm"]
-    assert np.isfinite(rel) and np.isfinite(gn), ("update", B, rel, gn)
-    assert rel < 1e-2 and gn < 1e-2, ("update vs fp32", B, max_steps, rel, gn, i1["precision"])
+    ghp = grad_of(agent, ro, th0, "auto")
+    g32 = grad_of(agent, ro, th0, 0)
+    rel = float((ghp - g32).norm() / g32.norm())
+    note = ""
+    if rel > 3e-3:
+        # Weak, heavily cancelling gradient: both against the float64 gradient of the same samples (torch, on the device)
+        g64 = grad_float64(agent, ro, th0)
+        e32, ehp = float((g32 - g64).norm() / g64.norm()), float((ghp - g64).norm() / g64.norm())
+        note = f" [vs float64: fp32 kernels {e32:.1e}, tensor cores {ehp:.1e}]"
+    assert np.isfinite(rel) and rel < 1e-2, ("gradient vs fp32 kernels", B, max_steps, rel, note)
     n_cases += 1
-    print(f"case {n_cases}: B={B} horizon={horizon} max_steps={max_steps} greedy={greedy} T={T} update rel {rel:.3f} OK", flush=True)
+    print(f"case {n_cases}: B={B} horizon={horizon} max_steps={max_steps} greedy={greedy} T={T} gradient rel {rel:.4f}{note} OK", flush=True)
 print("stress OK:", n_cases, "cases")
