@@ -10,6 +10,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.cuda.set_device(0)
 lib = _lib.load()
+if os.environ.get("NO_PIPE"):
+    b2048.debug_set("no_update_pipe", True)
 env = b2048.Batched2048Env(1, b2048.Game2048EnvConfig(obs_mode="log2", obs_log2_scale=0.0625))
 agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
                              b2048.ReinforceAgentConfig())

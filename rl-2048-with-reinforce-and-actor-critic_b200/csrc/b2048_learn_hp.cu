@@ -1341,8 +1341,13 @@ int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* ma
         const int64_t Rmax = (h->pipe_split >> 24) ? (int64_t)(h->pipe_split >> 24) * 16 : 288;   // 288 slots x 206 KB = 59 MB of the 126 MB L2
         const int64_t R = n_tiles < Rmax ? n_tiles : Rmax;
         const int64_t need = hp_workspace(R * TC_M).total + n_tiles * 16 + 2048;
-        if (!(h->debug & (1u << B2048_DBG_NO_UPDATE_PIPE)) && n_tiles >= 4 * (int64_t)h->num_sms && need <= workspace_bytes)
-            return launch_backward_hp_piped(h, board, mask_flags, action, coef, mlp, grads, n, head_mode, ws, R, stream);
+        if (!(h->debug & (1u << B2048_DBG_NO_UPDATE_PIPE)) && n_tiles >= 4 * (int64_t)h->num_sms && need <= workspace_bytes) {
+            const int st = launch_backward_hp_piped(h, board, mask_flags, action, coef, mlp, grads, n, head_mode, ws, R, stream);
+            if (st == B2048_OK) return st;
+            // the cooperative launch was refused (e.g. the device cannot hold all CTAs at once because it is shared): nothing of
+            // the pipeline has run, so the chunked kernel sequence below does the same work
+            cudaGetLastError();
+        }
     }
     const HpWorkspace w = hp_workspace(chunk);
     uint8_t* img = ws + w.img;

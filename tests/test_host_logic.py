@@ -3,12 +3,13 @@
 bit-exactly with the independent cell-by-cell CPU oracle.  No GPU needed."""
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import pytest
 
 import oracle
-from helpers import ENV_CONFIGS, GOLDEN, P, full_env_kwargs, host_check_lib, random_boards
+from helpers import ENV_CONFIGS, GOLDEN, P, ROOT, full_env_kwargs, host_check_lib, random_boards
 
 
 def test_row_tables_match_reference_fixture():
@@ -201,3 +202,40 @@ def test_episode_rank_weights_vs_reference_fixture():
             vals, counts = np.unique(r, return_counts=True)
             uniq = np.isin(r, vals[counts == 1])
             assert np.allclose(got[uniq], want[uniq], rtol=1e-6), k
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_ncu_summary():
+    """bench.py's roofline.traffic comes from profiles/*.csv (dram__bytes_read + dram__bytes_write per launch), not from a literal."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t, src = bench.profile_traffic(["r02_ncu_step_fast_kernel.csv", "r01_ncu_step_fast_kernel.csv"], "step_fast")
+    assert src is not None and src.startswith("profiles/") and 1.8e7 < t < 2.4e7          # ~19 MB per 1 M-board launch
+    assert bench.profile_traffic(["does_not_exist.csv"]) == (None, None)
+    # unit handling: the update pipeline's summary mixes Mbyte and Gbyte
+    t2, _ = bench.profile_traffic(["r02_ncu_update_pipe_kernel.csv"], "update_pipe")
+    assert t2 is not None and 1e9 < t2 < 4e9
+
+
+def test_debug_options_match_the_header():
+    """_lib.DEBUG_OPTIONS mirrors the B2048_DBG_* enum of include/b2048.h."""
+    import re
+    sys.path.insert(0, ROOT)
+    import b2048
+    from b2048 import _lib
+    hdr = open(os.path.join(ROOT, "include", "b2048.h")).read()
+    enum = dict((m.group(1).lower(), int(m.group(2))) for m in re.finditer(r"B2048_DBG_(?:PARAM_)?([A-Z_]+) = (\d+)", hdr))
+    for name, val in _lib.DEBUG_OPTIONS.items():
+        assert enum[name] == val, (name, val, enum)
+    assert enum["count"] == 1 + max(v for k, v in _lib.DEBUG_OPTIONS.items() if k != "pipe_split")
+
+
+def test_trainer_tile_histogram_is_the_references_list():
+    """max_tile_counts is a list over [16, 32, ..., 4096] like runner.py:557, :617-624 (tiles outside the bins are not counted)."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from b2048 import trainer
+    exps = torch.tensor([4, 4, 5, 11, 12, 3, 13], dtype=torch.uint8)      # 16, 16, 32, 2048, 4096, 8, 8192
+    assert trainer.tile_histogram(exps) == [2, 1, 0, 0, 0, 0, 0, 1, 1]
+    assert trainer.TILE_BINS == [16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
