@@ -1,5 +1,6 @@
-"""Small pass over the tensor-core kernels for compute-sanitizer (memcheck): fused rollout, TC update (actor and
-critic), symmetry kernel.  Sizes are the smallest that take the tensor-core paths."""
+"""Small pass over the tensor-core kernels for compute-sanitizer (memcheck): fused rollout, the default (split-fp16) update in
+its chunked form (actor and critic, value forward) and as the persistent pipeline, the single-bf16 opt-in, the symmetry
+kernel.  Sizes are the smallest that take each path."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, b2048
@@ -9,9 +10,18 @@ env = b2048.Batched2048Env(4096 + 37, b2048.Game2048EnvConfig(**kw), seed=3)
 agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
                              b2048.ReinforceAgentConfig(use_critic=True, optimizer="adam", baseline_mode="batch_norm", augmentation=False))
 ro = agent.rollout_many(env, precision=1)
-info = agent.update_from_rollout(ro, precision=1)
+info = agent.update_from_rollout(ro)                    # float32-grade tensor-core path; n < 4 x 148 tiles: chunked kernels
+mode = info["precision"]
+info1 = agent.update_from_rollout(ro, precision=1)      # single-bf16 opt-in
 ro2 = agent.rollout_many(env, horizon=8, precision=1)
 from b2048 import symmetry
 ro3 = symmetry.augment_rollout(ro2)
+# the persistent pipeline: >= 4 x 148 tiles of 128 samples, more tiles than ring slots would need n > 36,864: take ~80 K samples
+env2 = b2048.Batched2048Env(4096, b2048.Game2048EnvConfig(**kw), seed=4)
+agent2 = b2048.ReinforceAgent(env2, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                              b2048.ReinforceAgentConfig(baseline_mode="batch"))
+ro4 = agent2.rollout_many(env2, precision=1)
+info2 = agent2.update_from_rollout(ro4)
 torch.cuda.synchronize()
-print("memcheck case OK", ro.T, info["actor_grad_norm"], info["critic_grad_norm"], ro3.B)
+print("memcheck case OK", ro.T, mode, info["actor_grad_norm"], info["critic_grad_norm"], info1["actor_grad_norm"], ro3.B,
+      int(ro4.length.sum()), info2["actor_grad_norm"])
