@@ -602,16 +602,25 @@ class ReinforceAgent:
                                                 _ptr(adv), _ptr(coef), _ptr(stats), pre, _ptr(ep_mean), _stream()),
                            "b2048_advantages")
 
+        fell_back = []
+
         def backward(net: DeviceMLP, cf: torch.Tensor, head_mode: int):
             if live is not None:
                 cf = cf.index_select(0, live)
-            net.grad.zero_()
             ws_floats = int(lib.b2048_backward_workspace_floats(C.byref(net.desc), min(chunk, n)))
             ws = self._buf("bwd_ws", (ws_floats,), torch.float32)
-            with torch.cuda.device(dev):
-                _lib.check(lib.b2048_mlp_backward(h, _ptr(boards), _ptr(mflags) if self._use_mask else None, _ptr(acts),
-                                                  _ptr(cf), C.byref(net.desc), _ptr(net.grad), n, head_mode, _ptr(ws),
-                                                  ws_floats, min(chunk, n), prec, _stream()), "b2048_mlp_backward")
+            for p_try in ((prec, 0) if prec in (2, 3) else (prec,)):
+                net.grad.zero_()
+                with torch.cuda.device(dev):
+                    _lib.check(lib.b2048_mlp_backward(h, _ptr(boards), _ptr(mflags) if self._use_mask else None, _ptr(acts),
+                                                      _ptr(cf), C.byref(net.desc), _ptr(net.grad), n, head_mode, _ptr(ws),
+                                                      ws_floats, min(chunk, n), p_try, _stream()), "b2048_mlp_backward")
+                # The split-fp16 path keeps activations and (loss-scaled) deltas in fp16: a network whose activations leave
+                # the fp16 range (> 65504) would give a non-finite gradient.  Never apply that: redo the pass in fp32.
+                if p_try == 0 or bool(torch.isfinite(net.grad).all()):
+                    break
+                fell_back.append(head_mode)
+                self._logger.warning("tensor-core gradient not finite (fp16 range exceeded); recomputing on the fp32 kernels")
 
         def apply(net: DeviceMLP, lr: float, sign: float, t_adam: int) -> float:
             sumsq = self._buf("sumsq_" + str(sign), (1,), torch.float64)
@@ -625,11 +634,12 @@ class ReinforceAgent:
         if cfg.use_critic and self._critic is not None:
             # critic block (reinforce_agent.py:403-498): V(s_t) for every stored state, TD(0) errors, critic grads
             values = self._buf("values", (T, B), torch.float32)
-            if live is None:
-                self._values(boards, values, prec)
-            else:
-                vc = self._buf("values_c", (n,), torch.float32)
-                self._values(boards, vc, prec)
+            vc = values.view(-1) if live is None else self._buf("values_c", (n,), torch.float32)
+            self._values(boards, vc, prec)
+            if prec in (2, 3) and not bool(torch.isfinite(vc).all()):        # fp16 range exceeded in the value forward
+                fell_back.append(1)
+                self._values(boards, vc, 0)
+            if live is not None:
                 values.zero_()
                 values.view(-1)[live] = vc
             td = self._buf("td", (T, B), torch.float32)
@@ -662,7 +672,7 @@ class ReinforceAgent:
                 self._adam_t_c += 1
             ss_c = apply(self._critic, cfg.critic_learning_rate, -1.0, getattr(self, "_adam_t_c", 0))
         info["advantages"] = adv
-        info["precision"] = self._update_mode_name(prec, n)
+        info["precision"] = self._update_mode_name(prec, n) + (" [fell back to fp32: non-finite fp16 intermediates]" if fell_back else "")
         info["actor_grad_norm"] = float(ss_a.cpu()[0]) ** 0.5
         if ss_c is not None:
             info["critic_grad_norm"] = float(ss_c.cpu()[0]) ** 0.5

@@ -230,3 +230,27 @@ def test_hp_update_pipeline_matches_chunked_kernels_and_oracle(b2048, head_mode,
     a, b = split_grads(g_pipe, n_out), split_grads(g_or, n_out)
     for l in range(3):
         assert rel_err(a[l][0], b[l][0]) < 1e-2 and rel_err(a[l][1], b[l][1]) < 1e-2, (l, rel_err(a[l][0], b[l][0]), rel_err(a[l][1], b[l][1]))
+
+
+def test_auto_update_never_applies_a_non_finite_fp16_gradient(b2048):
+    """A network whose hidden activations exceed the fp16 range (first-layer weights scaled by 1e6) makes the split-fp16
+    path produce non-finite values; the default update detects that and redoes the pass on the fp32 kernels."""
+    n = 8192
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 12
+    benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=9, gid0=0)
+    agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                 b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode="batch", learning_rate=1e-3))
+    ro = agent.rollout_many(benv, precision=0)
+    p = agent.params
+    p["W"][0] = (p["W"][0] * 1e6).astype(np.float32)
+    p["W"][1] = (p["W"][1] * 1e-6).astype(np.float32)
+    agent.params = p
+    th0 = agent._actor.theta.clone()
+    info = agent.update_from_rollout(ro, precision="auto")
+    assert "fell back to fp32" in info["precision"], info["precision"]
+    d_auto = (agent._actor.theta - th0).cpu().numpy()
+    agent._actor.theta.copy_(th0)
+    info0 = agent.update_from_rollout(ro, precision=0)
+    d_32 = (agent._actor.theta - th0).cpu().numpy()
+    assert np.isfinite(d_auto).all() and np.isfinite(info["actor_grad_norm"])
+    assert rel_err(d_auto, d_32) < 1e-4
