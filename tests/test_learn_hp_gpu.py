@@ -254,3 +254,36 @@ def test_auto_update_never_applies_a_non_finite_fp16_gradient(b2048):
     d_32 = (agent._actor.theta - th0).cpu().numpy()
     assert np.isfinite(d_auto).all() and np.isfinite(info["actor_grad_norm"])
     assert rel_err(d_auto, d_32) < 1e-4
+
+
+def test_full_size_actor_critic_update_auto_vs_fp32(b2048):
+    """BASELINE.json configs[3] size (262,144 boards, actor + separate critic, TD(0), Adam): the default tensor-core update
+    (two pipeline launches + the float32-grade value forward) against the fp32 kernels on the same rollout — TD errors to 1e-4,
+    both unclipped gradients to 1e-2."""
+    n = 262144
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 40
+    benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=77, gid0=0)
+    agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                 b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode="batch_norm", learning_rate=1e-4,
+                                                            critic_learning_rate=5e-4, use_critic=True, optimizer="adam",
+                                                            model_seed=2, max_grad_norm=1e30))
+    ro = agent.rollout_many(benv, precision="auto")
+    st = agent.save_state()
+    outs = []
+    for prec in ("auto", 0):
+        agent.load_state(st)
+        info = agent.update_from_rollout(ro, precision=prec)
+        outs.append((agent._actor.grad.clone(), agent._critic.grad.clone(), info["td"].clone(), info["precision"]))
+    (ga1, gc1, td1, m1), (ga0, gc0, td0, m0) = outs
+    ea = float((ga1 - ga0).norm() / ga0.norm()); ec = float((gc1 - gc0).norm() / gc0.norm())
+    et = float((td1 - td0).norm() / td0.norm())
+    print(f"configs[3] size, {int(ro.length.sum())} samples, {m1}: actor grad {ea:.2e}, critic grad {ec:.2e}, td {et:.2e} vs fp32 kernels")
+    assert m1.startswith("fp16 split tcgen05") and "fell back" not in m1
+    assert et < 1e-4 and ea < 1e-2 and ec < 1e-2, (et, ea, ec)
+
+
+def test_sharded_sweep_leg_runs_on_one_gpu(b2048):
+    """The BASELINE.json configs[4] bench leg (16-step episodes via max_steps = 16, one update) at a small size."""
+    r = b2048.bench_sharded_sweep(torch.device("cuda", 0), total_boards=1 << 16, horizon=16, iters=1)
+    assert r["horizon"] == 16 and r["samples"] > 0.9 * 16 * (1 << 16) and np.isfinite(r["actor_grad_norm"])
+    assert r["update_precision"].startswith("fp16 split tcgen05")
