@@ -652,6 +652,8 @@ extern "C" int b2048_create(b2048_handle** out) {
     b2048_handle* h = new b2048_handle();
     h->tc_image = nullptr;
     h->hp_image = nullptr;
+    h->gen_image = nullptr;
+    h->gen_image_bytes = 0;
     h->attrs = 0u;
     h->debug = 0u;
     h->pipe_split = 0u;
@@ -691,6 +693,7 @@ extern "C" int b2048_destroy(b2048_handle* h) {
     cudaFree(h->d_tables);
     if (h->tc_image) cudaFree(h->tc_image);
     if (h->hp_image) cudaFree(h->hp_image);
+    if (h->gen_image) cudaFree(h->gen_image);
     delete h;
     return B2048_OK;
 }

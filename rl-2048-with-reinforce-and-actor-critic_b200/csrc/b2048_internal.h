@@ -14,6 +14,8 @@ struct b2048_handle {
     int smem_optin;      // max opt-in dynamic shared memory per block
     uint8_t* tc_image;   // bf16 weight image of the tensor-core policy kernel (lazily allocated)
     uint8_t* hp_image;   // split-fp16 weight image of the float32-grade forward kernel (lazily allocated)
+    uint8_t* gen_image;  // weight images of the shape-generic tensor-core kernels (b2048_mlp_gen.cu; lazily allocated)
+    size_t gen_image_bytes;
     unsigned pipe_split; // B2048_DBG_PARAM_PIPE_SPLIT: CTAs per role of the update pipeline (0 = default split)
     unsigned debug;      // bit B2048_DBG_* set through b2048_debug_set (test / profiling switches; 0 in production)
     unsigned attrs;      // bit k set: the opt-in shared-memory attribute of kernel family k has been set on THIS device

@@ -28,6 +28,12 @@ int64_t backward_hp_workspace_bytes(int64_t chunk);
 int launch_backward_hp(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                        uint8_t* workspace, int64_t workspace_bytes, int64_t chunk, cudaStream_t stream);
+bool gen_shape_ok(const b2048_mlp_desc* mlp);
+bool gen_supported(const b2048_handle* h, const b2048_mlp_desc* mlp);
+int64_t gen_workspace_bytes(const b2048_mlp_desc* mlp, int64_t chunk);
+int launch_backward_gen(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action, const float* coef,
+                        const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode, uint8_t* workspace, int64_t chunk,
+                        cudaStream_t stream);
 int launch_backward_tc(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action,
                        const float* coef, const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode,
                        uint8_t* workspace, int64_t chunk, cudaStream_t stream);
@@ -499,6 +505,9 @@ extern "C" int64_t b2048_backward_workspace_floats(const b2048_mlp_desc* mlp, in
         const int64_t tc = (backward_tc_workspace_bytes(chunk) + 3) / 4, hp = (backward_hp_workspace_bytes(chunk) + 3) / 4;
         floats = floats > tc ? floats : tc;
         floats = floats > hp ? floats : hp;
+    } else if (gen_shape_ok(mlp)) {
+        const int64_t gn = (gen_workspace_bytes(mlp, chunk) + 3) / 4;
+        floats = floats > gn ? floats : gn;
     }
     return floats;
 }
@@ -525,10 +534,17 @@ extern "C" int b2048_mlp_backward(b2048_handle* h, const uint64_t* board, const 
             return launch_backward_hp(h, board, mask_flags, action, coef, mlp, grads, n, head_mode,
                                       reinterpret_cast<uint8_t*>(workspace), workspace_floats * 4 - 1024, chunk < n ? chunk : n,
                                       (cudaStream_t)stream);
+        // every other ReLU shape with 64-multiple hidden layers (the reference's documented one-hot [256, 128, 64] network):
+        // the shape-generic kernels of b2048_mlp_gen.cu, same arithmetic
+        if (!backward_hp_supported(h, mlp) && gen_supported(h, mlp) && n >= 4096 &&
+            workspace_floats * 4 >= gen_workspace_bytes(mlp, chunk < n ? chunk : n))
+            return launch_backward_gen(h, board, mask_flags, action, coef, mlp, grads, n, head_mode,
+                                       reinterpret_cast<uint8_t*>(workspace), chunk < n ? chunk : n, (cudaStream_t)stream);
         if (precision == 3)
             return fail(B2048_ERR_UNSUPPORTED,
-                        "b2048_mlp_backward: the split-fp16 tcgen05 path needs a 16-256-256-(<=4) ReLU network, log2 "
-                        "observations, n >= 4096 and a workspace of b2048_backward_workspace_floats()");
+                        "b2048_mlp_backward: the split-fp16 tcgen05 path needs a ReLU network with 1-4 hidden layers of 64 / 128 / "
+                        "192 / 256 units, log2 or one-hot observations, n >= 4096 and a workspace of "
+                        "b2048_backward_workspace_floats()");
     }
     if (precision == 1) {                     // single-bf16 tensor cores: an explicit opt-in (5 % class gradient error)
         const bool ok = backward_tc_supported(h, mlp) && n >= 4096 &&

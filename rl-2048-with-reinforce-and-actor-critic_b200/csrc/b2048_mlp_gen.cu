@@ -1,0 +1,877 @@
+// b2048_mlp_gen.cu — the tensor-core MLP kernels for EVERY layer shape the reference's generic MLP is configured with
+// (src/MLP.py:45-94, :159-196: any number of hidden layers, one-hot 272-wide or 16-wide input), in particular its
+// documented one-hot [256, 128, 64] configuration (runner.py:27-47).  The kernels of b2048_policy_tc.cu / b2048_learn_hp.cu
+// are hand-specialised for the runner-default 16-256-256-4 network; these are shape-generic:
+//
+//  gen_mlp_kernel    one persistent CTA per SM walks 128-sample tiles; per tile it runs a short PROGRAM of GEMMs on
+//                    tcgen05: the forward layers and — for an update — the head delta (masked softmax / value head, I/O
+//                    warps) and the backward delta GEMMs, all in one launch.  Activations never leave the SM between
+//                    layers: every GEMM's epilogue (16 warps: TMEM -> bias / ReLU / mask -> fp16) writes the next GEMM's A
+//                    operand into one 128 KB shared-memory buffer of 128-byte-swizzled K-major slabs.  The weights do not
+//                    fit next to it (the one-hot network's split image is 444 KB), so they STREAM: a loader lane pulls
+//                    64-wide K-slab units [N rows x 128 B] from the L2-resident image through a 3-slot ring of bulk copies.
+//                    Forward precision: every product is three MMAs on fp16 hi + lo operands (float32 grade; the one-hot /
+//                    log2 inputs are exact in fp16, so layer 0 needs two), or one MMA (rollout policy steps).  Backward:
+//                    fp16 deltas with a power-of-two loss scale, as in b2048_learn_hp.cu.  For the dW GEMMs the hi halves of
+//                    the activations and the deltas leave as slab images (bulk shared -> global copies by the MMA lane).
+//  gen_dw_kernel     dW_l = A_{l-1}^T DL_l (_backpropagation, src/reinforce_agent.py:639-678) for one layer: the slab
+//                    images are read back MN-major; split over 128-feature M tiles and sample ranges; the one-hot / log2
+//                    input of layer 0 is regenerated from the packed boards in shared memory instead of being stored.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "b2048_device.cuh"
+#include "b2048_internal.h"
+#include "b2048_tc.cuh"
+
+namespace b2 {
+
+constexpr int GN_MAXL = 5;                     // weight matrices: up to 4 hidden layers + the head
+constexpr int GN_MAXU = 64;                    // streamed weight units per tile
+constexpr int GN_MAXG = 2 * GN_MAXL - 1;       // GEMMs per tile (forward + backward)
+constexpr int GN_SLAB = 16384;                 // [128 rows x 128 B], SWIZZLE_128B: 64 features of 128 samples
+constexpr int GN_SLOT = 32768;                 // weight ring slot: one unit of up to 256 rows x 128 B
+constexpr int GN_NSLOT = 3;
+constexpr int GS_A = 0;                        // A buffer: hi slabs 0..3, lo slabs 4..7 (a 272-wide input uses slabs 0..4)
+constexpr int GS_W = 8 * GN_SLAB;
+constexpr int GS_BAR = GS_W + GN_NSLOT * GN_SLOT;
+constexpr int GS_TOTAL = GS_BAR + 256;
+constexpr int GN_THREADS = 22 * 32;            // 16 epilogue warps, MMA warp, weight loader, 4 I/O warps
+constexpr int GN_MASK_WORDS = 4 * 4 * 4 * 128; // per CTA: [hidden layer][slab][column group][row] 16-bit ReLU masks
+static_assert(GS_TOTAL <= 232448, "gen_mlp_kernel exceeds the shared memory of an sm_100 CTA");
+
+struct GUnit {            // one streamed weight unit = the B operand of up to 8 MMAs
+    uint32_t off;         // byte offset inside the weight image
+    uint16_t rows;        // B rows (the MMA's N); bytes = rows * 128
+    uint8_t layer, slab;  // weight matrix, 64-wide K slab
+    uint8_t ksteps;       // valid K = 16 steps of the slab (1..4)
+    uint8_t kind;         // 0: forward hi, 1: forward lo, 2: backward (fp16 W read as [in][out])
+    uint16_t pad;
+};
+struct GGemm {
+    uint8_t u0, nu;       // its units
+    uint8_t layer, bwd;   // forward: z_layer = a_{layer-1} W_layer;  backward: delta_{layer-1} = delta_layer W_layer^T
+    uint16_t N;           // accumulator columns
+    uint8_t a_lo;         // the A operand has a lo half (split forward, layer > 0)
+    uint8_t head;         // forward head GEMM: read by the I/O warps
+};
+struct GenProg {
+    GUnit unit[GN_MAXU];
+    GGemm gemm[GN_MAXG];
+    int n_units, n_gemm, L, fb, split;
+    int kin, in_slabs, obs_mode, n_out;
+    float obs_scale;
+    int width[GN_MAXL];   // accumulator width of layer l (hidden: its size; head: 16)
+    uint32_t img_bytes;
+};
+
+struct GenArgs {
+    GenProg p;
+    const float* bias[GN_MAXL];
+    const uint8_t* img;
+    const uint64_t* board;
+    int64_t n;
+    // ---- forward-only outputs (each nullable)
+    float* out;                 // [n][n_out] head outputs
+    uint8_t* action;
+    float* probs;
+    float* logits;
+    const uint8_t* mask_flags;  // legal masks (sampling and the policy head's softmax)
+    PhiloxKeys keys;
+    uint64_t gid0;
+    uint32_t t;
+    int greedy;
+    // ---- update mode (p.fb)
+    const uint8_t* act_in;
+    const float* coef;
+    const float* scale;         // device float[2]: loss scale S and 1 / S
+    int head_mode;
+    uint8_t* himg[GN_MAXL];     // hi activation images a_{l+1} of the hidden layers, [tile][slab][128 x 128 B]
+    uint8_t* dlimg[GN_MAXL];    // delta images of every layer (head: one slab)
+    float* gb_head;
+    uint16_t* mask_scratch;     // [grid][GN_MASK_WORDS]
+};
+
+__host__ __device__ constexpr uint32_t idesc_h(int m, int n) {          // kind::f16, A/B fp16, D fp32
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// a wait that cannot hang the device: a legitimate wait lasts micro- to milliseconds; after ~2 s the kernel traps
+__device__ __forceinline__ uint32_t gtry(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void gwait(uint32_t bar, uint32_t parity) {
+    if (gtry(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!gtry(bar, parity))
+        if (clock64() - t0 > 4000000000LL) __trap();
+}
+__device__ __forceinline__ uint32_t gpack(float a, float b) {
+    __half2 p = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void g_bulk_load(uint32_t dst, const uint8_t* src, uint32_t bytes, uint32_t bar) {
+    for (uint32_t off = 0; off < bytes; off += 16384u) {
+        const uint32_t sz = bytes - off < 16384u ? bytes - off : 16384u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                     "l"(src + off), "r"(sz), "r"(bar)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void g_bulk_store(uint8_t* dst, uint32_t src, uint32_t bytes) {
+    for (uint32_t off = 0; off < bytes; off += 16384u)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src + off), "r"(16384u)
+                     : "memory");
+}
+
+// Row `row` of the network input as fp16 K-major slab rows (zero-filled): slabs slab0 .. slab0 + nslabs - 1 of the input
+// go to dst, dst + GN_SLAB, ...  one-hot: feature cell * 17 + exponent (env.py:131-150); log2: exponent * scale.
+__device__ __forceinline__ void encode_input_row(uint64_t bd, int row, uint8_t* dst, int slab0, int nslabs, int obs_mode,
+                                                 float scale) {
+    const int sw = row & 7;
+    for (int s = 0; s < nslabs; ++s) {
+        uint8_t* p = dst + s * GN_SLAB + row * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(p + c * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (obs_mode == B2048_OBS_ONEHOT) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int f = c * 17 + (int)((bd >> (4 * c)) & 0xFull);
+            const int s = (f >> 6) - slab0, k = f & 63;
+            if (s >= 0 && s < nslabs)
+                *reinterpret_cast<uint16_t*>(dst + s * GN_SLAB + row * 128 + (((k >> 3) ^ sw) << 4) + (k & 7) * 2) = 0x3C00u;   // 1.0
+        }
+    } else if (slab0 == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float v = (float)((uint32_t)(bd >> (4 * c)) & 0xFu) * scale;
+            *reinterpret_cast<__half*>(dst + row * 128 + (((c >> 3) ^ sw) << 4) + (c & 7) * 2) = __float2half_rn(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight image
+struct GenPrepArgs {
+    GenProg p;
+    const float* W[GN_MAXL];
+    int dims[GN_MAXL + 1];
+    uint8_t* img;
+};
+__global__ void __launch_bounds__(256) gen_prepare_kernel(const __grid_constant__ GenPrepArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int u = 0; u < a.p.n_units; ++u) {
+        const GUnit un = a.p.unit[u];
+        const int K = a.dims[un.layer], N = a.dims[un.layer + 1];
+        const float* W = a.W[un.layer];
+        for (int idx = tid; idx < (int)un.rows * 64; idx += nth) {
+            const int r = idx >> 6, k = idx & 63;
+            float v = 0.0f;
+            if (un.kind < 2) {              // forward: B[n = out feature r][k = in feature]
+                const int kg = un.slab * 64 + k;
+                if (kg < K && r < N) v = W[(size_t)kg * N + r];
+            } else {                        // backward: B[n = in feature r][k = out feature]
+                const int jg = un.slab * 64 + k;
+                if (r < K && jg < N) v = W[(size_t)r * N + jg];
+            }
+            __half hv = __float2half_rn(v);
+            if (un.kind == 1) hv = __float2half_rn(v - __half2float(hv));
+            *reinterpret_cast<__half*>(a.img + un.off + (size_t)r * 128 + (size_t)((((k >> 3) ^ (r & 7))) << 4) + (k & 7) * 2) = hv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the tile kernel
+__global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_constant__ GenArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GS_BAR);
+    const uint32_t w_full0 = s_u32(&bars[0]), w_empty0 = s_u32(&bars[3]);
+    const uint32_t bar_io = s_u32(&bars[6]), bar_epi = s_u32(&bars[7]), bar_acc_e = s_u32(&bars[8]), bar_acc_h = s_u32(&bars[9]),
+                   bar_free = s_u32(&bars[10]);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GS_BAR + 128);
+    const GenProg& P = a.p;
+
+    if (tid == 0) {
+        for (int i = 0; i < GN_NSLOT; ++i) { mbar_init(w_full0 + 8u * i, 1); mbar_init(w_empty0 + 8u * i, 1); }
+        mbar_init(bar_io, 4);        // the I/O warps have written an A operand (the tile's input; its head deltas)
+        mbar_init(bar_epi, 16);      // the epilogue warps have written an A operand
+        mbar_init(bar_acc_e, 1);     // an accumulator for the epilogue warps is complete
+        mbar_init(bar_acc_h, 1);     // the head accumulator (I/O warps) is complete
+        mbar_init(bar_free, 1);      // update mode: the tile's last image has left the A buffer
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_tiles = (a.n + TC_M - 1) / TC_M;
+    const uint32_t sA = s_u32(smem + GS_A), sW = s_u32(smem + GS_W);
+
+    if (warp == 16) {
+        // ============================ MMA lane: GEMM program, image stores ============================
+        if (lane == 0) {
+            uint32_t U = 0, nio = 0, nepi = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int G = 0; G < P.n_gemm; ++G) {
+                    const GGemm gm = P.gemm[G];
+                    const bool from_io = G == 0 || (gm.bwd && G == P.L);
+                    if (from_io) { gwait(bar_io, nio & 1u); ++nio; }
+                    else { gwait(bar_epi, nepi & 1u); ++nepi; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const bool store = P.fb && G > 0;
+                    if (store) {       // the A operand of this GEMM is an image the dW GEMMs read
+                        int nsl;
+                        uint8_t* dst;
+                        if (!gm.bwd) { nsl = P.width[gm.layer - 1] >> 6; dst = a.himg[gm.layer - 1]; }
+                        else { nsl = gm.layer == P.L - 1 ? 1 : (P.width[gm.layer] >> 6); dst = a.dlimg[gm.layer]; }
+                        g_bulk_store(dst + (size_t)tile * nsl * GN_SLAB, sA, (uint32_t)(nsl * GN_SLAB));
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    const uint32_t dcol = tmem_base + (uint32_t)(G & 1) * 256u;
+                    const uint32_t idesc = idesc_h(TC_M, gm.N);
+                    uint32_t acc = 0u;
+                    for (int u = gm.u0; u < gm.u0 + gm.nu; ++u, ++U) {
+                        const GUnit un = P.unit[u];
+                        const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
+                        gwait(w_full0 + 8u * slot, use & 1u);
+                        const uint32_t wb = sW + slot * GN_SLOT, ah = sA + (uint32_t)un.slab * GN_SLAB;
+                        for (int q = 0; q < un.ksteps; ++q) {
+                            umma_f16(dcol, desc_sw128(ah + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, acc);
+                            acc = 1u;
+                        }
+                        if (un.kind == 0 && gm.a_lo)
+                            for (int q = 0; q < un.ksteps; ++q)
+                                umma_f16(dcol, desc_sw128(ah + 4u * GN_SLAB + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, 1u);
+                        umma_commit(w_empty0 + 8u * slot);
+                    }
+                    // the epilogue of this GEMM overwrites the A buffer: the image store must have read it
+                    if (store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    umma_commit(gm.head ? bar_acc_h : bar_acc_e);
+                }
+                if (P.fb) {            // delta_0 (the last epilogue's output) is only an image
+                    gwait(bar_epi, nepi & 1u); ++nepi;
+                    const int nsl = P.width[0] >> 6;
+                    g_bulk_store(a.dlimg[0] + (size_t)tile * nsl * GN_SLAB, sA, (uint32_t)(nsl * GN_SLAB));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(bar_free);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+    } else if (warp == 17) {
+        // ============================ weight loader ============================
+        if (lane == 0) {
+            uint32_t U = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int u = 0; u < P.n_units; ++u, ++U) {
+                    const GUnit un = P.unit[u];
+                    const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
+                    if (use > 0) gwait(w_empty0 + 8u * slot, (use - 1u) & 1u);
+                    const uint32_t bar = w_full0 + 8u * slot, bytes = (uint32_t)un.rows * 128u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                    g_bulk_load(sW + slot * GN_SLOT, a.img + un.off, bytes, bar);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 16) {
+        // ============================ epilogue warps: accumulator -> next A operand ============================
+        const int q = warp & 3, g = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint16_t* msk = a.mask_scratch ? a.mask_scratch + (size_t)blockIdx.x * GN_MASK_WORDS : nullptr;
+        uint8_t* a_row = smem + GS_A + row * 128;
+        uint32_t ne = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int G = 0; G < P.n_gemm; ++G) {
+                const GGemm gm = P.gemm[G];
+                if (gm.head) continue;
+                gwait(bar_acc_e, ne & 1u); ++ne;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t dcol = tlane + (uint32_t)(G & 1) * 256u;
+                const int nsl = gm.N >> 6;
+                if (!gm.bwd) {
+                    const float* bias = a.bias[gm.layer];
+                    for (int s = 0; s < nsl; ++s) {
+                        uint32_t r[16];
+                        tmem_ld16(dcol + (uint32_t)(s * 64 + g * 16), r);
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float z = __uint_as_float(r[i]) + __ldg(bias + s * 64 + g * 16 + i);
+                            m |= (z > 0.0f ? 1u : 0u) << i;
+                            r[i] = __float_as_uint(fmaxf(z, 0.0f));
+                        }
+                        if (msk) msk[((gm.layer * 4 + s) * 4 + g) * 128 + row] = (uint16_t)m;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float x0 = __uint_as_float(r[8 * c + 2 * k]), x1 = __uint_as_float(r[8 * c + 2 * k + 1]);
+                                hi[k] = gpack(x0, x1);
+                                const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi[k]));
+                                lo[k] = gpack(x0 - hf.x, x1 - hf.y);
+                            }
+                            const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                            *reinterpret_cast<uint4*>(a_row + s * GN_SLAB + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (P.split) *reinterpret_cast<uint4*>(a_row + (4 + s) * GN_SLAB + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                    }
+                } else {
+                    // delta_{layer-1} = D . [z_{layer-1} > 0]
+                    for (int s = 0; s < nsl; ++s) {
+                        uint32_t r[16];
+                        tmem_ld16(dcol + (uint32_t)(s * 64 + g * 16), r);
+                        const uint32_t m = msk[(((gm.layer - 1) * 4 + s) * 4 + g) * 128 + row];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int i0 = 8 * c + 2 * k;
+                                const float x0 = (m >> i0) & 1u ? __uint_as_float(r[i0]) : 0.0f;
+                                const float x1 = (m >> (i0 + 1)) & 1u ? __uint_as_float(r[i0 + 1]) : 0.0f;
+                                o[k] = gpack(x0, x1);
+                            }
+                            const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                            *reinterpret_cast<uint4*>(a_row + s * GN_SLAB + sw) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_epi);
+            }
+        }
+    } else {
+        // ============================ I/O warps (18..21), one thread per sample ============================
+        const int q = warp & 3;             // a TMEM load may only touch the lane quarter warp % 4
+        const int row = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t hcol = (uint32_t)((P.L - 1) & 1) * 256u;     // the head GEMM is GEMM L - 1
+        const float* bh = a.bias[P.L - 1];
+        float b4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b4[j] = j < P.n_out ? __ldg(bh + j) : 0.0f;
+        const float S = P.fb ? a.scale[0] : 1.0f;
+        const bool use_mask = a.mask_flags != nullptr;
+        uint32_t lt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int64_t s = tile * TC_M + row;
+            const bool valid = s < a.n;
+            const uint64_t bd = valid ? a.board[s] : 0ull;
+            uint32_t fl = 0xFu, act = 0u;
+            float cf = 0.0f;
+            if (valid) {
+                if (use_mask) fl = a.mask_flags[s];
+                if (P.fb) { cf = a.coef[s]; if (a.act_in) act = a.act_in[s]; }
+            }
+            uint32_t w3 = 0u;
+            if (valid && !P.fb && a.action && !a.greedy) w3 = stream_keyed(a.keys, a.gid0 + (uint64_t)s, a.t, B2048_DOM_STEP).w3;
+            // the A buffer is free: forward-only, the previous tile's head GEMM has completed (waited for below); update mode,
+            // its last image has been read out
+            if (P.fb && lt > 0) gwait(bar_free, (lt - 1u) & 1u);
+            encode_input_row(bd, row, smem + GS_A, 0, P.in_slabs, P.obs_mode, P.obs_scale);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_io);
+            gwait(bar_acc_h, lt & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r4[4];
+            tmem_ld4(tlane + hcol, r4);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            float lg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lg[j] = __uint_as_float(r4[j]) + b4[j];
+            float p[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (!P.fb || a.head_mode == 0) {
+                float m[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m[j] = (j >= P.n_out) ? -INFINITY : ((use_mask && !((fl >> j) & 1u)) ? -1e9f : lg[j]);   // MLP.py:144-146
+                const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { p[j] = expf(m[j] - mx); sum += p[j]; }
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) p[j] *= inv;
+            }
+            if (!P.fb) {
+                if (valid) {
+                    for (int j = 0; j < P.n_out; ++j) {
+                        if (a.out) a.out[s * P.n_out + j] = lg[j];
+                        if (a.logits) a.logits[s * P.n_out + j] = lg[j];
+                        if (a.probs) a.probs[s * P.n_out + j] = p[j];
+                    }
+                    if (a.action) {
+                        uint32_t ac = 0;
+                        if (a.greedy) {      // int(np.argmax(probs * mask)): first maximum wins (reinforce_agent.py:179-185)
+                            float best = -1.0f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float qj = (j < P.n_out && (!use_mask || ((fl >> j) & 1u))) ? p[j] : (j < P.n_out ? 0.0f : -1.0f);
+                                if (qj > best) { best = qj; ac = (uint32_t)j; }
+                            }
+                        } else {             // rng.choice(4, p=probs) as an inverse CDF on the board's Philox word 3 (reinforce_agent.py:187)
+                            const float c0 = p[0], c1 = c0 + p[1], c2 = c1 + p[2], c3 = c2 + p[3];
+                            const float u = ((float)(w3 >> 8) + 0.5f) * (1.0f / 16777216.0f) * c3;
+                            ac = (u >= c0 ? 1u : 0u) + (u >= c1 ? 1u : 0u) + (u >= c2 ? 1u : 0u);
+                            if (!(p[ac] > 0.0f)) {
+                                if (p[3] > 0.0f) ac = 3;
+                                if (p[2] > 0.0f) ac = 2;
+                                if (p[1] > 0.0f) ac = 1;
+                                if (p[0] > 0.0f) ac = 0;
+                            }
+                        }
+                        a.action[s] = (uint8_t)ac;
+                    }
+                }
+            } else {
+                float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (a.head_mode == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < P.n_out) d[j] = cf * ((act == (uint32_t)j ? 1.0f : 0.0f) - p[j]);     // reinforce_agent.py:340-344
+                } else {
+                    d[0] = cf;                                                                        // dLoss/dV * weight
+                }
+                // head deltas as the fp16 A operand of the first backward GEMM (K = 16: chunks 0 and 1 of slab 0) — the head GEMM has
+                // completed, so the A buffer is free
+                uint8_t* a_row = smem + GS_A + row * 128;
+                const int sw = row & 7;
+                *reinterpret_cast<uint4*>(a_row + ((0 ^ sw) << 4)) = make_uint4(gpack(d[0] * S, d[1] * S), gpack(d[2] * S, d[3] * S), 0u, 0u);
+                *reinterpret_cast<uint4*>(a_row + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_io);
+                // head bias gradient (unscaled float32 sum over the warp's 32 samples)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = d[j];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                    if (lane == 0 && j < P.n_out && v != 0.0f) atomicAdd(a.gb_head + j, v);
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 16) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ dW GEMMs
+struct GenDwArgs {
+    const uint8_t* aimg;       // activation image of the layer's input, or NULL: regenerated from the boards (layer 0)
+    const uint64_t* board;
+    int obs_mode;
+    float obs_scale;
+    const uint8_t* bimg;       // delta image of the layer
+    int a_slabs, b_slabs;      // slabs per tile of the two images
+    int N;                     // MMA N: the layer's width (head: 16)
+    int K_real, N_real;        // dW is [K_real][N_real] row-major
+    float* gW;
+    float* gb;                 // nullable (head: accumulated by gen_mlp_kernel)
+    const float* inv_scale;
+    int64_t n_tiles, n;
+    int mtiles, ksplit, stages;
+    uint32_t tmem_cols;
+};
+constexpr int GD_THREADS = 10 * 32;    // loader, MMA, 4 column-sum / read-out warps, 4 input-generator warps
+
+__global__ void __launch_bounds__(GD_THREADS, 1) gen_dw_kernel(const __grid_constant__ GenDwArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int stage_bytes = 2 * GN_SLAB + a.b_slabs * GN_SLAB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.stages * stage_bytes);
+    const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[4]), bar_done = s_u32(&bars[8]);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.stages * stage_bytes + 128);
+    const int mt = (int)blockIdx.x % a.mtiles, ks = (int)blockIdx.x / a.mtiles;
+    const bool gen = a.aimg == nullptr;
+    const int a_have = a.a_slabs - 2 * mt < 2 ? a.a_slabs - 2 * mt : 2;
+    const int ncs = (mt == 0 && a.gb != nullptr) ? a.b_slabs : 0;      // column-sum warps (bias gradient) of this CTA
+    if (tid == 0) {
+        for (int i = 0; i < a.stages; ++i) { mbar_init(full0 + 8u * i, gen ? 5 : 1); mbar_init(empty0 + 8u * i, 1 + ncs); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // a missing second A slab (a 64- or 272-feature input) stays zero for the whole kernel
+    for (int i = tid; i < a.stages * 2 * GN_SLAB / 16; i += GD_THREADS) {
+        const int st = i / (2 * GN_SLAB / 16), o = i % (2 * GN_SLAB / 16);
+        *reinterpret_cast<uint4*>(smem + st * stage_bytes + o * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_my = ks < a.n_tiles ? (a.n_tiles - ks + a.ksplit - 1) / a.ksplit : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int64_t it = 0; it < n_my; ++it) {
+                const int st = (int)(it % a.stages);
+                const int64_t use = it / a.stages, tile = ks + it * a.ksplit;
+                if (use > 0) gwait(empty0 + 8u * st, (uint32_t)(use - 1) & 1u);
+                const uint32_t bar = full0 + 8u * st;
+                const uint32_t ab = gen ? 0u : (uint32_t)(a_have * GN_SLAB), bb = (uint32_t)(a.b_slabs * GN_SLAB);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ab + bb) : "memory");
+                const uint32_t sa = s_u32(smem + st * stage_bytes);
+                if (!gen) g_bulk_load(sa, a.aimg + ((size_t)tile * a.a_slabs + 2 * mt) * GN_SLAB, ab, bar);
+                g_bulk_load(sa + 2u * GN_SLAB, a.bimg + (size_t)tile * a.b_slabs * GN_SLAB, bb, bar);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_h(128, a.N) | kIdescAMn | kIdescBMn;
+            for (int64_t it = 0; it < n_my; ++it) {
+                const int st = (int)(it % a.stages);
+                gwait(full0 + 8u * st, (uint32_t)(it / a.stages) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = s_u32(smem + st * stage_bytes), sb = sa + 2u * GN_SLAB;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)            // 16 samples per MMA; M = 128 features = two slabs, N = a.N
+                    umma_f16(tmem_base, desc_sw128_mn(sa + (uint32_t)kk * 2048u, GN_SLAB), desc_sw128_mn(sb + (uint32_t)kk * 2048u, GN_SLAB),
+                             idesc, (it | kk) ? 1u : 0u);
+                umma_commit(empty0 + 8u * st);
+            }
+            umma_commit(bar_done);
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ---- bias gradient: column sums of the staged delta image (CTAs of M tile 0), then the accumulator read-out
+        const int cw = warp - 2, chunk = lane & 7, rsub = lane >> 3;
+        const float inv = *a.inv_scale;
+        if (cw < ncs) {
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+            for (int64_t it = 0; it < n_my; ++it) {
+                const int st = (int)(it % a.stages);
+                gwait(full0 + 8u * st, (uint32_t)(it / a.stages) & 1u);
+                const uint8_t* x = smem + st * stage_bytes + 2 * GN_SLAB + cw * GN_SLAB;
+#pragma unroll 4
+                for (int r = rsub; r < 128; r += 4) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(x + r * 128 + ((chunk ^ (r & 7)) << 4));
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+                    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+                    acc[0] += f0.x; acc[1] += f0.y; acc[2] += f1.x; acc[3] += f1.y; acc[4] += f2.x; acc[5] += f2.y; acc[6] += f3.x; acc[7] += f3.y;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * st);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                acc[e] += __shfl_xor_sync(0xFFFFFFFFu, acc[e], 8);
+                acc[e] += __shfl_xor_sync(0xFFFFFFFFu, acc[e], 16);
+            }
+            if (lane < 8 && n_my > 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = cw * 64 + chunk * 8 + e;
+                    if (c < a.N_real && acc[e] != 0.0f) atomicAdd(a.gb + c, acc[e] * inv);
+                }
+            }
+        }
+        if (n_my > 0) {
+            gwait(bar_done, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int m = mt * 128 + q * 32 + lane;                    // input feature
+            for (int c0 = 0; c0 < a.N; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tlane + (uint32_t)c0, r);
+                if (m < a.K_real) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float v = __uint_as_float(r[i]) * inv;
+                        if (c0 + i < a.N_real && v != 0.0f) atomicAdd(a.gW + (size_t)m * a.N_real + (c0 + i), v);
+                    }
+                }
+            }
+        }
+    } else if (gen) {
+        // ---- layer 0: the input rows of the tile, regenerated from the packed boards (M tile mt = slabs 2 mt, 2 mt + 1)
+        const int row = (warp - 6) * 32 + lane;
+        for (int64_t it = 0; it < n_my; ++it) {
+            const int st = (int)(it % a.stages);
+            const int64_t use = it / a.stages, tile = ks + it * a.ksplit;
+            const int64_t s = tile * 128 + row;
+            const uint64_t bd = s < a.n ? a.board[s] : 0ull;
+            if (use > 0) gwait(empty0 + 8u * st, (uint32_t)(use - 1) & 1u);
+            encode_input_row(bd, row, smem + st * stage_bytes, 2 * mt, a_have, a.obs_mode, a.obs_scale);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8u * st);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ loss scale
+// S = the power of two that brings max |coef| into [32, 64) (as b2048_learn_hp.cu): scale[0] = S, scale[1] = 1 / S, [2] = bits of max
+__global__ void __launch_bounds__(256) gen_absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f && isfinite(m)) atomicMax(out_bits, __float_as_uint(m));
+}
+__global__ void gen_scale_kernel(float* __restrict__ scale) {
+    const float m = __uint_as_float(reinterpret_cast<uint32_t*>(scale)[2]);
+    int e = 0;
+    if (m > 0.0f) frexpf(m, &e);
+    int sh = 6 - e;
+    sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+    scale[0] = ldexpf(1.0f, sh);
+    scale[1] = ldexpf(1.0f, -sh);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Shapes: 1..4 hidden layers whose sizes are multiples of 64 up to 256, ReLU, log2 (16-wide) or one-hot (272-wide) input,
+// 1..4 outputs.  (Raw observations reach 32768 per input and could leave the fp16 range in the activations.)
+bool gen_shape_ok(const b2048_mlp_desc* mlp) {
+    if (!mlp || mlp->n_layers < 2 || mlp->n_layers > GN_MAXL || mlp->activation != B2048_ACTV_RELU) return false;
+    if (!((mlp->obs_mode == B2048_OBS_LOG2 && mlp->dims[0] == 16) || (mlp->obs_mode == B2048_OBS_ONEHOT && mlp->dims[0] == 272))) return false;
+    for (int l = 1; l < mlp->n_layers; ++l)
+        if (mlp->dims[l] < 64 || mlp->dims[l] > 256 || mlp->dims[l] % 64 != 0) return false;
+    const int n_out = mlp->dims[mlp->n_layers];
+    if (n_out < 1 || n_out > 4) return false;
+    for (int l = 0; l < mlp->n_layers; ++l)
+        if (!mlp->W[l] || !mlp->b[l]) return false;
+    return true;
+}
+bool gen_supported(const b2048_handle* h, const b2048_mlp_desc* mlp) { return gen_shape_ok(mlp) && h->smem_optin >= 227 * 1024; }
+
+static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenProg& p) {
+    memset(&p, 0, sizeof(p));
+    const int L = mlp->n_layers;
+    p.L = L; p.fb = fb ? 1 : 0; p.split = split ? 1 : 0;
+    p.kin = mlp->dims[0]; p.in_slabs = (p.kin + 63) / 64; p.obs_mode = mlp->obs_mode; p.n_out = mlp->dims[L];
+    p.obs_scale = mlp->obs_log2_scale;
+    for (int l = 0; l < L; ++l) p.width[l] = l == L - 1 ? 16 : mlp->dims[l + 1];
+    uint32_t off = 0;
+    int nu = 0, ng = 0;
+    for (int l = 0; l < L; ++l) {            // forward
+        const int K = mlp->dims[l], slabs = (K + 63) / 64;
+        GGemm& g = p.gemm[ng++];
+        g.u0 = (uint8_t)nu; g.layer = (uint8_t)l; g.bwd = 0; g.N = (uint16_t)p.width[l]; g.a_lo = (split && l > 0) ? 1 : 0;
+        g.head = l == L - 1 ? 1 : 0;
+        for (int s = 0; s < slabs; ++s) {
+            const int ks = (K - 64 * s) >= 64 ? 4 : (K - 64 * s + 15) / 16;
+            for (int part = 0; part < (split ? 2 : 1); ++part) {
+                GUnit& u = p.unit[nu++];
+                u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = (uint8_t)s; u.ksteps = (uint8_t)ks;
+                u.kind = (uint8_t)part;
+                off += (uint32_t)u.rows * 128u;
+            }
+        }
+        g.nu = (uint8_t)(nu - g.u0);
+    }
+    if (fb) {
+        for (int l = L - 1; l >= 1; --l) {   // delta_{l-1} = delta_l W_l^T: K = width of layer l, rows = width of layer l - 1
+            const int Kp = p.width[l], slabs = (Kp + 63) / 64;
+            GGemm& g = p.gemm[ng++];
+            g.u0 = (uint8_t)nu; g.layer = (uint8_t)l; g.bwd = 1; g.N = (uint16_t)p.width[l - 1]; g.a_lo = 0; g.head = 0;
+            for (int s = 0; s < slabs; ++s) {
+                GUnit& u = p.unit[nu++];
+                u.off = off; u.rows = (uint16_t)p.width[l - 1]; u.layer = (uint8_t)l; u.slab = (uint8_t)s;
+                u.ksteps = (uint8_t)((Kp - 64 * s) >= 64 ? 4 : (Kp - 64 * s + 15) / 16);
+                u.kind = 2;
+                off += (uint32_t)u.rows * 128u;
+            }
+            g.nu = (uint8_t)(nu - g.u0);
+        }
+    }
+    p.n_units = nu; p.n_gemm = ng; p.img_bytes = off;
+}
+
+struct GenWorkspace {
+    int64_t himg[GN_MAXL], dlimg[GN_MAXL], scale, img, masks, total;
+};
+static GenWorkspace gen_workspace(const b2048_mlp_desc* mlp, int64_t chunk, int num_sms) {
+    GenWorkspace w;
+    memset(&w, 0, sizeof(w));
+    const int L = mlp->n_layers;
+    const int64_t tiles = (chunk + TC_M - 1) / TC_M;
+    int64_t o = 0;
+    for (int l = 0; l < L - 1; ++l) { w.himg[l] = o; o += tiles * (mlp->dims[l + 1] / 64) * GN_SLAB; }
+    for (int l = 0; l < L; ++l) { w.dlimg[l] = o; o += tiles * (l == L - 1 ? 1 : mlp->dims[l + 1] / 64) * GN_SLAB; }
+    w.scale = o; o += 1024;
+    GenProg p;
+    build_program(mlp, true, true, p);
+    w.img = o; o += ((int64_t)p.img_bytes + 1023) / 1024 * 1024;
+    w.masks = o; o += (int64_t)num_sms * GN_MASK_WORDS * 2;
+    w.total = o;
+    return w;
+}
+int64_t gen_workspace_bytes(const b2048_mlp_desc* mlp, int64_t chunk) { return gen_workspace(mlp, chunk, 256).total + 2048; }
+
+static int gen_attrs(b2048_handle* h) {
+    if (!(h->attrs & 32u)) {
+        cudaError_t e = cudaFuncSetAttribute(gen_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
+        e = cudaFuncSetAttribute(gen_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_dw_kernel)");
+        h->attrs |= 32u;
+    }
+    return B2048_OK;
+}
+
+static int gen_prepare(const b2048_mlp_desc* mlp, const GenProg& p, uint8_t* img, cudaStream_t stream) {
+    GenPrepArgs pa;
+    pa.p = p;
+    for (int l = 0; l < GN_MAXL; ++l) pa.W[l] = l < mlp->n_layers ? mlp->W[l] : nullptr;
+    for (int l = 0; l <= GN_MAXL; ++l) pa.dims[l] = l <= mlp->n_layers ? mlp->dims[l] : 0;
+    pa.img = img;
+    gen_prepare_kernel<<<128, 256, 0, stream>>>(pa);
+    return check_cuda(cudaGetLastError(), "gen_prepare_kernel launch");
+}
+
+static int ensure_gen_image(b2048_handle* h, size_t bytes) {
+    if (h->gen_image && h->gen_image_bytes >= bytes) return B2048_OK;
+    if (h->gen_image) { cudaDeviceSynchronize(); cudaFree(h->gen_image); h->gen_image = nullptr; h->gen_image_bytes = 0; }
+    const size_t cap = (bytes + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+    cudaError_t e = cudaMalloc(&h->gen_image, cap);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMalloc(gen_image)");
+    h->gen_image_bytes = cap;
+    return B2048_OK;
+}
+
+static void gen_fill_common(GenArgs& a, const b2048_mlp_desc* mlp, const GenProg& p) {
+    memset(&a, 0, sizeof(a));
+    a.p = p;
+    for (int l = 0; l < mlp->n_layers; ++l) a.bias[l] = mlp->b[l];
+}
+
+// Forward-only launch behind b2048_mlp_forward (split != 0: float32 grade, precision 3 / auto; else one fp16 MMA per product,
+// precision 1) and b2048_policy_step (precision 1: logits -> masked softmax -> sample / greedy).  B2048_ERR_UNSUPPORTED
+// (silent) for shapes outside gen_supported().
+int launch_forward_gen(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags, float* out,
+                       uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, int greedy,
+                       int split, bool rebuild_image, cudaStream_t stream) {
+    if (!gen_supported(h, mlp) || n < 4096) return B2048_ERR_UNSUPPORTED;
+    { int st = gen_attrs(h); if (st != B2048_OK) return st; }
+    GenProg p;
+    build_program(mlp, split != 0, false, p);
+    // one image area per precision so that a policy image (single) and a value image (split) do not evict each other
+    const size_t half = (size_t)2 << 20;
+    { int st = ensure_gen_image(h, 2 * half); if (st != B2048_OK) return st; }
+    if (p.img_bytes > half) return B2048_ERR_UNSUPPORTED;
+    uint8_t* img = h->gen_image + (split ? half : 0);
+    if (rebuild_image) { int st = gen_prepare(mlp, p, img, stream); if (st != B2048_OK) return st; }
+    GenArgs a;
+    gen_fill_common(a, mlp, p);
+    a.img = img; a.board = board; a.n = n;
+    a.out = out; a.action = action; a.probs = probs; a.logits = logits; a.mask_flags = mask_flags;
+    a.keys = make_keys(seed); a.gid0 = gid0; a.t = t; a.greedy = greedy;
+    const int64_t tiles = (n + TC_M - 1) / TC_M;
+    const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "gen_mlp_kernel launch");
+}
+
+// Same contract as the fp32 body of b2048_mlp_backward (grads accumulated; flat layout W_0, b_0, W_1, b_1, ...).
+int launch_backward_gen(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags, const uint8_t* action, const float* coef,
+                        const b2048_mlp_desc* mlp, float* grads, int64_t n, int head_mode, uint8_t* workspace, int64_t chunk,
+                        cudaStream_t stream) {
+    { int st = gen_attrs(h); if (st != B2048_OK) return st; }
+    const int L = mlp->n_layers;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+    const GenWorkspace w = gen_workspace(mlp, chunk, 256);
+    GenProg p;
+    build_program(mlp, true, true, p);
+    { int st = gen_prepare(mlp, p, ws + w.img, stream); if (st != B2048_OK) return st; }
+    float* scale = reinterpret_cast<float*>(ws + w.scale);
+    cudaError_t e = cudaMemsetAsync(scale, 0, 16, stream);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(scale)");
+    gen_absmax_kernel<<<h->num_sms * 4, 256, 0, stream>>>(coef, n, reinterpret_cast<uint32_t*>(scale) + 2);
+    gen_scale_kernel<<<1, 1, 0, stream>>>(scale);
+    float* gW[GN_MAXL];
+    float* gb[GN_MAXL];
+    {
+        float* g = grads;
+        for (int l = 0; l < L; ++l) { gW[l] = g; g += (int64_t)mlp->dims[l] * mlp->dims[l + 1]; gb[l] = g; g += mlp->dims[l + 1]; }
+    }
+    for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+        const int64_t cn = (n - c0) < chunk ? (n - c0) : chunk;
+        const int64_t tiles = (cn + TC_M - 1) / TC_M;
+        const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+        GenArgs a;
+        gen_fill_common(a, mlp, p);
+        a.img = ws + w.img; a.board = board + c0; a.n = cn;
+        a.mask_flags = mask_flags ? mask_flags + c0 : nullptr;
+        a.act_in = action ? action + c0 : nullptr;
+        a.coef = coef + c0; a.scale = scale; a.head_mode = head_mode;
+        for (int l = 0; l < L - 1; ++l) a.himg[l] = ws + w.himg[l];
+        for (int l = 0; l < L; ++l) a.dlimg[l] = ws + w.dlimg[l];
+        a.gb_head = gb[L - 1];
+        a.mask_scratch = reinterpret_cast<uint16_t*>(ws + w.masks);
+        gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        int st = check_cuda(cudaGetLastError(), "gen_mlp_kernel launch");
+        if (st != B2048_OK) return st;
+        for (int l = 0; l < L; ++l) {
+            GenDwArgs d;
+            memset(&d, 0, sizeof(d));
+            const int K = mlp->dims[l];
+            d.aimg = l == 0 ? nullptr : ws + w.himg[l - 1];
+            d.board = board + c0; d.obs_mode = mlp->obs_mode; d.obs_scale = mlp->obs_log2_scale;
+            d.bimg = ws + w.dlimg[l];
+            d.a_slabs = (K + 63) / 64;
+            d.b_slabs = l == L - 1 ? 1 : mlp->dims[l + 1] / 64;
+            d.N = p.width[l];
+            d.K_real = K; d.N_real = mlp->dims[l + 1];
+            d.gW = gW[l]; d.gb = l == L - 1 ? nullptr : gb[l];
+            d.inv_scale = scale + 1;
+            d.n_tiles = tiles; d.n = cn;
+            d.mtiles = (K + 127) / 128;
+            int ksplit = h->num_sms / d.mtiles;
+            if (ksplit < 1) ksplit = 1;
+            if ((int64_t)ksplit > tiles) ksplit = (int)tiles;
+            d.ksplit = ksplit;
+            const int stage_bytes = (2 + d.b_slabs) * GN_SLAB;
+            int stages = (227 * 1024 - 256) / stage_bytes;
+            d.stages = stages > 4 ? 4 : stages;
+            d.tmem_cols = d.N <= 32 ? 32u : (d.N <= 64 ? 64u : (d.N <= 128 ? 128u : 256u));
+            const size_t smem = (size_t)d.stages * stage_bytes + 256;
+            gen_dw_kernel<<<d.mtiles * d.ksplit, GD_THREADS, smem, stream>>>(d);
+            st = check_cuda(cudaGetLastError(), "gen_dw_kernel launch");
+            if (st != B2048_OK) return st;
+        }
+    }
+    return B2048_OK;
+}
+
+}  // namespace b2

@@ -149,6 +149,9 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
                      uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t,
                      int greedy, cudaStream_t stream, bool rebuild_image);
 int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n, cudaStream_t stream);
+int launch_forward_gen(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags, float* out,
+                       uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, int greedy,
+                       int split, bool rebuild_image, cudaStream_t stream);
 int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n,
                       cudaStream_t stream);
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
@@ -281,10 +284,13 @@ static int policy_step_impl(b2048_handle* h, const uint64_t* board, const uint8_
     if (precision == 1) {
         st = launch_policy_tc(h, mlp, board, mask_flags, action, probs, logits, n, seed, gid0, t, greedy, (cudaStream_t)stream,
                               rebuild_image);
+        if (st == B2048_ERR_UNSUPPORTED)      // other shapes: the shape-generic kernel, one fp16 MMA per product
+            st = launch_forward_gen(h, mlp, board, mask_flags, nullptr, action, probs, logits, n, seed, gid0, t, greedy, 0,
+                                    rebuild_image, (cudaStream_t)stream);
         if (st == B2048_ERR_UNSUPPORTED)
             return fail(B2048_ERR_UNSUPPORTED,
-                        "b2048_policy_step: precision 1 (bf16 tcgen05) implements the 16-256-256-4 ReLU policy on raw/log2 "
-                        "observations only; use precision 0");
+                        "b2048_policy_step: precision 1 (tcgen05) implements ReLU policies with 1-4 hidden layers of 64 / 128 / 192 / "
+                        "256 units on log2 / one-hot observations (16-256-256-4 also on raw ones), n >= 4096; use precision 0");
         return st;
     }
     if (precision != 0) return fail(B2048_ERR_INVALID, "b2048_policy_step: precision must be 0 (fp32) or 1 (bf16 tcgen05)");
@@ -308,14 +314,18 @@ extern "C" int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b
                "b2048_mlp_forward: precision must be 0 (fp32), 1 (bf16 tcgen05), 2 (auto) or 3 (split-fp16 tcgen05)");
     if (precision == 2 || precision == 3) {   // float32-grade tensor-core forward (what "auto" selects)
         int st = launch_forward_hp(h, mlp, board, out, n, (cudaStream_t)stream);
+        if (st == B2048_ERR_UNSUPPORTED)
+            st = launch_forward_gen(h, mlp, board, nullptr, out, nullptr, nullptr, nullptr, n, 0, 0, 0, 1, 1, true, (cudaStream_t)stream);
         if (st != B2048_ERR_UNSUPPORTED) return st;
         if (precision == 3)
             return fail(B2048_ERR_UNSUPPORTED,
-                        "b2048_mlp_forward: precision 3 (split-fp16 tcgen05) implements 16-256-256-(<=4) ReLU networks on log2 "
-                        "observations with n >= 4096 only");
+                        "b2048_mlp_forward: precision 3 (split-fp16 tcgen05) implements ReLU networks with 1-4 hidden layers of 64 / 128 / "
+                        "192 / 256 units on log2 / one-hot observations with n >= 4096 only");
     }
     if (precision == 1) {
         int st = launch_forward_tc(h, mlp, board, out, n, (cudaStream_t)stream);
+        if (st == B2048_ERR_UNSUPPORTED)
+            st = launch_forward_gen(h, mlp, board, nullptr, out, nullptr, nullptr, nullptr, n, 0, 0, 0, 1, 0, true, (cudaStream_t)stream);
         if (st != B2048_ERR_UNSUPPORTED) return st;
         return fail(B2048_ERR_UNSUPPORTED,
                     "b2048_mlp_forward: precision 1 (bf16 tcgen05) implements 16-256-256-(<=4) ReLU networks on raw/log2 "

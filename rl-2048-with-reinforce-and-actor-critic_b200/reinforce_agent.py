@@ -256,16 +256,31 @@ class ReinforceAgent:
 
     def _update_mode_name(self, prec: int, n: int) -> str:
         """Which arithmetic b2048_mlp_backward ran for `prec` on n samples (include/b2048.h)."""
-        tc_ok = self.tc_supported() and n >= 4096
-        if prec in (2, 3) and tc_ok and self._actor.obs_mode == "log2":
+        big = n >= 4096
+        if prec in (2, 3) and big and self._fused_shape() and self._actor.obs_mode == "log2":
             return "fp16 split tcgen05 (float32-grade forward, fp16 backward with loss scale)"
-        if prec == 1 and tc_ok:
+        if prec in (2, 3) and big and self._generic_tc_shape():
+            return "fp16 split tcgen05, shape-generic kernels (float32-grade forward, fp16 backward with loss scale)"
+        if prec == 1 and big and self._fused_shape():
             return "bf16 tcgen05"
         return "fp32 CUDA cores"
 
-    def tc_supported(self) -> bool:
+    def _fused_shape(self) -> bool:
+        """The runner-default 16-256-256-4 ReLU network: hand-specialised kernels (fused persistent rollout, update pipeline)."""
         a = self._actor
         return (a.dims == [16, 256, 256, 4] and a.activation == "ReLU" and a.obs_mode in ("raw", "log2"))
+
+    def _generic_tc_shape(self) -> bool:
+        """Shapes of the shape-generic tcgen05 kernels (csrc/b2048_mlp_gen.cu): ReLU, 1-4 hidden layers of 64 / 128 / 192 / 256
+        units, log2 or one-hot observations — e.g. the reference's documented one-hot [256, 128, 64] network (runner.py:27-47)."""
+        a = self._actor
+        hidden = a.dims[1:-1]
+        return (a.activation == "ReLU" and a.obs_mode in ("log2", "onehot") and 1 <= len(hidden) <= 4 and
+                all(h % 64 == 0 and 64 <= h <= 256 for h in hidden) and 1 <= a.dims[-1] <= 4)
+
+    def tc_supported(self) -> bool:
+        """True when batches of >= 4096 boards run on the tensor cores (policy steps at precision 1, updates at "auto")."""
+        return self._fused_shape() or self._generic_tc_shape()
 
     def _values(self, boards: torch.Tensor, out: torch.Tensor, precision: int = 0) -> None:
         with torch.cuda.device(self.device):
@@ -398,7 +413,7 @@ class ReinforceAgent:
         # Run-to-termination on the fused tensor-core kernel: every chunk plays only the boards that are still alive
         # (slot_map), so finished episodes cost nothing.  Slices beyond an episode's end are then never written: the
         # rewards buffer is zeroed first (total_reward sums whole columns) and the final state is gathered below.
-        compact = (not fixed) and int(precision) == 1 and B >= 4096 and self.tc_supported() and \
+        compact = (not fixed) and int(precision) == 1 and B >= 4096 and self._fused_shape() and \
             not debug_get("no_fused_rollout") and not debug_get("no_compact_rollout")
         if compact:
             rewards.zero_()

@@ -111,7 +111,7 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
            "boards_per_gpu": boards,
            "network": ("272-256-128-64-4 ReLU actor + 272-256-128-64-1 critic, one-hot observations (runner.py:27-47)" if onehot else
                        "16-256-256-4 ReLU actor" + (" + 16-256-256-1 critic" if use_critic else "")),
-           "rollout_precision": "bf16 tcgen05 (fused persistent kernel)" if (agent.tc_supported() and precision != 0) else "fp32 CUDA cores",
+           "rollout_precision": ("bf16 tcgen05 (fused persistent kernel)" if agent._fused_shape() else "fp16 tcgen05 (shape-generic policy kernel + step kernel)") if (agent.tc_supported() and precision != 0) else "fp32 CUDA cores",
            "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],
            "update_ms": last["update_ms"], "update_precision": agent.last_update_info.get("precision"),
            "T": last["T"], "mean_len": last["mean_len"], "mean_return": last["mean_return"],
