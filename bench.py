@@ -22,7 +22,8 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
   train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
              one update; 65,536 / 262,144 boards per GPU)
   train_iter_actor_critic_onehot   secondary: the reference's documented configuration (one-hot observations, hidden
-             [256, 128, 64], Adam) on the fp32 CUDA-core kernels (shape outside the tensor-core path)
+             [256, 128, 64], Adam) at configs[3]'s 262,144 boards per GPU, on the shape-generic
+             tcgen05 kernels (csrc/b2048_mlp_gen.cu)
   sharded_sweep  secondary, N >= 2 only: BASELINE.json configs[4] — 64 M boards in total, 16-step episodes, one update
   summary    the key numbers of every leg once more, LAST in the line (a truncated tail still shows them)
 
@@ -452,8 +453,8 @@ def run_b200(args):
             extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision="auto")
             extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision="auto",
                                                                       use_critic=True, iters=3)
-            # SURVEY.md section 8d config 4 as the reference documents it (one-hot 272-256-128-64 networks): outside the
-            # shapes the tensor-core kernels implement, so rollout and update run on the fp32 CUDA-core kernels
+            # SURVEY.md section 8d config 4 as the reference documents it (one-hot 272-256-128-64 networks): the shape-generic
+            # tensor-core kernels (gen_mlp_kernel / gen_dw_kernel)
             extra["train_iter_actor_critic_onehot"] = b2048.bench_train_iter(dev, boards=args.onehot_boards, info=info, precision="auto",
                                                                              use_critic=True, iters=2, network="onehot")
             if world > 1 and not args.no_sweep:
@@ -510,7 +511,7 @@ def main():
     ap.add_argument("--lean", action="store_true", help="board-only state (no score/step/max_tile arrays)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
-    ap.add_argument("--onehot-boards", type=int, default=16384, help="actor-critic leg on the reference's documented one-hot network")
+    ap.add_argument("--onehot-boards", type=int, default=262144, help="actor-critic leg on the reference's documented one-hot network")
     ap.add_argument("--no-sweep", action="store_true", help="skip the BASELINE.json configs[4] leg (runs at N >= 2)")
     ap.add_argument("--sweep-boards", type=int, default=64 << 20, help="total boards of the configs[4] leg")
     ap.add_argument("--batches", type=int, default=12, help="resident 1 M-board batches the timed launches rotate over")
