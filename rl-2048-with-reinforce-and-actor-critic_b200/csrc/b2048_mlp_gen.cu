@@ -38,7 +38,8 @@ constexpr int GN_NSLOT = 3;
 constexpr int GS_A = 0;                        // A buffer: hi slabs 0..3, lo slabs 4..7 (a 272-wide input uses slabs 0..4)
 constexpr int GS_W = 8 * GN_SLAB;
 constexpr int GS_BAR = GS_W + GN_NSLOT * GN_SLOT;
-constexpr int GS_TOTAL = GS_BAR + 256;
+constexpr int GS_ONES = GS_BAR + 256;          // constant A operand of the bias MMAs: every row = e0 + e1 (fp16), 256 B
+constexpr int GS_TOTAL = GS_ONES + 256;
 constexpr int GN_THREADS = 22 * 32;            // 16 epilogue warps, MMA warp, weight loader, 4 I/O warps
 constexpr int GN_MASK_WORDS = 4 * 4 * 4 * 128; // per CTA: [hidden layer][slab][column group][row] 16-bit ReLU masks
 static_assert(GS_TOTAL <= 232448, "gen_mlp_kernel exceeds the shared memory of an sm_100 CTA");
@@ -48,8 +49,8 @@ struct GUnit {            // one streamed weight unit = the B operand of up to 8
     uint16_t rows;        // B rows (the MMA's N); bytes = rows * 128
     uint8_t layer, slab;  // weight matrix, 64-wide K slab
     uint8_t ksteps;       // valid K = 16 steps of the slab (1..4)
-    uint8_t kind;         // 0: forward hi, 1: forward lo, 2: backward (fp16 W read as [in][out])
-    uint16_t pad;
+    uint8_t kind;         // 0: forward hi, 1: forward lo, 2: backward (fp16 W read as [in][out]), 3: bias [rows x 16] (k = 0: hi, 1: lo)
+    uint16_t bytes16;     // unit size / 16
 };
 struct GGemm {
     uint8_t u0, nu;       // its units
@@ -80,6 +81,8 @@ struct GenArgs {
     float* probs;
     float* logits;
     const uint8_t* mask_flags;  // legal masks (sampling and the policy head's softmax)
+    const int32_t* slot_map;    // policy steps of a run-to-termination rollout: sample s is board slot_map[s] (NULL: s)
+    const int32_t* n_dev;       // with slot_map: the number of listed boards, read on the device (NULL: n)
     PhiloxKeys keys;
     uint64_t gid0;
     uint32_t t;
@@ -93,6 +96,7 @@ struct GenArgs {
     uint8_t* dlimg[GN_MAXL];    // delta images of every layer (head: one slab)
     float* gb_head;
     uint16_t* mask_scratch;     // [grid][GN_MASK_WORDS]
+    long long* dbg;             // optional phase clocks of CTA 0 (B2048_DBG_TC_CLOCKS), 64 slots per tile for the first 4 tiles
 };
 
 __host__ __device__ constexpr uint32_t idesc_h(int m, int n) {          // kind::f16, A/B fp16, D fp32
@@ -134,16 +138,15 @@ __device__ __forceinline__ void g_bulk_store(uint8_t* dst, uint32_t src, uint32_
                      : "memory");
 }
 
-// Row `row` of the network input as fp16 K-major slab rows (zero-filled): slabs slab0 .. slab0 + nslabs - 1 of the input
-// go to dst, dst + GN_SLAB, ...  one-hot: feature cell * 17 + exponent (env.py:131-150); log2: exponent * scale.
+// Row `row` of the network input as fp16 K-major slab rows: slabs slab0 .. slab0 + nslabs - 1 of the input go to dst,
+// dst + GN_SLAB, ...  one-hot: feature cell * 17 + exponent (env.py:131-150) — the caller has zero-filled the slabs (linearly:
+// a per-row fill would be an 8-way bank conflict); log2: exponent * scale in the first 16 features (nothing else is read).
+__device__ __forceinline__ void zero_slabs_128(uint8_t* dst, int nslabs, int t128) {
+    for (int i = t128; i < nslabs * (GN_SLAB / 16); i += 128) *reinterpret_cast<uint4*>(dst + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+}
 __device__ __forceinline__ void encode_input_row(uint64_t bd, int row, uint8_t* dst, int slab0, int nslabs, int obs_mode,
                                                  float scale) {
     const int sw = row & 7;
-    for (int s = 0; s < nslabs; ++s) {
-        uint8_t* p = dst + s * GN_SLAB + row * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(p + c * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
     if (obs_mode == B2048_OBS_ONEHOT) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -165,6 +168,7 @@ __device__ __forceinline__ void encode_input_row(uint64_t bd, int row, uint8_t* 
 struct GenPrepArgs {
     GenProg p;
     const float* W[GN_MAXL];
+    const float* b[GN_MAXL];
     int dims[GN_MAXL + 1];
     uint8_t* img;
 };
@@ -174,6 +178,17 @@ __global__ void __launch_bounds__(256) gen_prepare_kernel(const __grid_constant_
         const GUnit un = a.p.unit[u];
         const int K = a.dims[un.layer], N = a.dims[un.layer + 1];
         const float* W = a.W[un.layer];
+        if (un.kind == 3) {                 // [rows / 8][2 k-chunks][8 rows][16 B], no swizzle: k = 0 -> hi(b[n]), k = 1 -> lo(b[n]), rest 0
+            for (int idx = tid; idx < (int)un.rows * 16; idx += nth) {
+                const int r = idx >> 4, k = idx & 15;
+                const float v = r < N ? a.b[un.layer][r] : 0.0f;
+                __half hv = __float2half_rn(v);
+                if (k == 1) hv = a.p.split ? __float2half_rn(v - __half2float(hv)) : __float2half_rn(0.0f);
+                if (k > 1) hv = __float2half_rn(0.0f);
+                *reinterpret_cast<__half*>(a.img + un.off + (size_t)(r >> 3) * 256 + (size_t)(k >> 3) * 128 + (size_t)(r & 7) * 16 + (k & 7) * 2) = hv;
+            }
+            continue;
+        }
         for (int idx = tid; idx < (int)un.rows * 64; idx += nth) {
             const int r = idx >> 6, k = idx & 63;
             float v = 0.0f;
@@ -197,19 +212,25 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GS_BAR);
     const uint32_t w_full0 = s_u32(&bars[0]), w_empty0 = s_u32(&bars[3]);
-    const uint32_t bar_io = s_u32(&bars[6]), bar_epi = s_u32(&bars[7]), bar_acc_e = s_u32(&bars[8]), bar_acc_h = s_u32(&bars[9]),
-                   bar_free = s_u32(&bars[10]);
+    const uint32_t bar_io = s_u32(&bars[6]), bar_acc_e = s_u32(&bars[8]), bar_acc_h = s_u32(&bars[9]), bar_free = s_u32(&bars[10]);
+    const uint32_t bar_slab0 = s_u32(&bars[11]);   // [11..14] slab s of the A operand written by the epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GS_BAR + 128);
     const GenProg& P = a.p;
 
     if (tid == 0) {
         for (int i = 0; i < GN_NSLOT; ++i) { mbar_init(w_full0 + 8u * i, 1); mbar_init(w_empty0 + 8u * i, 1); }
         mbar_init(bar_io, 4);        // the I/O warps have written an A operand (the tile's input; its head deltas)
-        mbar_init(bar_epi, 16);      // the epilogue warps have written an A operand
+        for (int i = 0; i < 4; ++i) mbar_init(bar_slab0 + 8u * i, 16);   // the epilogue warps have written slab i of an A operand
         mbar_init(bar_acc_e, 1);     // an accumulator for the epilogue warps is complete
         mbar_init(bar_acc_h, 1);     // the head accumulator (I/O warps) is complete
         mbar_init(bar_free, 1);      // update mode: the tile's last image has left the A buffer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 64) {      // ONES operand: [2 k-chunks][8 rows][8 halves]; chunk 0 of every row = (1, 1, 0, ...)
+        const int e = tid & 7, chunk = tid >> 5;
+        reinterpret_cast<uint32_t*>(smem + GS_ONES)[tid] = 0u;
+        if (chunk == 0 && (e & 3) == 0) reinterpret_cast<uint32_t*>(smem + GS_ONES)[tid] = 0x3C003C00u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 16) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u) : "memory");
@@ -219,54 +240,84 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t n_tiles = (a.n + TC_M - 1) / TC_M;
+    const int64_t n_eff = a.n_dev ? (int64_t)*a.n_dev : a.n;        // uniform over the grid
+    const int64_t n_tiles = (n_eff + TC_M - 1) / TC_M;
     const uint32_t sA = s_u32(smem + GS_A), sW = s_u32(smem + GS_W);
 
     if (warp == 16) {
         // ============================ MMA lane: GEMM program, image stores ============================
+        // A GEMM whose A operand comes from the epilogue warps starts on K slab s as soon as THAT slab has been written (per-slab
+        // barriers): the epilogue of GEMM G runs under the MMAs of GEMM G + 1 (accumulators alternate between two TMEM regions).
         if (lane == 0) {
-            uint32_t U = 0, nio = 0, nepi = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t U = 0, nio = 0, spar = 0;      // spar: phase parity of the four slab barriers
+            const uint64_t d_ones = desc_ones(s_u32(smem + GS_ONES));
+            auto slab_ready = [&](int sl) {
+                gwait(bar_slab0 + 8u * (uint32_t)sl, (spar >> sl) & 1u);
+                spar ^= 1u << sl;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            };
+            int lt = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                long long* dc = (a.dbg && blockIdx.x == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
+                if (dc) dc[0] = clock64();
                 for (int G = 0; G < P.n_gemm; ++G) {
                     const GGemm gm = P.gemm[G];
                     const bool from_io = G == 0 || (gm.bwd && G == P.L);
-                    if (from_io) { gwait(bar_io, nio & 1u); ++nio; }
-                    else { gwait(bar_epi, nepi & 1u); ++nepi; }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    long long wsum = 0;
+                    if (from_io) {
+                        gwait(bar_io, nio & 1u); ++nio;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (dc) dc[1 + 3 * G] = clock64();
+                    }
+                    // in update mode the A operand of every GEMM but the first is an image the dW GEMMs read
                     const bool store = P.fb && G > 0;
-                    if (store) {       // the A operand of this GEMM is an image the dW GEMMs read
-                        int nsl;
-                        uint8_t* dst;
-                        if (!gm.bwd) { nsl = P.width[gm.layer - 1] >> 6; dst = a.himg[gm.layer - 1]; }
-                        else { nsl = gm.layer == P.L - 1 ? 1 : (P.width[gm.layer] >> 6); dst = a.dlimg[gm.layer]; }
-                        g_bulk_store(dst + (size_t)tile * nsl * GN_SLAB, sA, (uint32_t)(nsl * GN_SLAB));
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    uint8_t* img_dst = nullptr;
+                    if (store) {
+                        const int nsl = !gm.bwd ? (P.width[gm.layer - 1] >> 6) : (gm.layer == P.L - 1 ? 1 : (P.width[gm.layer] >> 6));
+                        img_dst = (!gm.bwd ? a.himg[gm.layer - 1] : a.dlimg[gm.layer]) + (size_t)tile * nsl * GN_SLAB;
                     }
                     const uint32_t dcol = tmem_base + (uint32_t)(G & 1) * 256u;
                     const uint32_t idesc = idesc_h(TC_M, gm.N);
                     uint32_t acc = 0u;
                     for (int u = gm.u0; u < gm.u0 + gm.nu; ++u, ++U) {
                         const GUnit un = P.unit[u];
-                        const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
-                        gwait(w_full0 + 8u * slot, use & 1u);
-                        const uint32_t wb = sW + slot * GN_SLOT, ah = sA + (uint32_t)un.slab * GN_SLAB;
-                        for (int q = 0; q < un.ksteps; ++q) {
-                            umma_f16(dcol, desc_sw128(ah + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, acc);
-                            acc = 1u;
+                        if (un.kind == 0 || un.kind == 2) {      // first unit of K slab un.slab
+                            if (!from_io) { slab_ready(un.slab); if (dc && un.slab == 0) dc[1 + 3 * G] = clock64(); }
+                            if (store) {
+                                g_bulk_store(img_dst + (size_t)un.slab * GN_SLAB, sA + (uint32_t)un.slab * GN_SLAB, GN_SLAB);
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
                         }
-                        if (un.kind == 0 && gm.a_lo)
-                            for (int q = 0; q < un.ksteps; ++q)
-                                umma_f16(dcol, desc_sw128(ah + 4u * GN_SLAB + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, 1u);
+                        const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
+                        const long long w0 = dc ? clock64() : 0;
+                        gwait(w_full0 + 8u * slot, use & 1u);
+                        if (dc) wsum += clock64() - w0;
+                        const uint32_t wb = sW + slot * GN_SLOT, ah = sA + (uint32_t)un.slab * GN_SLAB;
+                        if (un.kind == 3) {
+                            umma_f16(dcol, d_ones, desc_nosw_k16(wb), idesc, acc);
+                            acc = 1u;
+                        } else {
+                            for (int q = 0; q < un.ksteps; ++q) {
+                                umma_f16(dcol, desc_sw128(ah + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, acc);
+                                acc = 1u;
+                            }
+                            if (un.kind == 0 && gm.a_lo)
+                                for (int q = 0; q < un.ksteps; ++q)
+                                    umma_f16(dcol, desc_sw128(ah + 4u * GN_SLAB + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, 1u);
+                        }
                         umma_commit(w_empty0 + 8u * slot);
                     }
-                    // the epilogue of this GEMM overwrites the A buffer: the image store must have read it
+                    // the epilogue of this GEMM overwrites the A buffer: the image stores must have read it
                     if (store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     umma_commit(gm.head ? bar_acc_h : bar_acc_e);
+                    if (dc) { dc[2 + 3 * G] = clock64(); dc[3 + 3 * G] = wsum; }
                 }
                 if (P.fb) {            // delta_0 (the last epilogue's output) is only an image
-                    gwait(bar_epi, nepi & 1u); ++nepi;
                     const int nsl = P.width[0] >> 6;
-                    g_bulk_store(a.dlimg[0] + (size_t)tile * nsl * GN_SLAB, sA, (uint32_t)(nsl * GN_SLAB));
+                    for (int sl = 0; sl < nsl; ++sl) {
+                        slab_ready(sl);
+                        g_bulk_store(a.dlimg[0] + ((size_t)tile * nsl + sl) * GN_SLAB, sA + (uint32_t)sl * GN_SLAB, GN_SLAB);
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     mbar_arrive(bar_free);
@@ -284,7 +335,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                     const GUnit un = P.unit[u];
                     const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
                     if (use > 0) gwait(w_empty0 + 8u * slot, (use - 1u) & 1u);
-                    const uint32_t bar = w_full0 + 8u * slot, bytes = (uint32_t)un.rows * 128u;
+                    const uint32_t bar = w_full0 + 8u * slot, bytes = (uint32_t)un.bytes16 * 16u;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
                     g_bulk_load(sW + slot * GN_SLOT, a.img + un.off, bytes, bar);
                 }
@@ -293,53 +344,55 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         __syncwarp();
     } else if (warp < 16) {
         // ============================ epilogue warps: accumulator -> next A operand ============================
+        // (biases arrive through the bias MMA; mask bit of column i of a 16-column group sits at bit 15 - i)
         const int q = warp & 3, g = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint16_t* msk = a.mask_scratch ? a.mask_scratch + (size_t)blockIdx.x * GN_MASK_WORDS : nullptr;
         uint8_t* a_row = smem + GS_A + row * 128;
         uint32_t ne = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int lt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            long long* dc = (a.dbg && blockIdx.x == 0 && tid == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
             for (int G = 0; G < P.n_gemm; ++G) {
                 const GGemm gm = P.gemm[G];
                 if (gm.head) continue;
                 gwait(bar_acc_e, ne & 1u); ++ne;
+                if (dc) dc[32 + 2 * G] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t dcol = tlane + (uint32_t)(G & 1) * 256u;
+                const uint32_t dcol = tlane + (uint32_t)(G & 1) * 256u + (uint32_t)(g * 16);
                 const int nsl = gm.N >> 6;
-                if (!gm.bwd) {
-                    const float* bias = a.bias[gm.layer];
-                    for (int s = 0; s < nsl; ++s) {
-                        uint32_t r[16];
-                        tmem_ld16(dcol + (uint32_t)(s * 64 + g * 16), r);
+                uint32_t r[2][16];
+                tmem_ld16_issue(dcol, r[0]);                 // the TMEM load of slab s + 1 is in flight while slab s is converted
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    if (s >= nsl) break;
+                    uint32_t (&rc)[16] = r[s & 1];
+                    tmem_ld_wait(rc);
+                    if (s + 1 < nsl) tmem_ld16_issue(dcol + (uint32_t)((s + 1) * 64), r[(s + 1) & 1]);
+                    if (!gm.bwd) {
                         uint32_t m = 0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float z = __uint_as_float(r[i]) + __ldg(bias + s * 64 + g * 16 + i);
-                            m |= (z > 0.0f ? 1u : 0u) << i;
-                            r[i] = __float_as_uint(fmaxf(z, 0.0f));
-                        }
+                        for (int i = 0; i < 16; ++i) m = __funnelshift_l(0u - rc[i], m, 1);     // z > 0  <=>  sign bit of -bits(z)
                         if (msk) msk[((gm.layer * 4 + s) * 4 + g) * 128 + row] = (uint16_t)m;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const float x0 = __uint_as_float(r[8 * c + 2 * k]), x1 = __uint_as_float(r[8 * c + 2 * k + 1]);
-                                hi[k] = gpack(x0, x1);
-                                const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi[k]));
-                                lo[k] = gpack(x0 - hf.x, x1 - hf.y);
+                                const uint32_t b0 = rc[8 * c + 2 * k], b1 = rc[8 * c + 2 * k + 1];
+                                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi[k]) : "f"(__uint_as_float(b1)), "f"(__uint_as_float(b0)));
+                                if (P.split) {
+                                    const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi[k]));
+                                    lo[k] = gpack(fmaxf(__uint_as_float(b0), 0.0f) - hf.x, fmaxf(__uint_as_float(b1), 0.0f) - hf.y);
+                                }
                             }
                             const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
                             *reinterpret_cast<uint4*>(a_row + s * GN_SLAB + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                             if (P.split) *reinterpret_cast<uint4*>(a_row + (4 + s) * GN_SLAB + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
-                    }
-                } else {
-                    // delta_{layer-1} = D . [z_{layer-1} > 0]
-                    for (int s = 0; s < nsl; ++s) {
-                        uint32_t r[16];
-                        tmem_ld16(dcol + (uint32_t)(s * 64 + g * 16), r);
+                    } else {
+                        // delta_{layer-1} = D . [z_{layer-1} > 0]
                         const uint32_t m = msk[(((gm.layer - 1) * 4 + s) * 4 + g) * 128 + row];
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
@@ -347,19 +400,20 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int i0 = 8 * c + 2 * k;
-                                const float x0 = (m >> i0) & 1u ? __uint_as_float(r[i0]) : 0.0f;
-                                const float x1 = (m >> (i0 + 1)) & 1u ? __uint_as_float(r[i0 + 1]) : 0.0f;
+                                const float x0 = (m >> (15 - i0)) & 1u ? __uint_as_float(rc[i0]) : 0.0f;
+                                const float x1 = (m >> (14 - i0)) & 1u ? __uint_as_float(rc[i0 + 1]) : 0.0f;
                                 o[k] = gpack(x0, x1);
                             }
                             const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
                             *reinterpret_cast<uint4*>(a_row + s * GN_SLAB + sw) = make_uint4(o[0], o[1], o[2], o[3]);
                         }
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_slab0 + 8u * (uint32_t)s);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_epi);
+                if (dc) dc[33 + 2 * G] = clock64();
             }
         }
     } else {
@@ -376,8 +430,11 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         const bool use_mask = a.mask_flags != nullptr;
         uint32_t lt = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-            const int64_t s = tile * TC_M + row;
-            const bool valid = s < a.n;
+            long long* dc = (a.dbg && blockIdx.x == 0 && warp == 18 && lane == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
+            if (dc) dc[52] = clock64();
+            const int64_t slot = tile * TC_M + row;
+            const bool valid = slot < n_eff;
+            const int64_t s = (valid && a.slot_map) ? (int64_t)a.slot_map[slot] : slot;     // the board behind the slot
             const uint64_t bd = valid ? a.board[s] : 0ull;
             uint32_t fl = 0xFu, act = 0u;
             float cf = 0.0f;
@@ -390,11 +447,18 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
             // the A buffer is free: forward-only, the previous tile's head GEMM has completed (waited for below); update mode,
             // its last image has been read out
             if (P.fb && lt > 0) gwait(bar_free, (lt - 1u) & 1u);
+            if (dc) dc[53] = clock64();
+            if (P.obs_mode == B2048_OBS_ONEHOT) {
+                zero_slabs_128(smem + GS_A, P.in_slabs, tid - 18 * 32);
+                asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four I/O warps only
+            }
             encode_input_row(bd, row, smem + GS_A, 0, P.in_slabs, P.obs_mode, P.obs_scale);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_io);
+            if (dc) dc[54] = clock64();
             gwait(bar_acc_h, lt & 1u);
+            if (dc) dc[55] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t r4[4];
             tmem_ld4(tlane + hcol, r4);
@@ -472,6 +536,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                     if (lane == 0 && j < P.n_out && v != 0.0f) atomicAdd(a.gb_head + j, v);
                 }
             }
+            if (dc) dc[56] = clock64();
         }
     }
 
@@ -606,14 +671,24 @@ __global__ void __launch_bounds__(GD_THREADS, 1) gen_dw_kernel(const __grid_cons
             const int q = warp & 3;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
             const int m = mt * 128 + q * 32 + lane;                    // input feature
+            const bool vec4 = (a.N_real & 3) == 0 && (reinterpret_cast<uintptr_t>(a.gW) & 15) == 0;
             for (int c0 = 0; c0 < a.N; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tlane + (uint32_t)c0, r);
                 if (m < a.K_real) {
+                    float* dst = a.gW + (size_t)m * a.N_real + c0;
+                    if (vec4 && c0 + 16 <= a.N_real) {          // four 128-bit reductions instead of 16 scalar atomics
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float v = __uint_as_float(r[i]) * inv;
-                        if (c0 + i < a.N_real && v != 0.0f) atomicAdd(a.gW + (size_t)m * a.N_real + (c0 + i), v);
+                        for (int i = 0; i < 16; i += 4)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i]) * inv),
+                                         "f"(__uint_as_float(r[i + 1]) * inv), "f"(__uint_as_float(r[i + 2]) * inv), "f"(__uint_as_float(r[i + 3]) * inv)
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float v = __uint_as_float(r[i]) * inv;
+                            if (c0 + i < a.N_real && v != 0.0f) atomicAdd(dst + i, v);
+                        }
                     }
                 }
             }
@@ -627,6 +702,10 @@ __global__ void __launch_bounds__(GD_THREADS, 1) gen_dw_kernel(const __grid_cons
             const int64_t s = tile * 128 + row;
             const uint64_t bd = s < a.n ? a.board[s] : 0ull;
             if (use > 0) gwait(empty0 + 8u * st, (uint32_t)(use - 1) & 1u);
+            if (a.obs_mode == B2048_OBS_ONEHOT) {
+                zero_slabs_128(smem + st * stage_bytes, a_have, tid - 6 * 32);
+                asm volatile("bar.sync 2, 128;" ::: "memory");                     // the four generator warps only
+            }
             encode_input_row(bd, row, smem + st * stage_bytes, 2 * mt, a_have, a.obs_mode, a.obs_scale);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -695,8 +774,16 @@ static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenPro
                 GUnit& u = p.unit[nu++];
                 u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = (uint8_t)s; u.ksteps = (uint8_t)ks;
                 u.kind = (uint8_t)part;
+                u.bytes16 = (uint16_t)(u.rows * 8);
                 off += (uint32_t)u.rows * 128u;
             }
+        }
+        if (l < L - 1) {                     // hidden layers: the bias comes in through one more MMA (head: added by the I/O warps)
+            GUnit& u = p.unit[nu++];
+            u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = 0; u.ksteps = 1; u.kind = 3;
+            u.bytes16 = (uint16_t)(u.rows * 2);
+            off += (uint32_t)u.rows * 32u;
+            off = (off + 1023u) & ~1023u;     // the next unit is a 128-byte-swizzled operand
         }
         g.nu = (uint8_t)(nu - g.u0);
     }
@@ -710,6 +797,7 @@ static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenPro
                 u.off = off; u.rows = (uint16_t)p.width[l - 1]; u.layer = (uint8_t)l; u.slab = (uint8_t)s;
                 u.ksteps = (uint8_t)((Kp - 64 * s) >= 64 ? 4 : (Kp - 64 * s + 15) / 16);
                 u.kind = 2;
+                u.bytes16 = (uint16_t)(u.rows * 8);
                 off += (uint32_t)u.rows * 128u;
             }
             g.nu = (uint8_t)(nu - g.u0);
@@ -753,7 +841,7 @@ static int gen_attrs(b2048_handle* h) {
 static int gen_prepare(const b2048_mlp_desc* mlp, const GenProg& p, uint8_t* img, cudaStream_t stream) {
     GenPrepArgs pa;
     pa.p = p;
-    for (int l = 0; l < GN_MAXL; ++l) pa.W[l] = l < mlp->n_layers ? mlp->W[l] : nullptr;
+    for (int l = 0; l < GN_MAXL; ++l) { pa.W[l] = l < mlp->n_layers ? mlp->W[l] : nullptr; pa.b[l] = l < mlp->n_layers ? mlp->b[l] : nullptr; }
     for (int l = 0; l <= GN_MAXL; ++l) pa.dims[l] = l <= mlp->n_layers ? mlp->dims[l] : 0;
     pa.img = img;
     gen_prepare_kernel<<<128, 256, 0, stream>>>(pa);
@@ -770,6 +858,31 @@ static int ensure_gen_image(b2048_handle* h, size_t bytes) {
     return B2048_OK;
 }
 
+static long long* g_dbg_buf = nullptr;
+static void gen_dbg_begin(b2048_handle* h, GenArgs& a, cudaStream_t stream) {
+    if (!(h->debug & (1u << B2048_DBG_TC_CLOCKS))) return;
+    if (!g_dbg_buf) cudaMalloc(&g_dbg_buf, 256 * sizeof(long long));
+    cudaMemsetAsync(g_dbg_buf, 0, 256 * sizeof(long long), stream);
+    a.dbg = g_dbg_buf;
+}
+static void gen_dbg_end(const GenArgs& a, cudaStream_t stream) {
+    if (!a.dbg) return;
+    long long hb[256];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hb, g_dbg_buf, sizeof(hb), cudaMemcpyDeviceToHost);
+    for (int lt = 0; lt < 4; ++lt) {
+        const long long* d = hb + 64 * lt;
+        const long long t0 = d[0];
+        if (t0 == 0) continue;
+        fprintf(stderr, "[gen_mlp clock] tile %d (cycles from the MMA lane's tile start): io: loop top %lld loads done %lld input written %lld head ready %lld "
+                        "tile end %lld\n", lt, d[52] - t0, d[53] - t0, d[54] - t0, d[55] - t0, d[56] - t0);
+        for (int G = 0; G < a.p.n_gemm; ++G)
+            fprintf(stderr, "    GEMM %d (%s layer %d, N %d, %d units): A ready %lld, all MMAs issued %lld (weight waits %lld) | epilogue: acc ready %lld done %lld\n",
+                    G, a.p.gemm[G].bwd ? "bwd" : "fwd", a.p.gemm[G].layer, a.p.gemm[G].N, a.p.gemm[G].nu, d[1 + 3 * G] - t0, d[2 + 3 * G] - t0,
+                    d[3 + 3 * G], a.p.gemm[G].head ? 0 : d[32 + 2 * G] - t0, a.p.gemm[G].head ? 0 : d[33 + 2 * G] - t0);
+    }
+}
+
 static void gen_fill_common(GenArgs& a, const b2048_mlp_desc* mlp, const GenProg& p) {
     memset(&a, 0, sizeof(a));
     a.p = p;
@@ -781,8 +894,8 @@ static void gen_fill_common(GenArgs& a, const b2048_mlp_desc* mlp, const GenProg
 // (silent) for shapes outside gen_supported().
 int launch_forward_gen(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags, float* out,
                        uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, int greedy,
-                       int split, bool rebuild_image, cudaStream_t stream) {
-    if (!gen_supported(h, mlp) || n < 4096) return B2048_ERR_UNSUPPORTED;
+                       int split, bool rebuild_image, cudaStream_t stream, const int32_t* slot_map, const int32_t* n_dev) {
+    if (!gen_supported(h, mlp) || (n < 4096 && slot_map == nullptr)) return B2048_ERR_UNSUPPORTED;
     { int st = gen_attrs(h); if (st != B2048_OK) return st; }
     GenProg p;
     build_program(mlp, split != 0, false, p);
@@ -797,9 +910,12 @@ int launch_forward_gen(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_
     a.img = img; a.board = board; a.n = n;
     a.out = out; a.action = action; a.probs = probs; a.logits = logits; a.mask_flags = mask_flags;
     a.keys = make_keys(seed); a.gid0 = gid0; a.t = t; a.greedy = greedy;
+    a.slot_map = slot_map; a.n_dev = slot_map ? n_dev : nullptr;
     const int64_t tiles = (n + TC_M - 1) / TC_M;
     const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+    gen_dbg_begin(h, a, stream);
     gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+    gen_dbg_end(a, stream);
     return check_cuda(cudaGetLastError(), "gen_mlp_kernel launch");
 }
 
@@ -839,7 +955,9 @@ int launch_backward_gen(b2048_handle* h, const uint64_t* board, const uint8_t* m
         for (int l = 0; l < L; ++l) a.dlimg[l] = ws + w.dlimg[l];
         a.gb_head = gb[L - 1];
         a.mask_scratch = reinterpret_cast<uint16_t*>(ws + w.masks);
+        if (c0 == 0) gen_dbg_begin(h, a, stream);
         gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        gen_dbg_end(a, stream);
         int st = check_cuda(cudaGetLastError(), "gen_mlp_kernel launch");
         if (st != B2048_OK) return st;
         for (int l = 0; l < L; ++l) {

@@ -151,7 +151,9 @@ int launch_policy_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t*
 int launch_forward_hp(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n, cudaStream_t stream);
 int launch_forward_gen(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, const uint8_t* mask_flags, float* out,
                        uint8_t* action, float* probs, float* logits, int64_t n, uint64_t seed, uint64_t gid0, uint32_t t, int greedy,
-                       int split, bool rebuild_image, cudaStream_t stream);
+                       int split, bool rebuild_image, cudaStream_t stream, const int32_t* slot_map = nullptr,
+                       const int32_t* n_dev = nullptr);
+bool gen_supported(const b2048_handle* h, const b2048_mlp_desc* mlp);
 int launch_forward_tc(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_t* board, float* out, int64_t n,
                       cudaStream_t stream);
 int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boards, uint8_t* flags, uint8_t* actions,
@@ -252,15 +254,24 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
                                    seed, gid0, t0, use_mask, greedy, slot_map, n_slots, n_slots_dev, (cudaStream_t)stream);
         if (st != B2048_ERR_UNSUPPORTED) return st;
     }
-    B2_REQUIRE(slot_map == nullptr, "b2048_rollout_many: slot_map needs the fused tensor-core rollout kernel (precision 1, "
-                                    "16-256-256-4 ReLU policy, plain reward configuration, B >= 4096)");
+    // Shapes of the shape-generic tensor-core policy kernel: the POLICY step visits only the listed boards; the step kernel
+    // passes finished boards through untouched anyway (ep_len != 0).
+    const bool gen_slots = slot_map != nullptr;
+    if (gen_slots) {
+        B2_REQUIRE(precision == 1 && gen_supported(h, mlp) && ep_len != nullptr && n_slots >= 0 && n_slots <= B,
+                   "b2048_rollout_many: slot_map needs a tensor-core policy (precision 1; the fused 16-256-256-4 rollout kernel with "
+                   "a plain reward configuration and B >= 4096, or a shape of the generic tcgen05 policy kernel) and ep_len");
+        if (n_slots == 0) return B2048_OK;
+    }
     for (int32_t k = 0; k < n_steps; ++k) {
         const int64_t t = (int64_t)t_begin + k;
         const uint32_t t_env = t0 + (uint32_t)t + 1u;
         uint64_t* b_in = boards + t * B;
         uint8_t* f_in = flags + t * B;
-        int st = policy_step_impl(h, b_in, use_mask ? f_in : nullptr, mlp, actions + t * B, nullptr, nullptr, B, seed, gid0,
-                                  t_env, greedy, precision, stream, k == 0);
+        int st = gen_slots ? launch_forward_gen(h, mlp, b_in, use_mask ? f_in : nullptr, nullptr, actions + t * B, nullptr, nullptr,
+                                                n_slots, seed, gid0, t_env, greedy, 0, k == 0, (cudaStream_t)stream, slot_map, n_slots_dev)
+                           : policy_step_impl(h, b_in, use_mask ? f_in : nullptr, mlp, actions + t * B, nullptr, nullptr, B, seed, gid0,
+                                              t_env, greedy, precision, stream, k == 0);
         if (st != B2048_OK) return st;
         st = b2048_step_many(h, b_in, b_in + B, score, step, max_exp, actions + t * B, nullptr, f_in, nullptr, &c, nullptr,
                              rewards + t * B, nullptr, f_in + B, nullptr, ep_len, (uint32_t)(t + 1), B, seed, gid0, t_env,

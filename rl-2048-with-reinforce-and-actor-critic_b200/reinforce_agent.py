@@ -413,8 +413,8 @@ class ReinforceAgent:
         # Run-to-termination on the fused tensor-core kernel: every chunk plays only the boards that are still alive
         # (slot_map), so finished episodes cost nothing.  Slices beyond an episode's end are then never written: the
         # rewards buffer is zeroed first (total_reward sums whole columns) and the final state is gathered below.
-        compact = (not fixed) and int(precision) == 1 and B >= 4096 and self._fused_shape() and \
-            not debug_get("no_fused_rollout") and not debug_get("no_compact_rollout")
+        compact = (not fixed) and int(precision) == 1 and B >= 4096 and not debug_get("no_compact_rollout") and \
+            ((self._fused_shape() and not debug_get("no_fused_rollout")) or (not self._fused_shape() and self._generic_tc_shape()))
         if compact:
             rewards.zero_()
             # Live-board bookkeeping stays on the device: after every chunk b2048_compact_live rebuilds the list and its

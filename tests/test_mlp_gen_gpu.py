@@ -241,3 +241,65 @@ def test_gen_actor_critic_update_matches_fp32(b2048):
     for k in (0, 1):
         a, b = deltas["auto"][k], deltas[0][k]
         assert np.mean(np.sign(a) == np.sign(b)) > 0.97
+
+
+def _gen_rollout(b2048, n, max_steps, compact, greedy=False, hidden=(256, 128, 64), obs_mode="onehot", seed=4242, gid0=17):
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = max_steps; kw["obs_mode"] = obs_mode
+    b2048.debug_set("no_compact_rollout", not compact)
+    try:
+        benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=gid0)
+        agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=list(hidden), activation="ReLU", init_distribution="HeNormal"),
+                                     b2048.ReinforceAgentConfig(model_seed=3))
+        assert agent.tc_supported() and not agent._fused_shape()
+        ro = agent.rollout_many(benv, greedy=greedy, precision=1, check_every=16)
+        torch.cuda.synchronize()
+    finally:
+        b2048.debug_set("no_compact_rollout", False)
+    return kw, benv, ro
+
+
+def test_gen_rollout_compact_equals_plain_loop(b2048):
+    """Run-to-termination rollout of the one-hot network: the policy kernel visiting only the live boards of every chunk
+    (slot_map, device-side count) produces bit for bit the rollout of the loop that evaluates every board at every step."""
+    outs = []
+    for compact in (False, True):
+        kw, benv, ro = _gen_rollout(b2048, 20000, 70, compact)
+        outs.append((ro.T, ro.length.cpu().numpy(), ro.actions.cpu().numpy(), ro.rewards.cpu().numpy(), ro.boards.cpu().numpy(),
+                     benv.score.cpu().numpy(), benv.board.cpu().numpy()))
+    (Ta, La, Aa, Ra, Ba, Sa, Fa), (Tb, Lb, Ab, Rb, Bb, Sb, Fb) = outs
+    assert (La == Lb).all() and (Sa == Sb).all() and (Fa == Fb).all()
+    T = min(Ta, Tb)
+    live = np.arange(T)[:, None] < La[None, :]
+    assert (Aa[:T][live] == Ab[:T][live]).all() and (Ra[:T][live] == Rb[:T][live]).all() and (Ba[:T][live] == Bb[:T][live]).all()
+
+
+@pytest.mark.parametrize("n,max_steps,hidden,obs_mode", [(32768, 120, (256, 128, 64), "onehot"), (8192, 40, (128,), "log2")])
+def test_gen_rollout_replays_in_oracle(b2048, n, max_steps, hidden, obs_mode):
+    """Rollout with the shape-generic tcgen05 policy kernel + the step kernel against the CPU oracle: the recorded actions
+    replayed through oracle.step_many reproduce every live board, reward and flags byte, the lengths and the final counters."""
+    seed, gid0 = 4242, 17
+    kw, benv, ro = _gen_rollout(b2048, n, max_steps, True, hidden=hidden, obs_mode=obs_mode, seed=seed, gid0=gid0)
+    T = ro.T
+    boards = ro.boards.cpu().numpy().view(np.uint64); flags = ro.flags.cpu().numpy()
+    actions = ro.actions.cpu().numpy(); rewards = ro.rewards.cpu().numpy(); length = ro.length.cpu().numpy()
+    okw = dict(kw); okw.pop("size")
+    cfg = oracle.make_cfg(action_mode="buffer", auto_reset=False, **okw)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    assert (st["board"] == boards[0]).all()
+    assert length.min() >= 1 and length.max() == T <= max_steps
+    for t in range(T):
+        live = length > t
+        prev = {k: st[k].copy() for k in ("board", "score", "step", "max_exp")}
+        o = oracle.step_many(st, cfg, seed, gid0, t + 1, action=actions[t])
+        assert (st["board"][live] == boards[t + 1][live]).all(), t
+        assert (o["reward"][live] == rewards[t][live]).all(), t
+        assert (o["flags"][live] == flags[t + 1][live]).all(), t
+        dead = ~live
+        for k in prev:
+            st[k][dead] = prev[k][dead]
+    assert (benv.board.cpu().numpy().view(np.uint64) == st["board"]).all()
+    assert (benv.score.cpu().numpy() == st["score"]).all()
+    assert (benv.step_count.cpu().numpy() == st["step"]).all()
+    m = flags[:T] & 0xF
+    livem = np.arange(T)[:, None] < length[None, :]
+    assert ((((m >> actions) & 1) == 1) | (m == 0))[livem].all()
