@@ -216,7 +216,10 @@ typedef struct b2048_mlp_desc {
  *   mask_flags : per-board flags byte (low 4 bits = legal mask); NULL = no mask
  *   action     : out uint8; probs/logits: optional out float32 [n, n_out]
  *   greedy     : 1 = first argmax of probs*mask (reinforce_agent.py:179-185)
- *   precision  : 0 = fp32 CUDA cores (parity path); 1 = bf16 tcgen05 tensor cores (n >= 4096) */
+ *   precision  : 0 = fp32 CUDA cores (parity path); 1 = tcgen05 tensor cores (n >= 4096): the hand-specialised bf16 kernel for the
+ *                16-256-256-4 ReLU policy (raw / log2 observations), the shape-generic fp16 kernel (csrc/b2048_mlp_gen.cu) for
+ *                every other ReLU policy with 1-4 hidden layers of 64 / 128 / 192 / 256 units on log2 / one-hot observations
+ *                (e.g. the reference's documented one-hot [256, 128, 64] network, runner.py:27-47); B2048_ERR_UNSUPPORTED else */
 int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mask_flags,
                       const b2048_mlp_desc* mlp /* host struct, device pointers inside */,
                       uint8_t* action, float* probs, float* logits,
@@ -232,8 +235,9 @@ int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mas
  * precision 1 with the 16-256-256-4 ReLU policy and a plain reward configuration runs the whole chunk as ONE
  * persistent kernel (tcgen05 policy + env step); anything else is a policy-kernel / step-kernel loop.
  * slot_map (device int32[n_slots], may be NULL): play only the listed boards — run-to-termination callers pass the
- * boards still alive at the start of the chunk, so finished episodes cost nothing; slices t > ep_len[b] of a board
- * that is not listed are left untouched.  Fused kernel only.
+ * boards still alive at the start of the chunk, so finished episodes cost nothing.  Fused kernel: slices t > ep_len[b] of a
+ * board that is not listed are left untouched.  Other shapes of the generic tcgen05 policy kernel (precision 1): the POLICY
+ * step visits only the listed boards, the step kernel passes the finished ones through.  Anything else: B2048_ERR_INVALID.
  * n_slots_dev (device int32[1], may be NULL): the number of listed boards is read from device memory (as written by
  * b2048_compact_live) and n_slots is only an upper bound for the launch — the host can then enqueue the next chunk
  * without waiting for the count. */
@@ -250,10 +254,11 @@ int b2048_compact_live(b2048_handle* h, const int32_t* ep_len, int64_t B, int32_
                        void* stream);
 
 /* forward_logits only (MLP.py:159-196): out[n, n_out] = logits (actor) or V(s) (critic, n_out = 1).
- *   precision : 0 = fp32 CUDA cores; 1 = single-bf16 tcgen05 (16-256-256-(<=4) ReLU, raw / log2 observations, n >= 4096,
- *               else B2048_ERR_UNSUPPORTED; 1e-2 class); 3 = split-fp16 tcgen05 (every operand as fp16 hi + lo, three
- *               MMAs per product: 1e-5 of the float64 result; same shapes, log2 observations, else
- *               B2048_ERR_UNSUPPORTED); 2 = precision 3 when it applies, else fp32. */
+ *   precision : 0 = fp32 CUDA cores; 1 = single-precision tcgen05 (1e-2 class; n >= 4096: bf16 for 16-256-256-(<=4) ReLU on raw /
+ *               log2 observations, fp16 on the shape-generic kernel for the other tensor-core shapes, see b2048_policy_step; else
+ *               B2048_ERR_UNSUPPORTED); 3 = split-fp16 tcgen05 (every operand as fp16 hi + lo, three MMAs per product: 1e-5
+ *               of the float64 result; the same shapes on log2 / one-hot observations, else B2048_ERR_UNSUPPORTED);
+ *               2 = precision 3 when it applies, else fp32. */
 int b2048_mlp_forward(b2048_handle* h, const uint64_t* board, const b2048_mlp_desc* mlp, float* out,
                       int64_t n, int32_t precision, void* stream);
 
@@ -305,9 +310,11 @@ int b2048_td_errors(b2048_handle* h, const float* reward, const float* value, co
  * workspace: device floats, at least b2048_backward_workspace_floats(mlp, chunk); samples are processed
  * `chunk` at a time.
  *   precision : 0 = fp32 CUDA cores;
- *               3 = float32-grade tensor-core path (16-256-256-(<=4) ReLU network, log2 observations, n >= 4096; anything
- *                   else returns B2048_ERR_UNSUPPORTED): forward with split-fp16 operands (hi + lo, three tcgen05.mma
- *                   per product), backward deltas and dW GEMMs in fp16 with a power-of-two loss scale, fp32 accumulation.
+ *               3 = float32-grade tensor-core path (n >= 4096; 16-256-256-(<=4) ReLU on log2 observations: the persistent
+ *                   update pipeline; every other ReLU network with 1-4 hidden layers of 64 / 128 / 192 / 256 units on log2 /
+ *                   one-hot observations: gen_mlp_kernel + gen_dw_kernel; anything else returns B2048_ERR_UNSUPPORTED):
+ *                   forward with split-fp16 operands (hi + lo, three tcgen05.mma per product), backward deltas and dW GEMMs
+ *                   in fp16 with a power-of-two loss scale, fp32 accumulation.
  *                   Within 1e-2 of the float32 gradient also on heavily cancelling (zero-mean advantage) batches;
  *               2 = precision 3 when it applies, else fp32 (what the host layer's "auto" passes);
  *               1 = single-bf16 tensor cores (raw / log2 observations), an explicit opt-in: its forward pass flips ReLU

@@ -64,6 +64,7 @@ struct GenProg {
     GGemm gemm[GN_MAXG];
     int n_units, n_gemm, L, fb, split;
     int kin, in_slabs, obs_mode, n_out;
+    int act;              // B2048_ACTV_RELU / B2048_ACTV_SIGMOID (MLP.py:130-136)
     float obs_scale;
     int width[GN_MAXL];   // accumulator width of layer l (hidden: its size; head: 16)
     uint32_t img_bytes;
@@ -95,7 +96,8 @@ struct GenArgs {
     uint8_t* himg[GN_MAXL];     // hi activation images a_{l+1} of the hidden layers, [tile][slab][128 x 128 B]
     uint8_t* dlimg[GN_MAXL];    // delta images of every layer (head: one slab)
     float* gb_head;
-    uint16_t* mask_scratch;     // [grid][GN_MASK_WORDS]
+    uint16_t* mask_scratch;     // [grid][GN_MASK_WORDS]  (ReLU)
+    uint4* dsig_scratch;        // [grid][GN_MASK_WORDS][2]: s (1 - s) of every hidden unit as fp16 (Sigmoid, update mode)
     long long* dbg;             // optional phase clocks of CTA 0 (B2048_DBG_TC_CLOCKS), 64 slots per tile for the first 4 tiles
 };
 
@@ -349,6 +351,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         const int row = q * 32 + lane;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         uint16_t* msk = a.mask_scratch ? a.mask_scratch + (size_t)blockIdx.x * GN_MASK_WORDS : nullptr;
+        uint4* dsg = a.dsig_scratch ? a.dsig_scratch + (size_t)blockIdx.x * GN_MASK_WORDS * 2 : nullptr;
         uint8_t* a_row = smem + GS_A + row * 128;
         uint32_t ne = 0;
         int lt = 0;
@@ -370,7 +373,47 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                     uint32_t (&rc)[16] = r[s & 1];
                     tmem_ld_wait(rc);
                     if (s + 1 < nsl) tmem_ld16_issue(dcol + (uint32_t)((s + 1) * 64), r[(s + 1) & 1]);
-                    if (!gm.bwd) {
+                    if (!gm.bwd && P.act == B2048_ACTV_SIGMOID) {
+                        // a = 1 / (1 + exp(-z)) (MLP.py:132); the update keeps s (1 - s) for the backward pass
+                        uint32_t dg[8];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float s0 = 1.0f / (1.0f + expf(-__uint_as_float(rc[8 * c + 2 * k])));
+                                const float s1 = 1.0f / (1.0f + expf(-__uint_as_float(rc[8 * c + 2 * k + 1])));
+                                hi[k] = gpack(s0, s1);
+                                const float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi[k]));
+                                lo[k] = gpack(s0 - hf.x, s1 - hf.y);
+                                dg[4 * c + k] = gpack(s0 * (1.0f - s0), s1 * (1.0f - s1));
+                            }
+                            const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                            *reinterpret_cast<uint4*>(a_row + s * GN_SLAB + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (P.split) *reinterpret_cast<uint4*>(a_row + (4 + s) * GN_SLAB + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                        if (dsg) {
+                            uint4* d = dsg + (size_t)(((gm.layer * 4 + s) * 4 + g) * 128 + row) * 2;
+                            d[0] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
+                            d[1] = make_uint4(dg[4], dg[5], dg[6], dg[7]);
+                        }
+                    } else if (gm.bwd && P.act == B2048_ACTV_SIGMOID) {
+                        // delta_{layer-1} = D . s (1 - s)
+                        const uint4* d = dsg + (size_t)((((gm.layer - 1) * 4 + s) * 4 + g) * 128 + row) * 2;
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const uint4 dv = d[c];
+                            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+                            uint32_t o[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 df = __half22float2(*reinterpret_cast<const __half2*>(&dw[k]));
+                                o[k] = gpack(__uint_as_float(rc[8 * c + 2 * k]) * df.x, __uint_as_float(rc[8 * c + 2 * k + 1]) * df.y);
+                            }
+                            const int sw = ((g * 2 + c) ^ (row & 7)) << 4;
+                            *reinterpret_cast<uint4*>(a_row + s * GN_SLAB + sw) = make_uint4(o[0], o[1], o[2], o[3]);
+                        }
+                    } else if (!gm.bwd) {
                         uint32_t m = 0;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) m = __funnelshift_l(0u - rc[i], m, 1);     // z > 0  <=>  sign bit of -bits(z)
@@ -739,10 +782,11 @@ __global__ void gen_scale_kernel(float* __restrict__ scale) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// Shapes: 1..4 hidden layers whose sizes are multiples of 64 up to 256, ReLU, log2 (16-wide) or one-hot (272-wide) input,
-// 1..4 outputs.  (Raw observations reach 32768 per input and could leave the fp16 range in the activations.)
+// Shapes: 1..4 hidden layers whose sizes are multiples of 64 up to 256, ReLU or Sigmoid, log2 (16-wide) or one-hot (272-wide)
+// input, 1..4 outputs.  (Raw observations reach 32768 per input and could leave the fp16 range in the activations.)
 bool gen_shape_ok(const b2048_mlp_desc* mlp) {
-    if (!mlp || mlp->n_layers < 2 || mlp->n_layers > GN_MAXL || mlp->activation != B2048_ACTV_RELU) return false;
+    if (!mlp || mlp->n_layers < 2 || mlp->n_layers > GN_MAXL) return false;
+    if (mlp->activation != B2048_ACTV_RELU && mlp->activation != B2048_ACTV_SIGMOID) return false;
     if (!((mlp->obs_mode == B2048_OBS_LOG2 && mlp->dims[0] == 16) || (mlp->obs_mode == B2048_OBS_ONEHOT && mlp->dims[0] == 272))) return false;
     for (int l = 1; l < mlp->n_layers; ++l)
         if (mlp->dims[l] < 64 || mlp->dims[l] > 256 || mlp->dims[l] % 64 != 0) return false;
@@ -760,6 +804,7 @@ static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenPro
     p.L = L; p.fb = fb ? 1 : 0; p.split = split ? 1 : 0;
     p.kin = mlp->dims[0]; p.in_slabs = (p.kin + 63) / 64; p.obs_mode = mlp->obs_mode; p.n_out = mlp->dims[L];
     p.obs_scale = mlp->obs_log2_scale;
+    p.act = mlp->activation;
     for (int l = 0; l < L; ++l) p.width[l] = l == L - 1 ? 16 : mlp->dims[l + 1];
     uint32_t off = 0;
     int nu = 0, ng = 0;
@@ -821,7 +866,7 @@ static GenWorkspace gen_workspace(const b2048_mlp_desc* mlp, int64_t chunk, int 
     GenProg p;
     build_program(mlp, true, true, p);
     w.img = o; o += ((int64_t)p.img_bytes + 1023) / 1024 * 1024;
-    w.masks = o; o += (int64_t)num_sms * GN_MASK_WORDS * 2;
+    w.masks = o; o += (int64_t)num_sms * GN_MASK_WORDS * (mlp->activation == B2048_ACTV_SIGMOID ? 32 : 2);
     w.total = o;
     return w;
 }
@@ -954,7 +999,8 @@ int launch_backward_gen(b2048_handle* h, const uint64_t* board, const uint8_t* m
         for (int l = 0; l < L - 1; ++l) a.himg[l] = ws + w.himg[l];
         for (int l = 0; l < L; ++l) a.dlimg[l] = ws + w.dlimg[l];
         a.gb_head = gb[L - 1];
-        a.mask_scratch = reinterpret_cast<uint16_t*>(ws + w.masks);
+        if (mlp->activation == B2048_ACTV_SIGMOID) a.dsig_scratch = reinterpret_cast<uint4*>(ws + w.masks);
+        else a.mask_scratch = reinterpret_cast<uint16_t*>(ws + w.masks);
         if (c0 == 0) gen_dbg_begin(h, a, stream);
         gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
         gen_dbg_end(a, stream);

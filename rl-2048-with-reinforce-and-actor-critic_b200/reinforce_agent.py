@@ -271,11 +271,11 @@ class ReinforceAgent:
         return (a.dims == [16, 256, 256, 4] and a.activation == "ReLU" and a.obs_mode in ("raw", "log2"))
 
     def _generic_tc_shape(self) -> bool:
-        """Shapes of the shape-generic tcgen05 kernels (csrc/b2048_mlp_gen.cu): ReLU, 1-4 hidden layers of 64 / 128 / 192 / 256
-        units, log2 or one-hot observations — e.g. the reference's documented one-hot [256, 128, 64] network (runner.py:27-47)."""
+        """Shapes of the shape-generic tcgen05 kernels (csrc/b2048_mlp_gen.cu): ReLU or Sigmoid, 1-4 hidden layers of 64 / 128 /
+        192 / 256 units, log2 or one-hot observations — e.g. the reference's documented one-hot [256, 128, 64] network (runner.py:27-47)."""
         a = self._actor
         hidden = a.dims[1:-1]
-        return (a.activation == "ReLU" and a.obs_mode in ("log2", "onehot") and 1 <= len(hidden) <= 4 and
+        return (a.activation in ("ReLU", "Sigmoid") and a.obs_mode in ("log2", "onehot") and 1 <= len(hidden) <= 4 and
                 all(h % 64 == 0 and 64 <= h <= 256 for h in hidden) and 1 <= a.dims[-1] <= 4)
 
     def tc_supported(self) -> bool:

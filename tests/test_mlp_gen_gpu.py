@@ -23,7 +23,14 @@ SHAPES = {  # name -> (obs_mode, hidden sizes)
     "log2_128": ("log2", [128]),                          # one hidden layer
     "log2_64_192_64_128": ("log2", [64, 192, 64, 128]),   # four hidden layers, every slab count
     "onehot_256_256": ("onehot", [256, 256]),
+    "sigmoid_log2_128_64": ("log2", [128, 64], "Sigmoid"),          # the dataclass-default activation (MLP.py:13)
+    "sigmoid_onehot_256_128": ("onehot", [256, 128], "Sigmoid"),
 }
+
+
+def shape_of(name):
+    t = SHAPES[name]
+    return t[0], t[1], (t[2] if len(t) > 2 else "ReLU")
 
 
 @pytest.fixture(scope="module")
@@ -34,9 +41,9 @@ def b2048():
     return m
 
 
-def make_gen_agent(b2048, obs_mode, hidden, seed=0, use_critic=False, **agent_kw):
+def make_gen_agent(b2048, obs_mode, hidden, seed=0, use_critic=False, actv="ReLU", **agent_kw):
     env = b2048.Batched2048Env(1, b2048.Game2048EnvConfig(obs_mode=obs_mode, obs_log2_scale=0.0625))
-    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=list(hidden), activation="ReLU", init_distribution="HeNormal"),
+    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=list(hidden), activation=actv, init_distribution="HeNormal"),
                                  b2048.ReinforceAgentConfig(use_critic=use_critic, **agent_kw))
     rng = np.random.default_rng(seed)
     kin = 272 if obs_mode == "onehot" else 16
@@ -50,12 +57,12 @@ def make_gen_agent(b2048, obs_mode, hidden, seed=0, use_critic=False, **agent_kw
     return agent
 
 
-def forward64(params, X):
+def forward64(params, X, actv="ReLU"):
     a = X.astype(np.float64)
     L = len(params["W"])
     for i in range(L):
         z = a @ params["W"][i].astype(np.float64) + params["b"][i].astype(np.float64)
-        a = np.maximum(z, 0.0) if i < L - 1 else z
+        a = (np.maximum(z, 0.0) if actv == "ReLU" else 1.0 / (1.0 + np.exp(-z))) if i < L - 1 else z
     return a
 
 
@@ -68,15 +75,15 @@ def split_flat(flat, dims):
     return out
 
 
-def oracle_grads(params, boards, masks, actions, coef, head_mode, obs_mode):
+def oracle_grads(params, boards, masks, actions, coef, head_mode, obs_mode, actv="ReLU"):
     X = learner.encode(boards, obs_mode, 0.0625)
-    out, acts, pres = learner.forward(params, X, "ReLU")
+    out, acts, pres = learner.forward(params, X, actv)
     if head_mode == 0:
         p = learner.probs_from_logits(out, masks)
         d = coef[:, None] * (np.eye(4, dtype=np.float32)[actions] - p)
     else:
         d = coef[:, None].astype(np.float32)
-    return learner.backprop(params, acts, pres, d, "ReLU")
+    return learner.backprop(params, acts, pres, d, actv)
 
 
 def mlp_forward(agent, net, boards, precision):
@@ -96,14 +103,14 @@ def mlp_forward(agent, net, boards, precision):
 def test_gen_forward_split_vs_float64(b2048, shape, n):
     """b2048_mlp_forward precision 3 on the generic kernel: head outputs (actor logits and the critic's V) within 1e-5 of the
     float64 forward; ragged last tile; more tiles than CTAs."""
-    obs_mode, hidden = SHAPES[shape]
+    obs_mode, hidden, actv = shape_of(shape)
     rng = np.random.default_rng(17)
     boards = random_boards(rng, n)
-    agent = make_gen_agent(b2048, obs_mode, hidden, seed=6, use_critic=True)
+    agent = make_gen_agent(b2048, obs_mode, hidden, seed=6, use_critic=True, actv=actv)
     X = learner.encode(boards, obs_mode, 0.0625)
     for net, params in ((agent._actor, agent.params), (agent._critic, agent.critic_params)):
         got = mlp_forward(agent, net, boards, HP)
-        ref = forward64(params, X)
+        ref = forward64(params, X, actv)
         err = rel_err(got, ref)
         print(f"{shape} n = {n} n_out = {net.dims[-1]}: split-fp16 forward vs float64 {err:.2e}")
         assert err < 1e-5, (shape, err)
@@ -116,13 +123,13 @@ def test_gen_policy_step_vs_fp32(b2048, shape):
     """b2048_policy_step precision 1 on the generic kernel (one fp16 MMA per product): logits / probabilities within 1e-2 of
     the fp32 kernel; sampled actions are legal and agree with the fp32 kernel's wherever the uniform is not within the
     probability difference of a CDF edge; greedy actions agree wherever the top-2 gap exceeds the logit error."""
-    obs_mode, hidden = SHAPES[shape]
+    obs_mode, hidden, actv = shape_of(shape)
     rng = np.random.default_rng(3)
     n = 128 * 40 + 5
     boards = random_boards(rng, n)
     masks, done = oracle.mask_done(boards)
     masks = np.where(masks == 0, 0xF, masks).astype(np.uint8)
-    agent = make_gen_agent(b2048, obs_mode, hidden, seed=2)
+    agent = make_gen_agent(b2048, obs_mode, hidden, seed=2, actv=actv)
     bd, fl = dev64(boards), torch.from_numpy(masks).cuda()
     res = {}
     for prec in (0, 1):
@@ -145,7 +152,7 @@ def test_gen_policy_step_vs_fp32(b2048, shape):
     assert np.mean(a0 == a1) > 0.99 and np.mean(g0 == g1) > 0.99
     # against the reference restatement
     X = learner.encode(boards, obs_mode, 0.0625)
-    out, _, _ = learner.forward(agent.params, X, "ReLU")
+    out, _, _ = learner.forward(agent.params, X, actv)
     assert rel_err(l1, out) < 1e-2
 
 
@@ -153,20 +160,22 @@ def test_gen_policy_step_vs_fp32(b2048, shape):
     ("onehot_256_128_64", 0, 50000, 16384, False), ("onehot_256_128_64", 1, 20000, 1 << 20, False),
     ("onehot_256_128_64", 0, 128 * 170 + 37, 1 << 20, True), ("onehot_256_128_64", 1, 33000, 8192, True),
     ("log2_128", 0, 30000, 1 << 20, True), ("log2_64_192_64_128", 0, 4096, 4096, False),
-    ("log2_64_192_64_128", 1, 128 * 160 + 1, 1 << 20, True), ("onehot_256_256", 0, 25000, 1 << 20, True)])
+    ("log2_64_192_64_128", 1, 128 * 160 + 1, 1 << 20, True), ("onehot_256_256", 0, 25000, 1 << 20, True),
+    ("sigmoid_log2_128_64", 0, 30000, 8192, True), ("sigmoid_log2_128_64", 1, 128 * 150 + 3, 1 << 20, False),
+    ("sigmoid_onehot_256_128", 0, 20000, 1 << 20, True)])
 def test_gen_backward_vs_fp32(b2048, shape, head_mode, n, chunk, zero_mean):
     """b2048_mlp_backward precision 3 on the generic kernels: every gradient tensor within 1e-2 of the float32 restatement of
     the reference AND of the fp32 kernels — coherent and zero-mean (heavily cancelling) coefficients, one chunk and several,
     ragged tiles, more tiles than CTAs, policy and value heads."""
-    obs_mode, hidden = SHAPES[shape]
+    obs_mode, hidden, actv = shape_of(shape)
     rng = np.random.default_rng(5 + head_mode)
     boards, masks, actions, coef = make_case(rng, n, zero_mean=zero_mean, scale=1e-4)
-    agent = make_gen_agent(b2048, obs_mode, hidden, seed=3, use_critic=(head_mode == 1))
+    agent = make_gen_agent(b2048, obs_mode, hidden, seed=3, use_critic=(head_mode == 1), actv=actv)
     net, params = (agent._critic, agent.critic_params) if head_mode == 1 else (agent._actor, agent.params)
     args = (boards, masks if head_mode == 0 else None, actions if head_mode == 0 else None, coef, head_mode)
     g_hp, _ = call_backward(b2048, agent, net, *args, HP, chunk)
     g_32, _ = call_backward(b2048, agent, net, *args, 0, chunk)
-    gW, gb = oracle_grads(params, boards, masks if head_mode == 0 else None, actions, coef, head_mode, obs_mode)
+    gW, gb = oracle_grads(params, boards, masks if head_mode == 0 else None, actions, coef, head_mode, obs_mode, actv)
     a, b = split_flat(g_hp, net.dims), split_flat(g_32, net.dims)
     errs = {}
     for l in range(len(net.dims) - 1):

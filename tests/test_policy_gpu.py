@@ -230,18 +230,30 @@ def test_update_large_batch_vs_oracle(b2048):
     critic = b2048.init_model_params(16, [128, 64], 1, np.random.default_rng(6), "HeNormal")
     kw = dict(gamma=0.97, learning_rate=3e-3, baseline_mode="batch_norm", optimizer="adam", use_critic=True,
               critic_learning_rate=1e-3, max_grad_norm=0.7)
-    agent = make_agent(b2048, dict(obs_mode="log2", obs_log2_scale=0.25), dict(hidden_sizes=[128, 64], activation="ReLU"), kw,
-                       actor=actor, critic=critic)
     L = learner.Learner(actor, critic, activation="ReLU", obs_mode="log2", obs_scale=0.25, gamma=0.97, lr=3e-3,
                         baseline="batch_norm", optimizer="adam", use_critic=True, critic_lr=1e-3, max_grad_norm=0.7)
     out = L.update(eps)
-    info = agent.update_from_rollout(episodes_to_rollout(b2048, eps), chunk=5000)
-    assert abs(info["actor_grad_norm"] - out["actor_grad_norm"]) < TOL * out["actor_grad_norm"]
-    assert abs(info["critic_grad_norm"] - out["critic_grad_norm"]) < TOL * out["critic_grad_norm"]
-    new, newc = agent.params, agent.critic_params
-    for l in range(3):
-        assert rel_err(new["W"][l] - actor["W"][l], L.actor["W"][l] - actor["W"][l]) < TOL
-        assert rel_err(newc["W"][l] - critic["W"][l], L.critic["W"][l] - critic["W"][l]) < TOL
+    # fp32 kernels at the float32 bar; "auto" = the shape-generic tensor-core kernels for this 16-128-64 network (13 K samples)
+    # at north_star's tensor-core bar
+    for prec, tol in ((0, TOL), ("auto", 1e-2)):
+        agent = make_agent(b2048, dict(obs_mode="log2", obs_log2_scale=0.25), dict(hidden_sizes=[128, 64], activation="ReLU"), kw,
+                           actor={k: [x.copy() for x in v] for k, v in actor.items()},
+                           critic={k: [x.copy() for x in v] for k, v in critic.items()})
+        info = agent.update_from_rollout(episodes_to_rollout(b2048, eps), chunk=5000, precision=prec)
+        assert ("tcgen05" in info["precision"]) == (prec == "auto"), info["precision"]
+        assert abs(info["actor_grad_norm"] - out["actor_grad_norm"]) < tol * out["actor_grad_norm"]
+        assert abs(info["critic_grad_norm"] - out["critic_grad_norm"]) < tol * out["critic_grad_norm"]
+        new, newc = agent.params, agent.critic_params
+        for l in range(3):
+            da, ra = new["W"][l] - actor["W"][l], L.actor["W"][l] - actor["W"][l]
+            dc, rc = newc["W"][l] - critic["W"][l], L.critic["W"][l] - critic["W"][l]
+            if prec == 0:
+                assert rel_err(da, ra) < tol and rel_err(dc, rc) < tol
+            else:
+                # Adam's first step is lr * g / (|g| + eps) ~ lr * sign(g): a gradient element below the tensor-core path's
+                # 5e-4-class error may change sign, so the steps are compared by sign agreement (the gradients themselves are
+                # held to 1e-2 in tests/test_mlp_gen_gpu.py)
+                assert np.mean(np.sign(da) == np.sign(ra)) > 0.995 and np.mean(np.sign(dc) == np.sign(rc)) > 0.995
 
 
 def fixed_seed_iter(base_seed):

@@ -73,8 +73,10 @@ def test_tc_policy_vs_fp32(b2048, obs_mode, scale, n):
 
 def test_tc_policy_unsupported_shape_is_loud(b2048):
     env = b2048.Batched2048Env(1, b2048.Game2048EnvConfig(obs_mode="log2"))
-    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[64, 64], activation="ReLU", init_distribution="HeNormal"),
+    # (hidden sizes that are not multiples of 64, or Sigmoid: outside the hand-specialised AND the shape-generic tcgen05 kernels)
+    agent = b2048.ReinforceAgent(env, b2048.MLPConfig(hidden_sizes=[64, 48], activation="ReLU", init_distribution="HeNormal"),
                                  b2048.ReinforceAgentConfig())
+    assert not agent.tc_supported()
     bd = torch.zeros(4096, dtype=torch.int64, device="cuda")
     act = torch.zeros(4096, dtype=torch.uint8, device="cuda")
     with pytest.raises(b2048.B2048Error):
