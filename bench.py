@@ -19,6 +19,8 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
   env_multi_step  secondary: env-steps/s with 64 steps per launch (state kept in registers across the steps)
   env_trained_boards  secondary: the same env-step measurement on boards harvested from a trained policy (north_star)
   rollout    secondary: policy-rollout steps/s (MLP 16-256-256-4 forward + masked sampling + env step), 65,536 boards
+  rollout_onehot  secondary: the same for the reference's documented one-hot 272-256-128-64-4 policy (shape-generic tcgen05
+             policy kernel + step kernel), 262,144 boards
   train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
              one update; 65,536 / 262,144 boards per GPU)
   train_iter_actor_critic_onehot   secondary: the reference's documented configuration (one-hot observations, hidden
@@ -444,6 +446,19 @@ def run_b200(args):
                                      "kernel": "b2::policy_tc_kernel<rollout>", "traffic": tr,
                                      "traffic_source": (tr_src + " (DRAM bytes of the profiled 16-step launch on 65,536 boards)") if tr_src else None}
                 extra[key] = r
+            # the reference's documented one-hot 272-256-128-64-4 policy on the shape-generic tcgen05 policy kernel (262,144 boards)
+            r = b2048.bench_rollout(dev, boards=262144, gid0=rank * 262144, precision=1, steps=32, network="onehot")
+            v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            r["value_all_gpus"] = float(v.item())
+            burst, sustained, src = measured_tensor_peaks()
+            r["roofline"] = {"bound": "tensor", "achieved": r["achieved_tflops"], "peak": sustained, "unit": "TFLOP/s",
+                             "frac": r["achieved_tflops"] / sustained, "peak_burst": burst, "peak_source": src,
+                             "algorithmic_flops_per_rollout_step": r["flops_per_step"], "kernel": "b2::gen_mlp_kernel<ReLU> (+ step_kernel)",
+                             "traffic": None,
+                             "note": "MMA phases are shared-memory bound: the weights stream through a 3-slot ring (DESIGN.md section 3)"}
+            extra["rollout_onehot"] = r
             r = b2048.bench_env_trained_boards(dev, boards=n, gid0=rank * n)
             v = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
             if world > 1:
@@ -471,6 +486,8 @@ def run_b200(args):
             "e2e_pcie_gbs_per_gpu": line["e2e"]["pcie_gbs_per_gpu"],
             "env_multi_step_per_s": g(extra, "env_multi_step", "value"),
             "rollout_steps_per_s": g(extra, "rollout", "value_all_gpus"), "rollout_tensor_frac": g(extra, "rollout", "roofline", "frac"),
+            "rollout_onehot_steps_per_s": g(extra, "rollout_onehot", "value_all_gpus"),
+            "rollout_onehot_tensor_frac": g(extra, "rollout_onehot", "roofline", "frac"),
             "train_iter_rollout_ms": g(extra, "train_iter", "rollout_ms"), "train_iter_update_ms": g(extra, "train_iter", "update_ms"),
             "train_iter_update_mode": g(extra, "train_iter", "update_precision"),
             "train_iter_update_ms_bf16": g(extra, "train_iter", "update_ms_bf16"),

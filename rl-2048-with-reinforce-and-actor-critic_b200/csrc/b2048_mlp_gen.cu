@@ -51,18 +51,34 @@ struct GUnit {            // one streamed weight unit = the B operand of up to 8
     uint8_t ksteps;       // valid K = 16 steps of the slab (1..4)
     uint8_t kind;         // 0: forward hi, 1: forward lo, 2: backward (fp16 W read as [in][out]), 3: bias [rows x 16] (k = 0: hi, 1: lo)
     uint16_t bytes16;     // unit size / 16
+    uint16_t slot_off16;  // offset of the unit inside its ring slot / 16
+    uint16_t pad;
+};
+struct GFill {            // consecutive units of one GEMM that travel in ONE ring slot (<= 32 KB): one bulk load, one slot release.
+    uint32_t off;         // A tcgen05.commit drains the MMA pipeline (~400 cycles measured), so slots are released per fill, not per unit
+    uint16_t bytes16;
+    uint8_t u0, nu;
 };
 struct GGemm {
+    uint8_t f0, nf;       // its fills (ring slots)
     uint8_t u0, nu;       // its units
     uint8_t layer, bwd;   // forward: z_layer = a_{layer-1} W_layer;  backward: delta_{layer-1} = delta_layer W_layer^T
     uint16_t N;           // accumulator columns
     uint8_t a_lo;         // the A operand has a lo half (split forward, layer > 0)
     uint8_t head;         // forward head GEMM: read by the I/O warps
+    uint8_t from_io;      // its A operand is written by the I/O warps (the tile's input; the head deltas)
+    uint8_t pad;
 };
+// Per-unit issue record of the MMA warp (tile-invariant; lane l keeps records l and l + 32 in registers, a shuffle broadcasts one):
+// [0..15] offset in the ring slot / 16, [16..18] K steps, [19..20] kind, [21] first unit of its fill, [22] last unit of its fill,
+// [23] first unit of a K slab written by the epilogue warps (wait for the slab), [24..26] K slab, [27] the slab leaves as an image
+constexpr uint32_t GR_FIRST = 1u << 21, GR_LAST = 1u << 22, GR_SLABWAIT = 1u << 23, GR_STORE = 1u << 27;
 struct GenProg {
     GUnit unit[GN_MAXU];
+    GFill fill[GN_MAXU];
     GGemm gemm[GN_MAXG];
-    int n_units, n_gemm, L, fb, split;
+    uint32_t rec[GN_MAXU];
+    int n_units, n_fills, n_gemm, L, fb, split;
     int kin, in_slabs, obs_mode, n_out;
     int act;              // B2048_ACTV_RELU / B2048_ACTV_SIGMOID (MLP.py:130-136)
     float obs_scale;
@@ -121,6 +137,17 @@ __device__ __forceinline__ void gwait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!gtry(bar, parity))
         if (clock64() - t0 > 4000000000LL) __trap();
+}
+// tcgen05.mma from the 32-bit halves of the two shared-memory descriptors (the upper halves are compile-time constants)
+__device__ __forceinline__ void umma_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ uint32_t gpack(float a, float b) {
     __half2 p = __floats2half2_rn(a, b);
@@ -191,8 +218,9 @@ __global__ void __launch_bounds__(256) gen_prepare_kernel(const __grid_constant_
             }
             continue;
         }
-        for (int idx = tid; idx < (int)un.rows * 64; idx += nth) {
-            const int r = idx >> 6, k = idx & 63;
+        const bool compact = un.ksteps == 1;      // a single K = 16 step: [rows / 8][2 k-chunks][8 rows][16 B], no swizzle (a quarter of the slab)
+        for (int idx = tid; idx < (int)un.rows * (compact ? 16 : 64); idx += nth) {
+            const int r = compact ? idx >> 4 : idx >> 6, k = compact ? idx & 15 : idx & 63;
             float v = 0.0f;
             if (un.kind < 2) {              // forward: B[n = out feature r][k = in feature]
                 const int kg = un.slab * 64 + k;
@@ -203,12 +231,17 @@ __global__ void __launch_bounds__(256) gen_prepare_kernel(const __grid_constant_
             }
             __half hv = __float2half_rn(v);
             if (un.kind == 1) hv = __float2half_rn(v - __half2float(hv));
-            *reinterpret_cast<__half*>(a.img + un.off + (size_t)r * 128 + (size_t)((((k >> 3) ^ (r & 7))) << 4) + (k & 7) * 2) = hv;
+            const size_t eo = compact ? (size_t)(r >> 3) * 256 + (size_t)(k >> 3) * 128 + (size_t)(r & 7) * 16 + (k & 7) * 2
+                                      : (size_t)r * 128 + (size_t)((((k >> 3) ^ (r & 7))) << 4) + (k & 7) * 2;
+            *reinterpret_cast<__half*>(a.img + un.off + eo) = hv;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ the tile kernel
+// kAct: the hidden activation is a compile-time choice (the Sigmoid epilogue would cost the ReLU one registers);
+// kDbg compiles the phase clocks in (B2048_DBG_TC_CLOCKS)
+template <int kAct, bool kDbg>
 __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -247,24 +280,24 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
     const uint32_t sA = s_u32(smem + GS_A), sW = s_u32(smem + GS_W);
 
     if (warp == 16) {
-        // ============================ MMA lane: GEMM program, image stores ============================
+        // ============================ MMA warp: GEMM program, image stores ============================
         // A GEMM whose A operand comes from the epilogue warps starts on K slab s as soon as THAT slab has been written (per-slab
         // barriers): the epilogue of GEMM G runs under the MMAs of GEMM G + 1 (accumulators alternate between two TMEM regions).
-        if (lane == 0) {
-            uint32_t U = 0, nio = 0, spar = 0;      // spar: phase parity of the four slab barriers
-            const uint64_t d_ones = desc_ones(s_u32(smem + GS_ONES));
-            auto slab_ready = [&](int sl) {
-                gwait(bar_slab0 + 8u * (uint32_t)sl, (spar >> sl) & 1u);
-                spar ^= 1u << sl;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            };
+        // All 32 lanes walk the program CONVERGENTLY (loop counters, table reads and descriptor words stay in uniform registers);
+        // only the asynchronous instructions themselves are issued by lane 0 (with the whole loop under `if (lane == 0)` every
+        // tcgen05.mma cost ~25 vector instructions: ELECT / R2UR per operand).
+        {
+            const bool leader = lane == 0;
+            uint32_t U = 0, nio = 0, spar = 0;      // ring fills consumed; I/O hand-offs; phase parity of the four slab barriers
+            constexpr uint32_t HI_SW = 0x40004040u, HI_NOSW = 0x4010u, HI_ONES = 0x4000u;     // upper descriptor words (b2048_tc.cuh)
+            const uint32_t ones_lo = (s_u32(smem + GS_ONES) >> 4) | (8u << 16);
             int lt = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-                long long* dc = (a.dbg && blockIdx.x == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
+                long long* dc = (kDbg && a.dbg && blockIdx.x == 0 && lt < 4 && leader) ? a.dbg + 64 * lt : nullptr;
                 if (dc) dc[0] = clock64();
                 for (int G = 0; G < P.n_gemm; ++G) {
                     const GGemm gm = P.gemm[G];
-                    const bool from_io = G == 0 || (gm.bwd && G == P.L);
+                    const bool from_io = gm.from_io != 0;
                     long long wsum = 0;
                     if (from_io) {
                         gwait(bar_io, nio & 1u); ++nio;
@@ -281,51 +314,77 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                     const uint32_t dcol = tmem_base + (uint32_t)(G & 1) * 256u;
                     const uint32_t idesc = idesc_h(TC_M, gm.N);
                     uint32_t acc = 0u;
-                    for (int u = gm.u0; u < gm.u0 + gm.nu; ++u, ++U) {
-                        const GUnit un = P.unit[u];
-                        if (un.kind == 0 || un.kind == 2) {      // first unit of K slab un.slab
-                            if (!from_io) { slab_ready(un.slab); if (dc && un.slab == 0) dc[1 + 3 * G] = clock64(); }
-                            if (store) {
-                                g_bulk_store(img_dst + (size_t)un.slab * GN_SLAB, sA + (uint32_t)un.slab * GN_SLAB, GN_SLAB);
-                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                            }
-                        }
+                    for (int f = gm.f0; f < gm.f0 + gm.nf; ++f, ++U) {
+                        const GFill fl = P.fill[f];
                         const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
-                        const long long w0 = dc ? clock64() : 0;
-                        gwait(w_full0 + 8u * slot, use & 1u);
-                        if (dc) wsum += clock64() - w0;
-                        const uint32_t wb = sW + slot * GN_SLOT, ah = sA + (uint32_t)un.slab * GN_SLAB;
-                        if (un.kind == 3) {
-                            umma_f16(dcol, d_ones, desc_nosw_k16(wb), idesc, acc);
-                            acc = 1u;
-                        } else {
-                            for (int q = 0; q < un.ksteps; ++q) {
-                                umma_f16(dcol, desc_sw128(ah + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, acc);
-                                acc = 1u;
+                        bool loaded = false;
+                        for (int u = fl.u0; u < fl.u0 + fl.nu; ++u) {
+                            const GUnit un = P.unit[u];
+                            if (un.kind == 0 || un.kind == 2) {      // first unit of K slab un.slab
+                                if (!from_io) {
+                                    gwait(bar_slab0 + 8u * (uint32_t)un.slab, (spar >> un.slab) & 1u);
+                                    spar ^= 1u << un.slab;
+                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                    if (dc && un.slab == 0) dc[1 + 3 * G] = clock64();
+                                }
+                                if (store && leader) {
+                                    g_bulk_store(img_dst + (size_t)un.slab * GN_SLAB, sA + (uint32_t)un.slab * GN_SLAB, GN_SLAB);
+                                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                }
                             }
-                            if (un.kind == 0 && gm.a_lo)
-                                for (int q = 0; q < un.ksteps; ++q)
-                                    umma_f16(dcol, desc_sw128(ah + 4u * GN_SLAB + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), idesc, 1u);
+                            if (!loaded) {
+                                const long long w0 = dc ? clock64() : 0;
+                                gwait(w_full0 + 8u * slot, use & 1u);
+                                if (dc) wsum += clock64() - w0;
+                                loaded = true;
+                            }
+                            const uint32_t wb_lo = ((sW + slot * GN_SLOT) >> 4) + (uint32_t)un.slot_off16;
+                            const uint32_t a_lo = ((sA + (uint32_t)un.slab * GN_SLAB) >> 4) | (1u << 16);
+                            if (un.kind == 3) {                      // bias: constant ones A operand, [N x 16] no-swizzle B
+                                if (leader) umma_w(dcol, ones_lo, HI_ONES, wb_lo | (8u << 16), HI_NOSW, idesc, acc);
+                                acc = 1u;
+                            } else if (un.ksteps == 1) {             // compact single-K-step unit (no-swizzle B)
+                                if (leader) umma_w(dcol, a_lo, HI_SW, wb_lo | (8u << 16), HI_NOSW, idesc, acc);
+                                acc = 1u;
+                                if (un.kind == 0 && gm.a_lo && leader) umma_w(dcol, a_lo + (4u * GN_SLAB >> 4), HI_SW, wb_lo | (8u << 16), HI_NOSW, idesc, 1u);
+                            } else {
+                                const uint32_t b_lo = wb_lo | (1u << 16);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (q < un.ksteps) {
+                                        if (leader) umma_w(dcol, a_lo + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, acc);
+                                        acc = 1u;
+                                    }
+                                }
+                                if (un.kind == 0 && gm.a_lo) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        if (q < un.ksteps && leader) umma_w(dcol, a_lo + (4u * GN_SLAB >> 4) + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, 1u);
+                                }
+                            }
                         }
-                        umma_commit(w_empty0 + 8u * slot);
+                        if (leader) umma_commit(w_empty0 + 8u * slot);
                     }
                     // the epilogue of this GEMM overwrites the A buffer: the image stores must have read it
-                    if (store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    umma_commit(gm.head ? bar_acc_h : bar_acc_e);
+                    if (store && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (leader) umma_commit(gm.head ? bar_acc_h : bar_acc_e);
                     if (dc) { dc[2 + 3 * G] = clock64(); dc[3 + 3 * G] = wsum; }
                 }
                 if (P.fb) {            // delta_0 (the last epilogue's output) is only an image
                     const int nsl = P.width[0] >> 6;
                     for (int sl = 0; sl < nsl; ++sl) {
-                        slab_ready(sl);
-                        g_bulk_store(a.dlimg[0] + ((size_t)tile * nsl + sl) * GN_SLAB, sA + (uint32_t)sl * GN_SLAB, GN_SLAB);
+                        gwait(bar_slab0 + 8u * (uint32_t)sl, (spar >> sl) & 1u);
+                        spar ^= 1u << sl;
+                        if (leader) g_bulk_store(a.dlimg[0] + ((size_t)tile * nsl + sl) * GN_SLAB, sA + (uint32_t)sl * GN_SLAB, GN_SLAB);
                     }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    mbar_arrive(bar_free);
+                    if (leader) {
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(bar_free);
+                    }
                 }
             }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
         __syncwarp();
     } else if (warp == 17) {
@@ -333,13 +392,13 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         if (lane == 0) {
             uint32_t U = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int u = 0; u < P.n_units; ++u, ++U) {
-                    const GUnit un = P.unit[u];
+                for (int f = 0; f < P.n_fills; ++f, ++U) {
+                    const GFill fl = P.fill[f];
                     const uint32_t slot = U % GN_NSLOT, use = U / GN_NSLOT;
                     if (use > 0) gwait(w_empty0 + 8u * slot, (use - 1u) & 1u);
-                    const uint32_t bar = w_full0 + 8u * slot, bytes = (uint32_t)un.bytes16 * 16u;
+                    const uint32_t bar = w_full0 + 8u * slot, bytes = (uint32_t)fl.bytes16 * 16u;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                    g_bulk_load(sW + slot * GN_SLOT, a.img + un.off, bytes, bar);
+                    g_bulk_load(sW + slot * GN_SLOT, a.img + fl.off, bytes, bar);
                 }
             }
         }
@@ -356,7 +415,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         uint32_t ne = 0;
         int lt = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-            long long* dc = (a.dbg && blockIdx.x == 0 && tid == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
+            long long* dc = (kDbg && a.dbg && blockIdx.x == 0 && tid == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
             for (int G = 0; G < P.n_gemm; ++G) {
                 const GGemm gm = P.gemm[G];
                 if (gm.head) continue;
@@ -373,7 +432,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                     uint32_t (&rc)[16] = r[s & 1];
                     tmem_ld_wait(rc);
                     if (s + 1 < nsl) tmem_ld16_issue(dcol + (uint32_t)((s + 1) * 64), r[(s + 1) & 1]);
-                    if (!gm.bwd && P.act == B2048_ACTV_SIGMOID) {
+                    if (!gm.bwd && kAct == B2048_ACTV_SIGMOID) {
                         // a = 1 / (1 + exp(-z)) (MLP.py:132); the update keeps s (1 - s) for the backward pass
                         uint32_t dg[8];
 #pragma unroll
@@ -397,7 +456,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                             d[0] = make_uint4(dg[0], dg[1], dg[2], dg[3]);
                             d[1] = make_uint4(dg[4], dg[5], dg[6], dg[7]);
                         }
-                    } else if (gm.bwd && P.act == B2048_ACTV_SIGMOID) {
+                    } else if (gm.bwd && kAct == B2048_ACTV_SIGMOID) {
                         // delta_{layer-1} = D . s (1 - s)
                         const uint4* d = dsg + (size_t)((((gm.layer - 1) * 4 + s) * 4 + g) * 128 + row) * 2;
 #pragma unroll
@@ -473,8 +532,8 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         const bool use_mask = a.mask_flags != nullptr;
         uint32_t lt = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-            long long* dc = (a.dbg && blockIdx.x == 0 && warp == 18 && lane == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
-            if (dc) dc[52] = clock64();
+            long long* dc = (kDbg && a.dbg && blockIdx.x == 0 && warp == 18 && lane == 0 && lt < 4) ? a.dbg + 64 * lt : nullptr;
+            if (dc) dc[60] = clock64();
             const int64_t slot = tile * TC_M + row;
             const bool valid = slot < n_eff;
             const int64_t s = (valid && a.slot_map) ? (int64_t)a.slot_map[slot] : slot;     // the board behind the slot
@@ -490,7 +549,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
             // the A buffer is free: forward-only, the previous tile's head GEMM has completed (waited for below); update mode,
             // its last image has been read out
             if (P.fb && lt > 0) gwait(bar_free, (lt - 1u) & 1u);
-            if (dc) dc[53] = clock64();
+            if (dc) dc[61] = clock64();
             if (P.obs_mode == B2048_OBS_ONEHOT) {
                 zero_slabs_128(smem + GS_A, P.in_slabs, tid - 18 * 32);
                 asm volatile("bar.sync 1, 128;" ::: "memory");                     // the four I/O warps only
@@ -499,9 +558,9 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_io);
-            if (dc) dc[54] = clock64();
+            if (dc) dc[62] = clock64();
             gwait(bar_acc_h, lt & 1u);
-            if (dc) dc[55] = clock64();
+            if (dc) dc[63] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t r4[4];
             tmem_ld4(tlane + hcol, r4);
@@ -579,7 +638,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                     if (lane == 0 && j < P.n_out && v != 0.0f) atomicAdd(a.gb_head + j, v);
                 }
             }
-            if (dc) dc[56] = clock64();
+            if (dc) dc[59] = clock64();
         }
     }
 
@@ -798,6 +857,41 @@ bool gen_shape_ok(const b2048_mlp_desc* mlp) {
 }
 bool gen_supported(const b2048_handle* h, const b2048_mlp_desc* mlp) { return gen_shape_ok(mlp) && h->smem_optin >= 227 * 1024; }
 
+// packs the units [u0, u1) of one GEMM (contiguous in the image) into ring-slot fills of at most GN_SLOT bytes
+static void pack_fills(GenProg& p, GGemm& g, int u0, int u1) {
+    g.f0 = (uint8_t)p.n_fills; g.u0 = (uint8_t)u0; g.nu = (uint8_t)(u1 - u0);
+    int u = u0;
+    while (u < u1) {
+        GFill& f = p.fill[p.n_fills++];
+        f.off = p.unit[u].off; f.u0 = (uint8_t)u;
+        uint32_t bytes = 0;
+        while (u < u1) {
+            const uint32_t start = p.unit[u].off - f.off, ub = (uint32_t)p.unit[u].bytes16 * 16u;
+            if (start + ub > (uint32_t)GN_SLOT) break;
+            p.unit[u].slot_off16 = (uint16_t)(start / 16u);
+            bytes = start + ub;
+            ++u;
+        }
+        f.nu = (uint8_t)(u - f.u0); f.bytes16 = (uint16_t)(bytes / 16u);
+    }
+    g.nf = (uint8_t)(p.n_fills - g.f0);
+    const int G = (int)(&g - p.gemm);
+    g.from_io = (G == 0 || (g.bwd && G == p.L)) ? 1 : 0;
+    for (int f = g.f0; f < g.f0 + g.nf; ++f) {
+        const GFill& fl = p.fill[f];
+        for (int k = fl.u0; k < fl.u0 + fl.nu; ++k) {
+            const GUnit& un = p.unit[k];
+            uint32_t r = (uint32_t)un.slot_off16 | ((uint32_t)un.ksteps << 16) | ((uint32_t)un.kind << 19) | ((uint32_t)un.slab << 24);
+            if (k == fl.u0) r |= GR_FIRST;
+            if (k == fl.u0 + fl.nu - 1) r |= GR_LAST;
+            const bool slab_first = un.kind == 0 || un.kind == 2;
+            if (slab_first && !g.from_io) r |= GR_SLABWAIT;
+            if (slab_first && p.fb && G > 0) r |= GR_STORE;
+            p.rec[k] = r;
+        }
+    }
+}
+
 static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenProg& p) {
     memset(&p, 0, sizeof(p));
     const int L = mlp->n_layers;
@@ -811,7 +905,8 @@ static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenPro
     for (int l = 0; l < L; ++l) {            // forward
         const int K = mlp->dims[l], slabs = (K + 63) / 64;
         GGemm& g = p.gemm[ng++];
-        g.u0 = (uint8_t)nu; g.layer = (uint8_t)l; g.bwd = 0; g.N = (uint16_t)p.width[l]; g.a_lo = (split && l > 0) ? 1 : 0;
+        const int g_u0 = nu;
+        g.layer = (uint8_t)l; g.bwd = 0; g.N = (uint16_t)p.width[l]; g.a_lo = (split && l > 0) ? 1 : 0;
         g.head = l == L - 1 ? 1 : 0;
         for (int s = 0; s < slabs; ++s) {
             const int ks = (K - 64 * s) >= 64 ? 4 : (K - 64 * s + 15) / 16;
@@ -819,8 +914,8 @@ static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenPro
                 GUnit& u = p.unit[nu++];
                 u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = (uint8_t)s; u.ksteps = (uint8_t)ks;
                 u.kind = (uint8_t)part;
-                u.bytes16 = (uint16_t)(u.rows * 8);
-                off += (uint32_t)u.rows * 128u;
+                u.bytes16 = (uint16_t)(ks == 1 ? u.rows * 2 : u.rows * 8);     // a single-K-step unit is stored compactly (K = 16 only)
+                off += (uint32_t)u.bytes16 * 16u;
             }
         }
         if (l < L - 1) {                     // hidden layers: the bias comes in through one more MMA (head: added by the I/O warps)
@@ -828,24 +923,25 @@ static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenPro
             u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = 0; u.ksteps = 1; u.kind = 3;
             u.bytes16 = (uint16_t)(u.rows * 2);
             off += (uint32_t)u.rows * 32u;
-            off = (off + 1023u) & ~1023u;     // the next unit is a 128-byte-swizzled operand
         }
-        g.nu = (uint8_t)(nu - g.u0);
+        pack_fills(p, g, g_u0, nu);
+        off = (off + 1023u) & ~1023u;         // every fill starts a 128-byte-swizzled operand: 1024-byte aligned in the image, too
     }
     if (fb) {
         for (int l = L - 1; l >= 1; --l) {   // delta_{l-1} = delta_l W_l^T: K = width of layer l, rows = width of layer l - 1
             const int Kp = p.width[l], slabs = (Kp + 63) / 64;
             GGemm& g = p.gemm[ng++];
-            g.u0 = (uint8_t)nu; g.layer = (uint8_t)l; g.bwd = 1; g.N = (uint16_t)p.width[l - 1]; g.a_lo = 0; g.head = 0;
+            const int g_u0 = nu;
+            g.layer = (uint8_t)l; g.bwd = 1; g.N = (uint16_t)p.width[l - 1]; g.a_lo = 0; g.head = 0;
             for (int s = 0; s < slabs; ++s) {
                 GUnit& u = p.unit[nu++];
                 u.off = off; u.rows = (uint16_t)p.width[l - 1]; u.layer = (uint8_t)l; u.slab = (uint8_t)s;
                 u.ksteps = (uint8_t)((Kp - 64 * s) >= 64 ? 4 : (Kp - 64 * s + 15) / 16);
                 u.kind = 2;
-                u.bytes16 = (uint16_t)(u.rows * 8);
-                off += (uint32_t)u.rows * 128u;
+                u.bytes16 = (uint16_t)(u.ksteps == 1 ? u.rows * 2 : u.rows * 8);
+                off += (uint32_t)u.bytes16 * 16u;
             }
-            g.nu = (uint8_t)(nu - g.u0);
+            pack_fills(p, g, g_u0, nu);
         }
     }
     p.n_units = nu; p.n_gemm = ng; p.img_bytes = off;
@@ -874,7 +970,13 @@ int64_t gen_workspace_bytes(const b2048_mlp_desc* mlp, int64_t chunk) { return g
 
 static int gen_attrs(b2048_handle* h) {
     if (!(h->attrs & 32u)) {
-        cudaError_t e = cudaFuncSetAttribute(gen_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
+        e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_SIGMOID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
+        e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
+        e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_SIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
         e = cudaFuncSetAttribute(gen_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_dw_kernel)");
@@ -920,11 +1022,22 @@ static void gen_dbg_end(const GenArgs& a, cudaStream_t stream) {
         const long long t0 = d[0];
         if (t0 == 0) continue;
         fprintf(stderr, "[gen_mlp clock] tile %d (cycles from the MMA lane's tile start): io: loop top %lld loads done %lld input written %lld head ready %lld "
-                        "tile end %lld\n", lt, d[52] - t0, d[53] - t0, d[54] - t0, d[55] - t0, d[56] - t0);
+                        "tile end %lld\n", lt, d[60] - t0, d[61] - t0, d[62] - t0, d[63] - t0, d[59] - t0);
         for (int G = 0; G < a.p.n_gemm; ++G)
-            fprintf(stderr, "    GEMM %d (%s layer %d, N %d, %d units): A ready %lld, all MMAs issued %lld (weight waits %lld) | epilogue: acc ready %lld done %lld\n",
-                    G, a.p.gemm[G].bwd ? "bwd" : "fwd", a.p.gemm[G].layer, a.p.gemm[G].N, a.p.gemm[G].nu, d[1 + 3 * G] - t0, d[2 + 3 * G] - t0,
+            fprintf(stderr, "    GEMM %d (%s layer %d, N %d, %d fills): A ready %lld, all MMAs issued %lld (weight waits %lld) | epilogue: acc ready %lld done %lld\n",
+                    G, a.p.gemm[G].bwd ? "bwd" : "fwd", a.p.gemm[G].layer, a.p.gemm[G].N, a.p.gemm[G].nf, d[1 + 3 * G] - t0, d[2 + 3 * G] - t0,
                     d[3 + 3 * G], a.p.gemm[G].head ? 0 : d[32 + 2 * G] - t0, a.p.gemm[G].head ? 0 : d[33 + 2 * G] - t0);
+    }
+}
+
+static void gen_launch(const GenArgs& a, int grid, cudaStream_t stream) {
+    const bool sig = a.p.act == B2048_ACTV_SIGMOID;
+    if (a.dbg) {
+        if (sig) gen_mlp_kernel<B2048_ACTV_SIGMOID, true><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        else gen_mlp_kernel<B2048_ACTV_RELU, true><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+    } else {
+        if (sig) gen_mlp_kernel<B2048_ACTV_SIGMOID, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        else gen_mlp_kernel<B2048_ACTV_RELU, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
     }
 }
 
@@ -959,7 +1072,7 @@ int launch_forward_gen(b2048_handle* h, const b2048_mlp_desc* mlp, const uint64_
     const int64_t tiles = (n + TC_M - 1) / TC_M;
     const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     gen_dbg_begin(h, a, stream);
-    gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+    gen_launch(a, grid, stream);
     gen_dbg_end(a, stream);
     return check_cuda(cudaGetLastError(), "gen_mlp_kernel launch");
 }
@@ -1002,7 +1115,7 @@ int launch_backward_gen(b2048_handle* h, const uint64_t* board, const uint8_t* m
         if (mlp->activation == B2048_ACTV_SIGMOID) a.dsig_scratch = reinterpret_cast<uint4*>(ws + w.masks);
         else a.mask_scratch = reinterpret_cast<uint16_t*>(ws + w.masks);
         if (c0 == 0) gen_dbg_begin(h, a, stream);
-        gen_mlp_kernel<<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        gen_launch(a, grid, stream);
         gen_dbg_end(a, stream);
         int st = check_cuda(cudaGetLastError(), "gen_mlp_kernel launch");
         if (st != B2048_OK) return st;

@@ -14,9 +14,13 @@ RUNNER_ENV = dict(obs_mode="log2", obs_log2_scale=0.0625, reward_mode="log2", ba
 FLOPS_PER_STEP = 2 * (16 * 256 + 256 * 256 + 256 * 4)
 
 
-def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, precision=0, gid0: int = 0):
-    env = Batched2048Env(boards, Game2048EnvConfig(**RUNNER_ENV), device=dev, seed=0xB200, gid0=gid0)
-    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, precision=0, gid0: int = 0, network: str = "default"):
+    """network="onehot": the reference's documented one-hot 272-256-128-64-4 policy (runner.py:27-47) — on the tensor cores
+    that is the shape-generic policy kernel + the step kernel, two launches per step."""
+    onehot = network == "onehot"
+    env = Batched2048Env(boards, Game2048EnvConfig(**(ONEHOT_ENV if onehot else RUNNER_ENV)), device=dev, seed=0xB200, gid0=gid0)
+    hidden = [256, 128, 64] if onehot else [256, 256]
+    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=hidden, activation="ReLU", init_distribution="HeNormal"),
                            ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
     env.reset_many()
     agent.rollout_many(env, horizon=steps, precision=precision, reset=False)   # warm-up; also sizes the rollout buffers
@@ -28,13 +32,17 @@ def bench_rollout(dev, boards: int = 65536, steps: int = 64, warmup: int = 8, pr
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     rate = boards * steps / (ms * 1e-3)
+    dims = agent._actor.dims
+    flops = 2 * sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    fused = agent._fused_shape()
     return {"metric": "policy-rollout steps/s", "value": rate, "unit": "rollout-steps/s", "boards": boards, "steps": steps,
-            "ms_per_step": ms / steps, "mlp": "16-256-256-4 ReLU",
-            "precision": "fp32 CUDA cores" if precision == 0 else "bf16 tcgen05 (TMEM accumulators)",
-            "flops_per_step": FLOPS_PER_STEP, "achieved_tflops": rate * FLOPS_PER_STEP / 1e12,
-            # fp32: policy kernel + step kernel per step; tcgen05: image prep + ONE persistent policy+env kernel per
-            # 256-step chunk (policy_tc_kernel<rollout>)
-            "gpu_launches": 2 * steps if precision == 0 else 2 * ((steps + 255) // 256)}
+            "ms_per_step": ms / steps, "mlp": "-".join(str(d) for d in dims) + " ReLU" + (" (one-hot observations)" if onehot else ""),
+            "precision": "fp32 CUDA cores" if precision == 0 else ("bf16 tcgen05 (TMEM accumulators)" if fused else
+                                                                   "fp16 tcgen05, shape-generic policy kernel (TMEM accumulators)"),
+            "flops_per_step": flops, "achieved_tflops": rate * flops / 1e12,
+            # fp32 / generic shapes: policy kernel + step kernel per step; fused tcgen05: image prep + ONE persistent policy+env
+            # kernel per 256-step chunk (policy_tc_kernel<rollout>)
+            "gpu_launches": 2 * steps if (precision == 0 or not fused) else 2 * ((steps + 255) // 256)}
 
 
 # the reference's documented configuration (runner.py:10-63): one-hot observations,
