@@ -340,28 +340,36 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
                             }
                             const uint32_t wb_lo = ((sW + slot * GN_SLOT) >> 4) + (uint32_t)un.slot_off16;
                             const uint32_t a_lo = ((sA + (uint32_t)un.slab * GN_SLAB) >> 4) | (1u << 16);
-                            if (un.kind == 3) {                      // bias: constant ones A operand, [N x 16] no-swizzle B
-                                if (leader) umma_w(dcol, ones_lo, HI_ONES, wb_lo | (8u << 16), HI_NOSW, idesc, acc);
-                                acc = 1u;
-                            } else if (un.ksteps == 1) {             // compact single-K-step unit (no-swizzle B)
-                                if (leader) umma_w(dcol, a_lo, HI_SW, wb_lo | (8u << 16), HI_NOSW, idesc, acc);
-                                acc = 1u;
-                                if (un.kind == 0 && gm.a_lo && leader) umma_w(dcol, a_lo + (4u * GN_SLAB >> 4), HI_SW, wb_lo | (8u << 16), HI_NOSW, idesc, 1u);
-                            } else {
-                                const uint32_t b_lo = wb_lo | (1u << 16);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    if (q < un.ksteps) {
-                                        if (leader) umma_w(dcol, a_lo + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, acc);
-                                        acc = 1u;
+                            // one divergent region per unit, straight-line inside: the warp's scalar instruction stream is the
+                            // critical path of the kernel (issuing NO MMAs at all leaves the kernel time unchanged), and every
+                            // branch / convergence barrier around a tcgen05.mma costs more than the instruction itself
+                            if (leader) {
+                                const uint32_t b_ns = wb_lo | (8u << 16), b_lo = wb_lo | (1u << 16);
+                                const uint32_t a_l2 = a_lo + (uint32_t)(4 * GN_SLAB >> 4);
+                                const bool lo_part = un.kind == 0 && gm.a_lo;
+                                if (un.kind == 3) {                  // bias: constant ones A operand, [N x 16] no-swizzle B
+                                    umma_w(dcol, ones_lo, HI_ONES, b_ns, HI_NOSW, idesc, acc);
+                                } else if (un.ksteps == 4) {
+                                    umma_w(dcol, a_lo, HI_SW, b_lo, HI_SW, idesc, acc);
+                                    umma_w(dcol, a_lo + 2u, HI_SW, b_lo + 2u, HI_SW, idesc, 1u);
+                                    umma_w(dcol, a_lo + 4u, HI_SW, b_lo + 4u, HI_SW, idesc, 1u);
+                                    umma_w(dcol, a_lo + 6u, HI_SW, b_lo + 6u, HI_SW, idesc, 1u);
+                                    if (lo_part) {
+                                        umma_w(dcol, a_l2, HI_SW, b_lo, HI_SW, idesc, 1u);
+                                        umma_w(dcol, a_l2 + 2u, HI_SW, b_lo + 2u, HI_SW, idesc, 1u);
+                                        umma_w(dcol, a_l2 + 4u, HI_SW, b_lo + 4u, HI_SW, idesc, 1u);
+                                        umma_w(dcol, a_l2 + 6u, HI_SW, b_lo + 6u, HI_SW, idesc, 1u);
                                     }
-                                }
-                                if (un.kind == 0 && gm.a_lo) {
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q)
-                                        if (q < un.ksteps && leader) umma_w(dcol, a_lo + (4u * GN_SLAB >> 4) + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, 1u);
+                                } else if (un.ksteps == 1) {         // compact single-K-step unit (no-swizzle B)
+                                    umma_w(dcol, a_lo, HI_SW, b_ns, HI_NOSW, idesc, acc);
+                                    if (lo_part) umma_w(dcol, a_l2, HI_SW, b_ns, HI_NOSW, idesc, 1u);
+                                } else {                             // 2 or 3 K steps (an input width that is not a multiple of 64)
+                                    for (uint32_t q = 0; q < un.ksteps; ++q) umma_w(dcol, a_lo + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, q ? 1u : acc);
+                                    if (lo_part)
+                                        for (uint32_t q = 0; q < un.ksteps; ++q) umma_w(dcol, a_l2 + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, 1u);
                                 }
                             }
+                            acc = 1u;
                         }
                         if (leader) umma_commit(w_empty0 + 8u * slot);
                     }
