@@ -71,7 +71,7 @@ def make_sharded_env(total_boards: int, config, info: DistInfo, seed: int = 0, d
     return Batched2048Env(stop - start, config, device=dev, seed=seed, gid0=start, **kw)
 
 
-def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = None):
+def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = None, precision="auto"):
     """update_from_rollout with gradients / baseline sums all-reduced over ranks; n_traj = global episode count
     so that every rank applies exactly the update a single process holding all episodes would apply."""
     if total_episodes is None:
@@ -79,7 +79,7 @@ def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = 
         allreduce_sum_(n)
         total_episodes = int(n.item())
     rollout.n_traj = total_episodes
-    return agent.update_from_rollout(rollout, allreduce=allreduce_sum_ if info.is_distributed else None)
+    return agent.update_from_rollout(rollout, allreduce=allreduce_sum_ if info.is_distributed else None, precision=precision)
 
 
 def episode_rank_weights(total_reward: torch.Tensor, weights_conf, info: DistInfo | None = None) -> torch.Tensor:

@@ -52,7 +52,7 @@ def main():
         env = bd.make_sharded_env(total, cfg, info, seed=seed + 1)
         agent = make_agent(env, baseline)
         ro = agent.rollout_many(env)
-        upd = bd.sharded_update(agent, ro, info)
+        upd = bd.sharded_update(agent, ro, info, precision=0)     # fp32 kernels on both sides: the sharding / collective logic is under test
         theta = agent._actor.theta.clone()
         chk = theta.clone()
         dist.broadcast(chk, src=0)
@@ -61,7 +61,7 @@ def main():
             env1 = b2048.Batched2048Env(total, cfg, device=dev, seed=seed + 1)
             a1 = make_agent(env1, baseline)
             r1 = a1.rollout_many(env1)
-            u1 = a1.update_from_rollout(r1)
+            u1 = a1.update_from_rollout(r1, precision=0)
             d_ref = (a1._actor.theta - torch.from_numpy(np.concatenate(
                 [np.concatenate([W.reshape(-1), b]) for W, b in zip(*[make_agent(env1, baseline).params[k] for k in ("W", "b")])])).to(dev))
             d_got = theta - (a1._actor.theta - d_ref)
@@ -125,7 +125,7 @@ def main():
         ro = agent.rollout_many(env)
         ro.n_traj = n_ep
         calls.clear()
-        upd = agent.update_from_rollout(ro, allreduce=counting_allreduce)
+        upd = agent.update_from_rollout(ro, allreduce=counting_allreduce, precision=0)
         assert len(calls) == expect_calls, (name, calls)
         theta = agent._actor.theta.clone()
         ctheta = None if agent._critic is None else agent._critic.theta.clone()
@@ -133,7 +133,7 @@ def main():
             env1 = b2048.Batched2048Env(n_ep, cfg, device=dev, seed=seed + 3)
             a1 = b2048.ReinforceAgent(env1, mlp, acfg)
             c0 = None if a1._critic is None else a1._critic.theta.clone()
-            u1 = a1.update_from_rollout(a1.rollout_many(env1))
+            u1 = a1.update_from_rollout(a1.rollout_many(env1), precision=0)
             rel = float(((theta - th0) - (a1._actor.theta - th0)).norm() / (a1._actor.theta - th0).norm())
             msg = f"{name}: {len(calls)} all-reduce(s) per update {calls}; actor update rel err {rel:.2e}"
             assert rel < 1e-3, msg
@@ -142,6 +142,43 @@ def main():
                 msg += f", critic {relc:.2e}"
                 assert relc < 1e-3, msg
             print(msg)
+    # ---- 5. the shape-generic tensor-core kernels (the reference's documented one-hot 272-256-128-64 network, actor + critic):
+    #         the rollout (generic policy kernel on the live boards + step kernel) is sharding-invariant bit for bit, and the
+    #         all-reduced tensor-core update equals the single-process one (fp16 loss scales are per rank: 1e-3)
+    cfg_oh = b2048.Game2048EnvConfig(**dict(ENV, obs_mode="onehot", obs_log2_scale=1.0, max_steps=60))
+    acfg = b2048.ReinforceAgentConfig(gamma=0.99, learning_rate=1e-2, critic_learning_rate=1e-2, model_seed=3, use_critic=True,
+                                      baseline_mode="batch")
+    mlp = b2048.MLPConfig(hidden_sizes=[256, 128, 64], activation="ReLU", init_distribution="HeNormal")
+    env = bd.make_sharded_env(total, cfg_oh, info, seed=seed + 5)
+    agent = b2048.ReinforceAgent(env, mlp, acfg)
+    th0, c0 = agent._actor.theta.clone(), agent._critic.theta.clone()
+    ro = agent.rollout_many(env, precision=1)
+    lo, hi = bd.shard_range(total, info.rank, info.world_size)
+    T_all = torch.tensor([ro.T], device=dev)
+    dist.all_reduce(T_all, op=dist.ReduceOp.MAX)
+    Tm = int(T_all.item())
+    acts = torch.zeros((Tm, total), dtype=torch.int32, device=dev)
+    lens = torch.zeros(total, dtype=torch.int32, device=dev)
+    acts[: ro.T, lo:hi] = ro.actions.int() * (torch.arange(ro.T, device=dev).unsqueeze(1) < ro.length.unsqueeze(0))
+    lens[lo:hi] = ro.length
+    bd.allreduce_sum_(acts)
+    bd.allreduce_sum_(lens)
+    upd = bd.sharded_update(agent, ro, info)
+    theta, ctheta = agent._actor.theta.clone(), agent._critic.theta.clone()
+    if info.rank == 0:
+        env1 = b2048.Batched2048Env(total, cfg_oh, device=dev, seed=seed + 5)
+        a1 = b2048.ReinforceAgent(env1, mlp, acfg)
+        r1 = a1.rollout_many(env1, precision=1)
+        assert torch.equal(r1.length, lens), "generic rollout: episode lengths differ between sharded and single-GPU runs"
+        live = torch.arange(r1.T, device=dev).unsqueeze(1) < r1.length.unsqueeze(0)
+        assert torch.equal((r1.actions.int() * live)[:Tm], acts[: r1.T]), "generic rollout: actions differ"
+        u1 = a1.update_from_rollout(r1)
+        assert "shape-generic" in upd["precision"] and "shape-generic" in u1["precision"], (upd["precision"], u1["precision"])
+        rel = float(((theta - th0) - (a1._actor.theta - th0)).norm() / (a1._actor.theta - th0).norm())
+        relc = float(((ctheta - c0) - (a1._critic.theta - c0)).norm() / (a1._critic.theta - c0).norm())
+        print(f"shape-generic tensor-core kernels, one-hot 272-256-128-64 actor + critic: rollout sharding invariance OK; "
+              f"update rel err actor {rel:.2e} critic {relc:.2e}")
+        assert rel < 1e-3 and relc < 1e-3
     dist.barrier()
     if info.rank == 0:
         print("multi-GPU check OK")
