@@ -72,7 +72,7 @@ struct GGemm {
 // Per-unit issue record of the MMA warp (tile-invariant; lane l keeps records l and l + 32 in registers, a shuffle broadcasts one):
 // [0..15] offset in the ring slot / 16, [16..18] K steps, [19..20] kind, [21] first unit of its fill, [22] last unit of its fill,
 // [23] first unit of a K slab written by the epilogue warps (wait for the slab), [24..26] K slab, [27] the slab leaves as an image
-constexpr uint32_t GR_FIRST = 1u << 21, GR_LAST = 1u << 22, GR_SLABWAIT = 1u << 23, GR_STORE = 1u << 27;
+constexpr uint32_t GR_FIRST = 1u << 21, GR_LAST = 1u << 22, GR_SLABWAIT = 1u << 23, GR_STORE = 1u << 27, GR_LOPART = 1u << 28;
 struct GenProg {
     GUnit unit[GN_MAXU];
     GFill fill[GN_MAXU];
@@ -84,6 +84,112 @@ struct GenProg {
     float obs_scale;
     int width[GN_MAXL];   // accumulator width of layer l (hidden: its size; head: 16)
     uint32_t img_bytes;
+};
+
+
+// ---- the program builder: constexpr, so that the host builds the table-driven program of ANY supported network with it and the
+//      kernel can be instantiated with the program of one network as compile-time constants (straight-line MMA issue, see SpecProg)
+struct NetDims { int L, kin, obs_mode, n_out, act; int hid[GN_MAXL]; };
+
+// packs the units [u0, u1) of GEMM G (contiguous in the image) into ring-slot fills of at most GN_SLOT bytes
+__host__ __device__ constexpr void pack_fills(GenProg& p, int G, int u0, int u1) {
+    GGemm& g = p.gemm[G];
+    g.f0 = (uint8_t)p.n_fills; g.u0 = (uint8_t)u0; g.nu = (uint8_t)(u1 - u0);
+    int u = u0;
+    while (u < u1) {
+        GFill& f = p.fill[p.n_fills++];
+        f.off = p.unit[u].off; f.u0 = (uint8_t)u;
+        uint32_t bytes = 0;
+        while (u < u1) {
+            const uint32_t start = p.unit[u].off - f.off, ub = (uint32_t)p.unit[u].bytes16 * 16u;
+            if (start + ub > (uint32_t)GN_SLOT) break;
+            p.unit[u].slot_off16 = (uint16_t)(start / 16u);
+            bytes = start + ub;
+            ++u;
+        }
+        f.nu = (uint8_t)(u - f.u0); f.bytes16 = (uint16_t)(bytes / 16u);
+    }
+    g.nf = (uint8_t)(p.n_fills - g.f0);
+    g.from_io = (G == 0 || (g.bwd && G == p.L)) ? 1 : 0;
+    for (int f = g.f0; f < g.f0 + g.nf; ++f) {
+        const GFill& fl = p.fill[f];
+        for (int k = fl.u0; k < fl.u0 + fl.nu; ++k) {
+            const GUnit& un = p.unit[k];
+            uint32_t r = (uint32_t)un.slot_off16 | ((uint32_t)un.ksteps << 16) | ((uint32_t)un.kind << 19) | ((uint32_t)un.slab << 24);
+            if (k == fl.u0) r |= GR_FIRST;
+            if (k == fl.u0 + fl.nu - 1) r |= GR_LAST;
+            const bool slab_first = un.kind == 0 || un.kind == 2;
+            if (slab_first && !g.from_io) r |= GR_SLABWAIT;
+            if (slab_first && p.fb && G > 0) r |= GR_STORE;
+            if (un.kind == 0 && g.a_lo) r |= GR_LOPART;
+            p.rec[k] = r;
+        }
+    }
+}
+
+__host__ __device__ constexpr GenProg make_prog(const NetDims& d, bool split, bool fb) {
+    GenProg p{};
+    const int L = d.L;
+    p.L = L; p.fb = fb ? 1 : 0; p.split = split ? 1 : 0;
+    p.kin = d.kin; p.in_slabs = (p.kin + 63) / 64; p.obs_mode = d.obs_mode; p.n_out = d.n_out;
+    p.obs_scale = 1.0f;
+    p.act = d.act;
+    for (int l = 0; l < L; ++l) p.width[l] = l == L - 1 ? 16 : d.hid[l];
+    uint32_t off = 0;
+    int nu = 0, ng = 0;
+    for (int l = 0; l < L; ++l) {            // forward
+        const int K = l == 0 ? d.kin : d.hid[l - 1], slabs = (K + 63) / 64;
+        const int G = ng++;
+        GGemm& g = p.gemm[G];
+        const int g_u0 = nu;
+        g.layer = (uint8_t)l; g.bwd = 0; g.N = (uint16_t)p.width[l]; g.a_lo = (split && l > 0) ? 1 : 0;
+        g.head = l == L - 1 ? 1 : 0;
+        for (int s = 0; s < slabs; ++s) {
+            const int ks = (K - 64 * s) >= 64 ? 4 : (K - 64 * s + 15) / 16;
+            for (int part = 0; part < (split ? 2 : 1); ++part) {
+                GUnit& u = p.unit[nu++];
+                u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = (uint8_t)s; u.ksteps = (uint8_t)ks;
+                u.kind = (uint8_t)part;
+                u.bytes16 = (uint16_t)(ks == 1 ? u.rows * 2 : u.rows * 8);     // a single-K-step unit is stored compactly (K = 16 only)
+                off += (uint32_t)u.bytes16 * 16u;
+            }
+        }
+        if (l < L - 1) {                     // hidden layers: the bias comes in through one more MMA (head: added by the I/O warps)
+            GUnit& u = p.unit[nu++];
+            u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = 0; u.ksteps = 1; u.kind = 3;
+            u.bytes16 = (uint16_t)(u.rows * 2);
+            off += (uint32_t)u.rows * 32u;
+        }
+        pack_fills(p, G, g_u0, nu);
+        off = (off + 1023u) & ~1023u;
+    }
+    if (fb) {
+        for (int l = L - 1; l >= 1; --l) {   // delta_{l-1} = delta_l W_l^T: K = width of layer l, rows = width of layer l - 1
+            const int Kp = p.width[l], slabs = (Kp + 63) / 64;
+            const int G = ng++;
+            GGemm& g = p.gemm[G];
+            const int g_u0 = nu;
+            g.layer = (uint8_t)l; g.bwd = 1; g.N = (uint16_t)p.width[l - 1]; g.a_lo = 0; g.head = 0;
+            for (int s = 0; s < slabs; ++s) {
+                GUnit& u = p.unit[nu++];
+                u.off = off; u.rows = (uint16_t)p.width[l - 1]; u.layer = (uint8_t)l; u.slab = (uint8_t)s;
+                u.ksteps = (uint8_t)((Kp - 64 * s) >= 64 ? 4 : (Kp - 64 * s + 15) / 16);
+                u.kind = 2;
+                u.bytes16 = (uint16_t)(u.ksteps == 1 ? u.rows * 2 : u.rows * 8);
+                off += (uint32_t)u.bytes16 * 16u;
+            }
+            pack_fills(p, G, g_u0, nu);
+        }
+    }
+    p.n_units = nu; p.n_gemm = ng; p.img_bytes = off;
+    return p;
+}
+
+// Programs known at compile time: kSpec 1 = the reference's documented one-hot 272-256-128-64 network (runner.py:27-47).
+template <int kSpec, bool kSplit, bool kFb> struct SpecProg;
+template <bool kSplit, bool kFb> struct SpecProg<1, kSplit, kFb> {
+    static constexpr NetDims D{4, 272, B2048_OBS_ONEHOT, 4, B2048_ACTV_RELU, {256, 128, 64, 0, 0}};
+    static constexpr GenProg P = make_prog(D, kSplit, kFb);
 };
 
 struct GenArgs {
@@ -238,10 +344,103 @@ __global__ void __launch_bounds__(256) gen_prepare_kernel(const __grid_constant_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ compile-time MMA program
+// The MMA warp's scalar instruction stream is the critical path of gen_mlp_kernel: issuing NO tcgen05.mma at all leaves the kernel
+// time unchanged, and ncu's source view shows ~2,500 instructions per tile in the table-driven loop for 67 MMA / commit
+// instructions.  For a network known at compile time (SpecProg) the whole per-tile program is unrolled from constants: no table
+// reads, no branching on unit kinds, descriptor offsets as immediates.
+struct MmaCtx {
+    uint32_t sA, sW, tmem_base, w_full0, w_empty0, bar_io, bar_slab0, bar_acc_e, bar_acc_h, ones_lo;
+    uint32_t U, nio, spar, slot, wb_base;
+    bool leader;
+};
+template <class SP, int G, int U, int UEND>
+struct UnitSeq {
+    static __device__ __forceinline__ void run(MmaCtx& c, uint8_t* img_dst) {
+        constexpr GGemm gm = SP::P.gemm[G];
+        constexpr uint32_t r = SP::P.rec[U];
+        constexpr uint32_t ks = (r >> 16) & 7u, kind = (r >> 19) & 3u, slab = (r >> 24) & 7u;
+        constexpr uint32_t idesc = idesc_h(TC_M, gm.N);
+        constexpr uint32_t HI_SW = 0x40004040u, HI_NOSW = 0x4010u, HI_ONES = 0x4000u;
+        constexpr uint32_t acc0 = U == gm.u0 ? 0u : 1u;
+        if constexpr ((r & GR_SLABWAIT) != 0) {
+            gwait(c.bar_slab0 + 8u * slab, (c.spar >> slab) & 1u);
+            c.spar ^= 1u << slab;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if constexpr ((r & GR_STORE) != 0) {
+            if (c.leader) {
+                g_bulk_store(img_dst + (size_t)slab * GN_SLAB, c.sA + slab * GN_SLAB, GN_SLAB);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if constexpr ((r & GR_FIRST) != 0) {
+            c.slot = c.U % GN_NSLOT;
+            gwait(c.w_full0 + 8u * c.slot, (c.U / GN_NSLOT) & 1u);
+            c.wb_base = (c.sW + c.slot * GN_SLOT) >> 4;
+        }
+        if (c.leader) {
+            const uint32_t dcol = c.tmem_base + (uint32_t)(G & 1) * 256u;
+            const uint32_t wb_lo = c.wb_base + (r & 0xFFFFu);
+            const uint32_t b_ns = wb_lo | (8u << 16), b_lo = wb_lo | (1u << 16);
+            const uint32_t a_lo = ((c.sA >> 4) | (1u << 16)) + slab * (uint32_t)(GN_SLAB >> 4);
+            const uint32_t a_l2 = a_lo + (uint32_t)(4 * GN_SLAB >> 4);
+            if constexpr (kind == 3) {
+                umma_w(dcol, c.ones_lo, HI_ONES, b_ns, HI_NOSW, idesc, acc0);
+            } else if constexpr (ks == 1) {
+                umma_w(dcol, a_lo, HI_SW, b_ns, HI_NOSW, idesc, acc0);
+                if constexpr ((r & GR_LOPART) != 0) umma_w(dcol, a_l2, HI_SW, b_ns, HI_NOSW, idesc, 1u);
+            } else {
+#pragma unroll
+                for (uint32_t q = 0; q < ks; ++q) umma_w(dcol, a_lo + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, q ? 1u : acc0);
+                if constexpr ((r & GR_LOPART) != 0) {
+#pragma unroll
+                    for (uint32_t q = 0; q < ks; ++q) umma_w(dcol, a_l2 + 2u * q, HI_SW, b_lo + 2u * q, HI_SW, idesc, 1u);
+                }
+            }
+            if constexpr ((r & GR_LAST) != 0) umma_commit(c.w_empty0 + 8u * c.slot);
+        }
+        if constexpr ((r & GR_LAST) != 0) ++c.U;
+        UnitSeq<SP, G, U + 1, UEND>::run(c, img_dst);
+    }
+};
+template <class SP, int G, int UEND>
+struct UnitSeq<SP, G, UEND, UEND> {
+    static __device__ __forceinline__ void run(MmaCtx&, uint8_t*) {}
+};
+template <class SP, int G, int GEND>
+struct GemmSeq {
+    static __device__ __forceinline__ void run(MmaCtx& c, const GenArgs& a, int64_t tile) {
+        constexpr GGemm gm = SP::P.gemm[G];
+        constexpr bool store = SP::P.fb != 0 && G > 0;
+        if constexpr (gm.from_io != 0) {
+            gwait(c.bar_io, c.nio & 1u); ++c.nio;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        uint8_t* img_dst = nullptr;
+        if constexpr (store) {
+            constexpr int nsl = !gm.bwd ? (SP::P.width[gm.layer - 1] >> 6) : (gm.layer == SP::P.L - 1 ? 1 : (SP::P.width[gm.layer] >> 6));
+            img_dst = (!gm.bwd ? a.himg[gm.layer - 1] : a.dlimg[gm.layer]) + (size_t)tile * nsl * GN_SLAB;
+        }
+        UnitSeq<SP, G, gm.u0, gm.u0 + gm.nu>::run(c, img_dst);
+        if (c.leader) {
+            if constexpr (store) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            umma_commit(gm.head ? c.bar_acc_h : c.bar_acc_e);
+        }
+        GemmSeq<SP, G + 1, GEND>::run(c, a, tile);
+    }
+};
+template <class SP, int GEND>
+struct GemmSeq<SP, GEND, GEND> {
+    static __device__ __forceinline__ void run(MmaCtx&, const GenArgs&, int64_t) {}
+};
+
 // ------------------------------------------------------------------------------------------------ the tile kernel
 // kAct: the hidden activation is a compile-time choice (the Sigmoid epilogue would cost the ReLU one registers);
 // kDbg compiles the phase clocks in (B2048_DBG_TC_CLOCKS)
-template <int kAct, bool kDbg>
+// kSpec != 0: the MMA warp runs the compile-time program of SpecProg<kSpec, kSplit, kFb> (the host launches it only for that network)
+template <int kAct, bool kDbg, int kSpec, bool kSplit, bool kFb>
 __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -286,7 +485,32 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gen_mlp_kernel(const __grid_con
         // All 32 lanes walk the program CONVERGENTLY (loop counters, table reads and descriptor words stay in uniform registers);
         // only the asynchronous instructions themselves are issued by lane 0 (with the whole loop under `if (lane == 0)` every
         // tcgen05.mma cost ~25 vector instructions: ELECT / R2UR per operand).
-        {
+        if constexpr (kSpec != 0) {
+            using SP = SpecProg<kSpec, kSplit, kFb>;
+            MmaCtx c;
+            c.sA = sA; c.sW = sW; c.tmem_base = tmem_base; c.w_full0 = w_full0; c.w_empty0 = w_empty0; c.bar_io = bar_io;
+            c.bar_slab0 = bar_slab0; c.bar_acc_e = bar_acc_e; c.bar_acc_h = bar_acc_h;
+            c.ones_lo = (s_u32(smem + GS_ONES) >> 4) | (8u << 16);
+            c.U = 0; c.nio = 0; c.spar = 0; c.slot = 0; c.wb_base = 0; c.leader = lane == 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                GemmSeq<SP, 0, SP::P.n_gemm>::run(c, a, tile);
+                if constexpr (kFb) {       // delta_0 (the last epilogue's output) is only an image
+                    constexpr int nsl = SP::P.width[0] >> 6;
+#pragma unroll
+                    for (int sl = 0; sl < nsl; ++sl) {
+                        gwait(bar_slab0 + 8u * (uint32_t)sl, (c.spar >> sl) & 1u);
+                        c.spar ^= 1u << sl;
+                        if (c.leader) g_bulk_store(a.dlimg[0] + ((size_t)tile * nsl + sl) * GN_SLAB, sA + (uint32_t)sl * GN_SLAB, GN_SLAB);
+                    }
+                    if (c.leader) {
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        mbar_arrive(bar_free);
+                    }
+                }
+            }
+            if (c.leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
             const bool leader = lane == 0;
             uint32_t U = 0, nio = 0, spar = 0;      // ring fills consumed; I/O hand-offs; phase parity of the four slab barriers
             constexpr uint32_t HI_SW = 0x40004040u, HI_NOSW = 0x4010u, HI_ONES = 0x4000u;     // upper descriptor words (b2048_tc.cuh)
@@ -865,94 +1089,12 @@ bool gen_shape_ok(const b2048_mlp_desc* mlp) {
 }
 bool gen_supported(const b2048_handle* h, const b2048_mlp_desc* mlp) { return gen_shape_ok(mlp) && h->smem_optin >= 227 * 1024; }
 
-// packs the units [u0, u1) of one GEMM (contiguous in the image) into ring-slot fills of at most GN_SLOT bytes
-static void pack_fills(GenProg& p, GGemm& g, int u0, int u1) {
-    g.f0 = (uint8_t)p.n_fills; g.u0 = (uint8_t)u0; g.nu = (uint8_t)(u1 - u0);
-    int u = u0;
-    while (u < u1) {
-        GFill& f = p.fill[p.n_fills++];
-        f.off = p.unit[u].off; f.u0 = (uint8_t)u;
-        uint32_t bytes = 0;
-        while (u < u1) {
-            const uint32_t start = p.unit[u].off - f.off, ub = (uint32_t)p.unit[u].bytes16 * 16u;
-            if (start + ub > (uint32_t)GN_SLOT) break;
-            p.unit[u].slot_off16 = (uint16_t)(start / 16u);
-            bytes = start + ub;
-            ++u;
-        }
-        f.nu = (uint8_t)(u - f.u0); f.bytes16 = (uint16_t)(bytes / 16u);
-    }
-    g.nf = (uint8_t)(p.n_fills - g.f0);
-    const int G = (int)(&g - p.gemm);
-    g.from_io = (G == 0 || (g.bwd && G == p.L)) ? 1 : 0;
-    for (int f = g.f0; f < g.f0 + g.nf; ++f) {
-        const GFill& fl = p.fill[f];
-        for (int k = fl.u0; k < fl.u0 + fl.nu; ++k) {
-            const GUnit& un = p.unit[k];
-            uint32_t r = (uint32_t)un.slot_off16 | ((uint32_t)un.ksteps << 16) | ((uint32_t)un.kind << 19) | ((uint32_t)un.slab << 24);
-            if (k == fl.u0) r |= GR_FIRST;
-            if (k == fl.u0 + fl.nu - 1) r |= GR_LAST;
-            const bool slab_first = un.kind == 0 || un.kind == 2;
-            if (slab_first && !g.from_io) r |= GR_SLABWAIT;
-            if (slab_first && p.fb && G > 0) r |= GR_STORE;
-            p.rec[k] = r;
-        }
-    }
-}
-
 static void build_program(const b2048_mlp_desc* mlp, bool split, bool fb, GenProg& p) {
-    memset(&p, 0, sizeof(p));
-    const int L = mlp->n_layers;
-    p.L = L; p.fb = fb ? 1 : 0; p.split = split ? 1 : 0;
-    p.kin = mlp->dims[0]; p.in_slabs = (p.kin + 63) / 64; p.obs_mode = mlp->obs_mode; p.n_out = mlp->dims[L];
+    NetDims d{};
+    d.L = mlp->n_layers; d.kin = mlp->dims[0]; d.obs_mode = mlp->obs_mode; d.n_out = mlp->dims[mlp->n_layers]; d.act = mlp->activation;
+    for (int l = 0; l + 1 < mlp->n_layers; ++l) d.hid[l] = mlp->dims[l + 1];
+    p = make_prog(d, split, fb);
     p.obs_scale = mlp->obs_log2_scale;
-    p.act = mlp->activation;
-    for (int l = 0; l < L; ++l) p.width[l] = l == L - 1 ? 16 : mlp->dims[l + 1];
-    uint32_t off = 0;
-    int nu = 0, ng = 0;
-    for (int l = 0; l < L; ++l) {            // forward
-        const int K = mlp->dims[l], slabs = (K + 63) / 64;
-        GGemm& g = p.gemm[ng++];
-        const int g_u0 = nu;
-        g.layer = (uint8_t)l; g.bwd = 0; g.N = (uint16_t)p.width[l]; g.a_lo = (split && l > 0) ? 1 : 0;
-        g.head = l == L - 1 ? 1 : 0;
-        for (int s = 0; s < slabs; ++s) {
-            const int ks = (K - 64 * s) >= 64 ? 4 : (K - 64 * s + 15) / 16;
-            for (int part = 0; part < (split ? 2 : 1); ++part) {
-                GUnit& u = p.unit[nu++];
-                u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = (uint8_t)s; u.ksteps = (uint8_t)ks;
-                u.kind = (uint8_t)part;
-                u.bytes16 = (uint16_t)(ks == 1 ? u.rows * 2 : u.rows * 8);     // a single-K-step unit is stored compactly (K = 16 only)
-                off += (uint32_t)u.bytes16 * 16u;
-            }
-        }
-        if (l < L - 1) {                     // hidden layers: the bias comes in through one more MMA (head: added by the I/O warps)
-            GUnit& u = p.unit[nu++];
-            u.off = off; u.rows = (uint16_t)p.width[l]; u.layer = (uint8_t)l; u.slab = 0; u.ksteps = 1; u.kind = 3;
-            u.bytes16 = (uint16_t)(u.rows * 2);
-            off += (uint32_t)u.rows * 32u;
-        }
-        pack_fills(p, g, g_u0, nu);
-        off = (off + 1023u) & ~1023u;         // every fill starts a 128-byte-swizzled operand: 1024-byte aligned in the image, too
-    }
-    if (fb) {
-        for (int l = L - 1; l >= 1; --l) {   // delta_{l-1} = delta_l W_l^T: K = width of layer l, rows = width of layer l - 1
-            const int Kp = p.width[l], slabs = (Kp + 63) / 64;
-            GGemm& g = p.gemm[ng++];
-            const int g_u0 = nu;
-            g.layer = (uint8_t)l; g.bwd = 1; g.N = (uint16_t)p.width[l - 1]; g.a_lo = 0; g.head = 0;
-            for (int s = 0; s < slabs; ++s) {
-                GUnit& u = p.unit[nu++];
-                u.off = off; u.rows = (uint16_t)p.width[l - 1]; u.layer = (uint8_t)l; u.slab = (uint8_t)s;
-                u.ksteps = (uint8_t)((Kp - 64 * s) >= 64 ? 4 : (Kp - 64 * s + 15) / 16);
-                u.kind = 2;
-                u.bytes16 = (uint16_t)(u.ksteps == 1 ? u.rows * 2 : u.rows * 8);
-                off += (uint32_t)u.bytes16 * 16u;
-            }
-            pack_fills(p, g, g_u0, nu);
-        }
-    }
-    p.n_units = nu; p.n_gemm = ng; p.img_bytes = off;
 }
 
 struct GenWorkspace {
@@ -978,13 +1120,15 @@ int64_t gen_workspace_bytes(const b2048_mlp_desc* mlp, int64_t chunk) { return g
 
 static int gen_attrs(b2048_handle* h) {
     if (!(h->attrs & 32u)) {
-        cudaError_t e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
-        e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_SIGMOID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
-        e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
-        e = cudaFuncSetAttribute(gen_mlp_kernel<B2048_ACTV_SIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL);
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, GS_TOTAL); };
+        set((const void*)gen_mlp_kernel<B2048_ACTV_RELU, false, 0, false, false>);
+        set((const void*)gen_mlp_kernel<B2048_ACTV_SIGMOID, false, 0, false, false>);
+        set((const void*)gen_mlp_kernel<B2048_ACTV_RELU, true, 0, false, false>);
+        set((const void*)gen_mlp_kernel<B2048_ACTV_SIGMOID, true, 0, false, false>);
+        set((const void*)gen_mlp_kernel<B2048_ACTV_RELU, false, 1, false, false>);
+        set((const void*)gen_mlp_kernel<B2048_ACTV_RELU, false, 1, true, false>);
+        set((const void*)gen_mlp_kernel<B2048_ACTV_RELU, false, 1, true, true>);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_mlp_kernel)");
         e = cudaFuncSetAttribute(gen_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gen_dw_kernel)");
@@ -1040,12 +1184,20 @@ static void gen_dbg_end(const GenArgs& a, cudaStream_t stream) {
 
 static void gen_launch(const GenArgs& a, int grid, cudaStream_t stream) {
     const bool sig = a.p.act == B2048_ACTV_SIGMOID;
-    if (a.dbg) {
-        if (sig) gen_mlp_kernel<B2048_ACTV_SIGMOID, true><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
-        else gen_mlp_kernel<B2048_ACTV_RELU, true><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+    const GenProg& p = a.p;
+    // the network whose program is compiled in (SpecProg<1>): one-hot 272-256-128-64, ReLU
+    const bool spec1 = !sig && !a.dbg && p.L == 4 && p.kin == 272 && p.obs_mode == B2048_OBS_ONEHOT && p.width[0] == 256 && p.width[1] == 128 &&
+                       p.width[2] == 64 && (p.fb == 0 || p.split == 1);
+    if (spec1) {
+        if (p.fb) gen_mlp_kernel<B2048_ACTV_RELU, false, 1, true, true><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        else if (p.split) gen_mlp_kernel<B2048_ACTV_RELU, false, 1, true, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        else gen_mlp_kernel<B2048_ACTV_RELU, false, 1, false, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+    } else if (a.dbg) {
+        if (sig) gen_mlp_kernel<B2048_ACTV_SIGMOID, true, 0, false, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        else gen_mlp_kernel<B2048_ACTV_RELU, true, 0, false, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
     } else {
-        if (sig) gen_mlp_kernel<B2048_ACTV_SIGMOID, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
-        else gen_mlp_kernel<B2048_ACTV_RELU, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        if (sig) gen_mlp_kernel<B2048_ACTV_SIGMOID, false, 0, false, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
+        else gen_mlp_kernel<B2048_ACTV_RELU, false, 0, false, false><<<grid, GN_THREADS, GS_TOTAL, stream>>>(a);
     }
 }
 
