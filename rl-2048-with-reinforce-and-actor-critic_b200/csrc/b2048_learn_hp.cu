@@ -184,6 +184,24 @@ struct FwdHpArgs {
 
 constexpr int FH_THREADS = 512 + 3 * 32 + 128;   // 16 epilogue warps, MMA warp, weight loader, image storer, 4 I/O warps
 
+// tcgen05.mma from the 32-bit halves of the two shared-memory descriptors (upper halves are compile-time constants), so that the
+// descriptor arithmetic of a convergent MMA warp stays in uniform registers (see fwd_role)
+__device__ __forceinline__ void umma_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+constexpr uint32_t DH_SW = 0x40004040u;     // upper word of desc_sw128: SBO 1024, version 1, 128-byte swizzle
+constexpr uint32_t DH_NOSW = 0x4010u;       // desc_nosw_k16: SBO 256, version 1
+constexpr uint32_t DH_ONES = 0x4000u;       // desc_ones: SBO 0, version 1
+__device__ __forceinline__ uint32_t dlo_sw(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t dlo_ns(uint32_t saddr) { return (saddr >> 4) | (8u << 16); }
+
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
     __half2 p = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);
@@ -233,32 +251,41 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
 
     if (warp == 16) {
         // ============================ MMA warp ============================
-        if (lane == 0) {
+        // All 32 lanes walk the loops convergently (counters and descriptor words in uniform registers); lane 0 issues the
+        // asynchronous instructions.  Under `if (lane == 0)` every tcgen05.mma cost ~25 vector instructions (64-bit descriptor
+        // arithmetic, ELECT / R2UR per operand) and the ~100 MMAs of a tile made the warp's scalar instruction stream — not
+        // shared memory — the bound of the forward role (measured the same way in b2048_mlp_gen.cu).
+        {
+            const bool leader = lane == 0;
             const uint8_t* gres = args.img + HP_RES;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_res), "r"((uint32_t)RES_BYTES) : "memory");
-            for (uint32_t off = 0; off < (uint32_t)RES_BYTES; off += 16384u) {
-                uint32_t sz = (uint32_t)RES_BYTES - off < 16384u ? (uint32_t)RES_BYTES - off : 16384u;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 s_u32(smem + FS_RES + off)),
-                             "l"(gres + off), "r"(sz), "r"(bar_res)
-                             : "memory");
+            if (leader) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_res), "r"((uint32_t)RES_BYTES) : "memory");
+                for (uint32_t off = 0; off < (uint32_t)RES_BYTES; off += 16384u) {
+                    uint32_t sz = (uint32_t)RES_BYTES - off < 16384u ? (uint32_t)RES_BYTES - off : 16384u;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     s_u32(smem + FS_RES + off)),
+                                 "l"(gres + off), "r"(sz), "r"(bar_res)
+                                 : "memory");
+                }
             }
             mbar_wait(bar_res, 0);
             const uint32_t sA1 = s_u32(smem + FS_A1), sW = s_u32(smem + FS_W), sA = s_u32(smem + FS_A);
             const uint32_t sRes = s_u32(smem + FS_RES);
-            const uint64_t dBias = desc_nosw_k16(sRes + RES_BIAS);
-            const uint64_t dOnes1 = desc_ones(sRes + RES_ONES1), dOnes2 = desc_ones(sRes + RES_ONES2);
+            const uint32_t lBias = dlo_ns(sRes + RES_BIAS), lOnes1 = dlo_ns(sRes + RES_ONES1), lOnes2 = dlo_ns(sRes + RES_ONES2);
+            const uint32_t lA1 = dlo_ns(sA1), lW1H = dlo_ns(sRes + RES_W1H), lW1L = dlo_ns(sRes + RES_W1L);
             auto issue_layer1 = [&](uint32_t ph) {
                 mbar_wait(bar_a1, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sRes + RES_W1H), kIdescF16, 0u);
-                umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sRes + RES_W1L), kIdescF16, 1u);
-                umma_f16(tmem_base, dOnes1, dBias, kIdescF16, 1u);
-                umma_commit(bar_d1);
+                if (leader) {
+                    umma_w(tmem_base, lA1, DH_NOSW, lW1H, DH_NOSW, kIdescF16, 0u);
+                    umma_w(tmem_base, lA1, DH_NOSW, lW1L, DH_NOSW, kIdescF16, 1u);
+                    umma_w(tmem_base, lOnes1, DH_ONES, lBias, DH_NOSW, kIdescF16, 1u);
+                    umma_commit(bar_d1);
+                }
             };
             uint32_t ph = 0, U = 0, F = 0;     // tile parity, streamed weight units consumed, activation ring fills consumed
             if (first < n_tiles) issue_layer1(0u);
-            const bool dbg = args.debug_clock != nullptr && rank == 0;
+            const bool dbg = args.debug_clock != nullptr && rank == 0 && leader;
             long long wa = 0, ww = 0, t_prev = dbg ? clock64() : 0;
             int lt = 0;
             for (int64_t tile = first; tile < n_tiles; tile += nranks, ++lt) {
@@ -274,34 +301,42 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
                     long long c0 = dbg ? clock64() : 0;
                     mbar_wait(a_full0 + 8u * st, au & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t ahi = sA + st * FS_ASTAGE, alo = ahi + 16384u;
+                    const uint32_t ahi = dlo_sw(sA + st * FS_ASTAGE), alo = ahi + (16384u >> 4);
                     uint32_t slot = U % 3u, use = U / 3u;
                     long long c1 = dbg ? clock64() : 0;
                     mbar_wait(w_full0 + 8u * slot, use & 1u);
                     if (dbg) { const long long c2 = clock64(); wa += c1 - c0; ww += c2 - c1; }
-                    uint32_t wb = sW + slot * HP_UNIT;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), kIdescF16,
-                                 (s | q) ? 1u : 0u);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16(tmem_base + 256u, desc_sw128(alo + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), kIdescF16, 1u);
-                    umma_commit(w_empty0 + 8u * slot);
+                    uint32_t wb = dlo_sw(sW + slot * HP_UNIT);
+                    if (leader) {
+                        umma_w(tmem_base + 256u, ahi, DH_SW, wb, DH_SW, kIdescF16, s ? 1u : 0u);
+                        umma_w(tmem_base + 256u, ahi + 2u, DH_SW, wb + 2u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, ahi + 4u, DH_SW, wb + 4u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, ahi + 6u, DH_SW, wb + 6u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, alo, DH_SW, wb, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, alo + 2u, DH_SW, wb + 2u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, alo + 4u, DH_SW, wb + 4u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, alo + 6u, DH_SW, wb + 6u, DH_SW, kIdescF16, 1u);
+                        umma_commit(w_empty0 + 8u * slot);
+                    }
                     ++U;
                     slot = U % 3u; use = U / 3u;
                     mbar_wait(w_full0 + 8u * slot, use & 1u);
-                    wb = sW + slot * HP_UNIT;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(wb + (uint32_t)q * 32u), kIdescF16, 1u);
-                    umma_commit(w_empty0 + 8u * slot);
+                    wb = dlo_sw(sW + slot * HP_UNIT);
+                    if (leader) {
+                        umma_w(tmem_base + 256u, ahi, DH_SW, wb, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, ahi + 2u, DH_SW, wb + 2u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, ahi + 4u, DH_SW, wb + 4u, DH_SW, kIdescF16, 1u);
+                        umma_w(tmem_base + 256u, ahi + 6u, DH_SW, wb + 6u, DH_SW, kIdescF16, 1u);
+                        umma_commit(w_empty0 + 8u * slot);
+                        umma_commit(a_free0 + 8u * st);
+                    }
                     ++U;
-                    umma_commit(a_free0 + 8u * st);
                     ++F;
                 }
-                umma_f16(tmem_base + 256u, dOnes2, dBias, kIdescF16, 1u);
-                umma_commit(bar_d2);
+                if (leader) {
+                    umma_w(tmem_base + 256u, lOnes2, DH_ONES, lBias, DH_NOSW, kIdescF16, 1u);
+                    umma_commit(bar_d2);
+                }
                 // ---- the next tile's layer 1 (D1 was drained before the last H1 slab arrival waited for above)
                 if (tile + nranks < n_tiles) issue_layer1(ph ^ 1u);
                 // ---- head: D3 (columns 256..271: that part of D2 is drained before the first H2 slab arrives)
@@ -309,22 +344,21 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
                     const uint32_t st = F & 1u, au = F >> 1;
                     mbar_wait(a_full0 + 8u * st, au & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t ahi = sA + st * FS_ASTAGE, alo = ahi + 16384u;
-                    const uint32_t w3h = sRes + RES_W3H + (uint32_t)s * 2048u, w3l = sRes + RES_W3L + (uint32_t)s * 2048u;
+                    const uint32_t ahi = dlo_sw(sA + st * FS_ASTAGE), alo = ahi + (16384u >> 4);
+                    const uint32_t w3h = dlo_sw(sRes + RES_W3H + (uint32_t)s * 2048u), w3l = dlo_sw(sRes + RES_W3L + (uint32_t)s * 2048u);
+                    if (leader) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(w3h + (uint32_t)q * 32u), kIdescHeadF16,
-                                 (s | q) ? 1u : 0u);
+                        for (uint32_t q = 0; q < 4; ++q)
+                            umma_w(tmem_base + 256u, ahi + 2u * q, DH_SW, w3h + 2u * q, DH_SW, kIdescHeadF16, (s | q) ? 1u : 0u);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16(tmem_base + 256u, desc_sw128(alo + (uint32_t)q * 32u), desc_sw128(w3h + (uint32_t)q * 32u), kIdescHeadF16, 1u);
+                        for (uint32_t q = 0; q < 4; ++q) umma_w(tmem_base + 256u, alo + 2u * q, DH_SW, w3h + 2u * q, DH_SW, kIdescHeadF16, 1u);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16(tmem_base + 256u, desc_sw128(ahi + (uint32_t)q * 32u), desc_sw128(w3l + (uint32_t)q * 32u), kIdescHeadF16, 1u);
-                    umma_commit(a_free0 + 8u * st);
+                        for (uint32_t q = 0; q < 4; ++q) umma_w(tmem_base + 256u, ahi + 2u * q, DH_SW, w3l + 2u * q, DH_SW, kIdescHeadF16, 1u);
+                        umma_commit(a_free0 + 8u * st);
+                    }
                     ++F;
                 }
-                umma_commit(bar_d3);
+                if (leader) umma_commit(bar_d3);
                 ph ^= 1u;
             }
         }
