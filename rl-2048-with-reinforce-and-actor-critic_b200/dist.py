@@ -71,15 +71,19 @@ def make_sharded_env(total_boards: int, config, info: DistInfo, seed: int = 0, d
     return Batched2048Env(stop - start, config, device=dev, seed=seed, gid0=start, **kw)
 
 
-def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = None, precision="auto"):
+def sharded_update(agent, rollout, info: DistInfo, total_episodes: int | None = None, precision="auto",
+                   exchange: str = "default"):
     """update_from_rollout with gradients / baseline sums all-reduced over ranks; n_traj = global episode count
-    so that every rank applies exactly the update a single process holding all episodes would apply."""
+    so that every rank applies exactly the update a single process holding all episodes would apply.
+    exchange="one_message": exactly one all-reduce per update (see ReinforceAgent.update_from_rollout); pass
+    total_episodes as well, otherwise the episode count is one more (8-byte) collective."""
     if total_episodes is None:
         n = torch.tensor([rollout.B], dtype=torch.int64, device=rollout.length.device)
         allreduce_sum_(n)
         total_episodes = int(n.item())
     rollout.n_traj = total_episodes
-    return agent.update_from_rollout(rollout, allreduce=allreduce_sum_ if info.is_distributed else None, precision=precision)
+    return agent.update_from_rollout(rollout, allreduce=allreduce_sum_ if info.is_distributed else None, precision=precision,
+                                     exchange=exchange)
 
 
 def episode_rank_weights(total_reward: torch.Tensor, weights_conf, info: DistInfo | None = None) -> torch.Tensor:

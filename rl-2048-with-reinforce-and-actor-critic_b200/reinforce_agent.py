@@ -533,6 +533,42 @@ class ReinforceAgent:
         from .symmetry import augment_rollout
         return augment_rollout(ro)
 
+    def _one_message_exchange(self, values, ro, n_traj, adv, coef, stats, ep_mean, backward, allreduce) -> None:
+        """The sharded update's exchange as exactly one all-reduce (north_star: "a single NCCL allreduce ... for
+        the policy gradient only").  With a 'batch' / 'batch_norm' baseline the per-sample coefficient is
+        (v - mean) / std * w / (T n) with GLOBAL mean / std (reinforce_agent.py:303-322, :864-881); the backward pass is
+        linear in it, so g = (g_A - mean g_B) / std with g_A from the coefficients v w / (T n) and g_B from w / (T n).  Both
+        are local sums; they travel with the critic gradient and the four float64 baseline sums in one float64 buffer."""
+        lib, h, dev, T, B = self._lib, self._h, self.device, ro.T, ro.B
+        mode = BASELINE[self.agent_config.baseline_mode]
+        na = self._actor.n_params
+        msg = self._buf("one_msg", (na + self._grad_all.numel() + 4,), torch.float64)
+        ones = self._buf("one_msg_ones", (T, B), torch.float32)
+        ones.fill_(1.0)
+        with torch.cuda.device(dev):
+            stats.zero_()
+            _lib.check(lib.b2048_weighted_stats(h, _ptr(values), _ptr(ro.length), _ptr(ro.ep_weight), T, B, _ptr(stats),
+                                                _stream()), "b2048_weighted_stats")
+        for k, v in enumerate((values, ones)):                       # g_A, then g_B
+            with torch.cuda.device(dev):
+                _lib.check(lib.b2048_advantages(h, _ptr(v), _ptr(ro.length), _ptr(ro.ep_weight), 0, n_traj, T, B, None,
+                                                _ptr(coef), _ptr(stats), 1, _ptr(ep_mean), _stream()), "b2048_advantages")
+            backward(self._actor, coef.reshape(-1), 0)
+            if k == 0:
+                msg[:na].copy_(self._actor.grad)
+        msg[na: na + self._grad_all.numel()].copy_(self._grad_all)   # [g_B | critic gradient]
+        msg[-4:].copy_(stats)
+        allreduce(msg)                                               # THE message of this update
+        stats.copy_(msg[-4:])
+        sw = msg[-4]
+        m = torch.where(sw < 1e-8, torch.zeros_like(sw), msg[-3] / sw.clamp_min(1e-300))          # advantage_kernel
+        var = torch.where(sw < 1e-8, torch.ones_like(sw), msg[-2] / sw.clamp_min(1e-300) - m * m)
+        mean32 = m.to(torch.float32)
+        std32 = var.clamp_min(0.0).sqrt().to(torch.float32).clamp_min(1e-8) if mode == 3 else torch.ones_like(mean32)
+        g_a, g_b = msg[:na], msg[na: 2 * na]
+        self._grad_all.copy_(msg[na: na + self._grad_all.numel()])   # critic part (and g_B, overwritten next)
+        self._actor.grad.copy_((g_a - mean32.to(torch.float64) * g_b) / std32.to(torch.float64))
+
     def update_batch(self, trajectories: list[dict[str, Any]]) -> None:
         """reinforce_agent.py:357-620 on reference-style trajectories (list of dicts from run_episode)."""
         if len(trajectories) == 0:
@@ -543,14 +579,22 @@ class ReinforceAgent:
         self.update_from_rollout(ro)
 
     def update_from_rollout(self, ro: Rollout, chunk: int = 1 << 20, allreduce=None,
-                            precision: int | str = "auto") -> dict[str, Any]:
+                            precision: int | str = "auto", exchange: str = "default") -> dict[str, Any]:
         """One policy-gradient update from device-resident rollout buffers.  `allreduce(tensor)` (optional) sums
         a tensor over ranks in place: the flat gradients and the advantage statistics are the only exchange.
         precision: 0 = fp32 CUDA cores, "auto" (default) = the float32-grade tensor-core path (split-fp16 forward, fp16
         backward; within 1e-2 of the reference's float32 gradient) whenever the network shape / batch allow it, else fp32;
         3 = that path or an error; 1 = single-bf16 tensor cores, an explicit opt-in (its forward flips ReLU units near zero:
-        3-30 % error on cancelling gradients; b2048_mlp_backward, include/b2048.h)."""
+        3-30 % error on cancelling gradients; b2048_mlp_backward, include/b2048.h).
+        exchange (sharded updates with a 'batch' / 'batch_norm' baseline): "default" = a 32-byte all-reduce of the four
+        float64 baseline sums, then ONE all-reduce of the flat gradient buffer [actor | critic]; "one_message" = exactly
+        one all-reduce per update: the backward deltas are linear in the per-sample coefficient, so each rank
+        accumulates g_A (coefficient w v / (T n)) and g_B (coefficient w / (T n)) locally, one float64 message
+        [g_A | g_B | critic gradient | sums] is summed over ranks and g = (g_A - mean g_B) / std is formed afterwards.
+        It costs a second actor backward pass, which is why it is an opt-in."""
         prec = 2 if precision == "auto" else int(precision)
+        if exchange not in ("default", "one_message"):
+            raise ValueError(f"Unknown exchange: {exchange}")
         cfg = self.agent_config
         if cfg.baseline_mode not in BASELINE:
             raise ValueError(f"Unknown baseline mode: {cfg.baseline_mode}")          # reinforce_agent.py:325
@@ -603,10 +647,11 @@ class ReinforceAgent:
         info: dict[str, Any] = {}
         mode = BASELINE[cfg.baseline_mode]
 
-        def advantages(values):
-            pre = 0
+        one_msg = exchange == "one_message" and allreduce is not None and mode >= 2
+
+        def advantages(values, pre=0):
             with torch.cuda.device(dev):
-                if allreduce is not None and mode >= 2:
+                if allreduce is not None and mode >= 2 and not pre:
                     # episodes are sharded over ranks: the baseline statistics are global sums
                     stats.zero_()
                     _lib.check(lib.b2048_weighted_stats(h, _ptr(values), _ptr(length), _ptr(ro.ep_weight), T, B,
@@ -665,18 +710,23 @@ class ReinforceAgent:
                                                float(cfg.huber_delta), n_traj, T, B, _ptr(td), _ptr(gcoef), _stream()),
                            "b2048_td_errors")
             backward(self._critic, gcoef.reshape(-1), 1)
-            advantages(td)                                           # advantages := baseline-processed TD errors (:495-498)
+            base_values = td                                         # advantages := baseline-processed TD errors (:495-498)
             info["td"] = td
         else:
             returns = self._buf("returns", (T, B), torch.float32)
             with torch.cuda.device(dev):
                 _lib.check(lib.b2048_reverse_scan_f64(_ptr(rewards), _ptr(returns), _ptr(length), float(cfg.gamma), T, B,
                                                       _stream()), "b2048_reverse_scan_f64")
-            advantages(returns)
+            base_values = returns
             info["returns"] = returns
-        backward(self._actor, coef.reshape(-1), 0)
-        if allreduce is not None:
-            allreduce(self._grad_all)        # ONE message per update: [actor gradient | critic gradient]
+        if one_msg:
+            self._one_message_exchange(base_values, ro, n_traj, adv, coef, stats, ep_mean, backward, allreduce)
+            advantages(base_values, pre=1)   # adv / coef as the default exchange reports them (global statistics)
+        else:
+            advantages(base_values)
+            backward(self._actor, coef.reshape(-1), 0)
+            if allreduce is not None:
+                allreduce(self._grad_all)    # ONE message per update: [actor gradient | critic gradient]
 
         if cfg.optimizer == "adam":
             self._adam_t += 1

@@ -7,7 +7,8 @@ runner.py:10-63, defaults runner.py:116-173) and writes the same artefacts (``co
 with the full optimiser state every ``train.checkpoint_every`` batches).  One training batch =
 ``train.batch_size`` episodes played in parallel on the GPU (``rollout_many``) followed by one
 ``update_from_rollout``; evaluation = greedy rollouts with the max-tile histogram (runner.py:737-828).
-Extra keys: ``train.precision`` ("auto" | 0 | 1), ``seed``.  Under torchrun the episodes are sharded over ranks.
+Extra keys: ``train.precision`` ("auto" | 0 | 1), ``train.exchange`` ("default" | "one_message": one all-reduce per update),
+``seed``.  Under torchrun the episodes are sharded over ranks.
 
     python -m torch.distributed.run ... b2048_runner.py -conf cfg.json      (or: python b2048_runner.py -conf cfg.json)
 """
@@ -119,7 +120,7 @@ def training(cfg: dict[str, Any], info: bd.DistInfo | None = None, device=None, 
             best = avg
         if global_step > 30 and is_record and info.rank == 0 and out_dir:
             agent.save_model(os.path.join(out_dir, f"best_avg_{avg:.2f}_step_{global_step}.npz"))
-        upd = bd.sharded_update(agent, ro, info, total_episodes=int(tr["batch_size"]))
+        upd = bd.sharded_update(agent, ro, info, total_episodes=int(tr["batch_size"]), exchange=tr.get("exchange", "default"))
         row = {"batch": global_step, "avg_reward": avg, "max_reward": mx, "min_reward": mn, "max_tile_counts": json.dumps(hist)}
         rows.append(dict(row, steps=int(ro.length.sum().item()), seconds=time.perf_counter() - t0,
                          grad_norm=upd.get("actor_grad_norm")))

@@ -112,10 +112,17 @@ def main():
         calls.append(int(t.numel()))
         return real_allreduce(t)
 
-    for name, kw, expect_calls in (("augmentation", dict(augmentation=True, baseline_mode="batch"), 2),
-                                   ("actor-critic", dict(use_critic=True, baseline_mode="batch_norm", optimizer="adam",
-                                                         critic_learning_rate=1e-3), 2),
-                                   ("actor-critic, baseline off", dict(use_critic=True, baseline_mode="off"), 1)):
+    #         exchange="one_message" (g = (g_A - mean g_B) / std formed after the exchange) issues exactly one
+    #         all-reduce per update whatever the baseline
+    ac_kw = dict(use_critic=True, baseline_mode="batch_norm", optimizer="adam", critic_learning_rate=1e-3)
+    for name, kw, expect_calls, exchange in (
+            ("augmentation", dict(augmentation=True, baseline_mode="batch"), 2, "default"),
+            ("actor-critic", ac_kw, 2, "default"),
+            ("actor-critic, baseline off", dict(use_critic=True, baseline_mode="off"), 1, "default"),
+            ("REINFORCE batch baseline, one-message exchange", dict(baseline_mode="batch"), 1, "one_message"),
+            ("REINFORCE batch_norm + augmentation, one-message exchange", dict(augmentation=True, baseline_mode="batch_norm"), 1,
+             "one_message"),
+            ("actor-critic, one-message exchange", ac_kw, 1, "one_message")):
         acfg = b2048.ReinforceAgentConfig(gamma=0.99, learning_rate=1e-2, model_seed=3, **kw)
         mlp = b2048.MLPConfig(hidden_sizes=[64, 64], activation="ReLU", init_distribution="HeNormal")
         n_ep = 6000 + 1
@@ -125,7 +132,7 @@ def main():
         ro = agent.rollout_many(env)
         ro.n_traj = n_ep
         calls.clear()
-        upd = agent.update_from_rollout(ro, allreduce=counting_allreduce, precision=0)
+        upd = agent.update_from_rollout(ro, allreduce=counting_allreduce, precision=0, exchange=exchange)
         assert len(calls) == expect_calls, (name, calls)
         theta = agent._actor.theta.clone()
         ctheta = None if agent._critic is None else agent._critic.theta.clone()

@@ -287,3 +287,69 @@ def test_sharded_sweep_leg_runs_on_one_gpu(b2048):
     r = b2048.bench_sharded_sweep(torch.device("cuda", 0), total_boards=1 << 16, horizon=16, iters=1)
     assert r["horizon"] == 16 and r["samples"] > 0.9 * 16 * (1 << 16) and np.isfinite(r["actor_grad_norm"])
     assert r["update_precision"].startswith("fp16 split tcgen05")
+
+
+class _Recorded(Exception):
+    pass
+
+
+@pytest.mark.parametrize("prec,use_critic,baseline", [(0, False, "batch"), (0, True, "batch_norm"), ("auto", False, "batch_norm"),
+                                                      ("auto", True, "batch")])
+def test_one_message_exchange_equals_single_process_update(b2048, prec, use_critic, baseline):
+    """exchange="one_message" (north_star: one all-reduce for the policy gradient): two emulated ranks, each
+    holding half of the episodes, exchange exactly ONE buffer [g_A | g_B | critic gradient | baseline sums] per update, and the
+    applied update equals the one a single process holding every episode applies with the default exchange
+    (reinforce_agent.py:303-322, :502-555: g = (g_A - mean g_B) / std by linearity of the backward pass)."""
+    n, seed = 8192, 77
+    kw = full_env_kwargs("runner_default"); kw["max_steps"] = 40
+    mlp = b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal")
+    acfg = b2048.ReinforceAgentConfig(gamma=0.99, baseline_mode=baseline, learning_rate=1e-2, critic_learning_rate=1e-3,
+                                      use_critic=use_critic, model_seed=5)
+    cfg = b2048.Game2048EnvConfig(**kw)
+    env1 = b2048.Batched2048Env(n, cfg, seed=seed, gid0=0)
+    single = b2048.ReinforceAgent(env1, mlp, acfg)
+    th0 = single._actor.theta.clone()
+    c0 = single._critic.theta.clone() if use_critic else None
+    u1 = single.update_from_rollout(single.rollout_many(env1, precision=0), precision=prec)
+    ranks = []
+    for lo, hi in ((0, n // 2 - 100), (n // 2 - 100, n)):
+        env = b2048.Batched2048Env(hi - lo, cfg, seed=seed, gid0=lo)
+        agent = b2048.ReinforceAgent(env, mlp, acfg)
+        ro = agent.rollout_many(env, precision=0)
+        ro.n_traj = n
+        ranks.append((agent, ro))
+    sent = []
+
+    def record(t):
+        sent.append(t.clone())
+        raise _Recorded()
+
+    for agent, ro in ranks:                      # phase 1: what every rank would send (parameters are not touched yet)
+        with pytest.raises(_Recorded):
+            agent.update_from_rollout(ro, allreduce=record, precision=prec, exchange="one_message")
+    assert len(sent) == 2 and sent[0].shape == sent[1].shape and sent[0].dtype == torch.float64
+    total = sent[0] + sent[1]
+    for agent, ro in ranks:                      # phase 2: the same update with the summed message delivered
+        calls = []
+
+        def deliver(t):
+            calls.append(int(t.numel()))
+            t.copy_(total)
+
+        upd = agent.update_from_rollout(ro, allreduce=deliver, precision=prec, exchange="one_message")
+        assert len(calls) == 1, calls
+        d_ref, d_got = single._actor.theta - th0, agent._actor.theta - th0
+        rel = float((d_got - d_ref).norm() / d_ref.norm())
+        gn = abs(upd["actor_grad_norm"] - u1["actor_grad_norm"]) / u1["actor_grad_norm"]
+        # fp32 kernels: only the summation order differs.  Tensor cores: g_A and mean g_B are each formed with the fp16 backward's
+        # rounding noise and then cancel (|g_A| ~ 3 |g|), so the bar is north_star's tensor-core tolerance, not the 2e-3 the
+        # default exchange reaches
+        tol = 1e-4 if prec == 0 else 1e-2
+        print(f"one-message exchange ({upd['precision']}, {baseline}, critic={use_critic}): 1 all-reduce of {calls[0]} float64; "
+              f"update rel err {rel:.2e}, grad-norm rel err {gn:.2e}")
+        assert rel < tol and gn < tol, (rel, gn)
+        if use_critic:
+            dc_ref, dc_got = single._critic.theta - c0, agent._critic.theta - c0
+            relc = float((dc_got - dc_ref).norm() / dc_ref.norm())
+            assert relc < tol, relc
+    assert torch.equal(ranks[0][0]._actor.theta, ranks[1][0]._actor.theta)
