@@ -238,7 +238,15 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # before any pinned allocation: staging buffers of the host-buffer (e2e) leg on the GPU's own NUMA node
+    numa = {"bound": False, "why": "--no-numa-bind"} if args.no_numa_bind else b2048.dist.bind_to_gpu_numa_node(local_rank)
     info = b2048.dist.init_distributed("nccl")
+    if world > 1:                       # every rank's node / outcome, for the line rank 0 prints
+        nn = torch.full((world, 2), 0, dtype=torch.int32, device=dev)
+        nn[rank, 0] = -1 if numa.get("numa_node") is None else int(numa["numa_node"])
+        nn[rank, 1] = int(bool(numa.get("bound")))
+        dist.all_reduce(nn)
+        numa["all_ranks_node"], numa["all_ranks_bound"] = nn[:, 0].tolist(), nn[:, 1].tolist()
     n = args.boards
     K, W = args.steps, max(3, args.warmup)
 
@@ -369,7 +377,7 @@ def run_b200(args):
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"random-legal batched env stepping, {n} packed boards per GPU "
                                    f"(BASELINE.json configs[1]), runner-default env, reset-on-done",
-                       "boards_per_gpu": n,
+                       "boards_per_gpu": n, "numa": numa,
                        "l2": f"inputs larger than L2: the launches rotate over {R} resident {n}-board batches "
                              f"({R * n * (22 if args.lean else 23) / 1e6:.0f} MB of state vs 126 MB L2), no flush kernel between them; "
                              "one CUDA-event pair around the K back-to-back launches",
@@ -527,6 +535,7 @@ def main():
     ap.add_argument("--boards", type=int, default=BOARDS_PER_GPU)
     ap.add_argument("--lean", action="store_true", help="board-only state (no score/step/max_tile arrays)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the process on whatever CPUs the launcher gave it")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--onehot-boards", type=int, default=262144, help="actor-critic leg on the reference's documented one-hot network")
     ap.add_argument("--no-sweep", action="store_true", help="skip the BASELINE.json configs[4] leg (runs at N >= 2)")
