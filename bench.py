@@ -23,6 +23,8 @@ reset-on-done).  One "step" = one fused `b2048_step_many` launch over all boards
              policy kernel + step kernel), 262,144 boards
   train_iter / train_iter_actor_critic   secondary: BASELINE.json configs[2] / configs[3] (rollout to termination +
              one update; 65,536 / 262,144 boards per GPU)
+  train_iter_actor_critic_shared   secondary: configs[3] as BASELINE.json words it (shared MLP trunk + value head, advantage
+             scan with lambda = 0.95) on the same kernels (b2048/shared_trunk.py)
   train_iter_actor_critic_onehot   secondary: the reference's documented configuration (one-hot observations, hidden
              [256, 128, 64], Adam) at configs[3]'s 262,144 boards per GPU, on the shape-generic
              tcgen05 kernels (csrc/b2048_mlp_gen.cu)
@@ -476,6 +478,9 @@ def run_b200(args):
             extra["train_iter"] = b2048.bench_train_iter(dev, boards=args.train_boards, info=info, precision="auto")
             extra["train_iter_actor_critic"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision="auto",
                                                                       use_critic=True, iters=3)
+            # configs[3]'s literal wording: one shared trunk with a policy head and a value head, lambda advantage scan
+            extra["train_iter_actor_critic_shared"] = b2048.bench_train_iter(dev, boards=args.ac_boards, info=info, precision="auto",
+                                                                             use_critic=True, iters=2, shared_trunk=True)
             # SURVEY.md section 8d config 4 as the reference documents it (one-hot 272-256-128-64 networks): the shape-generic
             # tensor-core kernels (gen_mlp_kernel / gen_dw_kernel)
             extra["train_iter_actor_critic_onehot"] = b2048.bench_train_iter(dev, boards=args.onehot_boards, info=info, precision="auto",
@@ -500,6 +505,8 @@ def run_b200(args):
             "train_iter_update_mode": g(extra, "train_iter", "update_precision"),
             "train_iter_update_ms_bf16": g(extra, "train_iter", "update_ms_bf16"),
             "ac_rollout_ms": g(extra, "train_iter_actor_critic", "rollout_ms"), "ac_update_ms": g(extra, "train_iter_actor_critic", "update_ms"),
+            "ac_shared_rollout_ms": g(extra, "train_iter_actor_critic_shared", "rollout_ms"),
+            "ac_shared_update_ms": g(extra, "train_iter_actor_critic_shared", "update_ms"),
             "ac_onehot_rollout_ms": g(extra, "train_iter_actor_critic_onehot", "rollout_ms"),
             "ac_onehot_update_ms": g(extra, "train_iter_actor_critic_onehot", "update_ms"),
             "ac_onehot_mode": g(extra, "train_iter_actor_critic_onehot", "update_precision"),

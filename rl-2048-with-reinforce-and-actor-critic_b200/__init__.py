@@ -13,10 +13,11 @@ from .env import Game2048Env
 from .MLP import (MLPConfig, DeviceMLP, encode_observation, init_model_params, load_model_params, save_model_params,
                   forward_logits, logits_to_probs)
 from .reinforce_agent import ReinforceAgent, ReinforceAgentConfig, Rollout
+from .shared_trunk import SharedTrunkActorCritic
 from .rollout_bench import bench_env_trained_boards, bench_rollout, bench_sharded_sweep, bench_train_iter
 from . import dist
 
 __all__ = ["B2048Error", "Batched2048Env", "Game2048EnvConfig", "debug_set", "get_handle", "make_env_cfg", "Game2048",
            "Game2048Env", "MLPConfig", "DeviceMLP", "encode_observation", "init_model_params", "load_model_params",
            "save_model_params", "forward_logits", "logits_to_probs", "ReinforceAgent", "ReinforceAgentConfig",
-           "Rollout"]
+           "Rollout", "SharedTrunkActorCritic"]

@@ -712,6 +712,13 @@ class ReinforceAgent:
             backward(self._critic, gcoef.reshape(-1), 1)
             base_values = td                                         # advantages := baseline-processed TD errors (:495-498)
             info["td"] = td
+            lam = float(getattr(self, "gae_lambda", 0.0))            # shared_trunk.py; 0 = the reference's TD(0) advantages
+            if lam > 0.0:
+                gae = self._buf("gae", (T, B), torch.float32)        # A_t = delta_t + gamma lambda A_{t+1}: the returns scan
+                with torch.cuda.device(dev):
+                    _lib.check(lib.b2048_reverse_scan_f64(_ptr(td), _ptr(gae), _ptr(length), float(cfg.gamma) * lam, T, B,
+                                                          _stream()), "b2048_reverse_scan_f64")
+                base_values = gae
         else:
             returns = self._buf("returns", (T, B), torch.float32)
             with torch.cuda.device(dev):
@@ -719,20 +726,25 @@ class ReinforceAgent:
                                                       _stream()), "b2048_reverse_scan_f64")
             base_values = returns
             info["returns"] = returns
+        shared = getattr(self, "_shared_net", None)                  # shared_trunk.py: one network, two heads, one optimizer
+        if one_msg and shared is not None:
+            raise ValueError("exchange='one_message' is implemented for separate actor / critic networks")
         if one_msg:
             self._one_message_exchange(base_values, ro, n_traj, adv, coef, stats, ep_mean, backward, allreduce)
             advantages(base_values, pre=1)   # adv / coef as the default exchange reports them (global statistics)
         else:
             advantages(base_values)
             backward(self._actor, coef.reshape(-1), 0)
+            if shared is not None:
+                self._merge_shared_grads()   # trunk gradient = policy part - value_coef x value part
             if allreduce is not None:
                 allreduce(self._grad_all)    # ONE message per update: [actor gradient | critic gradient]
 
         if cfg.optimizer == "adam":
             self._adam_t += 1
-        ss_a = apply(self._actor, cfg.learning_rate, +1.0, self._adam_t)
+        ss_a = apply(self._actor if shared is None else shared, cfg.learning_rate, +1.0, self._adam_t)
         ss_c = None
-        if cfg.use_critic and self._critic is not None:
+        if cfg.use_critic and self._critic is not None and shared is None:
             if cfg.optimizer == "adam":
                 self._adam_t_c += 1
             ss_c = apply(self._critic, cfg.critic_learning_rate, -1.0, getattr(self, "_adam_t_c", 0))

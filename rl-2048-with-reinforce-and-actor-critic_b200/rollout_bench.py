@@ -52,11 +52,13 @@ ONEHOT_ENV = dict(obs_mode="onehot", obs_log2_scale=1.0, reward_mode="log2", bas
 
 
 def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precision="auto", use_critic: bool = False,
-                     update_precisions=("auto",), network: str = "default"):
+                     update_precisions=("auto",), network: str = "default", shared_trunk: bool = False, gae_lambda: float = 0.95):
     """BASELINE.json configs[2]: REINFORCE rollout (to termination, max_steps 1024) + one update (gamma 0.99,
     baseline 'batch', SGD lr 1e-4, clip 1.0) on `boards` episodes per GPU; gradients all-reduced over ranks.
     use_critic=True is configs[3]: actor + separate critic (reference semantics, reinforce_agent.py:403-498), TD(0)
     advantages, Adam, both networks 16-256-256-{4,1} ReLU.
+    shared_trunk=True is configs[3]'s literal wording: ONE 16-256-256 trunk with a policy head and a value head
+    (shared_trunk.py), advantages from the lambda scan of the TD errors, one Adam step on the whole vector.
     update_precisions: the update of the LAST iteration is also timed (on a restored copy of the parameters) in these
     other modes of update_from_rollout, e.g. ("auto", 1) reports the default mode and the single-bf16 opt-in."""
     import sys
@@ -73,7 +75,12 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
                                      use_critic=True, optimizer="adam", model_seed=0) if use_critic else
                 ReinforceAgentConfig(gamma=0.99, learning_rate=1e-4, baseline_mode="batch", model_seed=0))
     hidden = [256, 128, 64] if onehot else [256, 256]
-    agent = ReinforceAgent(env, MLPConfig(hidden_sizes=hidden, activation="ReLU", init_distribution="HeNormal"), acfg)
+    mlp_cfg = MLPConfig(hidden_sizes=hidden, activation="ReLU", init_distribution="HeNormal")
+    if shared_trunk:
+        from .shared_trunk import SharedTrunkActorCritic
+        agent = SharedTrunkActorCritic(env, mlp_cfg, acfg, value_coef=0.5, gae_lambda=gae_lambda)
+    else:
+        agent = ReinforceAgent(env, mlp_cfg, acfg)
     use_critic = use_critic or onehot
     allreduce = bd.allreduce_sum_ if info.is_distributed else None
     out, alt = [], {}
@@ -118,6 +125,7 @@ def bench_train_iter(dev, boards: int = 65536, info=None, iters: int = 2, precis
     res = {"metric": ("actor-critic" if use_critic else "REINFORCE") + " iteration (rollout to termination + update)",
            "boards_per_gpu": boards,
            "network": ("272-256-128-64-4 ReLU actor + 272-256-128-64-1 critic, one-hot observations (runner.py:27-47)" if onehot else
+                       f"shared 16-256-256 ReLU trunk + policy head (4) + value head (1), GAE lambda {gae_lambda}" if shared_trunk else
                        "16-256-256-4 ReLU actor" + (" + 16-256-256-1 critic" if use_critic else "")),
            "rollout_precision": ("bf16 tcgen05 (fused persistent kernel)" if agent._fused_shape() else "fp16 tcgen05 (shape-generic policy kernel + step kernel)") if (agent.tc_supported() and precision != 0) else "fp32 CUDA cores",
            "episode_steps_per_s": last["episode_steps"] / (tot_ms * 1e-3), "rollout_ms": last["rollout_ms"],

@@ -8,7 +8,7 @@ with the full optimiser state every ``train.checkpoint_every`` batches).  One tr
 ``train.batch_size`` episodes played in parallel on the GPU (``rollout_many``) followed by one
 ``update_from_rollout``; evaluation = greedy rollouts with the max-tile histogram (runner.py:737-828).
 Extra keys: ``train.precision`` ("auto" | 0 | 1), ``train.exchange`` ("default" | "one_message": one all-reduce per update),
-``seed``.  Under torchrun the episodes are sharded over ranks.
+``seed``, and an optional section ``shared_trunk`` ({"value_coef", "gae_lambda"}: one network with a policy and a value head).  Under torchrun the episodes are sharded over ranks.
 
     python -m torch.distributed.run ... b2048_runner.py -conf cfg.json      (or: python b2048_runner.py -conf cfg.json)
 """
@@ -66,10 +66,20 @@ def tile_histogram(max_exp: torch.Tensor, info: bd.DistInfo | None = None) -> li
     return [int(c) for c in counts.tolist()]
 
 
+def make_agent(cfg: dict[str, Any], env):
+    """ReinforceAgent, or — with the extra section {"shared_trunk": {"value_coef": .., "gae_lambda": ..}} — the shared-trunk
+    actor-critic of shared_trunk.py (one network, policy + value heads)."""
+    st = cfg.get("shared_trunk")
+    if st is not None:
+        from .shared_trunk import SharedTrunkActorCritic
+        return SharedTrunkActorCritic(env, MLPConfig(**cfg["mlp"]), ReinforceAgentConfig(**cfg["agent"]),
+                                      value_coef=float(st.get("value_coef", 0.5)), gae_lambda=float(st.get("gae_lambda", 0.0)))
+    return ReinforceAgent(env, MLPConfig(**cfg["mlp"]), ReinforceAgentConfig(**cfg["agent"]))
+
+
 def build(cfg: dict[str, Any], num_envs: int, info: bd.DistInfo, device=None):
     env = bd.make_sharded_env(num_envs, Game2048EnvConfig(**cfg["env"]), info, seed=int(cfg["seed"]), device=device)
-    agent = ReinforceAgent(env, MLPConfig(**cfg["mlp"]), ReinforceAgentConfig(**cfg["agent"]))
-    return env, agent
+    return env, make_agent(cfg, env)
 
 
 def _global_stats(values: torch.Tensor, info: bd.DistInfo):
@@ -147,7 +157,7 @@ def evaluation(cfg: dict[str, Any], info: bd.DistInfo | None = None, device=None
     env = bd.make_sharded_env(int(ev["num_episodes"]), Game2048EnvConfig(**cfg["env"]), info, seed=int(cfg["seed"]) + 12345,
                               device=device)
     if agent is None:
-        agent = ReinforceAgent(env, MLPConfig(**cfg["mlp"]), ReinforceAgentConfig(**cfg["agent"]))
+        agent = make_agent(cfg, env)
         if ev.get("model_path"):
             agent.load_model(ev["model_path"])
     ro = agent.rollout_many(env, greedy=bool(ev.get("use_greedy", True)), precision=cfg["train"].get("precision", "auto"))
