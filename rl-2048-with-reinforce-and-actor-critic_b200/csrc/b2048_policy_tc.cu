@@ -124,6 +124,7 @@ struct PolicyTcArgs {
 // Pipelining: the MMAs of K slab g are issued as soon as group g has written slab g (tensor core runs under the
 // epilogues); A1 of tile i+1 is encoded right after epilogue 1 of tile i and MMA1(i+1) is issued as soon as layer 2
 // of tile i has been issued, so it runs under epilogue 2(i).  All hand-offs are mbarriers (phase = tile parity).
+constexpr int TC_H2_COL = 32;                                     // H2 (packed bf16 A operand of the head) inside the D2 region
 constexpr int TC_EPI_THREADS = 512;
 constexpr int TC_IO_THREADS = 128;
 constexpr int TC_THREADS = TC_EPI_THREADS + 32 + TC_IO_THREADS;   // 16 epilogue warps + MMA warp + 4 I/O warps
@@ -164,6 +165,37 @@ __device__ __forceinline__ void relu_store_slabs(uint32_t tlane_col0, uint8_t* a
     }
 }
 
+// Epilogue 2 keeps H2 ON THE TENSOR CORE'S SIDE: bf16(relu(D2)) goes back into tensor memory as the packed A operand of the
+// head MMAs (tcgen05.mma with A in TMEM: lane = row, one 32-bit column = two consecutive K elements) instead of into the A2
+// shared-memory buffer.  A2 therefore belongs to layer 2 alone, and epilogue 1 of the NEXT item starts right after this pass
+// instead of after the head MMAs.  Layout of the D2 region (256 columns): D3 = columns 0..15 (even K steps) + 16..31 (odd K
+// steps; the sampler adds the two), H2 = columns 32..159 (slab s, warp group g: 32 + 32 s + 8 g .. +7), i.e. written IN PLACE
+// over accumulator columns that belong to slabs <= s; columns 0..63 are drained before the first head MMA is issued.  Those columns are owned by other warps of the same lane quarter, so the four warps of a quarter meet at a
+// named barrier once per slab, after their loads of that slab have landed and before anyone stores it.
+__device__ __forceinline__ void relu_store_tmem(uint32_t tlane_d2, int q, int g, int lane, uint32_t bar0) {
+    uint32_t r[2][16];
+    tmem_ld16_issue(tlane_d2 + (uint32_t)(g * 16), r[0]);
+    tmem_ld_wait(r[0]);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (s + 1 < 4) tmem_ld16_issue(tlane_d2 + (uint32_t)((s + 1) * 64 + g * 16), r[(s + 1) & 1]);
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");              // every warp of the quarter holds slab s in registers
+        const uint32_t(&v)[16] = r[s & 1];
+        uint32_t w[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[c] = relu_pack(v[2 * c], v[2 * c + 1]);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
+                         tlane_d2 + (uint32_t)(TC_H2_COL + s * 32 + g * 8)),
+                     "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (s + 1 < 4) tmem_ld_wait(r[(s + 1) & 1]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");         // TMEM reads and writes ordered before the hand-off
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8u * s);
+    }
+}
+
 // kRollout = false: one policy step over all tiles (item = tile).
 // kRollout = true : the whole rollout loop of b2048_rollout_many in ONE launch.  A CTA owns the tiles
 //   first, first + grid, ... and walks the items (t, tile) for t = t_begin .. t_begin + n_steps - 1; boards are
@@ -197,7 +229,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
         for (int g = 0; g < 4; ++g) { mbar_init(bar_slab0 + 8u * g, TC_EPI_THREADS / 32); mbar_init(bar_hslab0 + 8u * g, TC_EPI_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {   // all 512 TMEM columns: D1 = columns 0..255, D2 = 256..511, D3 = 256..271 (over D2)
+    if (warp == 16) {   // all 512 TMEM columns: D1 = 0..255, D2 = 256..511, D3 = 256..287 (two partial sums) and H2 (packed bf16) = 288..415 (over D2)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -254,6 +286,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 for (int g = 0; g < 4; ++g) {
                     mbar_wait(bar_slab0 + 8u * g, ph);
                     if (g == 0 && item != 0) mbar_wait(bar_free, ph ^ 1u);   // D2/D3 drained by the previous tile
+                    if (g == 0 && args.debug_clock != nullptr && blockIdx.x == 0 && item < 4) args.debug_clock[64 + 4 * item] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -264,21 +297,35 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 }
                 umma_f16(tmem_base + 256u, dOnes2, dBias, kIdesc, 1u);           // + b2
                 umma_commit(bar_d2);
-                // ---- next tile's layer 1 runs under this tile's epilogue 2 (D1 was drained before the slab arrivals)
-                if (prefetch && item + 1 < n_items) issue_layer1(ph ^ 1u);
+                // ---- next tile's layer 1 runs under this tile's epilogue 2 (D1 was drained before the slab arrivals) — as soon
+                //      as its A1 is there: the head below must never queue behind a late A1 (the logits feed the sampler, the
+                //      env step and, through bar_free, the next item's layer 2), so A1 is probed, not waited for, until the
+                //      head has been issued
+                bool l1_pending = prefetch && item + 1 < n_items;
+                auto try_layer1 = [&]() {
+                    if (l1_pending && mbar_test(bar_a1, ph ^ 1u)) { issue_layer1(ph ^ 1u); l1_pending = false; }
+                };
                 // ---- head: D3 = H2 . W3^T, slab by slab as epilogue 2 produces them.  D3 overlays D2 columns 0..15,
                 //      which belong to slab 0 and have been drained by every warp before hslab[0] completes.
+                const bool mdbg = args.debug_clock != nullptr && blockIdx.x == 0 && item < 4;
                 for (int g = 0; g < 4; ++g) {
-                    mbar_wait(bar_hslab0 + 8u * g, ph);
+                    try_layer1();
+                    while (!mbar_test(bar_hslab0 + 8u * g, ph)) try_layer1();
+                    if (mdbg && g == 3) args.debug_clock[64 + 4 * item + 1] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t a_addr = sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u;
+                    for (int q = 0; q < 4; ++q) {                      // A = H2 in tensor memory: 8 columns per K = 16 step
+                        uint32_t a_tmem = tmem_base + 256u + (uint32_t)(TC_H2_COL + g * 32 + q * 8);
                         uint32_t b_addr = sW3 + (uint32_t)g * 2048u + (uint32_t)q * 32u;
-                        umma_f16(tmem_base + 256u, desc_sw128(a_addr), desc_sw128(b_addr), kIdescHead, (g | q) ? 1u : 0u);
+                        // two accumulators (even / odd K steps): an M128 N16 MMA is all latency (~110 cycles when it has to
+                        // wait for the previous one's D), so consecutive MMAs must not accumulate into the same columns
+                        umma_f16_ts(tmem_base + 256u + (uint32_t)((q & 1) * 16), a_tmem, desc_sw128(b_addr), kIdescHead,
+                                    (g | (q >> 1)) ? 1u : 0u);
                     }
                 }
                 umma_commit(bar_d3);
+                if (mdbg) args.debug_clock[64 + 4 * item + 2] = clock64();
+                if (l1_pending) issue_layer1(ph ^ 1u);
             }
             __syncwarp();
             ph ^= 1u;
@@ -294,19 +341,20 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
             const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == 0 && item < 8;
             long long* dc = dbg ? args.debug_clock + 8 * item : nullptr;
             if (dbg) dc[0] = clock64();
-            // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab.  A2 is free once the previous tile's head MMAs
-            //      (which read H2 out of the same buffer) have completed.
+            // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab.  A2 is free: the previous item's layer-2 MMAs completed
+            //      before its epilogue 2 ran (bar_d2), and its head reads H2 from tensor memory, not from A2.
             mbar_wait(bar_d1, ph);
-            if (item != 0) mbar_wait(bar_d3, ph ^ 1u);
             if (dbg) dc[1] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             relu_store_slabs(tlane, a2_row, row, g, lane, bar_slab0);
             if (dbg) dc[2] = clock64();
-            // ---- epilogue 2: H2 = bf16(relu(D2)), slab by slab, written over A2 (layer 2 has completed)
+            // ---- epilogue 2: H2 = bf16(relu(D2)), slab by slab, packed back into tensor memory (relu_store_tmem)
             mbar_wait(bar_d2, ph);
             if (dbg) dc[3] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            relu_store_slabs(tlane + 256u, a2_row, row, g, lane, bar_hslab0);
+            relu_store_tmem(tlane + 256u, q, g, lane, bar_hslab0);
+            if (args.debug_clock != nullptr && blockIdx.x == 0 && item < 4 && lane == 0)    // the slowest warp's end of epilogue 2
+                atomicMax(reinterpret_cast<unsigned long long*>(args.debug_clock) + 80 + item, (unsigned long long)clock64());
             if (lane == 0) mbar_arrive(bar_free);      // this warp's D2 reads were fenced before its hslab arrivals
             if (dbg) dc[4] = clock64();
             ph ^= 1u;
@@ -401,17 +449,22 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                     if (kRollout) wait_inputs_of(jn, rn);
                     encode_a1(jn, rn);
                 }
-                mbar_wait(bar_d3, ph);
                 const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == TC_EPI_THREADS + 32 && item < 8;
+                if (dbg && item < 4) args.debug_clock[64 + 4 * item + 3] = clock64();
+                mbar_wait(bar_d3, ph);
                 if (dbg) args.debug_clock[8 * item + 5] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t r4[4];
-                tmem_ld4(tlane + 256u, r4);
+                uint32_t r4[4], r4b[4];
+                tmem_ld4_issue(tlane + 256u, r4);
+                tmem_ld4(tlane + 256u + 16u, r4b);             // waits for both loads
+                asm volatile("" : "+r"(r4[0]), "+r"(r4[1]), "+r"(r4[2]), "+r"(r4[3]));
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_free);
-                const float lg0 = __uint_as_float(r4[0]) + sB3[0], lg1 = __uint_as_float(r4[1]) + sB3[1];
-                const float lg2 = __uint_as_float(r4[2]) + sB3[2], lg3 = __uint_as_float(r4[3]) + sB3[3];
+                const float lg0 = (__uint_as_float(r4[0]) + __uint_as_float(r4b[0])) + sB3[0];
+                const float lg1 = (__uint_as_float(r4[1]) + __uint_as_float(r4b[1])) + sB3[1];
+                const float lg2 = (__uint_as_float(r4[2]) + __uint_as_float(r4b[2])) + sB3[2];
+                const float lg3 = (__uint_as_float(r4[3]) + __uint_as_float(r4b[3])) + sB3[3];
                 uint32_t a = 0;
                 if (valid) {
                     float m0 = (use_mask && !(fl & 1u)) ? -1e9f : lg0, m1 = (use_mask && !(fl & 2u)) ? -1e9f : lg1;
@@ -602,11 +655,11 @@ int ensure_tc_image(b2048_handle* h) {
 static long long* debug_clock_buffer(const b2048_handle* h) {
     static long long* dbg_buf = nullptr;
     if (!(h->debug & (1u << B2048_DBG_TC_CLOCKS))) return nullptr;
-    if (!dbg_buf) { cudaMalloc(&dbg_buf, 80 * sizeof(long long)); cudaMemset(dbg_buf, 0, 80 * sizeof(long long)); }
+    if (!dbg_buf) { cudaMalloc(&dbg_buf, 96 * sizeof(long long)); cudaMemset(dbg_buf, 0, 96 * sizeof(long long)); }
     return dbg_buf;
 }
 static void print_debug_clock(long long* dbg, cudaStream_t stream) {
-    long long hbuf[80];
+    long long hbuf[96];
     cudaStreamSynchronize(stream);
     cudaMemcpy(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
     for (int k = 0; k < 6; ++k)
@@ -616,6 +669,12 @@ static void print_debug_clock(long long* dbg, cudaStream_t stream) {
                 k, hbuf[8 * k + 1] - hbuf[8 * k], hbuf[8 * k + 2] - hbuf[8 * k + 1], hbuf[8 * k + 3] - hbuf[8 * k + 2],
                 hbuf[8 * k + 4] - hbuf[8 * k + 3], hbuf[8 * k + 4] - hbuf[8 * k], hbuf[8 * k + 8] - hbuf[8 * k],
                 hbuf[8 * k + 5] - hbuf[8 * k], hbuf[8 * k + 6] - hbuf[8 * k + 5], hbuf[8 * k + 7] - hbuf[8 * k]);
+    for (int k = 0; k < 4; ++k)      // MMA warp / sampler, relative to the item's start (epilogue warps' clock 0)
+        fprintf(stderr, "[tc clock] item %d: mma: layer 2 starts +%lld, last H2 slab seen +%lld, d3 committed +%lld | sampler waits for d3 from +%lld\n",
+                k, hbuf[64 + 4 * k] - hbuf[8 * k], hbuf[64 + 4 * k + 1] - hbuf[8 * k], hbuf[64 + 4 * k + 2] - hbuf[8 * k],
+                hbuf[64 + 4 * k + 3] - hbuf[8 * k]);
+    for (int k = 0; k < 4; ++k) fprintf(stderr, "[tc clock] item %d: slowest epilogue warp leaves epilogue 2 at +%lld\n", k, hbuf[80 + k] - hbuf[8 * k]);
+    cudaMemset(dbg + 80, 0, 16 * sizeof(long long));
 }
 
 // Returns B2048_OK if the tensor-core path applies and was launched, B2048_ERR_UNSUPPORTED (without setting an
