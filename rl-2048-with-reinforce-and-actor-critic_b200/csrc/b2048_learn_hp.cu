@@ -41,8 +41,9 @@ constexpr int HP_RES = 8 * HP_UNIT;             // units in streaming order hi0,
 constexpr int RES_W1H = 0;                      // [32 row-groups][2 k-chunks][8 rows][16 B] (no swizzle), as IMG_W1
 constexpr int RES_W1L = 8192;
 constexpr int RES_BIAS = 16384;                 // k = 0: b1 hi, 1: b2 hi, 2: b1 lo, 3: b2 lo
-constexpr int RES_W3H = 24576;                  // 4 slabs [16 rows x 128 B] (SWIZZLE_128B), as IMG_W3
-constexpr int RES_W3L = 32768;
+constexpr int RES_W3H = 24576;                  // 4 slabs of [16 rows hi | 16 rows lo] x 128 B (SWIZZLE_128B): one N = 32 B operand
+constexpr int RES_W3L = RES_W3H + 2048;         // (slab s: hi at RES_W3H + 4096 s, lo 2048 B behind it)
+constexpr int RES_W3_SLAB = 4096;
 constexpr int RES_B3 = 40960;                   // float [4]
 constexpr int RES_ONES1 = 41216;                // every row = e0 + e2
 constexpr int RES_ONES2 = 41472;                // every row = e1 + e3
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256) hp_prepare_kernel(const float* __restrict
     for (int idx = tid; idx < TC_N3 * TC_H; idx += nth) {
         int j = idx / TC_H, k = idx - j * TC_H;
         int slab = k >> 6, kc = (k & 63) >> 3, ke = k & 7;
-        size_t off = (size_t)slab * 2048 + (size_t)j * 128 + (size_t)((kc ^ (j & 7)) * 16) + ke * 2;
+        size_t off = (size_t)slab * RES_W3_SLAB + (size_t)j * 128 + (size_t)((kc ^ (j & 7)) * 16) + ke * 2;
         __half hi, lo;
         split_f16(j < n_out ? W3[k * n_out + j] : 0.0f, hi, lo);
         *reinterpret_cast<__half*>(res + RES_W3H + off) = hi;
@@ -169,6 +170,7 @@ static_assert(FS_TOTAL <= 232448, "fwd_hp_kernel exceeds the shared memory of an
 
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(TC_H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);       // A/B fp16
 constexpr uint32_t kIdescHeadF16 = (1u << 4) | ((uint32_t)(TC_N3 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+constexpr uint32_t kIdescHead32F16 = (1u << 4) | ((uint32_t)((2 * TC_N3) >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // N = 32: [W3 hi | W3 lo]
 
 struct FwdHpArgs {
     const uint8_t* img;       // split-weight image (global)
@@ -339,21 +341,22 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
                 }
                 // ---- the next tile's layer 1 (D1 was drained before the last H1 slab arrival waited for above)
                 if (tile + nranks < n_tiles) issue_layer1(ph ^ 1u);
-                // ---- head: D3 (columns 256..271: that part of D2 is drained before the first H2 slab arrives)
+                // ---- head: D3 (columns 256..287: that part of D2 is drained before the first H2 slab arrives)
                 for (int s = 0; s < 4; ++s) {
                     const uint32_t st = F & 1u, au = F >> 1;
                     mbar_wait(a_full0 + 8u * st, au & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ahi = dlo_sw(sA + st * FS_ASTAGE), alo = ahi + (16384u >> 4);
-                    const uint32_t w3h = dlo_sw(sRes + RES_W3H + (uint32_t)s * 2048u), w3l = dlo_sw(sRes + RES_W3L + (uint32_t)s * 2048u);
+                    // An M128 N16 K16 MMA occupies the tensor pipe as long as a full-width one (~110-140 cycles, measured in
+                    // b2048_policy_tc.cu), so the three products are issued as TWO instructions per K step: H2hi x [W3hi | W3lo]
+                    // as one N = 32 MMA (columns 0..15: hi x hi, 16..31: hi x lo; the reader adds the halves) and H2lo x W3hi.
+                    const uint32_t w3 = dlo_sw(sRes + RES_W3H + (uint32_t)s * (uint32_t)RES_W3_SLAB);
                     if (leader) {
 #pragma unroll
                         for (uint32_t q = 0; q < 4; ++q)
-                            umma_w(tmem_base + 256u, ahi + 2u * q, DH_SW, w3h + 2u * q, DH_SW, kIdescHeadF16, (s | q) ? 1u : 0u);
+                            umma_w(tmem_base + 256u, ahi + 2u * q, DH_SW, w3 + 2u * q, DH_SW, kIdescHead32F16, (s | q) ? 1u : 0u);
 #pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q) umma_w(tmem_base + 256u, alo + 2u * q, DH_SW, w3h + 2u * q, DH_SW, kIdescHeadF16, 1u);
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q) umma_w(tmem_base + 256u, ahi + 2u * q, DH_SW, w3l + 2u * q, DH_SW, kIdescHeadF16, 1u);
+                        for (uint32_t q = 0; q < 4; ++q) umma_w(tmem_base + 256u, alo + 2u * q, DH_SW, w3 + 2u * q, DH_SW, kIdescHeadF16, 1u);
                         umma_commit(a_free0 + 8u * st);
                     }
                     ++F;
@@ -534,15 +537,17 @@ __device__ __forceinline__ void fwd_role(const FwdHpArgs& args, const PipeCtx& p
             if (next < n_tiles) encode_a1(next);
             mbar_wait(bar_d3, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r4[4];
-            tmem_ld4(tlane + 256u, r4);
+            uint32_t r4[4], r4b[4];
+            tmem_ld4_issue(tlane + 256u, r4);
+            tmem_ld4(tlane + 256u + 16u, r4b);                  // the hi x lo partial sums; the wait covers both loads
+            asm volatile("" : "+r"(r4[0]), "+r"(r4[1]), "+r"(r4[2]), "+r"(r4[3]));
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_d3r);
             if (s < args.n) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (j < args.n_out) args.out[srow * args.n_out + j] = __uint_as_float(r4[j]) + sB3[j];
+                    if (j < args.n_out) args.out[srow * args.n_out + j] = (__uint_as_float(r4[j]) + __uint_as_float(r4b[j])) + sB3[j];
             }
             if (piped) {
                 __threadfence();
@@ -1316,11 +1321,11 @@ static int launch_backward_hp_piped(b2048_handle* h, const uint64_t* board, cons
     a.d.h1 = a.f.h1; a.d.h2 = a.f.h2; a.d.dl2 = a.b.dl2; a.d.d3t = a.b.d3t;
     a.d.gW2 = gW2; a.d.gb2 = gb2; a.d.gW3 = gW3; a.d.inv_scale = scale + 1;
     a.d.n_tiles = n_tiles; a.d.n_out = n_out;
-    // role split: per tile the forward role needs ~14 K cycles, the backward role ~7.5 K, the dW2 role ~4.5 K, the dW3 role ~2.5 K (both bound by ~30 B/clk of L2 -> shared-memory bulk copies per SM)
+    // role split (148 SMs -> 78 / 40 / 16 / 14; swept again after the head of the forward role went from 48 to 32 MMAs): per tile the forward role needs ~12 K cycles, the backward role ~7.5 K, the dW2 role ~4.5 K, the dW3 role ~2.5 K (both bound by ~30 B/clk of L2 -> shared-memory bulk copies per SM)
     const int S = h->num_sms;
     a.nB = (h->pipe_split & 0xFF) ? (h->pipe_split & 0xFF) : (S * 27 + 50) / 100;
     a.nC2 = ((h->pipe_split >> 8) & 0xFF) ? ((h->pipe_split >> 8) & 0xFF) : (S * 11 + 50) / 100;
-    a.nC13 = ((h->pipe_split >> 16) & 0xFF) ? ((h->pipe_split >> 16) & 0xFF) : (S * 8 + 50) / 100;
+    a.nC13 = ((h->pipe_split >> 16) & 0xFF) ? ((h->pipe_split >> 16) & 0xFF) : (S * 19 + 100) / 200;   // 14 of 148: its 16 M128 N16 MMAs per tile cost 2.5 K cycles
     a.nF = S - a.nB - a.nC2 - a.nC13;
     if (a.nF < 1 || a.nB < 1 || a.nC2 < 1 || a.nC13 < 1) return fail(B2048_ERR_INVALID, "update pipeline: bad role split");
     void* params[] = {&a};
