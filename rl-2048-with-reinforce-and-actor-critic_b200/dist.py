@@ -5,8 +5,9 @@ GLOBAL board id, the Philox streams are keyed on that id (results are independen
 nothing is exchanged during rollouts.  Per update the only exchange is ONE all-reduce(SUM) of the flat
 gradient buffer [actor | critic] (285 KB per network for the runner-default MLP), preceded by a 32-byte
 all-reduce of the four float64 baseline sums when the baseline is "batch" / "batch_norm" (the global mean / std
-enter every sample's coefficient, so they have to exist before the gradient; folding them into the gradient
-message as g = g_A - mu g_B would need a second dW accumulation, +40 % of the update, to save a 32-byte message)."""
+enter every sample's coefficient, so they have to exist before the gradient).  exchange="one_message" (opt-in) folds
+both into exactly ONE float64 all-reduce [g_A | g_B | critic gradient | sums] and forms g = (g_A - mean g_B) / std
+afterwards; it runs the actor's backward pass twice (+40 % of the update), which is why it is not the default."""
 from __future__ import annotations
 
 import os

@@ -214,8 +214,10 @@ def test_bench_reads_roofline_traffic_from_the_committed_ncu_summary():
     assert src is not None and src.startswith("profiles/") and 1.8e7 < t < 2.4e7          # ~19 MB per 1 M-board launch
     assert bench.profile_traffic(["does_not_exist.csv"]) == (None, None)
     # unit handling: the update pipeline's summary mixes Mbyte and Gbyte
-    t2, _ = bench.profile_traffic(["r02_ncu_update_pipe_kernel.csv"], "update_pipe")
+    t2, _ = bench.profile_traffic(["r02_ncu_update_pipe_kernel_r288_276k.csv"], "update_pipe")      # 80 MB ring (superseded)
     assert t2 is not None and 1e9 < t2 < 4e9
+    t3, _ = bench.profile_traffic(["r02_ncu_update_pipe_kernel.csv"], "update_pipe")                # 59 MB ring: ~0.34 GB per 1 M samples
+    assert t3 is not None and 2e8 < t3 < 1e9
 
 
 def test_debug_options_match_the_header():
