@@ -186,6 +186,27 @@ def main():
         print(f"shape-generic tensor-core kernels, one-hot 272-256-128-64 actor + critic: rollout sharding invariance OK; "
               f"update rel err actor {rel:.2e} critic {relc:.2e}")
         assert rel < 1e-3 and relc < 1e-3
+    # ---- 6. shared-trunk actor-critic (shared_trunk.py) under sharding: ONE flat gradient (trunk | policy head | value head)
+    #         is exchanged after the value-view gradient has been merged locally; lambda scan + batch_norm baseline
+    acfg = b2048.ReinforceAgentConfig(gamma=0.99, learning_rate=1e-2, model_seed=3, baseline_mode="batch_norm", optimizer="adam")
+    mlp = b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal")
+    n_ep = 12000 + 1
+    env = bd.make_sharded_env(n_ep, cfg, info, seed=seed + 6)
+    agent = b2048.SharedTrunkActorCritic(env, mlp, acfg, value_coef=0.5, gae_lambda=0.9)
+    th0 = agent._shared_net.theta.clone()
+    ro = agent.rollout_many(env, precision="auto")
+    ro.n_traj = n_ep
+    calls.clear()
+    agent.update_from_rollout(ro, allreduce=counting_allreduce)
+    theta = agent._shared_net.theta.clone()
+    if info.rank == 0:
+        env1 = b2048.Batched2048Env(n_ep, cfg, device=dev, seed=seed + 6)
+        a1 = b2048.SharedTrunkActorCritic(env1, mlp, acfg, value_coef=0.5, gae_lambda=0.9)
+        a1.update_from_rollout(a1.rollout_many(env1, precision="auto"))
+        rel = float(((theta - th0) - (a1._shared_net.theta - th0)).norm() / (a1._shared_net.theta - th0).norm())
+        print(f"shared-trunk actor-critic (lambda 0.9, tensor-core update): {len(calls)} all-reduces per update {calls}; "
+              f"update rel err {rel:.2e}")
+        assert len(calls) == 2 and calls[1] == agent._shared_net.n_params and rel < 2e-3
     dist.barrier()
     if info.rank == 0:
         print("multi-GPU check OK")
