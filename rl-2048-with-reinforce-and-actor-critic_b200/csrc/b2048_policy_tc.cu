@@ -135,36 +135,9 @@ constexpr int SM_TBL = SM_ACT + 256;                              // fused rollo
 constexpr int SM_TOTAL_RO = SM_TBL + B2048_SMALL_BYTES;
 static_assert(SM_TOTAL_RO <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
-// One epilogue pass, SLAB-MAJOR: for every 64-column K slab s of the next layer's operand, warp (q, g) converts the 16
-// accumulator columns 64 s + 16 g .. +15 of its 32 rows (ReLU -> bf16), stores them into the 128B-swizzled slab and
-// arrives on that slab's barrier.  All 16 warps finish slab 0 first, so the tensor core starts on the next layer
-// after a quarter of the epilogue instead of after all of it.
-__device__ __forceinline__ void relu_store_slabs(uint32_t tlane_col0, uint8_t* a2_row, int row, int g, int lane,
-                                                 uint32_t bar0) {
-    // software-pipelined: the TMEM load of slab s + 1 is in flight while slab s is converted and stored
-    uint32_t r[2][16];
-    tmem_ld16_issue(tlane_col0 + (uint32_t)(g * 16), r[0]);
-    tmem_ld_wait(r[0]);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (s + 1 < 4) tmem_ld16_issue(tlane_col0 + (uint32_t)((s + 1) * 64 + g * 16), r[(s + 1) & 1]);
-        const uint32_t(&v)[16] = r[s & 1];
-        uint8_t* rowp = a2_row + s * 16384;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {                                           // two 16-byte chunks of 8 columns
-            uint32_t w0 = relu_pack(v[c * 8 + 0], v[c * 8 + 1]), w1 = relu_pack(v[c * 8 + 2], v[c * 8 + 3]);
-            uint32_t w2 = relu_pack(v[c * 8 + 4], v[c * 8 + 5]), w3 = relu_pack(v[c * 8 + 6], v[c * 8 + 7]);
-            int chunk = g * 2 + c;
-            *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row & 7)) * 16)) = make_uint4(w0, w1, w2, w3);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // smem writes -> visible to the tensor core
-        if (s + 1 < 4) tmem_ld_wait(r[(s + 1) & 1]);                            // next slab's accumulators have landed
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");         // accumulator reads ordered before reuse
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8u * s);   // ONE arrival per warp: 32 same-address arrivals would serialise
-    }
-}
-
+// Epilogue passes are SLAB-MAJOR: for every 64-column K slab s of the next layer's operand, warp (q, g) converts the 16
+// accumulator columns 64 s + 16 g .. +15 of its 32 rows (ReLU -> bf16) and arrives on that slab's barrier.  All 16 warps finish
+// slab 0 first, so the tensor core starts on the next layer after a quarter of the epilogue instead of after all of it.
 // Epilogue 2 keeps H2 ON THE TENSOR CORE'S SIDE: bf16(relu(D2)) goes back into tensor memory as the packed A operand of the
 // head MMAs (tcgen05.mma with A in TMEM: lane = row, one 32-bit column = two consecutive K elements) instead of into the A2
 // shared-memory buffer.  A2 therefore belongs to layer 2 alone, and epilogue 1 of the NEXT item starts right after this pass
@@ -172,7 +145,11 @@ __device__ __forceinline__ void relu_store_slabs(uint32_t tlane_col0, uint8_t* a
 // steps; the sampler adds the two), H2 = columns 32..159 (slab s, warp group g: 32 + 32 s + 8 g .. +7), i.e. written IN PLACE
 // over accumulator columns that belong to slabs <= s; columns 0..63 are drained before the first head MMA is issued.  Those columns are owned by other warps of the same lane quarter, so the four warps of a quarter meet at a
 // named barrier once per slab, after their loads of that slab have landed and before anyone stores it.
+// The same pass serves epilogue 1 (kDstCol = 0: H1 over the D1 region, the A operand of layer 2) — shared memory then holds
+// weights and A1 only, and no generic-proxy -> async-proxy fence sits in either epilogue.
+template <int kDstCol>
 __device__ __forceinline__ void relu_store_tmem(uint32_t tlane_d2, int q, int g, int lane, uint32_t bar0) {
+    static_assert(kDstCol >= 0 && kDstCol <= 32, "slab s must land in columns drained by slabs <= s");
     uint32_t r[2][16];
     tmem_ld16_issue(tlane_d2 + (uint32_t)(g * 16), r[0]);
     tmem_ld_wait(r[0]);
@@ -185,7 +162,7 @@ __device__ __forceinline__ void relu_store_tmem(uint32_t tlane_d2, int q, int g,
 #pragma unroll
         for (int c = 0; c < 8; ++c) w[c] = relu_pack(v[2 * c], v[2 * c + 1]);
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
-                         tlane_d2 + (uint32_t)(TC_H2_COL + s * 32 + g * 8)),
+                         tlane_d2 + (uint32_t)(kDstCol + s * 32 + g * 8)),
                      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                      : "memory");
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -252,7 +229,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
         // ============================ MMA / copy warp ============================
         // Lane 0 does the work; the other lanes stay converged with it (__syncwarp per tile) so that the final
         // aligned __syncthreads is reached by the whole warp together.
-        const uint32_t sA1 = s_u32(smem + SM_A1), sA2 = s_u32(smem + SM_A2);
+        const uint32_t sA1 = s_u32(smem + SM_A1);
         const uint32_t sW1 = s_u32(smem + IMG_W1), sW2 = s_u32(smem + IMG_W2), sW3 = s_u32(smem + IMG_W3);
         const uint64_t dBias = desc_nosw_k16(s_u32(smem + IMG_BIAS));
         const uint64_t dOnes1 = desc_ones(s_u32(smem + IMG_ONES1)), dOnes2 = desc_ones(s_u32(smem + IMG_ONES2));
@@ -289,10 +266,10 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                     if (g == 0 && args.debug_clock != nullptr && blockIdx.x == 0 && item < 4) args.debug_clock[64 + 4 * item] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t a_addr = sA2 + (uint32_t)g * 16384u + (uint32_t)q * 32u;
+                    for (int q = 0; q < 4; ++q) {                      // A = H1 in tensor memory (D1 region, 8 columns per K = 16 step)
+                        uint32_t a_tmem = tmem_base + (uint32_t)(g * 32 + q * 8);
                         uint32_t b_addr = sW2 + (uint32_t)g * 32768u + (uint32_t)q * 32u;
-                        umma_f16(tmem_base + 256u, desc_sw128(a_addr), desc_sw128(b_addr), kIdesc, (g | q) ? 1u : 0u);
+                        umma_f16_ts(tmem_base + 256u, a_tmem, desc_sw128(b_addr), kIdesc, (g | q) ? 1u : 0u);
                     }
                 }
                 umma_f16(tmem_base + 256u, dOnes2, dBias, kIdesc, 1u);           // + b2
@@ -303,7 +280,9 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 //      head has been issued
                 bool l1_pending = prefetch && item + 1 < n_items;
                 auto try_layer1 = [&]() {
-                    if (l1_pending && mbar_test(bar_a1, ph ^ 1u)) { issue_layer1(ph ^ 1u); l1_pending = false; }
+                    // layer 1 of the next item overwrites the D1 region that THIS item's layer 2 reads H1 from: only after
+                    // those MMAs have completed (bar_d2; the epilogue warps wait for the same phase)
+                    if (l1_pending && mbar_test(bar_d2, ph) && mbar_test(bar_a1, ph ^ 1u)) { issue_layer1(ph ^ 1u); l1_pending = false; }
                 };
                 // ---- head: D3 = H2 . W3^T, slab by slab as epilogue 2 produces them.  D3 overlays D2 columns 0..15,
                 //      which belong to slab 0 and have been drained by every warp before hslab[0] completes.
@@ -325,7 +304,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                 }
                 umma_commit(bar_d3);
                 if (mdbg) args.debug_clock[64 + 4 * item + 2] = clock64();
-                if (l1_pending) issue_layer1(ph ^ 1u);
+                if (l1_pending) { mbar_wait(bar_d2, ph); issue_layer1(ph ^ 1u); }
             }
             __syncwarp();
             ph ^= 1u;
@@ -335,24 +314,23 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
         const int q = warp & 3, g = warp >> 2;
         const int row = q * 32 + lane;                                          // board row inside the tile = TMEM lane
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint8_t* a2_row = smem + SM_A2 + row * 128;                             // this row's line in slab 0
         uint32_t ph = 0;
         for (int item = 0; item < n_items; ++item) {
             const bool dbg = args.debug_clock != nullptr && blockIdx.x == 0 && tid == 0 && item < 8;
             long long* dc = dbg ? args.debug_clock + 8 * item : nullptr;
             if (dbg) dc[0] = clock64();
-            // ---- epilogue 1: A2 = bf16(relu(D1)), slab by slab.  A2 is free: the previous item's layer-2 MMAs completed
-            //      before its epilogue 2 ran (bar_d2), and its head reads H2 from tensor memory, not from A2.
+            // ---- epilogue 1: H1 = bf16(relu(D1)), slab by slab, packed in place over the D1 region (columns 0..127): the A
+            //      operand of layer 2 in tensor memory
             mbar_wait(bar_d1, ph);
             if (dbg) dc[1] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            relu_store_slabs(tlane, a2_row, row, g, lane, bar_slab0);
+            relu_store_tmem<0>(tlane, q, g, lane, bar_slab0);
             if (dbg) dc[2] = clock64();
             // ---- epilogue 2: H2 = bf16(relu(D2)), slab by slab, packed back into tensor memory (relu_store_tmem)
             mbar_wait(bar_d2, ph);
             if (dbg) dc[3] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            relu_store_tmem(tlane + 256u, q, g, lane, bar_hslab0);
+            relu_store_tmem<TC_H2_COL>(tlane + 256u, q, g, lane, bar_hslab0);
             if (args.debug_clock != nullptr && blockIdx.x == 0 && item < 4 && lane == 0)    // the slowest warp's end of epilogue 2
                 atomicMax(reinterpret_cast<unsigned long long*>(args.debug_clock) + 80 + item, (unsigned long long)clock64());
             if (lane == 0) mbar_arrive(bar_free);      // this warp's D2 reads were fenced before its hslab arrivals
