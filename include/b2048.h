@@ -232,7 +232,7 @@ int b2048_policy_step(b2048_handle* h, const uint64_t* board, const uint8_t* mas
  * ep_len != NULL: run-to-termination bookkeeping (see b2048_step_many); ep_len == NULL with cfg->auto_reset: fixed
  * horizon with reset-on-done.  t0: the env's step index before step t = 0 (Philox counter = t0 + t + 1).
  * use_mask: feed the legal masks to the policy (Game2048EnvConfig.use_action_mask).
- * precision 1 with the 16-256-256-4 ReLU policy and a plain reward configuration runs the whole chunk as ONE
+ * precision 1 with the 16-256-256-4 ReLU policy and an action-mask-on env configuration (any reward shaping) runs the whole chunk as ONE
  * persistent kernel (tcgen05 policy + env step); anything else is a policy-kernel / step-kernel loop.
  * slot_map (device int32[n_slots], may be NULL): play only the listed boards — run-to-termination callers pass the
  * boards still alive at the start of the chunk, so finished episodes cost nothing.  Fused kernel: slices t > ep_len[b] of a

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(1024, 1) step_fast_kernel(const __grid_constan
             io.action = act_next; io.mask_in = fin_next;
             const uint32_t inext = i + stride;
             if (inext < n) request(inext);
-            step_fast_rnd<kAct, kTrack>(io, cfg, rnd, args.seed, args.gid0 + (uint64_t)i, args.t, T);
+            step_fast_rnd<kAct, kTrack, false>(io, cfg, rnd, args.seed, args.gid0 + (uint64_t)i, args.t, T);   // kPlain: unshaped rewards
             *reinterpret_cast<uint2*>(args.board_out + i) = make_uint2(io.lo, io.hi);
             if (kTrack) { args.score[i] = io.score; args.step[i] = io.step; args.max_exp[i] = (uint8_t)io.max_exp; }
             args.reward[i] = io.reward;
@@ -445,7 +445,9 @@ template <int kAct>
 static cudaError_t launch_fast(bool track, int grid, size_t smem, cudaStream_t s, const StepArgs& a, bool pdl) {
     const bool plain = a.ep_len == nullptr && a.action_out == nullptr && a.merge_sum == nullptr && a.debug_clock == nullptr &&
                        (kAct == B2048_ACT_BUFFER || kAct == B2048_ACT_RANDOM_ANY || a.flags_in != nullptr) &&
-                       a.n < ((int64_t)1 << 31) - (int64_t)grid * 1024;
+                       a.n < ((int64_t)1 << 31) - (int64_t)grid * 1024 &&
+                       // the plain specialisation compiles the reward-shaping terms out (step_fast_rnd<.., kShaped = false>)
+                       !cfg_is_shaped(a.cfg);
     if (plain) return track ? launch_fast_one<kAct, true, true>(grid, smem, s, a, pdl) : launch_fast_one<kAct, false, true>(grid, smem, s, a, pdl);
     return track ? launch_fast_one<kAct, true, false>(grid, smem, s, a, pdl) : launch_fast_one<kAct, false, false>(grid, smem, s, a, pdl);
 }
@@ -472,7 +474,7 @@ struct StepNArgs {
     PhiloxKeys keys;
 };
 
-template <int kAct, bool kTrack>
+template <int kAct, bool kTrack, bool kShaped>
 __global__ void __launch_bounds__(1024, 1) step_fast_n_kernel(const __grid_constant__ StepNArgs args) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(1024, 1) step_fast_n_kernel(const __grid_const
         const uint64_t gid = args.gid0 + (uint64_t)i;
         for (int32_t k = 0; k < args.n_steps; ++k) {
             io.mask_in = io.flags & 0xFu;          // the flags of a step carry the legal mask of the board it returns
-            step_fast<kAct, kTrack>(io, cfg, args.keys, args.seed, gid, args.t + (uint32_t)k, T);
+            step_fast<kAct, kTrack, kShaped>(io, cfg, args.keys, args.seed, gid, args.t + (uint32_t)k, T);
             rsum += io.reward;
             eps += (io.flags & (B2048_F_DONE | B2048_F_TRUNC)) ? 1 : 0;
         }
@@ -677,7 +679,11 @@ extern "C" int b2048_create(b2048_handle** out) {
         B2_SET(B2048_ACT_RANDOM_LEGAL, true); B2_SET(B2048_ACT_RANDOM_LEGAL, false);
         B2_SET(B2048_ACT_RANDOM_ANY, true); B2_SET(B2048_ACT_RANDOM_ANY, false);
         B2_SET(B2048_ACT_PRIORITY, true); B2_SET(B2048_ACT_PRIORITY, false);
-#define B2_SET_N(A, TR) B2_CUDA(cudaFuncSetAttribute(step_fast_n_kernel<A, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES))
+#define B2_SET_N(A, TR)                                                                                                               \
+    do {                                                                                                                              \
+        B2_CUDA(cudaFuncSetAttribute(step_fast_n_kernel<A, TR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES)); \
+        B2_CUDA(cudaFuncSetAttribute(step_fast_n_kernel<A, TR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2048_TABLES_BYTES));  \
+    } while (0)
         B2_SET_N(B2048_ACT_RANDOM_LEGAL, true); B2_SET_N(B2048_ACT_RANDOM_LEGAL, false);
         B2_SET_N(B2048_ACT_RANDOM_ANY, true); B2_SET_N(B2048_ACT_RANDOM_ANY, false);
         B2_SET_N(B2048_ACT_PRIORITY, true); B2_SET_N(B2048_ACT_PRIORITY, false);
@@ -759,8 +765,7 @@ extern "C" int b2048_step_many(b2048_handle* h, const uint64_t* board_in, uint64
     const bool use_smem = h->smem_optin >= B2048_LUT_BYTES && n >= (int64_t)32768;
     const bool all_track = score && step && max_exp, none_track = !score && !step && !max_exp;
     const bool fast = h->smem_optin >= B2048_TABLES_BYTES && n >= (int64_t)32768 && (all_track || none_track) &&
-                      cfg->use_action_mask && cfg->empty_tile_reward == 0.0 && cfg->merge_reward == 0.0 &&
-                      cfg->bonus_mode == B2048_BONUS_OFF && cfg->endgame_penalty == 0.0 && reward != nullptr &&
+                      cfg->use_action_mask && (cfg->bonus_mode == B2048_BONUS_OFF || all_track) && reward != nullptr &&
                       reward64 == nullptr && spawn_replay == nullptr && (obs == nullptr || cfg->obs_mode == B2048_OBS_NONE) &&
                       !(h->debug & (1u << B2048_DBG_NO_FAST_STEP));
     if (fast) {
@@ -822,13 +827,12 @@ extern "C" int b2048_step_many_n(b2048_handle* h, uint64_t* board, uint32_t* sco
                "b2048_step_many_n: needs a device-side action mode (random_legal, random_any or priority)");
     const bool all_track = score && step && max_exp, none_track = !score && !step && !max_exp;
     const bool ok = h->smem_optin >= B2048_TABLES_BYTES && (all_track || none_track) && cfg->use_action_mask &&
-                    cfg->empty_tile_reward == 0.0 && cfg->merge_reward == 0.0 && cfg->bonus_mode == B2048_BONUS_OFF &&
-                    cfg->endgame_penalty == 0.0 &&
+                    (cfg->bonus_mode == B2048_BONUS_OFF || all_track) &&
                     (cfg->reward_mode == B2048_REWARD_SUM || cfg->reward_mode == B2048_REWARD_LOG2);
     if (!ok)
         return fail(B2048_ERR_UNSUPPORTED,
-                    "b2048_step_many_n: implemented for the plain reward configuration (base reward x scale + step "
-                    "reward, action mask on) with score / step / max_exp all present or all absent; call "
+                    "b2048_step_many_n: implemented for action-mask-on configurations (the new-max-tile bonus needs the "
+                    "tracked counters) with score / step / max_exp all present or all absent; call "
                     "b2048_step_many n_steps times otherwise");
     StepNArgs a;
     a.board = board; a.score = score; a.step = step; a.max_exp = max_exp; a.flags = flags; a.reward_last = reward_last;
@@ -836,10 +840,13 @@ extern "C" int b2048_step_many_n(b2048_handle* h, uint64_t* board, uint32_t* sco
     a.flags_valid = flags_valid; a.seed = seed; a.gid0 = gid0; a.t = t; a.cfg = *cfg; a.keys = make_keys(seed);
     const int grid = grid_for(n, 1024, h->num_sms, 1);
     cudaStream_t s = (cudaStream_t)stream;
+    const bool shaped = cfg_is_shaped(*cfg);
 #define B2_LAUNCH_N(A)                                                                                      \
     do {                                                                                                    \
-        if (all_track) step_fast_n_kernel<A, true><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);                \
-        else step_fast_n_kernel<A, false><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);                         \
+        if (all_track && shaped) step_fast_n_kernel<A, true, true><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);    \
+        else if (all_track) step_fast_n_kernel<A, true, false><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);        \
+        else if (shaped) step_fast_n_kernel<A, false, true><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);           \
+        else step_fast_n_kernel<A, false, false><<<grid, 1024, B2048_TABLES_BYTES, s>>>(a);                      \
     } while (0)
     if (cfg->action_mode == B2048_ACT_RANDOM_LEGAL) B2_LAUNCH_N(B2048_ACT_RANDOM_LEGAL);
     else if (cfg->action_mode == B2048_ACT_PRIORITY) B2_LAUNCH_N(B2048_ACT_PRIORITY);

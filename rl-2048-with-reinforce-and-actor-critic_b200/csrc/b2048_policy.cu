@@ -260,7 +260,7 @@ extern "C" int b2048_rollout_many(b2048_handle* h, uint64_t* boards, uint8_t* fl
     if (gen_slots) {
         B2_REQUIRE(precision == 1 && gen_supported(h, mlp) && ep_len != nullptr && n_slots >= 0 && n_slots <= B,
                    "b2048_rollout_many: slot_map needs a tensor-core policy (precision 1; the fused 16-256-256-4 rollout kernel with "
-                   "a plain reward configuration and B >= 4096, or a shape of the generic tcgen05 policy kernel) and ep_len");
+                   "an action-mask-on env configuration and B >= 4096, or a shape of the generic tcgen05 policy kernel) and ep_len");
         if (n_slots == 0) return B2048_OK;
     }
     for (int32_t k = 0; k < n_steps; ++k) {

@@ -181,7 +181,7 @@ __device__ __forceinline__ void relu_store_tmem(uint32_t tlane_d2, int q, int g,
 //   word) and writes slice t + 1 of the record — which the same thread reads back when the tile comes round again.
 //   The MMA / epilogue warps see nothing but a longer item stream: weights, TMEM and barriers stay set up for the
 //   whole rollout, and a step costs no launch, no image reload and no separate env kernel.
-template <bool kRollout>
+template <bool kRollout, bool kShaped = false>     // kShaped: the env configuration has reward-shaping terms (rollout only)
 __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_THREADS, 1)
     policy_tc_kernel(const __grid_constant__ PolicyTcArgs args) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                         args.ro_flags[o] = (uint8_t)io.flags;
                     } else {
                         io.action = sAct[grp * TC_M + row];
-                        step_fast_rnd<B2048_ACT_BUFFER, true>(io, args.cfg, rr, args.seed, args.gid0 + (uint64_t)b, t_env, T);
+                        step_fast_rnd<B2048_ACT_BUFFER, true, kShaped>(io, args.cfg, rr, args.seed, args.gid0 + (uint64_t)b, t_env, T);
                         if (args.ep_len && (io.flags & (B2048_F_DONE | B2048_F_TRUNC))) {
                             args.ep_len[b] = (int32_t)(slice + 1);
                             cur.ep = (int32_t)(slice + 1);
@@ -623,8 +623,10 @@ int ensure_tc_image(b2048_handle* h) {
     if (!(h->attrs & 1u)) {
         cudaError_t e = cudaFuncSetAttribute(policy_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL2);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel)");
-        e = cudaFuncSetAttribute(policy_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
+        e = cudaFuncSetAttribute(policy_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout>)");
+        e = cudaFuncSetAttribute(policy_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_RO);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(policy_tc_kernel<rollout, shaped>)");
         h->attrs |= 1u;
     }
     return B2048_OK;
@@ -721,8 +723,8 @@ int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boar
     const bool net_ok = mlp->n_layers == 3 && mlp->dims[0] == 16 && mlp->dims[1] == TC_H && mlp->dims[2] == TC_H &&
                         mlp->dims[3] == 4 && mlp->activation == B2048_ACTV_RELU &&
                         (mlp->obs_mode == B2048_OBS_RAW || mlp->obs_mode == B2048_OBS_LOG2) && h->smem_optin >= SM_TOTAL_RO;
-    const bool env_ok = score && step && max_exp && cfg->use_action_mask && cfg->empty_tile_reward == 0.0 &&
-                        cfg->merge_reward == 0.0 && cfg->bonus_mode == B2048_BONUS_OFF && cfg->endgame_penalty == 0.0 &&
+    // every action-mask-on reward configuration (step_fast_rnd carries the shaping terms; the counters are always tracked here)
+    const bool env_ok = score && step && max_exp && cfg->use_action_mask &&
                         (cfg->reward_mode == B2048_REWARD_SUM || cfg->reward_mode == B2048_REWARD_LOG2);
     // slot_map: only the listed boards are played (n_slots of them); without it all B boards
     const int64_t n = slot_map ? n_slots : B;
@@ -742,7 +744,8 @@ int launch_rollout_tc(b2048_handle* h, const b2048_mlp_desc* mlp, uint64_t* boar
     a.ro_stride = B;
     int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
     a.debug_clock = debug_clock_buffer(h);
-    policy_tc_kernel<true><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);
+    if (cfg_is_shaped(*cfg)) policy_tc_kernel<true, true><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);
+    else policy_tc_kernel<true, false><<<grid, TC_THREADS + TC_ENV_THREADS, SM_TOTAL_RO, stream>>>(a);
     if (a.debug_clock) print_debug_clock(a.debug_clock, stream);
     return check_cuda(cudaGetLastError(), "policy_tc_kernel<rollout> launch");
 }

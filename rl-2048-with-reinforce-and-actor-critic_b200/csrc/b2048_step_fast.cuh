@@ -1,5 +1,6 @@
-// b2048_step_fast.cuh — instruction-lean body of the fused env step for the common configuration
-// (reward = base term x scale + step_reward; no observation / float64 / replay outputs).
+// b2048_step_fast.cuh — instruction-lean body of the fused env step for the action-mask-on configurations
+// (every reward term of env.py:197-261 except the invalid-action penalty of mask-off envs; the new-max-tile bonus needs
+// the tracked counters; no observation / float64 / replay outputs).
 //
 // Same semantics as step_one (b2048_step.cuh; reference src/game2048.py:40-70, src/env.py:197-302) —
 // the two are checked against each other and against the CPU oracle by tests/host_check — but built
@@ -73,7 +74,9 @@ struct FastIO {
 // kAct: B2048_ACT_*; kTrack: score / step / max_exp kept (and truncation evaluated)
 // step_fast_rnd takes the board's Philox block of (gid, t, B2048_DOM_STEP) from the caller (the fused rollout kernel
 // shares it with the policy's sampling word); step_fast computes it.
-template <int kAct, bool kTrack>
+// kShaped = false: the caller guarantees empty_tile_reward = merge_reward = endgame_penalty = 0 and bonus off (the env-only
+// headline kernel: no instruction spent on them).
+template <int kAct, bool kTrack, bool kShaped = true>
 B2_HD void step_fast_rnd(FastIO& io, const b2048_env_cfg& cfg, const Rand4& rnd, uint64_t seed, uint64_t gid, uint32_t t,
                          const FastTables& T) {
 
@@ -154,10 +157,22 @@ B2_HD void step_fast_rnd(FastIO& io, const b2048_env_cfg& cfg, const Rand4& rnd,
 #else
         __builtin_clz(orm | 1u);
 #endif
-    if (kTrack && max_merged >= 3u && max_merged > io.max_exp) io.max_exp = max_merged;   // env.py:241-250 (bonus off)
     const uint32_t base = cfg.reward_mode == B2048_REWARD_SUM ? msum : (shr_fma<20>(agg) & 0xFFu);
     double r = dmul((double)base, cfg.base_reward_scale);
+    // shaping terms in the reference's order (env.py:226-259, as in step_one): empty cells of the NEW board (after the
+    // spawn), number of merges (agg bits 28..31), new-max-tile bonus, step reward, end-game penalty.  All uniform branches
+    // on launch constants; the plain configuration skips them.
+    if (kShaped && cfg.empty_tile_reward != 0.0) r = dadd(r, dmul(cfg.empty_tile_reward, (double)(n_empty - (val ? 1u : 0u))));
+    if (kShaped && cfg.merge_reward != 0.0) r = dadd(r, dmul(cfg.merge_reward, (double)(agg >> 28)));
+    if (kTrack && max_merged >= 3u && max_merged > io.max_exp) {                          // env.py:241-250
+        io.max_exp = max_merged;
+        if (kShaped && cfg.bonus_mode != B2048_BONUS_OFF) {
+            const double bonus = cfg.bonus_mode == B2048_BONUS_RAW ? (double)(1u << max_merged) : (double)max_merged;
+            r = dadd(r, dmul(bonus, cfg.bonus_scale));
+        }
+    }
     r = dadd(r, cfg.step_reward);
+    if (kShaped && done && cfg.endgame_penalty != 0.0) r = dadd(r, cfg.endgame_penalty);
     io.reward = (float)r;
 
     bool trunc = false;
@@ -174,10 +189,14 @@ B2_HD void step_fast_rnd(FastIO& io, const b2048_env_cfg& cfg, const Rand4& rnd,
     io.flags = f | mask;
 }
 
-template <int kAct, bool kTrack>
+template <int kAct, bool kTrack, bool kShaped = true>
 B2_HD void step_fast(FastIO& io, const b2048_env_cfg& cfg, const PhiloxKeys& keys, uint64_t seed, uint64_t gid,
                      uint32_t t, const FastTables& T) {
-    step_fast_rnd<kAct, kTrack>(io, cfg, stream_keyed(keys, gid, t, B2048_DOM_STEP), seed, gid, t, T);
+    step_fast_rnd<kAct, kTrack, kShaped>(io, cfg, stream_keyed(keys, gid, t, B2048_DOM_STEP), seed, gid, t, T);
+}
+// host side: does this configuration need the shaping terms?
+inline bool cfg_is_shaped(const b2048_env_cfg& c) {
+    return c.empty_tile_reward != 0.0 || c.merge_reward != 0.0 || c.endgame_penalty != 0.0 || c.bonus_mode != B2048_BONUS_OFF;
 }
 
 }  // namespace b2

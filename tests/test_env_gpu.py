@@ -297,6 +297,36 @@ def test_step_many_full_size_1m(b2048):
     assert ((env.flags.cpu().numpy()[:100000] & 0x0F) == m).all()
 
 
+@pytest.mark.parametrize("name,track", [("shaped_raw", True), ("onehot_log2bonus", True), ("shaped_nobonus", False)])
+def test_fast_step_kernel_shaped_rewards_vs_oracle(b2048, name, track):
+    """step_fast_kernel (n >= 32768, no float64 / obs / replay outputs) with reward shaping — empty-tile and merge rewards,
+    new-max-tile bonus (tracked state only), end-game penalty, env.py:226-259 — bit-equal float32 rewards, boards, flags and
+    counters against the CPU oracle; b2048_step_many_n (k steps per launch) gives the same boards."""
+    from helpers import full_env_kwargs
+    n, seed, gid0, T = 50000, 31337, 3 * 10**9, 90
+    if name == "shaped_nobonus":
+        kw = dict(full_env_kwargs("runner_default"), empty_tile_reward=0.05, merge_reward=0.3, step_reward=-0.01,
+                  endgame_penalty=-7.5, max_steps=70)
+    else:
+        kw = full_env_kwargs(name); kw["max_steps"] = kw["max_steps"] or 150
+    env = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=gid0, track_state=track)
+    env.reset_many()
+    okw = {k: v for k, v in kw.items() if k not in ("size", "obs_mode", "obs_log2_scale")}
+    cfg = oracle.make_cfg(action_mode="random_legal", auto_reset=True, **okw)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    for t in range(1, T + 1):
+        rew, fl = env.step_many(action_mode="random_legal", auto_reset=True)
+        o = oracle.step_many(st, cfg, seed, gid0, t, use_state=track)
+        assert (u64(env.board) == st["board"]).all() and (fl.cpu().numpy() == o["flags"]).all(), t
+        assert (rew.cpu().numpy() == o["reward"]).all(), t
+        if track:
+            assert (env.score.cpu().numpy() == st["score"]).all() and (env.max_exp.cpu().numpy() == st["max_exp"]).all()
+    env2 = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=gid0, track_state=track)
+    env2.reset_many()
+    env2.step_many_n(T, action_mode="random_legal", auto_reset=True)
+    assert torch.equal(env2.board, env.board)
+
+
 def test_symmetries_kernel_vs_reference_and_oracle(b2048):
     """b2048_symmetries vs the reference's get_symmetries outputs (fixture) and vs the oracle on a larger batch;
     augment_rollout uses it."""

@@ -140,6 +140,41 @@ def test_fast_step_body_vs_oracle(reward_mode, mode, track):
         flags_prev = fl.copy()
 
 
+@pytest.mark.parametrize("name,track", [("shaped_raw", True), ("onehot_log2bonus", True), ("shaped_nobonus", False),
+                                        ("shaped_nobonus", True)])
+def test_fast_step_body_shaped_rewards_vs_oracle(name, track):
+    """Reward shaping in the fast body (empty-tile / merge rewards, new-max-tile bonus, end-game penalty; env.py:226-259):
+    bit-equal float32 rewards, boards, flags and counters against the oracle on the reference-test env configurations."""
+    hc = host_check_lib()
+    n, T, seed, gid0 = 5000, 200, 123, 7 * 2**32
+    if name == "shaped_nobonus":
+        kw = dict(reward_mode="log2", base_reward_scale=0.5, empty_tile_reward=0.05, merge_reward=0.3, step_reward=-0.01,
+                  endgame_penalty=-7.5, max_steps=80)
+    else:
+        kw = {k: v for k, v in full_env_kwargs(name).items() if k not in ("size", "obs_mode", "obs_log2_scale")}
+        kw["max_steps"] = kw["max_steps"] or 150
+    cfg = oracle.make_cfg(action_mode="random_legal", auto_reset=True, **kw)
+    st = oracle.reset_many(n, seed, gid0, 0)
+    board = st["board"].copy(); score = st["score"].copy(); step = st["step"].copy(); mx = st["max_exp"].copy()
+    flags_prev = st["flags"].copy()
+    seen_bonus = False
+    for t in range(1, T + 1):
+        mx_before = st["max_exp"].copy()
+        o = oracle.step_many(st, cfg, seed, gid0, t, use_state=track)
+        act = np.zeros(n, np.uint8); ms = np.zeros(n, np.int32); rw = np.zeros(n, np.float32); fl = np.zeros(n, np.uint8)
+        hc.hc_step_fast_many(P(board), P(board), P(score) if track else None, P(step) if track else None,
+                             P(mx) if track else None, None, P(act), P(flags_prev), C.byref(cfg),
+                             P(ms), P(rw), P(fl), C.c_int64(n), C.c_uint64(seed), C.c_uint64(gid0), C.c_uint32(t))
+        assert (act == o["action"]).all() and (board == st["board"]).all(), t
+        assert (ms == o["merge_sum"]).all() and (fl == o["flags"]).all(), t
+        assert (rw == o["reward"]).all(), (t, np.flatnonzero(rw != o["reward"])[:5])
+        if track:
+            assert (score == st["score"]).all() and (step == st["step"]).all() and (mx == st["max_exp"]).all()
+            seen_bonus |= bool((st["max_exp"] > mx_before).any())
+        flags_prev = fl.copy()
+    assert not track or seen_bonus
+
+
 def test_fast_step_overflow_and_dense_boards():
     hc = host_check_lib()
     rng = np.random.default_rng(9)

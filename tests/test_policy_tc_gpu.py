@@ -173,8 +173,10 @@ def test_fused_rollout_greedy_equals_two_kernel_loop(b2048):
     assert (Aa[:T][live] == Ab[:T][live]).all() and (Ra[:T][live] == Rb[:T][live]).all()
 
 
-@pytest.mark.parametrize("n,horizon,max_steps", [(65536, None, 150), (262144, None, 40), (65536, 48, 30), (262144, 20, 1024)])
-def test_fused_tc_rollout_replays_in_oracle(b2048, n, horizon, max_steps):
+@pytest.mark.parametrize("n,horizon,max_steps,env_name", [(65536, None, 150, "runner_default"), (262144, None, 40, "runner_default"),
+                                                          (65536, 48, 30, "runner_default"), (262144, 20, 1024, "runner_default"),
+                                                          (65536, None, 120, "shaped_log2"), (65536, 40, 25, "shaped_log2")])
+def test_fused_tc_rollout_replays_in_oracle(b2048, n, horizon, max_steps, env_name):
     """The fused persistent tcgen05 rollout kernel (policy_tc_kernel<rollout>, 16-256-256-4) against the CPU ORACLE
     directly (not against the repo's other path): the recorded actions replayed through oracle.step_many reproduce
     every live board, reward and flags byte, the episode lengths, and the final score / step / max-tile counters —
@@ -182,6 +184,8 @@ def test_fused_tc_rollout_replays_in_oracle(b2048, n, horizon, max_steps):
     from helpers import full_env_kwargs
     seed, gid0 = 4242, 17
     kw = full_env_kwargs("runner_default"); kw["max_steps"] = max_steps
+    if env_name == "shaped_log2":     # every reward-shaping term of env.py:226-259 inside the fused kernel (step_fast_rnd)
+        kw.update(empty_tile_reward=0.05, merge_reward=0.3, bonus_mode="log2", bonus_scale=2.0, step_reward=-0.01, endgame_penalty=-7.5)
     benv = b2048.Batched2048Env(n, b2048.Game2048EnvConfig(**kw), seed=seed, gid0=gid0)
     agent = b2048.ReinforceAgent(benv, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
                                  b2048.ReinforceAgentConfig(model_seed=3))
