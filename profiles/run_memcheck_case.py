@@ -25,3 +25,17 @@ info2 = agent2.update_from_rollout(ro4)
 torch.cuda.synchronize()
 print("memcheck case OK", ro.T, mode, info["actor_grad_norm"], info["critic_grad_norm"], info1["actor_grad_norm"], ro3.B,
       int(ro4.length.sum()), info2["actor_grad_norm"])
+# reward shaping on the fast paths (fused rollout kernel, shaped variant) and the shared-trunk agent's two descriptor views
+kw_s = dict(kw, empty_tile_reward=0.05, merge_reward=0.3, bonus_mode="log2", bonus_scale=2.0, endgame_penalty=-7.5)
+env3 = b2048.Batched2048Env(4096 + 5, b2048.Game2048EnvConfig(**kw_s), seed=5)
+agent3 = b2048.SharedTrunkActorCritic(env3, b2048.MLPConfig(hidden_sizes=[256, 256], activation="ReLU", init_distribution="HeNormal"),
+                                      b2048.ReinforceAgentConfig(baseline_mode="batch_norm", optimizer="adam"), gae_lambda=0.9)
+ro5 = agent3.rollout_many(env3, precision=1)
+info3 = agent3.update_from_rollout(ro5)
+env4 = b2048.Batched2048Env(40000, b2048.Game2048EnvConfig(**kw_s), seed=6)
+env4.reset_many()
+for _ in range(3):
+    env4.step_many(action_mode="random_legal", auto_reset=True)
+env4.step_many_n(5, action_mode="random_legal", auto_reset=True)
+torch.cuda.synchronize()
+print("memcheck case 2 OK", ro5.T, info3["actor_grad_norm"])
