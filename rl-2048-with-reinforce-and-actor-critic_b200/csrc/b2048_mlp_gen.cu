@@ -244,17 +244,7 @@ __device__ __forceinline__ void gwait(uint32_t bar, uint32_t parity) {
     while (!gtry(bar, parity))
         if (clock64() - t0 > 4000000000LL) __trap();
 }
-// tcgen05.mma from the 32-bit halves of the two shared-memory descriptors (the upper halves are compile-time constants)
-__device__ __forceinline__ void umma_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// umma_w (tcgen05.mma from 32-bit descriptor halves): b2048_tc.cuh
 __device__ __forceinline__ uint32_t gpack(float a, float b) {
     __half2 p = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&p);

@@ -227,13 +227,18 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
 
     if (warp == 16) {
         // ============================ MMA / copy warp ============================
-        // Lane 0 does the work; the other lanes stay converged with it (__syncwarp per tile) so that the final
-        // aligned __syncthreads is reached by the whole warp together.
-        const uint32_t sA1 = s_u32(smem + SM_A1);
-        const uint32_t sW1 = s_u32(smem + IMG_W1), sW2 = s_u32(smem + IMG_W2), sW3 = s_u32(smem + IMG_W3);
-        const uint64_t dBias = desc_nosw_k16(s_u32(smem + IMG_BIAS));
-        const uint64_t dOnes1 = desc_ones(s_u32(smem + IMG_ONES1)), dOnes2 = desc_ones(s_u32(smem + IMG_ONES2));
-        if (lane == 0) {
+        // All 32 lanes walk the loops CONVERGENTLY (item / slab counters, barrier probes and the 32-bit descriptor words live in
+        // uniform registers); lane 0 only issues the asynchronous instructions — no ELECT / R2UR waterfall and no BRA.U.ANY loop
+        // per tcgen05.mma as under `if (lane == 0) { whole loop }`.  Measured: the item period does not change, i.e. the ~130
+        // cycles every head MMA costs are NOT issue overhead either (nor the accumulate dependency, nor the A operand's source):
+        // the tensor pipe has a per-instruction floor of that size on this part, which a full-width M128 N256 K16 MMA (128
+        // cycles of math) hides and an M128 N16 K16 one (8 cycles) does not.
+        const bool leader = lane == 0;
+        const uint32_t lA1 = dlo_ns(s_u32(smem + SM_A1)), lW1 = dlo_ns(s_u32(smem + IMG_W1));
+        const uint32_t lW2 = dlo_sw(s_u32(smem + IMG_W2)), lW3 = dlo_sw(s_u32(smem + IMG_W3));
+        const uint32_t lBias = dlo_ns(s_u32(smem + IMG_BIAS));
+        const uint32_t lOnes1 = dlo_ns(s_u32(smem + IMG_ONES1)), lOnes2 = dlo_ns(s_u32(smem + IMG_ONES2));
+        if (leader) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"((uint32_t)IMG_BYTES)
                          : "memory");
             constexpr uint32_t kChunk = 16384;
@@ -244,71 +249,72 @@ __global__ void __launch_bounds__(kRollout ? TC_THREADS + TC_ENV_THREADS : TC_TH
                              "l"(args.img + off), "r"(sz), "r"(bar_img)
                              : "memory");
             }
-            mbar_wait(bar_img, 0);
         }
         __syncwarp();
-        auto issue_layer1 = [&](uint32_t ph) {   // D1 = A1 . W1^T + b1
+        mbar_wait(bar_img, 0);
+        auto issue_layer1 = [&](uint32_t ph) {   // D1 = A1 . W1^T + b1   (called by the whole warp)
             mbar_wait(bar_a1, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_f16(tmem_base, desc_nosw_k16(sA1), desc_nosw_k16(sW1), kIdesc, 0u);
-            umma_f16(tmem_base, dOnes1, dBias, kIdesc, 1u);
-            umma_commit(bar_d1);
+            if (leader) {
+                umma_w(tmem_base, lA1, DH_NOSW, lW1, DH_NOSW, kIdesc, 0u);
+                umma_w(tmem_base, lOnes1, DH_ONES, lBias, DH_NOSW, kIdesc, 1u);
+                umma_commit(bar_d1);
+            }
         };
         uint32_t ph = 0;
-        if (lane == 0 && n_items > 0) issue_layer1(0u);
+        if (n_items > 0) issue_layer1(0u);
         for (int item = 0; item < n_items; ++item) {
-            if (lane == 0) {
-                if (!prefetch && item != 0) issue_layer1(ph);
-                // ---- layer 2, slab by slab as epilogue 1 produces them
-                for (int g = 0; g < 4; ++g) {
-                    mbar_wait(bar_slab0 + 8u * g, ph);
-                    if (g == 0 && item != 0) mbar_wait(bar_free, ph ^ 1u);   // D2/D3 drained by the previous tile
-                    if (g == 0 && args.debug_clock != nullptr && blockIdx.x == 0 && item < 4) args.debug_clock[64 + 4 * item] = clock64();
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {                      // A = H1 in tensor memory (D1 region, 8 columns per K = 16 step)
-                        uint32_t a_tmem = tmem_base + (uint32_t)(g * 32 + q * 8);
-                        uint32_t b_addr = sW2 + (uint32_t)g * 32768u + (uint32_t)q * 32u;
-                        umma_f16_ts(tmem_base + 256u, a_tmem, desc_sw128(b_addr), kIdesc, (g | q) ? 1u : 0u);
-                    }
+            if (!prefetch && item != 0) issue_layer1(ph);
+            const bool mdbg = args.debug_clock != nullptr && blockIdx.x == 0 && item < 4 && leader;
+            // ---- layer 2, slab by slab as epilogue 1 produces them: A = H1 in tensor memory (D1 region, 8 columns per K = 16
+            //      step), B = the W2 slab in shared memory (descriptor low word + 2 per 32-byte K step, + 2048 per slab)
+            for (uint32_t g = 0; g < 4; ++g) {
+                mbar_wait(bar_slab0 + 8u * g, ph);
+                if (g == 0 && item != 0) mbar_wait(bar_free, ph ^ 1u);       // D2/D3 drained by the previous tile
+                if (g == 0 && mdbg) args.debug_clock[64 + 4 * item] = clock64();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = tmem_base + g * 32u, b0 = lW2 + g * 2048u;
+                if (leader) {
+                    umma_w_ts(tmem_base + 256u, a0, b0, DH_SW, kIdesc, g ? 1u : 0u);
+                    umma_w_ts(tmem_base + 256u, a0 + 8u, b0 + 2u, DH_SW, kIdesc, 1u);
+                    umma_w_ts(tmem_base + 256u, a0 + 16u, b0 + 4u, DH_SW, kIdesc, 1u);
+                    umma_w_ts(tmem_base + 256u, a0 + 24u, b0 + 6u, DH_SW, kIdesc, 1u);
                 }
-                umma_f16(tmem_base + 256u, dOnes2, dBias, kIdesc, 1u);           // + b2
-                umma_commit(bar_d2);
-                // ---- next tile's layer 1 runs under this tile's epilogue 2 (D1 was drained before the slab arrivals) — as soon
-                //      as its A1 is there: the head below must never queue behind a late A1 (the logits feed the sampler, the
-                //      env step and, through bar_free, the next item's layer 2), so A1 is probed, not waited for, until the
-                //      head has been issued
-                bool l1_pending = prefetch && item + 1 < n_items;
-                auto try_layer1 = [&]() {
-                    // layer 1 of the next item overwrites the D1 region that THIS item's layer 2 reads H1 from: only after
-                    // those MMAs have completed (bar_d2; the epilogue warps wait for the same phase)
-                    if (l1_pending && mbar_test(bar_d2, ph) && mbar_test(bar_a1, ph ^ 1u)) { issue_layer1(ph ^ 1u); l1_pending = false; }
-                };
-                // ---- head: D3 = H2 . W3^T, slab by slab as epilogue 2 produces them.  D3 overlays D2 columns 0..15,
-                //      which belong to slab 0 and have been drained by every warp before hslab[0] completes.
-                const bool mdbg = args.debug_clock != nullptr && blockIdx.x == 0 && item < 4;
-                for (int g = 0; g < 4; ++g) {
-                    try_layer1();
-                    while (!mbar_test(bar_hslab0 + 8u * g, ph)) try_layer1();
-                    if (mdbg && g == 3) args.debug_clock[64 + 4 * item + 1] = clock64();
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {                      // A = H2 in tensor memory: 8 columns per K = 16 step
-                        uint32_t a_tmem = tmem_base + 256u + (uint32_t)(TC_H2_COL + g * 32 + q * 8);
-                        uint32_t b_addr = sW3 + (uint32_t)g * 2048u + (uint32_t)q * 32u;
-                        // two accumulators (even / odd K steps): an M128 N16 MMA is all latency (~110 cycles when it has to
-                        // wait for the previous one's D), so consecutive MMAs must not accumulate into the same columns
-                        umma_f16_ts(tmem_base + 256u + (uint32_t)((q & 1) * 16), a_tmem, desc_sw128(b_addr), kIdescHead,
-                                    (g | (q >> 1)) ? 1u : 0u);
-                    }
-                }
-                umma_commit(bar_d3);
-                if (mdbg) args.debug_clock[64 + 4 * item + 2] = clock64();
-                if (l1_pending) { mbar_wait(bar_d2, ph); issue_layer1(ph ^ 1u); }
             }
-            __syncwarp();
+            if (leader) {
+                umma_w(tmem_base + 256u, lOnes2, DH_ONES, lBias, DH_NOSW, kIdesc, 1u);           // + b2
+                umma_commit(bar_d2);
+            }
+            // ---- next tile's layer 1 runs under this tile's epilogue 2 — as soon as its A1 is there AND this item's layer 2 has
+            //      completed (it overwrites the D1 region layer 2 reads H1 from; bar_d2, the phase the epilogue warps wait for too).
+            //      Both are probed, not waited for, until the head has been issued: the logits feed the sampler, the env step
+            //      and, through bar_free, the next item's layer 2.
+            bool l1_pending = prefetch && item + 1 < n_items;
+            auto try_layer1 = [&]() {
+                if (l1_pending && mbar_test(bar_d2, ph) && mbar_test(bar_a1, ph ^ 1u)) { issue_layer1(ph ^ 1u); l1_pending = false; }
+            };
+            // ---- head: D3 = H2 . W3^T, slab by slab as epilogue 2 produces them; A = H2 in tensor memory (D2 region, from
+            //      column TC_H2_COL).  D3 = D2 columns 0..31 (two partial sums, even / odd K steps), which belong to slab 0 and
+            //      have been drained by every warp before hslab[0] completes.
+            for (uint32_t g = 0; g < 4; ++g) {
+                try_layer1();
+                while (!mbar_test(bar_hslab0 + 8u * g, ph)) try_layer1();
+                if (mdbg && g == 3) args.debug_clock[64 + 4 * item + 1] = clock64();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = tmem_base + 256u + (uint32_t)TC_H2_COL + g * 32u, b0 = lW3 + g * 128u;
+                if (leader) {
+                    umma_w_ts(tmem_base + 256u, a0, b0, DH_SW, kIdescHead, g ? 1u : 0u);
+                    umma_w_ts(tmem_base + 256u + 16u, a0 + 8u, b0 + 2u, DH_SW, kIdescHead, g ? 1u : 0u);
+                    umma_w_ts(tmem_base + 256u, a0 + 16u, b0 + 4u, DH_SW, kIdescHead, 1u);
+                    umma_w_ts(tmem_base + 256u + 16u, a0 + 24u, b0 + 6u, DH_SW, kIdescHead, 1u);
+                }
+            }
+            if (leader) umma_commit(bar_d3);
+            if (mdbg) args.debug_clock[64 + 4 * item + 2] = clock64();
+            if (l1_pending) { mbar_wait(bar_d2, ph); issue_layer1(ph ^ 1u); }
             ph ^= 1u;
         }
+        __syncwarp();
     } else if (warp < 16) {
         // ============================ epilogue warps ============================
         const int q = warp & 3, g = warp >> 2;

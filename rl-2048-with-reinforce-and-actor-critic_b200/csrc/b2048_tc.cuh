@@ -96,6 +96,35 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// tcgen05.mma from the 32-bit halves of the two shared-memory descriptors (upper halves are compile-time constants), so that the
+// descriptor arithmetic of a convergent MMA warp stays in uniform registers (see fwd_role)
+__device__ __forceinline__ void umma_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+constexpr uint32_t DH_SW = 0x40004040u;     // upper word of desc_sw128: SBO 1024, version 1, 128-byte swizzle
+constexpr uint32_t DH_NOSW = 0x4010u;       // desc_nosw_k16: SBO 256, version 1
+constexpr uint32_t DH_ONES = 0x4000u;       // desc_ones: SBO 0, version 1
+__device__ __forceinline__ uint32_t dlo_sw(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t dlo_ns(uint32_t saddr) { return (saddr >> 4) | (8u << 16); }
+
+// the same with the A operand in tensor memory
+__device__ __forceinline__ void umma_w_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
